@@ -1,0 +1,212 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes binding of oracle/s3d_oracle.c (the plain-C restatement).
+
+All arrays are numpy float64 in the REFERENCE's host layouts (see s3d_oracle.h):
+vectors ghosted `(np2, np1, np0)` C-order, matrices `(7, nz, ny, nx)` C-order.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+PC = {"none": 0, "jacobi": 1, "sgs": 2, "strilu": 3}
+PDE = {"poisson": 0, "convdiff": 1}
+FUNC = {"test_rhs": 0, "manufactured_solution": 1, "manufactured_rhs": 2}
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class PcParams(C.Structure):
+    _fields_ = [("pc", C.c_int), ("napplysweeps", C.c_int), ("nbuildsweeps", C.c_int)]
+
+
+class SolveInfo(C.Structure):
+    _fields_ = [("converged", C.c_int), ("iters", C.c_int), ("resnorm", C.c_double)]
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libs3d_oracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_mesh_h.restype = C.c_double
+        for f in ("orc_norm_vector_l2", "orc_inner_vector_l2", "orc_norm_L2", "orc_compute_error_L2"):
+            getattr(L, f).restype = C.c_double
+        for f in ("orc_richardson", "orc_gcr", "orc_cg", "orc_bicgstab"):
+            getattr(L, f).restype = SolveInfo
+        _LIB = L
+    return _LIB
+
+
+def _d(a):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"], "need contiguous float64"
+    return a.ctypes.data_as(_dp)
+
+
+def _np(npdim):
+    return (C.c_int * 3)(*[int(v) for v in npdim])
+
+
+def _a3(v):
+    return (C.c_double * 3)(*[float(t) for t in v])
+
+
+class Mesh:
+    """npdim counts boundary points (reference convention); coords are the three 1-D arrays."""
+
+    def __init__(self, npdim, rmin=(-1.0, -1.0, -1.0), rmax=(1.0, 1.0, 1.0), grid="uniform"):
+        self.npdim = tuple(int(v) for v in npdim)
+        self.grid = grid
+        self.coords = []
+        for d in range(3):
+            c = np.zeros(self.npdim[d])
+            if grid == "uniform":
+                lib().orc_coords_uniform(self.npdim[d], C.c_double(rmin[d]), C.c_double(rmax[d]), _d(c))
+            else:
+                lib().orc_coords_chebyshev(self.npdim[d], C.c_double(rmin[d]), C.c_double(rmax[d]), _d(c))
+            self.coords.append(c)
+
+    @property
+    def n(self):
+        return tuple(v - 2 for v in self.npdim)  # (nx, ny, nz)
+
+    @property
+    def vshape(self):
+        return (self.npdim[2], self.npdim[1], self.npdim[0])
+
+    @property
+    def mshape(self):
+        nx, ny, nz = self.n
+        return (7, nz, ny, nx)
+
+    def zeros(self):
+        return np.zeros(self.vshape)
+
+    def h(self):
+        return lib().orc_mesh_h(_np(self.npdim), *[_d(c) for c in self.coords])
+
+    def _c(self):
+        return [_d(c) for c in self.coords]
+
+
+def lhs(mesh, pde="poisson", vel=(0, 0, 0), mu=0.0):
+    A = np.zeros(mesh.mshape)
+    if pde == "poisson":
+        lib().orc_lhs_poisson(_np(mesh.npdim), *mesh._c(), _d(A))
+    else:
+        lib().orc_lhs_convdiff(_np(mesh.npdim), *mesh._c(), _a3(vel), C.c_double(mu), _d(A))
+    return A
+
+
+def grid_function(mesh, pde="poisson", func="test_rhs", vel=(0, 0, 0), mu=0.0, bvals=None):
+    f = mesh.zeros()
+    bv = (C.c_double * 6)(*bvals) if bvals is not None else None
+    lib().orc_grid_function(_np(mesh.npdim), *mesh._c(), PDE[pde], FUNC[func], _a3(vel), C.c_double(mu), bv, _d(f))
+    return f
+
+
+def apply(mesh, A, x):
+    y = mesh.zeros()
+    lib().orc_apply(_np(mesh.npdim), _d(A), _d(x), _d(y))
+    return y
+
+
+def apply_res(mesh, A, b, x):
+    y = mesh.zeros()
+    lib().orc_apply_res(_np(mesh.npdim), _d(A), _d(b), _d(x), _d(y))
+    return y
+
+
+def vecaxpy(mesh, a, x, y):
+    lib().orc_vecaxpy(_np(mesh.npdim), C.c_double(a), _d(x), _d(y))
+
+
+def vecset(mesh, a, x):
+    lib().orc_vecset(_np(mesh.npdim), C.c_double(a), _d(x))
+
+
+def vecassign(mesh, x, y):
+    lib().orc_vecassign(_np(mesh.npdim), _d(x), _d(y))
+
+
+def vec_multi_axpy(mesh, a, xs, y):
+    n = len(xs)
+    arr = (_dp * n)(*[_d(x) for x in xs])
+    lib().orc_vec_multi_axpy(_np(mesh.npdim), n, (C.c_double * n)(*a), arr, _d(y))
+
+
+def norm_vector_l2(mesh, x):
+    return lib().orc_norm_vector_l2(_np(mesh.npdim), _d(x))
+
+
+def inner_vector_l2(mesh, x, y):
+    return lib().orc_inner_vector_l2(_np(mesh.npdim), _d(x), _d(y))
+
+
+def norm_L2(mesh, x):
+    return lib().orc_norm_L2(_np(mesh.npdim), *mesh._c(), _d(x))
+
+
+def compute_error_L2(mesh, x, y):
+    return lib().orc_compute_error_L2(_np(mesh.npdim), *mesh._c(), _d(x), _d(y))
+
+
+def jacobi_apply(mesh, A, r):
+    z = mesh.zeros()
+    lib().orc_jacobi_apply(_np(mesh.npdim), _d(A), _d(r), _d(z))
+    return z
+
+
+def sgs_setup(mesh, A):
+    d = np.zeros(mesh.mshape[1:])
+    lib().orc_sgs_setup(_np(mesh.npdim), _d(A), _d(d))
+    return d
+
+
+def strilu_setup(mesh, A, nbuildsweeps=1):
+    d = np.zeros(mesh.mshape[1:])
+    lib().orc_strilu_setup(_np(mesh.npdim), _d(A), int(nbuildsweeps), _d(d))
+    return d
+
+
+def sgs_like_apply(mesh, A, diaginv, r, nsweeps=1):
+    z = mesh.zeros()
+    lib().orc_sgs_like_apply(_np(mesh.npdim), _d(A), _d(diaginv), int(nsweeps), _d(r), _d(z))
+    return z
+
+
+def sgs_redblack_apply(mesh, A, diaginv, r):
+    z = mesh.zeros()
+    lib().orc_sgs_redblack_apply(_np(mesh.npdim), _d(A), _d(diaginv), _d(r), _d(z))
+    return z
+
+
+def solve(mesh, A, b, ksp="richardson", pc="jacobi", rtol=1e-6, maxiter=1000, restart=30,
+          apply_sweeps=1, build_sweeps=1, x0=None):
+    """Returns (x, info dict, hist ndarray of relative residuals per iteration)."""
+    x = mesh.zeros() if x0 is None else x0.copy()
+    hist = np.zeros(maxiter + restart + 1)
+    pp = PcParams(PC[pc], int(apply_sweeps), int(build_sweeps))
+    L = lib()
+    n = _np(mesh.npdim)
+    if ksp == "richardson":
+        info = L.orc_richardson(n, _d(A), pp, _d(b), _d(x), C.c_double(rtol), int(maxiter), _d(hist))
+    elif ksp == "gcr":
+        info = L.orc_gcr(n, _d(A), pp, _d(b), _d(x), C.c_double(rtol), int(maxiter), int(restart), _d(hist))
+    elif ksp == "cg":
+        info = L.orc_cg(n, _d(A), pp, _d(b), _d(x), C.c_double(rtol), int(maxiter), _d(hist))
+    elif ksp in ("bcgs", "bicgstab"):
+        info = L.orc_bicgstab(n, _d(A), pp, _d(b), _d(x), C.c_double(rtol), int(maxiter), _d(hist))
+    else:
+        raise ValueError("Need a valid solver option!")
+    return x, {"converged": bool(info.converged), "iters": info.iters, "resnorm": info.resnorm}, hist[: info.iters].copy()
