@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Struct3d native structured-grid path on B200.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]`; for N > 1 it is
+launched under torchrun, one rank per GPU.  Prints ONE JSON line (rank 0).
+
+Workload (BASELINE.json metric "7-pt SpMV HBM GB/s ... at 512^3"): Poisson 3-D on [-1,1]^3, uniform
+grid, fp64, 512^3 unknowns PER GPU (z-slab decomposition: N GPUs solve 512 x 512 x 512N; weak scaling).
+One step = one pass of the hot path over that grid: the halo exchange the path needs (N > 1) and
+y = A x through SMat::apply, the reference-facing call (SMat::apply, reference src/linalg/matvec.cpp:59).
+  value      aggregate algorithmic GB/s (72 B/point), data resident in HBM, CUDA-event
+             time over K steps, max over ranks;
+  e2e        the same call with HOST vectors: x uploaded from pinned host memory and y downloaded
+             inside the timed region, every step;
+  roofline   the SpMV kernel against the measured HBM copy peak (MEASURED_PEAKS.json);
+  cpu_baseline / --impl reference: the reference's own CPU SMat::apply (oracle/_ref, built from the
+             unmodified reference sources; falls back to the C port) on the box's host cores;
+  solve      extra, not part of the timed steps: CG+Jacobi on the same grid and BiCGSTAB+SGS on
+             convection-diffusion 256^3 through createSolver()/apply(), the reference's call sequence.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_SPMV = 72          # 7 coefficient streams + x + y, 8 B each
+BYTES_CG_ITER = 200      # credited unfused CG+Jacobi iteration
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, device copy burst)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def golden_field(n_real_total, shape):
+    idx = np.arange(1, n_real_total + 1, dtype=np.float64) * 0.6180339887
+    return (idx - np.floor(idx) - 0.5).reshape(shape)
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+
+def cpu_spmv(n, reps, threads=None):
+    """Times the reference's own CPU SMat::apply (or the C port when oracle/_ref is absent) on Poisson n^3."""
+    from oracle import cport, refshim
+    npd = (n + 2,) * 3
+    if refshim.available():
+        if threads:
+            refshim.set_num_threads(threads)
+        cores = refshim.num_threads()
+        _, _ = refshim._capture_stdout(lambda: None)
+        m, _t = refshim._capture_stdout(lambda: refshim.Mesh(npd))
+        A, x, y = refshim.Mat(m), refshim.Vec(m), refshim.Vec(m)
+        h2 = (2.0 / (n + 1)) ** 2
+        for s in range(7):                       # uniform Poisson coefficients; the serial reference assembly is not what is timed
+            A.a[s][...] = (6.0 if s == 3 else -1.0) / h2
+        x.a[1:-1, 1:-1, 1:-1] = golden_field(n ** 3, (n, n, n))
+        best = refshim.time_apply(A, x, y, reps)
+        kind = "reference"
+        chk = float(np.abs(y.a).max())
+    else:
+        cores = os.cpu_count()
+        m = cport.Mesh(npd)
+        A = np.empty(m.mshape)
+        h2 = (2.0 / (n + 1)) ** 2
+        for s in range(7):
+            A[s] = (6.0 if s == 3 else -1.0) / h2
+        x = m.zeros()
+        x[1:-1, 1:-1, 1:-1] = golden_field(n ** 3, (n, n, n))
+        cport.apply(m, A, x)
+        best = 1e300
+        for _ in range(reps):
+            t0 = time.perf_counter(); y = cport.apply(m, A, x); best = min(best, time.perf_counter() - t0)
+        kind = "port"
+        chk = float(np.abs(y).max())
+    gbs = BYTES_SPMV * n ** 3 / best / 1e9
+    return {"value": gbs, "unit": "GB/s", "cores": cores, "kind": kind, "ms": best * 1e3, "check_max_abs_y": chk,
+            "sample": f"Poisson {n}^3 fp64, SMat::apply (y = A x), best of {reps} after 1 warm-up, OMP threads = {cores}"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = a.size
+    t0 = time.time()
+    cb = cpu_spmv(n, max(1, a.steps))
+    line = {"impl": "reference", "metric": "spmv_7pt_fp64_hbm_gbs", "value": cb["value"], "unit": "GB/s", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": cb["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": f"poisson3d_uniform_{n}^3_fp64_7pt_spmv", "grid": f"{n}^3 unknowns (npdim {n + 2})",
+                                             "note": "reference CPU path on host cores; the reference is single-process, so every N reports the same single-host number"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.time() - t0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from struct3d_b200 import capi, hostapi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus and world > 1:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        obj = [capi.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        nccl_id = obj[0]
+    hostapi.init(local, rank, world, nccl_id)
+    ctx = capi.Context.from_handle(hostapi.cuda_ctx())
+    H = hostapi
+
+    def barrier():
+        H.sync()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = a.size
+    nzg = n * world                                   # weak scaling: 512 planes per GPU
+    null = open(os.devnull, "w")
+    mesh, _ = H._capture_stdout(lambda: H.Mesh((n + 2, n + 2, nzg + 2)))
+    pde, _ = H._capture_stdout(lambda: H.Pde("poisson"))
+    t0 = time.perf_counter()
+    A = pde.lhs(mesh)
+    H.sync()
+    t_assemble = time.perf_counter() - t0
+    x, y = H.Vec(mesh), H.Vec(mesh)
+    nx, ny, nzl = mesh.local
+    N_local = nx * ny * nzl
+    N_total = nx * ny * nzg
+    xh = np.zeros(mesh.vshape)
+    xh[1:-1, 1:-1, 1:-1] = golden_field(N_total, (nzg, ny, nx))[mesh.k0:mesh.k0 + nzl]
+    x.set(xh)
+    g = capi.make_grid(nx, ny, nzg, rank, world) if world > 1 else capi.make_grid(nx, ny, nzl)
+
+    # ---- device-resident steps
+    for _ in range(max(3, a.warmup)):
+        H.apply(A, x, y)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    ctx.timer_start()
+    for _ in range(a.steps):
+        H.apply(A, x, y)
+    ms_total = ctx.timer_stop_ms()
+    launches = ctx.launch_count() - l0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = max_over_ranks(ms_total / a.steps)
+    value = BYTES_SPMV * N_total / (ms_step * 1e-3) / 1e9
+
+    # kernel-only duration on this rank (no halo exchange): the roofline numerator
+    dA, dx, dy = A.device_ptr(), x.device_ptr(), y.device_ptr()
+    for _ in range(3):
+        ctx.spmv(g, dA, dx, dy)
+    H.sync()
+    ctx.timer_start()
+    for _ in range(a.steps):
+        ctx.spmv(g, dA, dx, dy)
+    ms_kernel = ctx.timer_stop_ms() / a.steps
+    peak, peak_src = peaks()
+    achieved = BYTES_SPMV * N_local / (ms_kernel * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("spmv_pair_512", {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "spmv_pair_kernel<false,false,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": BYTES_SPMV * N_local, "avg_launch_ms": ms_kernel}
+
+    # ---- end to end: host vectors in, host vectors out, every step
+    nbytes = xh.nbytes
+    hx_p, hy_p = ctx.host_alloc(nbytes), ctx.host_alloc(nbytes)
+    import ctypes as C
+    hx = np.ctypeslib.as_array(C.cast(hx_p, C.POINTER(C.c_double)), shape=(xh.size,)).reshape(xh.shape)
+    hy = np.ctypeslib.as_array(C.cast(hy_p, C.POINTER(C.c_double)), shape=(xh.size,)).reshape(xh.shape)
+    hx[...] = xh
+
+    def e2e_step():
+        ctx.call("s3d_vec_upload", C.byref(g), capi._ptr(dx), capi._ptr(hx_p))
+        H.apply(A, x, y)
+        ctx.call("s3d_vec_download", C.byref(g), capi._ptr(dy), capi._ptr(hy_p))
+
+    x.device_ptr()
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_steps = max(2, min(a.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    H.sync()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
+    e2e = {"value": BYTES_SPMV * N_total / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(nbytes),
+           "ms_per_step": e2e_ms, "steps": e2e_steps, "check_max_abs_y": float(np.abs(hy).max()),
+           "note": "per step: cudaMemcpy2DAsync of x from pinned host memory, SMat::apply, copy of y back to pinned host memory"}
+    ctx.host_free(hx_p); ctx.host_free(hy_p)
+
+    # ---- extras: the solvers through the reference's call sequence (not part of the timed steps)
+    solve = {}
+    if not a.no_solve:
+        b = H.Vec(mesh)
+        b.set(xh)
+        u = H.Vec(mesh)
+        opts = {"-s3d_ksp_type": "cg", "-s3d_pc_type": "jacobi", "-ksp_rtol": 1e-6, "-ksp_max_it": 20000}
+        H.set_options(opts)
+        (s, _) = H._capture_stdout(lambda: H.Solver(A))
+        s.update()
+        barrier()
+        t0 = time.perf_counter()
+        info, _ = H._capture_stdout(lambda: s.apply(b, u))
+        H.sync()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        solve["cg_jacobi_poisson"] = {"grid": f"{nx}x{ny}x{nzg}", "rhs": "golden non-eigenvector field (SURVEY 8d)", "rtol": 1e-6, "seconds": dt,
+                                      "iters": info["iters"], "converged": info["converged"], "rel_res": info["resnorm"] / H.norm_vector_l2(b),
+                                      "ms_per_iter": dt * 1e3 / max(1, info["iters"]),
+                                      "credited_gbs": BYTES_CG_ITER * N_total * info["iters"] / dt / 1e9, "moved_bytes_per_point_iter": 160}
+        del s, u, b
+        if world == 1 and n >= 256:
+            m2, _ = H._capture_stdout(lambda: H.Mesh((258, 258, 258)))
+            p2, _ = H._capture_stdout(lambda: H.Pde("convdiff", (0.577350269189626, 0.7, 0.3), 0.1))
+            A2, b2, u2 = p2.lhs(m2), p2.vector(m2, "manufactured_rhs"), H.Vec(m2)
+            for pc, extra in (("sgs", {"-s3d_sgs_ordering": "lexicographic"}), ("sgs", {"-s3d_sgs_ordering": "redblack"}), ("jacobi", {})):
+                o = {"-s3d_ksp_type": "bcgs", "-s3d_pc_type": pc, "-ksp_rtol": 1e-6, "-ksp_max_it": 5000, "-s3d_pc_apply_sweeps": 1,
+                     "-s3d_thread_chunk_size": 1024, "-s3d_pc_use_threaded_apply": "false"}
+                o.update(extra)
+                H.set_options(o)
+                H.vecset(0.0, u2)
+                (s2, _) = H._capture_stdout(lambda: H.Solver(A2))
+                s2.update()
+                H.sync()
+                t0 = time.perf_counter()
+                i2, _ = H._capture_stdout(lambda: s2.apply(b2, u2))
+                H.sync()
+                dt2 = time.perf_counter() - t0
+                key = "bicgstab_" + pc + ("_" + extra["-s3d_sgs_ordering"] if extra else "") + "_convdiff256"
+                solve[key] = {"seconds": dt2, "iters": i2["iters"], "converged": i2["converged"], "precapply_seconds": i2["precapplywtime"]}
+                del s2
+            del A2, b2, u2
+
+    cb = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        cb = cpu_spmv(n, 5)
+    if rank == 0:
+        line = {"metric": "spmv_7pt_fp64_hbm_gbs", "value": value, "unit": "GB/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"poisson3d_uniform_{n}^3_fp64_7pt_spmv", "grid_per_gpu": f"{nx}x{ny}x{nzl}", "grid_total": f"{nx}x{ny}x{nzg}",
+                           "decomposition": f"z-slabs x{world}, one-plane halo by NCCL send/recv" if world > 1 else "single GPU",
+                           "l2": f"inputs exceed L2: {BYTES_SPMV * N_local / 1e9:.2f} GB streamed per step vs 126 MB L2 (no flush needed)",
+                           "step": "halo exchange (N>1) + SMat::apply (y = A x)", "bytes_per_point": BYTES_SPMV},
+                "value_frac_of_measured_peak": value / (peak * world), "value_frac_of_nominal_8TBs": value / (8000.0 * world),
+                "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "assembly_seconds": t_assemble, "solve": solve}
+        if cb is not None:
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    barrier()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=512, help="unknowns per axis (per GPU along z)")
+    ap.add_argument("--no-solve", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,260 @@
+/* s3d_cuda.h -- C ABI of libs3d_cuda.so, the B200 (sm_100a) implementation of Struct3d's native
+ * structured-grid linear-algebra path.
+ *
+ * This is the only boundary between host code and the GPU.  The C++ host classes in
+ * struct3d_b200/host/ (SVec, SMat, SolverBase, PDEBase ... -- the reference's own interface,
+ * /root/reference/src/linalg/matvec.hpp:23-115, s3d_solverbase.hpp:34-54, pde/pdebase.hpp:14-62)
+ * call nothing but these functions; so do the Python tests and bench.py (through ctypes).
+ * Plain pointers and sizes only: no C++ types, no torch types.
+ *
+ * Conventions
+ *   - every function returns an int status: S3D_OK (0) or an S3D_ERR_* code; s3d_error_string()
+ *     gives the message of the last failure on that context.  There is NO CPU fallback: without a
+ *     CUDA device s3d_ctx_create fails and nothing else can be called.
+ *   - `double *` arguments named d_* / A / x / y ... are DEVICE pointers obtained from
+ *     s3d_vec_alloc / s3d_mat_alloc / s3d_scalars_alloc (or any 256-byte aligned device memory of
+ *     the documented length, e.g. a torch CUDA tensor's data_ptr()).  Arguments named h_* are HOST
+ *     pointers in the REFERENCE's host layouts (see below), so reference data moves over unchanged.
+ *   - all work is enqueued on the context's stream and is asynchronous; only functions that
+ *     return numbers to the host (`*_host`, downloads, s3d_ctx_sync) block.
+ *   - reductions are deterministic: fixed grid, fixed-order two-stage tree, no floating-point atomics.
+ *
+ * Device layout (DESIGN.md "Data layout in HBM")
+ *   vector : ghost-padded like the reference's SVec (one ghost layer per side, real points 1..n),
+ *            but each i-row is padded so that real point i=0 sits on a 128-byte boundary:
+ *            row = [vlead-1 pad][ghost][nx real][ghost][pad], vpitch = roundup(vlead+nx+1, 16) doubles;
+ *            plane = (ny+2) rows; (nz+2) planes.  Element (i,j,k) of the real grid (0-based) lives at
+ *            voff + k*vplane + j*vpitch + i.  Ghost entries are stored and read exactly like the
+ *            reference reads them (they impose the homogeneous Dirichlet condition, matvec.cpp:59-101)
+ *            and are never written by any operation except uploads, copies-with-ghosts and halo exchange.
+ *   matrix : 7 coefficient arrays, stencil-major {i-1, j-1, k-1, diag, i+1, j+1, k+1} like SMat::vals,
+ *            no ghosts, cpitch = roundup(nx, 16); element (i,j,k) of array s at
+ *            s*cstride + k*cplane + j*cpitch + i.  Every row starts on a 128-byte boundary.
+ * Host layouts (the reference's, src/cartmesh.hpp:141-154)
+ *   vector : (nx+2)(ny+2)(nz+2) doubles, index k*(ny+2)(nx+2) + j*(nx+2) + i, ghosts included;
+ *   matrix : per stencil array nx*ny*nz doubles, index k*ny*nx + j*nx + i.
+ */
+#ifndef S3D_CUDA_H
+#define S3D_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S3D_OK            0
+#define S3D_ERR_CUDA      1   /* a CUDA runtime call or kernel failed */
+#define S3D_ERR_ARG       2   /* bad argument (null pointer, size mismatch, unsupported option) */
+#define S3D_ERR_NCCL      3   /* an NCCL call failed */
+#define S3D_ERR_NODEVICE  4   /* no usable CUDA device: there is no CPU fallback */
+#define S3D_ERR_STATE     5   /* call not valid in the current state (e.g. halo exchange without a communicator) */
+
+#define S3D_NSTENCIL      7
+#define S3D_STENCIL_DIAG  3
+
+typedef struct s3d_ctx s3d_ctx;
+
+/* Local (per-rank z-slab) grid descriptor.  Fill it with s3d_grid_init(); read-only afterwards. */
+typedef struct s3d_grid {
+	int32_t nx, ny, nz;        /* real points owned by this rank (nz = local slab thickness) */
+	int32_t vlead;             /* doubles in front of real i=0 in a vector row (16: 128-byte aligned) */
+	int32_t vpitch;            /* vector row pitch in doubles */
+	int32_t cpitch;            /* coefficient row pitch in doubles */
+	int64_t vplane;            /* vpitch * (ny+2) */
+	int64_t voff;              /* offset of real point (0,0,0) = vplane + vpitch + vlead */
+	int64_t vlen;              /* doubles per vector = vplane * (nz+2) */
+	int64_t cplane;            /* cpitch * ny */
+	int64_t cstride;           /* doubles between consecutive stencil arrays */
+	int32_t nz_global;         /* real points along z of the whole grid */
+	int32_t k0;                /* global index of this rank's first real plane */
+	int32_t rank, nranks;      /* position in the z-slab decomposition (0,1 when not decomposed) */
+} s3d_grid;
+
+/* A scalar operand for the solver kernels: value = imm * (*num if num) / (*den if den).
+ * num/den are device pointers (typically reduction outputs), so Krylov coefficients such as
+ * alpha = (r,z)/(p,Ap) never round-trip through the host. */
+typedef struct s3d_scalar {
+	double        imm;
+	const double *num;
+	const double *den;
+} s3d_scalar;
+
+/* ------------------------------------------------------------------ context */
+
+/* device < 0 selects $LOCAL_RANK (or 0).  stream: an existing cudaStream_t to enqueue on (e.g.
+ * torch's current stream) or NULL to create a private non-blocking stream. */
+int  s3d_ctx_create(int device, void *stream, s3d_ctx **out);
+int  s3d_ctx_destroy(s3d_ctx *ctx);
+int  s3d_ctx_sync(s3d_ctx *ctx);
+int  s3d_ctx_device(const s3d_ctx *ctx);
+void *s3d_ctx_stream(const s3d_ctx *ctx);
+const char *s3d_error_string(const s3d_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t s3d_ctx_launch_count(const s3d_ctx *ctx);
+/* CUDA-event timing on the context's stream: start/stop bracket, elapsed in milliseconds */
+int  s3d_timer_start(s3d_ctx *ctx);
+int  s3d_timer_stop_ms(s3d_ctx *ctx, double *ms);
+
+/* kernel tuning knobs for sweeps ("spmv_by" in {4,8,16}, "spmv_kchunk" >= 0 where 0 = automatic,
+ * "spmv_variant" = what S3D_SPMV_AUTO resolves to) */
+int  s3d_tune_set(s3d_ctx *ctx, const char *key, int value);
+
+/* Replaces the size arithmetic of SVec::SVec / SMat::SMat (matvec.cpp:8-57).  nz is the local slab. */
+int  s3d_grid_init(s3d_grid *g, int nx, int ny, int nz);
+/* z-slab decomposition of a global grid: rank p of P owns planes [p*nz/P, (p+1)*nz/P). */
+int  s3d_grid_init_slab(s3d_grid *g, int nx, int ny, int nz_global, int rank, int nranks);
+
+/* ------------------------------------------------------------------ storage (SVec / SMat, matvec.hpp:23-89) */
+
+int  s3d_vec_alloc(s3d_ctx *ctx, const s3d_grid *g, double **d_out);          /* zero-filled, ghosts included */
+int  s3d_mat_alloc(s3d_ctx *ctx, const s3d_grid *g, double **d_out);          /* 7*cstride doubles, zero-filled */
+int  s3d_scalars_alloc(s3d_ctx *ctx, int n, double **d_out);                  /* n device doubles, zeroed */
+int  s3d_free(s3d_ctx *ctx, void *d_ptr);
+int  s3d_vec_upload(s3d_ctx *ctx, const s3d_grid *g, double *d_x, const double *h_x);     /* host ghosted layout -> device */
+int  s3d_vec_download(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, double *h_x);   /* blocks */
+int  s3d_mat_upload(s3d_ctx *ctx, const s3d_grid *g, double *d_A, int stencil, const double *h_vals);
+int  s3d_mat_download(s3d_ctx *ctx, const s3d_grid *g, const double *d_A, int stencil, double *h_vals);
+int  s3d_scalars_download(s3d_ctx *ctx, const double *d_s, int n, double *h_out);          /* blocks */
+int  s3d_scalars_upload(s3d_ctx *ctx, double *d_s, int n, const double *h_in);
+/* pinned host memory for callers that want overlapped transfers */
+int  s3d_host_alloc(s3d_ctx *ctx, size_t bytes, void **h_out);
+int  s3d_host_free(s3d_ctx *ctx, void *h_ptr);
+
+/* ------------------------------------------------------------------ SpMV (SMat::apply / apply_res, matvec.cpp:59-146) */
+
+#define S3D_SPMV_AUTO      0   /* pick the fastest variant for the grid */
+#define S3D_SPMV_MARCH     1   /* register z-marching, i-neighbours by warp shuffle, j-neighbours via L1 */
+#define S3D_SPMV_TMA       2   /* z-planes of x staged through shared memory by TMA (cp.async.bulk.tensor) */
+#define S3D_SPMV_NAIVE     3   /* one thread per point, all seven neighbours from global (the first correct version) */
+#define S3D_SPMV_PAIR      4   /* two points per thread, no marching: 128-bit loads, x-reuse through L1/L2 (the default) */
+
+/* y = A x (d_b == NULL) or y = b - A x.  The seven products are formed and summed in stencil order
+ * 0..6 with separately rounded multiplies and adds, exactly the reference's expression.
+ * Optional fused reductions into device scalars d_red (may be NULL):
+ *   d_w != NULL : d_red[0] = (w, y) over real points      (CG's (p, Ap): pass d_w = d_x)
+ *   want_yy     : d_red[1] = (y, y)                        (residual norm^2 for Richardson / BiCGSTAB)
+ * d_stop (may be NULL): device int; when *d_stop != 0 the launch does nothing (device-side convergence gate).
+ * In a z-slab decomposition the caller must have exchanged x's halo planes first (s3d_halo_exchange). */
+int  s3d_spmv(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_x, double *d_y,
+              const double *d_b, const double *d_w, int want_yy, double *d_red, const int *d_stop, int variant);
+
+/* ------------------------------------------------------------------ BLAS-1 (matvec.cpp:148-288), real points only */
+
+int  s3d_vecset(s3d_ctx *ctx, const s3d_grid *g, double a, double *d_x);                        /* vecset     :188 */
+int  s3d_vecassign(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, double *d_y);            /* vecassign  :203 */
+int  s3d_veccopy_all(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, double *d_y);          /* ghosts too: NoSolver::apply, s3d_solverbase.cpp:21-33 */
+int  s3d_vecaxpy(s3d_ctx *ctx, const s3d_grid *g, s3d_scalar a, const double *d_x, double *d_y);/* vecaxpy    :148  y += a x */
+/* y = a x + b y  (p = z + beta p of CG; b = 0 never reads y) */
+int  s3d_vecaxpby(s3d_ctx *ctx, const s3d_grid *g, s3d_scalar a, const double *d_x, s3d_scalar b, double *d_y);
+/* w = a x + b y, optionally d_red[0] = (w,w) */
+int  s3d_vecwaxpby(s3d_ctx *ctx, const s3d_grid *g, s3d_scalar a, const double *d_x, s3d_scalar b,
+                   const double *d_y, double *d_w, double *d_red);
+/* vec_multi_axpy :166  y += sum_l a[l] x_l in ONE pass (the reference makes n passes); a: n device doubles,
+ * xs: n device vector pointers (host array of device pointers), n <= 32 */
+int  s3d_vec_multi_axpy(s3d_ctx *ctx, const s3d_grid *g, int n, const double *d_a, const double *const *xs, double *d_y);
+/* d_red[l] = (x_l, y), l < n, one pass over y; n <= 32 */
+int  s3d_vec_multi_dot(s3d_ctx *ctx, const s3d_grid *g, int n, const double *const *xs, const double *d_y, double *d_red);
+int  s3d_dot(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, const double *d_y, double *d_red);  /* inner_vector_l2 :257 */
+int  s3d_nrm2sq(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, double *d_red);                   /* norm_vector_l2^2 :240 */
+/* norm_L2^2 :221 -- weights 1/8 (cx[i+1]-cx[i-1])(cy..)(cz..); h_c*: host 1-D coordinate arrays of n+2 entries */
+int  s3d_normL2sq(s3d_ctx *ctx, const s3d_grid *g, const double *h_cx, const double *h_cy, const double *h_cz,
+                  const double *d_x, double *d_red);
+/* blocking conveniences returning the reference's values (sqrt applied where the reference applies it) */
+int  s3d_dot_host(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, const double *d_y, double *h_out);
+int  s3d_nrm2_host(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, double *h_out);
+/* sum-allreduce n device scalars across the z-slab ranks (no-op for one rank) */
+int  s3d_allreduce_sum(s3d_ctx *ctx, double *d_s, int n);
+
+/* ------------------------------------------------------------------ preconditioners */
+
+/* JacobiPreconditioner::apply (s3d_jacobi.cpp:14-29): z = r / diag(A), a true division */
+int  s3d_jacobi_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_r, double *d_z);
+
+/* SGS_preconditioner::updateOperator (s3d_sgspreconditioners.cpp:122-135): dinv = 1/diag, matrix-compact layout (cstride doubles) */
+int  s3d_sgs_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, double *d_dinv);
+#define S3D_SGS_LEXICOGRAPHIC 0  /* the reference's ordering, executed as a tile-level dataflow wavefront: same arithmetic */
+#define S3D_SGS_REDBLACK      1  /* two-colour ordering: four fully parallel half-sweeps (changes the iteration) */
+/* SGS_like_preconditioner::apply (s3d_sgspreconditioners.cpp:14-115): z = (D+U)^-1 D (D+L)^-1 r.
+ * d_y: scratch vector (vlen doubles); it is re-zeroed by the call like the reference's temporary. */
+int  s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_dinv,
+                   const double *d_r, double *d_z, double *d_y, int ordering, int nsweeps);
+
+/* ------------------------------------------------------------------ fused solver steps (new: CG / BiCGSTAB) */
+
+/* CG step 1:  x += alpha p;  r -= alpha q;  d_red[0] = (r,r);  if A != NULL also d_red[1] = (r, r/diag(A))
+ * (the Jacobi-preconditioned (r,z) without storing z). */
+int  s3d_cg_update(s3d_ctx *ctx, const s3d_grid *g, s3d_scalar alpha, const double *d_p, const double *d_q,
+                   double *d_x, double *d_r, const double *A_or_null, double *d_red, const int *d_stop);
+/* CG step 2 with Jacobi folded in:  p = r/diag(A) + beta p */
+int  s3d_cg_direction_jacobi(s3d_ctx *ctx, const s3d_grid *g, s3d_scalar beta, const double *A, const double *d_r,
+                             double *d_p, const int *d_stop);
+/* BiCGSTAB:  p = r + beta (p - omega v) */
+int  s3d_bicg_direction(s3d_ctx *ctx, const s3d_grid *g, s3d_scalar beta, s3d_scalar omega, const double *d_r,
+                        const double *d_v, double *d_p, const int *d_stop);
+/* BiCGSTAB:  x += alpha ph + omega sh;  r = s - omega t;  d_red[0] = (r,r);  d_red[1] = (rhat, r) */
+int  s3d_bicg_update(s3d_ctx *ctx, const s3d_grid *g, s3d_scalar alpha, const double *d_ph, s3d_scalar omega,
+                     const double *d_sh, const double *d_s, const double *d_t, const double *d_rhat,
+                     double *d_x, double *d_r, double *d_red, const int *d_stop);
+/* Device-side convergence gate: if sqrt(*d_rr) <= rtol * sqrt(*d_bb) set *d_stop = 1, else ++*d_iters.
+ * Kernels given d_stop become no-ops once it is set, so the host may enqueue iterations ahead and
+ * poll, and x is exactly the iterate at which the test first passed. */
+#define S3D_CONV_STRICT   1   /* stop when rel <  rtol (GCR's inner test, s3d_gcr.cpp:57) instead of !(rel > rtol) */
+#define S3D_CONV_INITIAL  2   /* test the initial residual: do not count or record an iteration */
+#define S3D_STOP_CONVERGED 1
+#define S3D_STOP_BREAKDOWN 2
+#define S3D_STOP_MAXITER   3
+int  s3d_converge_test(s3d_ctx *ctx, const double *d_rr, const double *d_bb, double rtol, int maxiter, int flags,
+                       int *d_stop, int *d_iters, double *d_hist_or_null);
+/* tiny device-side scalar arithmetic so Krylov coefficients stay on the GPU:
+ *   op 0: out[l] = scale * a[l] / b[l], l < n       (GCR's beta_i = -(q_new,q_i)/(q_i,q_i))
+ *   op 1: out[0] = (a/b) * (c/d)                     (BiCGSTAB's beta; a, b or d == 0 sets *d_stop = 2)
+ *   op 2: out[0] = a / b                             (alpha, omega; b == 0 sets *d_stop = 2)
+ *   op 3: out[l] = a[l], l < n                       (keep a reduction result for later) */
+int  s3d_scalar_op(s3d_ctx *ctx, int op, double *d_out, const double *a, const double *b, const double *c,
+                   const double *d, int n, double scale, int *d_stop);
+/* Context-wide gate: while set, EVERY kernel this context launches (SpMV, BLAS-1, preconditioners ...) first
+ * reads *d_stop and does nothing when it is non-zero, unless the call passes its own d_stop.  A host-driven
+ * solver sets the gate to its stop flag for the duration of the loop; pass NULL to clear it. */
+int  s3d_ctx_set_gate(s3d_ctx *ctx, const int *d_stop);
+/* Accumulating GPU stopwatch (CUDA events on the stream) for phase timing such as SolveInfo::precapplywtime:
+ * begin/end may be called any number of times; total_ms synchronises and returns the sum, then resets the slot. */
+int  s3d_phase_begin(s3d_ctx *ctx, int slot);
+int  s3d_phase_end(s3d_ctx *ctx, int slot);
+int  s3d_phase_total_ms(s3d_ctx *ctx, int slot, double *ms);
+int  s3d_ints_alloc(s3d_ctx *ctx, int n, int **d_out);
+int  s3d_ints_download(s3d_ctx *ctx, const int *d_s, int n, int *h_out);
+int  s3d_ints_zero(s3d_ctx *ctx, int *d_s, int n);
+
+/* ------------------------------------------------------------------ assembly (src/pde) */
+
+/* PDEBase::computeLHS + Poisson::lhsmat_kernel (pdebase.cpp:123-150, poisson.cpp:28-52).
+ * h_cx/h_cy/h_cz: host 1-D coordinates incl. boundary points (nx+2, ny+2, nz_global+2 entries). */
+int  s3d_assemble_poisson(s3d_ctx *ctx, const s3d_grid *g, const double *h_cx, const double *h_cy,
+                          const double *h_cz, double *A);
+/* PDEBase::computeLHS + ConvDiff::lhsmat_kernel (convdiff.cpp:48-88): mu * diffusion, then first-order upwind */
+int  s3d_assemble_convdiff(s3d_ctx *ctx, const s3d_grid *g, const double *h_cx, const double *h_cy,
+                           const double *h_cz, const double vel[3], double mu, double *A);
+/* PDEBase::computeVector for separable functions f = sum_t X_t(x_i) Y_t(y_j) Z_t(z_k)  (pdebase.cpp:50-72):
+ * h_tx: nterms*(nx+2) host table, h_ty: nterms*(ny+2), h_tz: nterms*(nz_global+2), row t = term t, evaluated
+ * at the grid coordinates (boundary entries unused).  Each term is ((X*Y)*Z), terms are added in order.
+ * h_face (may be NULL): 6 per-face additive terms for the boundary-adjacent layers, in the reference's face
+ * order i-,i+,j-,j+,k-,k+ (Poisson::rhs_kernel, poisson.cpp:54-122), already divided by their spacing factor. */
+int  s3d_assemble_rhs_separable(s3d_ctx *ctx, const s3d_grid *g, int nterms, const double *h_tx, const double *h_ty,
+                                const double *h_tz, const double *h_face, double *d_f);
+
+/* ------------------------------------------------------------------ multi-GPU: z-slabs, one process per GPU */
+
+#define S3D_COMM_ID_BYTES 128
+int  s3d_comm_unique_id(void *id_out /* S3D_COMM_ID_BYTES */);       /* rank 0 creates, caller broadcasts */
+int  s3d_comm_init(s3d_ctx *ctx, int rank, int nranks, const void *id);
+int  s3d_comm_destroy(s3d_ctx *ctx);
+/* fills ghost planes k=-1 and k=nz of x with the neighbours' boundary planes (NCCL send/recv over NVLink);
+ * the global ends keep their Dirichlet zeros.  No-op for one rank. */
+int  s3d_halo_exchange(s3d_ctx *ctx, const s3d_grid *g, double *d_x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S3D_CUDA_H */

@@ -149,11 +149,12 @@ def main():
         R.Prec(A, "strilu", 1, 1).apply(b, zi)
         ax.a[...] = b.a
         R.vecaxpy(0.37, x, ax)
+        trhs, msol = P.vector(m, "test_rhs"), P.vector(m, "manufactured_solution")   # keep the owners alive: .a is a view
         np.savez_compressed(os.path.join(OUT, f"fields_{name}.npz"),
                             npdim=np.array(npdim), grid=grid, pde=pde, vel=np.array(vel), mu=mu,
                             cx=m.coords(0), cy=m.coords(1), cz=m.coords(2), A=A.stacked(), x=x.a,
-                            test_rhs=P.vector(m, "test_rhs").a, manufactured_rhs=b.a,
-                            manufactured_solution=P.vector(m, "manufactured_solution").a,
+                            test_rhs=trhs.a.copy(), manufactured_rhs=b.a.copy(),
+                            manufactured_solution=msol.a.copy(),
                             Ax=y.a, b_minus_Ax=res.a, jacobi_b=zj.a, sgs_b=zs.a, strilu_b=zi.a, b_plus_037x=ax.a,
                             dot_x_b=R.inner_vector_l2(x, b), norm_x=R.norm_vector_l2(x), normL2_x=R.norm_L2(x),
                             errL2_x_b=R.compute_error_L2(x, b), h=m.h())

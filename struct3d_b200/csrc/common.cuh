@@ -1,0 +1,178 @@
+// Internal header of libs3d_cuda.so (sm_100a only).  Nothing here is part of the ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <nccl.h>
+
+#include "s3d_cuda.h"
+
+struct s3d_ctx {
+	int device = 0;
+	int sm_count = 148;
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	// two-stage deterministic reductions: per-block partial sums + a ticket that elects the last block
+	double *partials = nullptr;
+	size_t partials_cap = 0;      // doubles
+	unsigned *ticket = nullptr;
+	// small device scratch: 1-D tables for assembly / weighted norms, pointer tables for multi-vector ops
+	double *tab = nullptr;
+	size_t tab_cap = 0;           // doubles
+	double *red_tmp = nullptr;    // 64 device doubles for the *_host conveniences
+	double *h_pinned = nullptr;   // 64 pinned doubles
+	// SGS dataflow bookkeeping (tile completion flags + work ticket)
+	int *sgs_flags = nullptr;
+	size_t sgs_flags_cap = 0;
+	// device-side gate applied to every launch that does not bring its own stop flag
+	const int *gate = nullptr;
+	// timing
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	struct Phase { cudaEvent_t *ev = nullptr; int used = 0, cap = 0; };
+	Phase phase[4];
+	int64_t launches = 0;
+	// z-slab communicator
+	ncclComm_t comm = nullptr;
+	int rank = 0, nranks = 1;
+	char err[512] = "";
+};
+
+int s3d_fail(s3d_ctx *ctx, int code, const char *fmt, ...);
+int s3d_ensure_partials(s3d_ctx *ctx, size_t ndoubles);
+int s3d_ensure_tab(s3d_ctx *ctx, size_t ndoubles);
+
+#define S3D_CUDA(ctx, call)                                                                     \
+	do {                                                                                        \
+		cudaError_t e__ = (call);                                                               \
+		if (e__ != cudaSuccess)                                                                 \
+			return s3d_fail((ctx), S3D_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,   \
+			                cudaGetErrorString(e__));                                           \
+	} while (0)
+
+#define S3D_NCCL(ctx, call)                                                                     \
+	do {                                                                                        \
+		ncclResult_t r__ = (call);                                                              \
+		if (r__ != ncclSuccess)                                                                 \
+			return s3d_fail((ctx), S3D_ERR_NCCL, "%s:%d %s -> %s", __FILE__, __LINE__, #call,   \
+			                ncclGetErrorString(r__));                                           \
+	} while (0)
+
+#define S3D_LAUNCHED(ctx)                                                                       \
+	do {                                                                                        \
+		(ctx)->launches++;                                                                      \
+		S3D_CUDA((ctx), cudaGetLastError());                                                    \
+	} while (0)
+
+#define S3D_REQUIRE(ctx, cond, msg)                                                             \
+	do {                                                                                        \
+		if (!(cond)) return s3d_fail((ctx), S3D_ERR_ARG, "%s: %s", __func__, (msg));            \
+	} while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device-side view of the grid (passed by value to kernels)
+struct GridDev {
+	int nx, ny, nz;
+	int vpitch, cpitch;
+	long long vplane, voff, cplane, cstride;
+};
+
+static inline GridDev to_dev(const s3d_grid *g)
+{
+	GridDev d;
+	d.nx = g->nx; d.ny = g->ny; d.nz = g->nz;
+	d.vpitch = g->vpitch; d.cpitch = g->cpitch;
+	d.vplane = g->vplane; d.voff = g->voff; d.cplane = g->cplane; d.cstride = g->cstride;
+	return d;
+}
+
+struct RedOut {
+	double *partials;
+	unsigned *ticket;
+	double *out;     // device scalars receiving the final sums (may be null: no reduction requested)
+};
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ double s3d_sval(const s3d_scalar &s)
+{
+	double v = s.imm;
+	if (s.num) v *= __ldg(s.num);
+	if (s.den) v /= __ldg(s.den);
+	return v;
+}
+
+__device__ __forceinline__ bool s3d_stopped(const int *stop) { return stop != nullptr && __ldg(stop) != 0; }
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+// Sums NR per-thread accumulators over the whole grid into ro.out[0..NR).
+// Stage 1: warp shuffle + shared memory inside the block, one partial per block.
+// Stage 2: the block that draws the last ticket adds the partials in a fixed order.
+// The result depends only on the launch geometry, never on scheduling: deterministic.
+// Every thread of every block must call this (it contains __syncthreads).
+template <int NR>
+__device__ __forceinline__ void grid_reduce(double (&acc)[NR], const RedOut &ro)
+{
+	__shared__ double sm[NR][32];
+	__shared__ bool is_last;
+	const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+	const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+	const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
+	const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
+	const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+
+#pragma unroll
+	for (int r = 0; r < NR; r++) {
+		const double w = warp_sum(acc[r]);
+		if (lane == 0) sm[r][warp] = w;
+	}
+	__syncthreads();
+	if (warp == 0) {
+#pragma unroll
+		for (int r = 0; r < NR; r++) {
+			double v = lane < nwarps ? sm[r][lane] : 0.0;
+			v = warp_sum(v);
+			if (lane == 0) ro.partials[(size_t)bid * NR + r] = v;
+		}
+	}
+	if (tid == 0) {
+		__threadfence();
+		const unsigned t = atomicAdd(ro.ticket, 1u);
+		is_last = (t == nblocks - 1);
+	}
+	__syncthreads();
+	if (!is_last) return;
+	__threadfence();
+#pragma unroll
+	for (int r = 0; r < NR; r++) {
+		double s = 0.0;
+		for (unsigned b = tid; b < nblocks; b += nthreads) s += __ldcg(&ro.partials[(size_t)b * NR + r]);
+		s = warp_sum(s);
+		__syncthreads();
+		if (lane == 0) sm[r][warp] = s;
+		__syncthreads();
+		if (warp == 0) {
+			double v = lane < nwarps ? sm[r][lane] : 0.0;
+			v = warp_sum(v);
+			if (lane == 0) ro.out[r] = v;
+		}
+	}
+	if (tid == 0) *ro.ticket = 0u;
+}
+
+// streaming (read-once / write-once) accesses: evict-first in L1 and L2 so the coefficient streams
+// do not push the x-planes out of cache
+__device__ __forceinline__ double2 ld_stream2(const double *p) { return __ldcs(reinterpret_cast<const double2 *>(p)); }
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream2(double *p, double2 v) { __stcs(reinterpret_cast<double2 *>(p), v); }
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
+
+#endif  // __CUDACC__

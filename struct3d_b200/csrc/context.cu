@@ -1,0 +1,446 @@
+// Context, grid descriptors, device storage, transfers, timers and the z-slab communicator.
+// Replaces the allocation/size arithmetic of SVec::SVec / SMat::SMat (reference src/linalg/matvec.cpp:8-57).
+#include <cstdarg>
+#include <cstdlib>
+#include <dlfcn.h>
+#include "common.cuh"
+
+// NCCL is bound at run time, not link time: a process that never decomposes the grid never loads it,
+// and a process that already has a libnccl.so.2 (e.g. the one bundled with torch) reuses that one
+// instead of pulling a second, possibly older, copy in front of it.
+namespace {
+struct NcclApi {
+	void *handle = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	const char *(*GetErrorString)(ncclResult_t) = nullptr;
+	bool ok = false;
+};
+NcclApi g_nccl;
+
+bool nccl_load()
+{
+	if (g_nccl.ok) return true;
+	if (!g_nccl.handle) g_nccl.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+	if (!g_nccl.handle) g_nccl.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+	if (!g_nccl.handle) return false;
+#define S3D_SYM(field, name) *(void **)(&g_nccl.field) = dlsym(g_nccl.handle, name); if (!g_nccl.field) return false
+	S3D_SYM(GetUniqueId, "ncclGetUniqueId");
+	S3D_SYM(CommInitRank, "ncclCommInitRank");
+	S3D_SYM(CommDestroy, "ncclCommDestroy");
+	S3D_SYM(GroupStart, "ncclGroupStart");
+	S3D_SYM(GroupEnd, "ncclGroupEnd");
+	S3D_SYM(Send, "ncclSend");
+	S3D_SYM(Recv, "ncclRecv");
+	S3D_SYM(AllReduce, "ncclAllReduce");
+	S3D_SYM(GetErrorString, "ncclGetErrorString");
+#undef S3D_SYM
+	g_nccl.ok = true;
+	return true;
+}
+}  // namespace
+#define ncclGetErrorString g_nccl.GetErrorString
+
+static char g_global_err[512] = "";
+
+int s3d_fail(s3d_ctx *ctx, int code, const char *fmt, ...)
+{
+	char *dst = ctx ? ctx->err : g_global_err;
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(dst, 512, fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+int s3d_ensure_partials(s3d_ctx *ctx, size_t n)
+{
+	if (n <= ctx->partials_cap) return S3D_OK;
+	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (ctx->partials) S3D_CUDA(ctx, cudaFree(ctx->partials));
+	ctx->partials = nullptr; ctx->partials_cap = 0;
+	size_t cap = 1 << 16;
+	while (cap < n) cap <<= 1;
+	S3D_CUDA(ctx, cudaMalloc(&ctx->partials, cap * sizeof(double)));
+	ctx->partials_cap = cap;
+	return S3D_OK;
+}
+
+int s3d_ensure_tab(s3d_ctx *ctx, size_t n)
+{
+	if (n <= ctx->tab_cap) return S3D_OK;
+	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (ctx->tab) S3D_CUDA(ctx, cudaFree(ctx->tab));
+	ctx->tab = nullptr; ctx->tab_cap = 0;
+	size_t cap = 1 << 14;
+	while (cap < n) cap <<= 1;
+	S3D_CUDA(ctx, cudaMalloc(&ctx->tab, cap * sizeof(double)));
+	ctx->tab_cap = cap;
+	return S3D_OK;
+}
+
+extern "C" {
+
+int s3d_ctx_create(int device, void *stream, s3d_ctx **out)
+{
+	if (!out) return S3D_ERR_ARG;
+	*out = nullptr;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		cudaGetLastError();
+		return s3d_fail(nullptr, S3D_ERR_NODEVICE, "no CUDA device visible; libs3d_cuda has no CPU fallback");
+	}
+	if (device < 0) {
+		const char *lr = getenv("LOCAL_RANK");
+		device = lr ? atoi(lr) % ndev : 0;
+	}
+	if (device >= ndev) return s3d_fail(nullptr, S3D_ERR_ARG, "device %d out of range (%d visible)", device, ndev);
+	s3d_ctx *ctx = new s3d_ctx();
+	ctx->device = device;
+#define CREATE_CHECK(call)                                                                 \
+	do {                                                                                   \
+		cudaError_t e__ = (call);                                                          \
+		if (e__ != cudaSuccess) {                                                          \
+			int rc__ = s3d_fail(nullptr, S3D_ERR_CUDA, "%s -> %s", #call, cudaGetErrorString(e__)); \
+			delete ctx;                                                                    \
+			return rc__;                                                                   \
+		}                                                                                  \
+	} while (0)
+	CREATE_CHECK(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CREATE_CHECK(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10)
+		fprintf(stderr, "libs3d_cuda: warning: built for sm_100a, device is sm_%d%d\n", prop.major, prop.minor);
+	ctx->sm_count = prop.multiProcessorCount;
+	if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
+	else { CREATE_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+	CREATE_CHECK(cudaMalloc(&ctx->ticket, sizeof(unsigned)));
+	CREATE_CHECK(cudaMemset(ctx->ticket, 0, sizeof(unsigned)));
+	CREATE_CHECK(cudaMalloc(&ctx->red_tmp, 64 * sizeof(double)));
+	CREATE_CHECK(cudaMemset(ctx->red_tmp, 0, 64 * sizeof(double)));
+	CREATE_CHECK(cudaMallocHost(&ctx->h_pinned, 64 * sizeof(double)));
+	CREATE_CHECK(cudaEventCreate(&ctx->ev0));
+	CREATE_CHECK(cudaEventCreate(&ctx->ev1));
+	CREATE_CHECK(cudaDeviceSynchronize());
+#undef CREATE_CHECK
+	int rc = s3d_ensure_partials(ctx, 1 << 16);
+	if (rc == S3D_OK) rc = s3d_ensure_tab(ctx, 1 << 14);
+	if (rc != S3D_OK) { delete ctx; return rc; }
+	*out = ctx;
+	return S3D_OK;
+}
+
+int s3d_ctx_destroy(s3d_ctx *ctx)
+{
+	if (!ctx) return S3D_OK;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
+	cudaFree(ctx->partials); cudaFree(ctx->ticket); cudaFree(ctx->tab); cudaFree(ctx->red_tmp);
+	cudaFree(ctx->sgs_flags);
+	cudaFreeHost(ctx->h_pinned);
+	cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+	delete ctx;
+	return S3D_OK;
+}
+
+int s3d_ctx_sync(s3d_ctx *ctx)
+{
+	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return S3D_OK;
+}
+
+int s3d_ctx_device(const s3d_ctx *ctx) { return ctx->device; }
+void *s3d_ctx_stream(const s3d_ctx *ctx) { return (void *)ctx->stream; }
+const char *s3d_error_string(const s3d_ctx *ctx) { return ctx ? ctx->err : g_global_err; }
+int64_t s3d_ctx_launch_count(const s3d_ctx *ctx) { return ctx->launches; }
+
+int s3d_timer_start(s3d_ctx *ctx)
+{
+	S3D_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	return S3D_OK;
+}
+int s3d_timer_stop_ms(s3d_ctx *ctx, double *ms)
+{
+	S3D_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+	S3D_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+	float f = 0;
+	S3D_CUDA(ctx, cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
+	*ms = f;
+	return S3D_OK;
+}
+
+int s3d_ctx_set_gate(s3d_ctx *ctx, const int *d_stop)
+{
+	ctx->gate = d_stop;
+	return S3D_OK;
+}
+
+static int phase_record(s3d_ctx *ctx, int slot, int parity)
+{
+	S3D_REQUIRE(ctx, slot >= 0 && slot < 4, "phase slot out of range");
+	s3d_ctx::Phase &p = ctx->phase[slot];
+	S3D_REQUIRE(ctx, (p.used & 1) == parity, "phase begin/end out of order");
+	if (p.used == p.cap) {
+		const int ncap = p.cap ? 2 * p.cap : 256;
+		cudaEvent_t *ne = (cudaEvent_t *)realloc(p.ev, ncap * sizeof(cudaEvent_t));
+		if (!ne) return s3d_fail(ctx, S3D_ERR_ARG, "out of host memory");
+		for (int i = p.cap; i < ncap; i++) S3D_CUDA(ctx, cudaEventCreate(&ne[i]));
+		p.ev = ne; p.cap = ncap;
+	}
+	S3D_CUDA(ctx, cudaEventRecord(p.ev[p.used++], ctx->stream));
+	return S3D_OK;
+}
+int s3d_phase_begin(s3d_ctx *ctx, int slot) { return phase_record(ctx, slot, 0); }
+int s3d_phase_end(s3d_ctx *ctx, int slot) { return phase_record(ctx, slot, 1); }
+int s3d_phase_total_ms(s3d_ctx *ctx, int slot, double *ms)
+{
+	S3D_REQUIRE(ctx, slot >= 0 && slot < 4 && ms, "bad argument");
+	s3d_ctx::Phase &p = ctx->phase[slot];
+	S3D_REQUIRE(ctx, (p.used & 1) == 0, "phase still open");
+	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	double total = 0;
+	for (int i = 0; i < p.used; i += 2) {
+		float f = 0;
+		S3D_CUDA(ctx, cudaEventElapsedTime(&f, p.ev[i], p.ev[i + 1]));
+		total += f;
+	}
+	p.used = 0;
+	*ms = total;
+	return S3D_OK;
+}
+
+// ------------------------------------------------------------------------------------ grid
+
+static int64_t roundup(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+int s3d_grid_init(s3d_grid *g, int nx, int ny, int nz)
+{
+	if (!g || nx < 1 || ny < 1 || nz < 1) return S3D_ERR_ARG;
+	memset(g, 0, sizeof(*g));
+	g->nx = nx; g->ny = ny; g->nz = nz;
+	g->vlead = 16;                                        // real i=0 on a 128-byte boundary
+	g->vpitch = (int32_t)roundup((int64_t)g->vlead + nx + 1, 16);
+	g->cpitch = (int32_t)roundup(nx, 16);
+	g->vplane = (int64_t)g->vpitch * (ny + 2);
+	g->voff = g->vplane + g->vpitch + g->vlead;
+	g->vlen = g->vplane * (nz + 2);
+	g->cplane = (int64_t)g->cpitch * ny;
+	g->cstride = roundup(g->cplane * nz, 32);
+	g->nz_global = nz; g->k0 = 0; g->rank = 0; g->nranks = 1;
+	return S3D_OK;
+}
+
+int s3d_grid_init_slab(s3d_grid *g, int nx, int ny, int nz_global, int rank, int nranks)
+{
+	if (!g || nranks < 1 || rank < 0 || rank >= nranks || nz_global < nranks) return S3D_ERR_ARG;
+	const int k0 = (int)((int64_t)rank * nz_global / nranks);
+	const int k1 = (int)((int64_t)(rank + 1) * nz_global / nranks);
+	const int rc = s3d_grid_init(g, nx, ny, k1 - k0);
+	if (rc != S3D_OK) return rc;
+	g->nz_global = nz_global; g->k0 = k0; g->rank = rank; g->nranks = nranks;
+	return S3D_OK;
+}
+
+// ------------------------------------------------------------------------------------ storage
+
+int s3d_vec_alloc(s3d_ctx *ctx, const s3d_grid *g, double **d_out)
+{
+	S3D_REQUIRE(ctx, g && d_out, "null argument");
+	S3D_CUDA(ctx, cudaMalloc(d_out, g->vlen * sizeof(double)));
+	S3D_CUDA(ctx, cudaMemsetAsync(*d_out, 0, g->vlen * sizeof(double), ctx->stream));
+	return S3D_OK;
+}
+
+int s3d_mat_alloc(s3d_ctx *ctx, const s3d_grid *g, double **d_out)
+{
+	S3D_REQUIRE(ctx, g && d_out, "null argument");
+	const size_t bytes = (size_t)g->cstride * S3D_NSTENCIL * sizeof(double);
+	S3D_CUDA(ctx, cudaMalloc(d_out, bytes));
+	S3D_CUDA(ctx, cudaMemsetAsync(*d_out, 0, bytes, ctx->stream));
+	return S3D_OK;
+}
+
+int s3d_scalars_alloc(s3d_ctx *ctx, int n, double **d_out)
+{
+	S3D_REQUIRE(ctx, n > 0 && d_out, "bad argument");
+	S3D_CUDA(ctx, cudaMalloc(d_out, n * sizeof(double)));
+	S3D_CUDA(ctx, cudaMemsetAsync(*d_out, 0, n * sizeof(double), ctx->stream));
+	return S3D_OK;
+}
+
+int s3d_ints_alloc(s3d_ctx *ctx, int n, int **d_out)
+{
+	S3D_REQUIRE(ctx, n > 0 && d_out, "bad argument");
+	S3D_CUDA(ctx, cudaMalloc(d_out, n * sizeof(int)));
+	S3D_CUDA(ctx, cudaMemsetAsync(*d_out, 0, n * sizeof(int), ctx->stream));
+	return S3D_OK;
+}
+
+int s3d_ints_zero(s3d_ctx *ctx, int *d_s, int n)
+{
+	S3D_CUDA(ctx, cudaMemsetAsync(d_s, 0, n * sizeof(int), ctx->stream));
+	return S3D_OK;
+}
+
+int s3d_ints_download(s3d_ctx *ctx, const int *d_s, int n, int *h_out)
+{
+	S3D_REQUIRE(ctx, n > 0 && n <= 128, "n out of range");
+	int *pin = reinterpret_cast<int *>(ctx->h_pinned);
+	S3D_CUDA(ctx, cudaMemcpyAsync(pin, d_s, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	memcpy(h_out, pin, n * sizeof(int));
+	return S3D_OK;
+}
+
+int s3d_free(s3d_ctx *ctx, void *d_ptr)
+{
+	if (!d_ptr) return S3D_OK;
+	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	S3D_CUDA(ctx, cudaFree(d_ptr));
+	return S3D_OK;
+}
+
+// host ghosted (nx+2)-pitch rows <-> device vpitch rows; the ghost column i=-1 sits at vlead-1
+int s3d_vec_upload(s3d_ctx *ctx, const s3d_grid *g, double *d_x, const double *h_x)
+{
+	S3D_REQUIRE(ctx, g && d_x && h_x, "null argument");
+	const size_t w = (size_t)(g->nx + 2) * sizeof(double);
+	S3D_CUDA(ctx, cudaMemcpy2DAsync(d_x + g->vlead - 1, (size_t)g->vpitch * sizeof(double), h_x, w, w,
+	                                (size_t)(g->ny + 2) * (g->nz + 2), cudaMemcpyHostToDevice, ctx->stream));
+	return S3D_OK;
+}
+
+int s3d_vec_download(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, double *h_x)
+{
+	S3D_REQUIRE(ctx, g && d_x && h_x, "null argument");
+	const size_t w = (size_t)(g->nx + 2) * sizeof(double);
+	S3D_CUDA(ctx, cudaMemcpy2DAsync(h_x, w, d_x + g->vlead - 1, (size_t)g->vpitch * sizeof(double), w,
+	                                (size_t)(g->ny + 2) * (g->nz + 2), cudaMemcpyDeviceToHost, ctx->stream));
+	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return S3D_OK;
+}
+
+int s3d_mat_upload(s3d_ctx *ctx, const s3d_grid *g, double *d_A, int s, const double *h_vals)
+{
+	S3D_REQUIRE(ctx, g && d_A && h_vals && s >= 0 && s < S3D_NSTENCIL, "bad argument");
+	const size_t w = (size_t)g->nx * sizeof(double);
+	S3D_CUDA(ctx, cudaMemcpy2DAsync(d_A + (size_t)s * g->cstride, (size_t)g->cpitch * sizeof(double), h_vals, w, w,
+	                                (size_t)g->ny * g->nz, cudaMemcpyHostToDevice, ctx->stream));
+	return S3D_OK;
+}
+
+int s3d_mat_download(s3d_ctx *ctx, const s3d_grid *g, const double *d_A, int s, double *h_vals)
+{
+	S3D_REQUIRE(ctx, g && d_A && h_vals && s >= 0 && s < S3D_NSTENCIL, "bad argument");
+	const size_t w = (size_t)g->nx * sizeof(double);
+	S3D_CUDA(ctx, cudaMemcpy2DAsync(h_vals, w, d_A + (size_t)s * g->cstride, (size_t)g->cpitch * sizeof(double), w,
+	                                (size_t)g->ny * g->nz, cudaMemcpyDeviceToHost, ctx->stream));
+	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return S3D_OK;
+}
+
+int s3d_scalars_download(s3d_ctx *ctx, const double *d_s, int n, double *h_out)
+{
+	S3D_REQUIRE(ctx, d_s && h_out && n > 0, "bad argument");
+	if (n <= 64) {
+		S3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, d_s, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+		S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		memcpy(h_out, ctx->h_pinned, n * sizeof(double));
+	} else {
+		S3D_CUDA(ctx, cudaMemcpyAsync(h_out, d_s, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+		S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	}
+	return S3D_OK;
+}
+
+int s3d_scalars_upload(s3d_ctx *ctx, double *d_s, int n, const double *h_in)
+{
+	S3D_REQUIRE(ctx, d_s && h_in && n > 0, "bad argument");
+	S3D_CUDA(ctx, cudaMemcpyAsync(d_s, h_in, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return S3D_OK;
+}
+
+int s3d_host_alloc(s3d_ctx *ctx, size_t bytes, void **h_out)
+{
+	S3D_CUDA(ctx, cudaMallocHost(h_out, bytes));
+	return S3D_OK;
+}
+int s3d_host_free(s3d_ctx *ctx, void *h_ptr)
+{
+	S3D_CUDA(ctx, cudaFreeHost(h_ptr));
+	return S3D_OK;
+}
+
+// ------------------------------------------------------------------------------------ z-slab communicator
+
+int s3d_comm_unique_id(void *id_out)
+{
+	static_assert(sizeof(ncclUniqueId) <= S3D_COMM_ID_BYTES, "id buffer too small");
+	ncclUniqueId id;
+	if (!nccl_load()) return s3d_fail(nullptr, S3D_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+	if (g_nccl.GetUniqueId(&id) != ncclSuccess) return S3D_ERR_NCCL;
+	memset(id_out, 0, S3D_COMM_ID_BYTES);
+	memcpy(id_out, &id, sizeof(id));
+	return S3D_OK;
+}
+
+int s3d_comm_init(s3d_ctx *ctx, int rank, int nranks, const void *idbytes)
+{
+	S3D_REQUIRE(ctx, nranks >= 1 && rank >= 0 && rank < nranks, "bad rank");
+	ctx->rank = rank; ctx->nranks = nranks;
+	if (nranks == 1) return S3D_OK;
+	S3D_REQUIRE(ctx, idbytes, "null id");
+	if (!nccl_load()) return s3d_fail(ctx, S3D_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+	ncclUniqueId id;
+	memcpy(&id, idbytes, sizeof(id));
+	S3D_CUDA(ctx, cudaSetDevice(ctx->device));
+	S3D_NCCL(ctx, g_nccl.CommInitRank(&ctx->comm, nranks, id, rank));
+	return S3D_OK;
+}
+
+int s3d_comm_destroy(s3d_ctx *ctx)
+{
+	if (ctx->comm) { S3D_NCCL(ctx, g_nccl.CommDestroy(ctx->comm)); ctx->comm = nullptr; }
+	ctx->rank = 0; ctx->nranks = 1;
+	return S3D_OK;
+}
+
+// One contiguous z-plane (vplane doubles: ghost rows and padding included, all zero there) per direction.
+// Plane nz (top real) goes up into the neighbour's ghost plane 0; plane 1 goes down into its ghost plane nz+1.
+int s3d_halo_exchange(s3d_ctx *ctx, const s3d_grid *g, double *d_x)
+{
+	if (g->nranks == 1) return S3D_OK;
+	if (!ctx->comm) return s3d_fail(ctx, S3D_ERR_STATE, "halo exchange needs s3d_comm_init");
+	const size_t n = (size_t)g->vplane;
+	const int up = g->rank + 1, dn = g->rank - 1;
+	S3D_NCCL(ctx, g_nccl.GroupStart());
+	if (up < g->nranks) {
+		S3D_NCCL(ctx, g_nccl.Send(d_x + n * g->nz, n, ncclDouble, up, ctx->comm, ctx->stream));
+		S3D_NCCL(ctx, g_nccl.Recv(d_x + n * (g->nz + 1), n, ncclDouble, up, ctx->comm, ctx->stream));
+	}
+	if (dn >= 0) {
+		S3D_NCCL(ctx, g_nccl.Send(d_x + n, n, ncclDouble, dn, ctx->comm, ctx->stream));
+		S3D_NCCL(ctx, g_nccl.Recv(d_x, n, ncclDouble, dn, ctx->comm, ctx->stream));
+	}
+	S3D_NCCL(ctx, g_nccl.GroupEnd());
+	return S3D_OK;
+}
+
+int s3d_allreduce_sum(s3d_ctx *ctx, double *d_s, int n)
+{
+	if (ctx->nranks == 1) return S3D_OK;
+	if (!ctx->comm) return s3d_fail(ctx, S3D_ERR_STATE, "allreduce needs s3d_comm_init");
+	S3D_NCCL(ctx, g_nccl.AllReduce(d_s, d_s, n, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+	return S3D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,357 @@
+// 7-point structured SpMV for sm_100a:  y = A x  and  y = b - A x
+// (reference: SMat::apply / SMat::apply_res, src/linalg/matvec.cpp:59-146).
+//
+// HBM-bound: 72 B/point algorithmic (7 coefficient streams + x + y; 80 with b), 13 flop/point,
+// so no tensor cores.  What matters is (1) every coefficient byte is read exactly once with
+// 128-bit, 128-byte-aligned, evict-first loads, (2) x is fetched from HBM once although each value
+// is used by seven points, (3) enough bytes in flight per SM to cover HBM latency.
+//
+// MARCH variant: a 32 x BY thread block owns a (64 i) x (BY j) column of the grid and marches
+// through a chunk of z-planes.  Each thread owns two consecutive i-points (one double2), keeps its
+// own x[k-1], x[k], x[k+1] in registers (so the k-neighbours cost no loads), gets x[i-1]/x[i+2] from
+// the neighbouring lanes by warp shuffle, and reads the j-1 / j+1 rows with aligned double2 loads
+// that hit L1/L2 (the rows were loaded as the centre rows of the previous plane step).  No shared
+// memory and no block barrier in the streaming loop: 10 independent 128-bit loads per thread per plane.
+//
+// Arithmetic: the seven products are rounded separately and added in stencil order 0..6
+// (__dmul_rn / __dadd_rn, never contracted to FMA), which is bit-for-bit the reference's expression
+// when the reference is compiled without FMA contraction (oracle/Makefile).
+#include "common.cuh"
+
+namespace {
+
+struct Tune { int by = 8; int kchunk = 0; int variant = S3D_SPMV_PAIR; };
+Tune g_tune;
+
+__device__ __forceinline__ double stencil7(double a0, double a1, double a2, double a3, double a4, double a5, double a6,
+                                           double x0, double x1, double x2, double x3, double x4, double x5, double x6)
+{
+	double s = __dmul_rn(a0, x0);
+	s = __dadd_rn(s, __dmul_rn(a1, x1));
+	s = __dadd_rn(s, __dmul_rn(a2, x2));
+	s = __dadd_rn(s, __dmul_rn(a3, x3));
+	s = __dadd_rn(s, __dmul_rn(a4, x4));
+	s = __dadd_rn(s, __dmul_rn(a5, x5));
+	s = __dadd_rn(s, __dmul_rn(a6, x6));
+	return s;
+}
+
+// grid: (ceil(nx/64), ceil(ny/BY), ceil(nz/kchunk)); block: (32, BY)
+template <int BY, bool RES, bool DOTW, bool DOTYY>
+__global__ void __launch_bounds__(32 * BY)
+spmv_march_kernel(const GridDev g, const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ y,
+                  const double *__restrict__ b, const double *__restrict__ w, const RedOut ro, const int *stop,
+                  const int kchunk)
+{
+	if (s3d_stopped(stop)) return;
+	const int lane = threadIdx.x;
+	const int i0 = (blockIdx.x * 32 + lane) * 2;
+	const int j = blockIdx.y * BY + threadIdx.y;
+	const int kbeg = blockIdx.z * kchunk;
+	const int kend = min(g.nz, kbeg + kchunk);
+	const bool active = (i0 < g.nx) && (j < g.ny);
+	const unsigned mask = __ballot_sync(0xffffffffu, active);
+	double acc[2] = {0.0, 0.0};
+
+	if (active) {
+		const bool pair = (i0 + 1 < g.nx);                                    // false only for the last point of an odd row
+		const bool edge_lo = (lane == 0);
+		const bool edge_hi = (lane == 31) || (((mask >> (lane + 1)) & 1u) == 0u);
+		const long long voffs = g.voff + (long long)kbeg * g.vplane + (long long)j * g.vpitch + i0;
+		const double *xp = x + voffs;
+		double *yp = y + voffs;
+		const double *bp = RES ? b + voffs : nullptr;
+		const double *wp = DOTW ? w + voffs : nullptr;
+		const double *ap = A + (long long)kbeg * g.cplane + (long long)j * g.cpitch + i0;
+		const long long cs = g.cstride;
+
+		double2 xm = ld2(xp - g.vplane);
+		double2 xc = ld2(xp);
+		for (int k = kbeg; k < kend; ++k) {
+			// the seven coefficient streams: read once, evict-first
+			const double2 a0 = ld_stream2(ap);
+			const double2 a1 = ld_stream2(ap + cs);
+			const double2 a2 = ld_stream2(ap + 2 * cs);
+			const double2 a3 = ld_stream2(ap + 3 * cs);
+			const double2 a4 = ld_stream2(ap + 4 * cs);
+			const double2 a5 = ld_stream2(ap + 5 * cs);
+			const double2 a6 = ld_stream2(ap + 6 * cs);
+			// x: the next plane (first touch of these values), and the two j-neighbour rows of this plane
+			const double2 xn = ld2(xp + g.vplane);
+			const double2 xjm = ld2(xp - g.vpitch);
+			const double2 xjp = ld2(xp + g.vpitch);
+			double2 bv = make_double2(0.0, 0.0);
+			if (RES) bv = ld_stream2(bp);
+			// i-neighbours from the adjacent lanes; the two warp-edge lanes read them from memory
+			double xl = __shfl_up_sync(mask, xc.y, 1);
+			double xr = __shfl_down_sync(mask, xc.x, 1);
+			if (edge_lo) xl = xp[-1];
+			if (edge_hi) xr = xp[2];
+
+			double y0 = stencil7(a0.x, a1.x, a2.x, a3.x, a4.x, a5.x, a6.x, xl, xjm.x, xm.x, xc.x, xc.y, xjp.x, xn.x);
+			double y1 = stencil7(a0.y, a1.y, a2.y, a3.y, a4.y, a5.y, a6.y, xc.x, xjm.y, xm.y, xc.y, xr, xjp.y, xn.y);
+			if (RES) { y0 = __dsub_rn(bv.x, y0); y1 = __dsub_rn(bv.y, y1); }
+			if (pair) st_stream2(yp, make_double2(y0, y1));
+			else *yp = y0;
+			if (DOTW) {
+				const double2 wv = (wp == xp) ? xc : ld2(wp);
+				acc[0] += wv.x * y0;
+				if (pair) acc[0] += wv.y * y1;
+			}
+			if (DOTYY) {
+				acc[1] += y0 * y0;
+				if (pair) acc[1] += y1 * y1;
+			}
+			xm = xc; xc = xn;
+			xp += g.vplane; yp += g.vplane; ap += g.cplane;
+			if (RES) bp += g.vplane;
+			if (DOTW) wp += g.vplane;
+		}
+	}
+	if (DOTW || DOTYY) grid_reduce<2>(acc, ro);
+}
+
+
+// PAIR variant: no marching.  Each thread computes two consecutive i-points of ONE plane; all five
+// x rows it needs (centre, j-1, j+1, k-1, k+1) are aligned double2 loads that hit L1/L2 after their
+// first touch, the i-neighbours come from the adjacent lanes.  12 independent 128-bit loads per thread,
+// few registers, maximal parallelism: x-reuse is left to the 126 MB L2 (three planes = 6 MB at 512^2),
+// which is protected by the evict-first policy of the coefficient / y streams.
+// grid: (ceil(nx/64), ceil(ny/8), nz); block: (32, 8)
+template <bool RES, bool DOTW, bool DOTYY>
+__global__ void __launch_bounds__(256)
+spmv_pair_kernel(const GridDev g, const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ y,
+                 const double *__restrict__ b, const double *__restrict__ w, const RedOut ro, const int *stop)
+{
+	if (s3d_stopped(stop)) return;
+	const int lane = threadIdx.x;
+	const int i0 = (blockIdx.x * 32 + lane) * 2;
+	const int j = blockIdx.y * 8 + threadIdx.y;
+	const int k = blockIdx.z;
+	const bool active = (i0 < g.nx) && (j < g.ny);
+	const unsigned mask = __ballot_sync(0xffffffffu, active);
+	double acc[2] = {0.0, 0.0};
+	if (active) {
+		const bool pair = (i0 + 1 < g.nx);
+		const bool edge_lo = (lane == 0);
+		const bool edge_hi = (lane == 31) || (((mask >> (lane + 1)) & 1u) == 0u);
+		const long long voffs = g.voff + (long long)k * g.vplane + (long long)j * g.vpitch + i0;
+		const double *xp = x + voffs;
+		const double *ap = A + (long long)k * g.cplane + (long long)j * g.cpitch + i0;
+		const long long cs = g.cstride;
+		const double2 a0 = ld_stream2(ap);
+		const double2 a1 = ld_stream2(ap + cs);
+		const double2 a2 = ld_stream2(ap + 2 * cs);
+		const double2 a3 = ld_stream2(ap + 3 * cs);
+		const double2 a4 = ld_stream2(ap + 4 * cs);
+		const double2 a5 = ld_stream2(ap + 5 * cs);
+		const double2 a6 = ld_stream2(ap + 6 * cs);
+		const double2 xc = ld2(xp);
+		const double2 xjm = ld2(xp - g.vpitch);
+		const double2 xjp = ld2(xp + g.vpitch);
+		const double2 xkm = ld2(xp - g.vplane);
+		const double2 xkp = ld2(xp + g.vplane);
+		double2 bv = make_double2(0.0, 0.0);
+		if (RES) bv = ld_stream2(b + voffs);
+		double xl = __shfl_up_sync(mask, xc.y, 1);
+		double xr = __shfl_down_sync(mask, xc.x, 1);
+		if (edge_lo) xl = xp[-1];
+		if (edge_hi) xr = xp[2];
+		double y0 = stencil7(a0.x, a1.x, a2.x, a3.x, a4.x, a5.x, a6.x, xl, xjm.x, xkm.x, xc.x, xc.y, xjp.x, xkp.x);
+		double y1 = stencil7(a0.y, a1.y, a2.y, a3.y, a4.y, a5.y, a6.y, xc.x, xjm.y, xkm.y, xc.y, xr, xjp.y, xkp.y);
+		if (RES) { y0 = __dsub_rn(bv.x, y0); y1 = __dsub_rn(bv.y, y1); }
+		if (pair) st_stream2(y + voffs, make_double2(y0, y1));
+		else y[voffs] = y0;
+		if (DOTW) {
+			const double2 wv = (w == x) ? xc : ld2(w + voffs);
+			acc[0] = wv.x * y0;
+			if (pair) acc[0] += wv.y * y1;
+		}
+		if (DOTYY) {
+			acc[1] = y0 * y0;
+			if (pair) acc[1] += y1 * y1;
+		}
+	}
+	if (DOTW || DOTYY) grid_reduce<2>(acc, ro);
+}
+
+// The first correct version: one thread per point, all neighbours straight from global memory.
+template <bool RES, bool DOTW, bool DOTYY>
+__global__ void __launch_bounds__(256)
+spmv_naive_kernel(const GridDev g, const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ y,
+                  const double *__restrict__ b, const double *__restrict__ w, const RedOut ro, const int *stop)
+{
+	if (s3d_stopped(stop)) return;
+	const int i = blockIdx.x * 64 + threadIdx.x;
+	const int j = blockIdx.y * 4 + threadIdx.y;
+	const int k = blockIdx.z;
+	double acc[2] = {0.0, 0.0};
+	if (i < g.nx && j < g.ny) {
+		const long long v = g.voff + (long long)k * g.vplane + (long long)j * g.vpitch + i;
+		const long long c = (long long)k * g.cplane + (long long)j * g.cpitch + i;
+		double s = stencil7(ld_stream(A + c), ld_stream(A + c + g.cstride), ld_stream(A + c + 2 * g.cstride),
+		                    ld_stream(A + c + 3 * g.cstride), ld_stream(A + c + 4 * g.cstride),
+		                    ld_stream(A + c + 5 * g.cstride), ld_stream(A + c + 6 * g.cstride),
+		                    x[v - 1], x[v - g.vpitch], x[v - g.vplane], x[v], x[v + 1], x[v + g.vpitch], x[v + g.vplane]);
+		if (RES) s = __dsub_rn(ld_stream(b + v), s);
+		__stcs(y + v, s);
+		if (DOTW) acc[0] = w[v] * s;
+		if (DOTYY) acc[1] = s * s;
+	}
+	if (DOTW || DOTYY) grid_reduce<2>(acc, ro);
+}
+
+template <int BY>
+int launch_march(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *x, double *y, const double *b,
+                 const double *w, bool yy, double *d_red, const int *stop, int kchunk)
+{
+	const GridDev gd = to_dev(g);
+	dim3 block(32, BY);
+	dim3 grid((g->nx + 63) / 64, (g->ny + BY - 1) / BY, (g->nz + kchunk - 1) / kchunk);
+	const bool red = (w != nullptr) || yy;
+	if (red) {
+		const int rc = s3d_ensure_partials(ctx, (size_t)grid.x * grid.y * grid.z * 2);
+		if (rc != S3D_OK) return rc;
+	}
+	RedOut ro{ctx->partials, ctx->ticket, d_red};
+#define GO(RES, DW, DY) spmv_march_kernel<BY, RES, DW, DY><<<grid, block, 0, ctx->stream>>>(gd, A, x, y, b, w, ro, stop, kchunk)
+	const int sel = (b ? 4 : 0) | (w ? 2 : 0) | (yy ? 1 : 0);
+	switch (sel) {
+	case 0: GO(false, false, false); break;
+	case 1: GO(false, false, true); break;
+	case 2: GO(false, true, false); break;
+	case 3: GO(false, true, true); break;
+	case 4: GO(true, false, false); break;
+	case 5: GO(true, false, true); break;
+	case 6: GO(true, true, false); break;
+	default: GO(true, true, true); break;
+	}
+#undef GO
+	S3D_LAUNCHED(ctx);
+	return S3D_OK;
+}
+
+int launch_naive(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *x, double *y, const double *b,
+                 const double *w, bool yy, double *d_red, const int *stop)
+{
+	const GridDev gd = to_dev(g);
+	dim3 block(64, 4);
+	dim3 grid((g->nx + 63) / 64, (g->ny + 3) / 4, g->nz);
+	const bool red = (w != nullptr) || yy;
+	if (red) {
+		const int rc = s3d_ensure_partials(ctx, (size_t)grid.x * grid.y * grid.z * 2);
+		if (rc != S3D_OK) return rc;
+	}
+	RedOut ro{ctx->partials, ctx->ticket, d_red};
+#define GO(RES, DW, DY) spmv_naive_kernel<RES, DW, DY><<<grid, block, 0, ctx->stream>>>(gd, A, x, y, b, w, ro, stop)
+	const int sel = (b ? 4 : 0) | (w ? 2 : 0) | (yy ? 1 : 0);
+	switch (sel) {
+	case 0: GO(false, false, false); break;
+	case 1: GO(false, false, true); break;
+	case 2: GO(false, true, false); break;
+	case 3: GO(false, true, true); break;
+	case 4: GO(true, false, false); break;
+	case 5: GO(true, false, true); break;
+	case 6: GO(true, true, false); break;
+	default: GO(true, true, true); break;
+	}
+#undef GO
+	S3D_LAUNCHED(ctx);
+	return S3D_OK;
+}
+
+
+int launch_pair(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *x, double *y, const double *b,
+                const double *w, bool yy, double *d_red, const int *stop)
+{
+	const GridDev gd = to_dev(g);
+	dim3 block(32, 8);
+	dim3 grid((g->nx + 63) / 64, (g->ny + 7) / 8, g->nz);
+	const bool red = (w != nullptr) || yy;
+	if (red) {
+		const int rc = s3d_ensure_partials(ctx, (size_t)grid.x * grid.y * grid.z * 2);
+		if (rc != S3D_OK) return rc;
+	}
+	RedOut ro{ctx->partials, ctx->ticket, d_red};
+#define GO(RES, DW, DY) spmv_pair_kernel<RES, DW, DY><<<grid, block, 0, ctx->stream>>>(gd, A, x, y, b, w, ro, stop)
+	const int sel = (b ? 4 : 0) | (w ? 2 : 0) | (yy ? 1 : 0);
+	switch (sel) {
+	case 0: GO(false, false, false); break;
+	case 1: GO(false, false, true); break;
+	case 2: GO(false, true, false); break;
+	case 3: GO(false, true, true); break;
+	case 4: GO(true, false, false); break;
+	case 5: GO(true, false, true); break;
+	case 6: GO(true, true, false); break;
+	default: GO(true, true, true); break;
+	}
+#undef GO
+	S3D_LAUNCHED(ctx);
+	return S3D_OK;
+}
+
+// z-chunk length: long marches amortise the two extra x-planes a chunk re-reads (2/kchunk of 8 B/pt),
+// but the grid still has to cover the 148 SMs several times over.
+int pick_kchunk(const s3d_ctx *ctx, const s3d_grid *g, int by)
+{
+	if (g_tune.kchunk > 0) return min(g_tune.kchunk, g->nz);
+	const long long tiles = (long long)((g->nx + 63) / 64) * ((g->ny + by - 1) / by);
+	const long long want = (long long)ctx->sm_count * 16;   // ~4 resident blocks per SM, ~4 waves
+	long long nchunks = (want + tiles - 1) / tiles;
+	if (nchunks < 1) nchunks = 1;
+	int kc = (int)((g->nz + nchunks - 1) / nchunks);
+	if (kc < 16) kc = 16;
+	if (kc > g->nz) kc = g->nz;
+	return kc;
+}
+
+}  // namespace
+
+int s3d_spmv_tma(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *x, double *y, const double *b,
+                 const double *w, bool yy, double *d_red, const int *stop);
+
+extern "C" {
+
+int s3d_tune_set(s3d_ctx *ctx, const char *key, int value)
+{
+	if (!key) return S3D_ERR_ARG;
+	if (!strcmp(key, "spmv_by")) {
+		S3D_REQUIRE(ctx, value == 4 || value == 8 || value == 16, "spmv_by must be 4, 8 or 16");
+		g_tune.by = value;
+	} else if (!strcmp(key, "spmv_kchunk")) g_tune.kchunk = value;
+	else if (!strcmp(key, "spmv_variant")) {
+		S3D_REQUIRE(ctx, value >= S3D_SPMV_MARCH && value <= S3D_SPMV_PAIR, "unknown SpMV variant");
+		g_tune.variant = value;
+	}
+	else return s3d_fail(ctx, S3D_ERR_ARG, "unknown tuning key %s", key);
+	return S3D_OK;
+}
+
+int s3d_spmv(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_x, double *d_y, const double *d_b,
+             const double *d_w, int want_yy, double *d_red, const int *d_stop, int variant)
+{
+	S3D_REQUIRE(ctx, g && A && d_x && d_y, "null argument");
+	S3D_REQUIRE(ctx, d_x != d_y, "x and y must not alias");
+	S3D_REQUIRE(ctx, !(d_w || want_yy) || d_red, "fused reductions need d_red");
+	if (variant == S3D_SPMV_AUTO) variant = g_tune.variant;
+	if (!d_stop) d_stop = ctx->gate;
+	switch (variant) {
+	case S3D_SPMV_MARCH: {
+		const int by = g_tune.by;
+		const int kc = pick_kchunk(ctx, g, by);
+		if (by == 4) return launch_march<4>(ctx, g, A, d_x, d_y, d_b, d_w, want_yy != 0, d_red, d_stop, kc);
+		if (by == 16) return launch_march<16>(ctx, g, A, d_x, d_y, d_b, d_w, want_yy != 0, d_red, d_stop, kc);
+		return launch_march<8>(ctx, g, A, d_x, d_y, d_b, d_w, want_yy != 0, d_red, d_stop, kc);
+	}
+	case S3D_SPMV_PAIR:
+		return launch_pair(ctx, g, A, d_x, d_y, d_b, d_w, want_yy != 0, d_red, d_stop);
+	case S3D_SPMV_NAIVE:
+		return launch_naive(ctx, g, A, d_x, d_y, d_b, d_w, want_yy != 0, d_red, d_stop);
+	case S3D_SPMV_TMA:
+		return s3d_spmv_tma(ctx, g, A, d_x, d_y, d_b, d_w, want_yy != 0, d_red, d_stop);
+	default:
+		return s3d_fail(ctx, S3D_ERR_ARG, "unknown SpMV variant %d", variant);
+	}
+}
+
+}  // extern "C"

@@ -1,0 +1,509 @@
+// Host-driven solver loops over device-resident data (reference: src/linalg/s3d_solverbase.cpp,
+// s3d_jacobi.cpp, s3d_sgspreconditioners.cpp, s3d_gcr.cpp, solverfactory.cpp; CG/BiCGSTAB are new).
+//
+// How a loop runs on the GPU.  The host only ENQUEUES kernels; every Krylov coefficient is a device
+// scalar (s3d_scalar operands: value = imm * *num / *den), every reduction lands in device memory,
+// and the convergence test is a one-thread kernel that raises a device flag.  While the loop runs,
+// that flag is the context-wide gate: once it is set, every later launch is a no-op, so x is exactly
+// the iterate at which the reference's test `resnorm/bnorm > rtol` first failed.  The host polls the
+// flag once per batch of iterations, so the only host<->device round trips are those polls.
+#include <algorithm>
+#include <climits>
+#include <cstring>
+#include "common_utils.hpp"
+#include "linalg/s3d_gcr.hpp"
+#include "linalg/s3d_jacobi.hpp"
+#include "linalg/s3d_krylov.hpp"
+#include "linalg/s3d_sgspreconditioners.hpp"
+#include "linalg/solverfactory.hpp"
+
+using s3d::Device;
+
+namespace {
+
+s3d_scalar imm(double a) { return s3d_scalar{a, nullptr, nullptr}; }
+s3d_scalar ratio(double sign, const double *num, const double *den) { return s3d_scalar{sign, num, den}; }
+
+// Device-side loop bookkeeping: stop flag, iteration counter, residual history.
+struct DeviceLoop {
+	const Device &d;
+	s3d_ctx *ctx;
+	int *flags;        // [0] stop, [1] iterations
+	double *hist;
+	int hist_cap;
+	int printed = 0;
+	int every;         // print "Step n: Rel res" every this many steps, like the reference
+	std::vector<sreal> &history;
+
+	DeviceLoop(int cap, int print_every, std::vector<sreal> &out)
+		: d(Device::get()), ctx(d.ctx()), flags(d.ints(2)), hist(d.scalars(cap)), hist_cap(cap), every(print_every), history(out)
+	{
+		history.clear();
+	}
+	~DeviceLoop()
+	{
+		s3d_ctx_set_gate(ctx, nullptr);
+		s3d_free(ctx, flags);
+		s3d_free(ctx, hist);
+	}
+	int *stop() const { return flags; }
+	int *iters() const { return flags + 1; }
+	void gate() { d.check(s3d_ctx_set_gate(ctx, flags), "s3d_ctx_set_gate"); }
+	void test(const double *rr, const double *bb, double rtol, int maxiter, int how)
+	{
+		d.check(s3d_converge_test(ctx, rr, bb, rtol, maxiter, how, stop(), iters(), hist), "s3d_converge_test");
+	}
+	// blocks until everything enqueued so far has run; returns the stop code, fills the iteration count
+	int poll(int &iterations)
+	{
+		int h[2] = {0, 0};
+		d.check(s3d_ints_download(ctx, flags, 2, h), "s3d_ints_download");
+		iterations = h[1];
+		const int have = std::min(iterations, hist_cap);
+		if (have > (int)history.size()) {
+			const int old = (int)history.size();
+			history.resize(have);
+			d.check(s3d_scalars_download(ctx, hist + old, have - old, history.data() + old), "s3d_scalars_download");
+		}
+		if (d.rank() == 0)
+			for (; printed < (int)history.size(); printed++)
+				if (printed % every == 0) {
+					std::printf("      Step %d: Rel res = %g\n", printed, history[printed]);
+					std::fflush(stdout);
+				}
+		return h[0];
+	}
+};
+
+// how many iterations to enqueue between polls: aim for ~2 ms of GPU work per batch
+int batch_size(const s3d_grid &g, double bytes_per_point_per_iter)
+{
+	const double t = (double)g.nx * g.ny * g.nz * bytes_per_point_per_iter / 6.0e12 + 15e-6;
+	const int b = (int)(2.0e-3 / t);
+	return std::max(1, std::min(64, b));
+}
+
+void allreduce(const Device &d, double *s, int n)
+{
+	if (d.nranks() > 1) d.check(s3d_allreduce_sum(d.ctx(), s, n), "s3d_allreduce_sum");
+}
+
+SolveInfo finish(const Device &d, const double *rr, const double *bb, double rtol, int iterations, int stopcode, int phase_slot)
+{
+	double h[2];
+	d.check(s3d_scalars_download(d.ctx(), rr, 1, &h[0]), "s3d_scalars_download");
+	d.check(s3d_scalars_download(d.ctx(), bb, 1, &h[1]), "s3d_scalars_download");
+	const sreal resnorm = std::sqrt(h[0]), bnorm = std::sqrt(h[1]);
+	double ms = 0;
+	d.check(s3d_phase_total_ms(d.ctx(), phase_slot, &ms), "s3d_phase_total_ms");
+	SolveInfo info;
+	info.converged = (stopcode != S3D_STOP_BREAKDOWN) && (resnorm / bnorm <= rtol);
+	info.iters = iterations;
+	info.resnorm = resnorm;
+	info.precapplywtime = ms * 1e-3;
+	return info;
+}
+
+struct TimedPrec {   // brackets a preconditioner application with the GPU stopwatch (SolveInfo::precapplywtime)
+	const Device &d;
+	explicit TimedPrec(const Device &dev) : d(dev) { d.check(s3d_phase_begin(d.ctx(), 0), "s3d_phase_begin"); }
+	~TimedPrec() { s3d_phase_end(d.ctx(), 0); }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------ base + identity
+
+SolverBase::SolverBase(const SMat &lhs, SolverBase *const precond) : A(lhs), prec{precond} {}
+
+SolverBase::~SolverBase() { delete prec; }
+
+NoSolver::NoSolver(const SMat &lhs, SolverBase *const) : SolverBase(lhs, nullptr) {}
+
+void NoSolver::updateOperator() {}
+
+SolveInfo NoSolver::apply(const SVec &b, SVec &x) const
+{
+	if (b.m != x.m) throw std::runtime_error("Arguments must be defined over a common mesh!");
+	const Device &d = Device::get();
+	d.check(s3d_veccopy_all(d.ctx(), &b.grid(), b.dev(), x.dev_w()), "s3d_veccopy_all");
+	return {false, 1, 1.0, 0.0};
+}
+
+// ------------------------------------------------------------------ preconditioners
+
+JacobiPreconditioner::JacobiPreconditioner(const SMat &lhs) : SolverBase(lhs, nullptr) {}
+
+void JacobiPreconditioner::updateOperator() {}
+
+SolveInfo JacobiPreconditioner::apply(const SVec &r, SVec &z) const
+{
+	const Device &d = Device::get();
+	d.check(s3d_jacobi_apply(d.ctx(), &A.grid(), A.dev(), r.dev(), z.dev_rw()), "s3d_jacobi_apply");
+	return {false, 1, 1.0, 0.0};
+}
+
+SGS_like_preconditioner::SGS_like_preconditioner(const SMat &lhs, const PreconParams parms)
+	: SolverBase(lhs, nullptr), diaginv{nullptr}, params(parms), order{S3D_SGS_LEXICOGRAPHIC}, scratch(lhs.m)
+{
+	const Device &d = Device::get();
+	diaginv = d.scalars((int)std::min<long long>(A.grid().cstride, INT_MAX));
+	if (s3d::options_has("-s3d_sgs_ordering")) {
+		const std::string o = petscoptions_get_string("-s3d_sgs_ordering", 40);
+		if (o == "redblack" || o == "multicolour" || o == "multicolor") order = S3D_SGS_REDBLACK;
+		else if (o == "lexicographic") order = S3D_SGS_LEXICOGRAPHIC;
+		else throw std::runtime_error("-s3d_sgs_ordering must be lexicographic or redblack");
+	}
+	if (d.nranks() > 1 && order == S3D_SGS_LEXICOGRAPHIC) {
+		if (d.rank() == 0) std::printf(" WARNING: SGS: lexicographic sweeps serialise across z-slabs; using the red-black ordering.\n");
+		order = S3D_SGS_REDBLACK;
+	}
+}
+
+SGS_like_preconditioner::~SGS_like_preconditioner()
+{
+	if (diaginv) s3d_free(Device::get().ctx(), diaginv);
+}
+
+SolveInfo SGS_like_preconditioner::apply(const SVec &r, SVec &z) const
+{
+	if (r.m != z.m || r.m != A.m) throw std::runtime_error("apply: Vectors and matrix must be defined over the same mesh!");
+	const Device &d = Device::get();
+	d.check(s3d_sgs_apply(d.ctx(), &A.grid(), A.dev(), diaginv, r.dev(), z.dev_rw(), scratch.dev_rw(), order,
+	                      std::max(1, params.napplysweeps)), "s3d_sgs_apply");
+	return {false, 1, -1.0, 0.0};
+}
+
+SGS_preconditioner::SGS_preconditioner(const SMat &lhs, const PreconParams parms) : SGS_like_preconditioner(lhs, parms) {}
+
+void SGS_preconditioner::updateOperator()
+{
+	const Device &d = Device::get();
+	d.check(s3d_sgs_setup(d.ctx(), &A.grid(), A.dev(), diaginv), "s3d_sgs_setup");
+}
+
+// ------------------------------------------------------------------ Richardson (s3d_solverbase.cpp:45-80)
+
+Richardson::Richardson(const SMat &lhs, SolverBase *const precond, const SolveParams params)
+	: SolverBase(lhs, precond), sparams(params) {}
+
+void Richardson::updateOperator() { if (prec) prec->updateOperator(); }
+
+SolveInfo Richardson::apply(const SVec &b, SVec &x) const
+{
+	if (b.m != x.m || b.m != A.m) throw std::runtime_error("All vectors and matrix should be defined over the same mesh!");
+	const Device &d = Device::get();
+	s3d_ctx *ctx = d.ctx();
+	const s3d_grid &g = A.grid();
+	SVec res(A.m), dx(A.m);
+	double *S = d.scalars(4);   // [0] (b,b)  [1] unused  [2] (r,r)
+	DeviceLoop loop(sparams.maxiter + 1, 10, history);
+
+	d.check(s3d_nrm2sq(ctx, &g, b.dev(), &S[0]), "s3d_nrm2sq");
+	allreduce(d, &S[0], 1);
+	auto residual = [&]() {
+		x.exchange_halo();
+		d.check(s3d_spmv(ctx, &g, A.dev(), x.dev(), res.dev_w(), b.dev(), nullptr, 1, &S[1], nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+		allreduce(d, &S[2], 1);
+	};
+	residual();
+	loop.test(&S[2], &S[0], sparams.rtol, sparams.maxiter, S3D_CONV_INITIAL);
+	loop.gate();
+	int iterations = 0;
+	int code = loop.poll(iterations);
+	const int batch = batch_size(g, 200);
+	while (!code) {
+		for (int i = 0; i < batch; i++) {
+			{ TimedPrec t(d); prec->apply(res, dx); }
+			d.check(s3d_vecaxpy(ctx, &g, imm(1.0), dx.dev(), x.dev_rw()), "s3d_vecaxpy");
+			residual();
+			loop.test(&S[2], &S[0], sparams.rtol, sparams.maxiter, 0);
+		}
+		code = loop.poll(iterations);
+	}
+	d.check(s3d_ctx_set_gate(ctx, nullptr), "s3d_ctx_set_gate");
+	const SolveInfo info = finish(d, &S[2], &S[0], sparams.rtol, iterations, code, 0);
+	d.release(S);
+	return info;
+}
+
+// ------------------------------------------------------------------ GCR (s3d_gcr.cpp:14-86)
+
+GCR::GCR(const SMat &lhs, SolverBase *const precond, const SolveParams params) : SolverBase(lhs, precond), sparams(params) {}
+
+void GCR::updateOperator() { if (prec) prec->updateOperator(); }
+
+SolveInfo GCR::apply(const SVec &b, SVec &x) const
+{
+	if (b.m != x.m || b.m != A.m) throw std::runtime_error("All vectors and matrix should be defined over the same mesh!");
+	const Device &d = Device::get();
+	s3d_ctx *ctx = d.ctx();
+	const s3d_grid &g = A.grid();
+	const int north = std::max(1, sparams.restart);
+	SVec res(A.m), z(A.m);
+	std::vector<SVec> p(north), q(north);
+	for (int i = 0; i < north; i++) { p[i].init(A.m); q[i].init(A.m); }
+
+	// scalars: [0] (b,b)  [1..2] spmv reductions  [3] (res,res)  [4..5] (res,q_k),(q_k,q_k)
+	//          QQ[i] = (q_i,q_i) cached (the reference recomputes the identical value)   DOT[i] = (q_new,q_i)   BETA[i]
+	double *S = d.scalars(8 + 3 * north);
+	double *QQ = S + 8, *DOT = QQ + north, *BETA = DOT + north;
+	DeviceLoop loop(sparams.maxiter + north + 1, 5, history);
+
+	d.check(s3d_nrm2sq(ctx, &g, b.dev(), &S[0]), "s3d_nrm2sq");
+	allreduce(d, &S[0], 1);
+	// before the first update the reference's resnorm is 1.0 and is never tested: give the final-result
+	// slot a defined value in case maxiter == 0
+	{ const double one = 1.0; d.check(s3d_scalars_upload(ctx, &S[3], 1, &one), "s3d_scalars_upload"); }
+	loop.gate();
+
+	int iterations = 0, code = 0;
+	while (!code && iterations < sparams.maxiter) {
+		x.exchange_halo();
+		d.check(s3d_spmv(ctx, &g, A.dev(), x.dev(), res.dev_w(), b.dev(), nullptr, 0, nullptr, nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+		{ TimedPrec t(d); prec->apply(res, p[0]); }
+		p[0].exchange_halo();
+		d.check(s3d_spmv(ctx, &g, A.dev(), p[0].dev(), q[0].dev_w(), nullptr, nullptr, 0, nullptr, nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+		for (int k = 0; k < north; k++) {
+			// alpha = (res,q_k)/(q_k,q_k): one pass over q_k
+			const double *two[2] = {res.dev(), q[k].dev()};
+			d.check(s3d_vec_multi_dot(ctx, &g, 2, two, q[k].dev(), &S[4]), "s3d_vec_multi_dot");
+			allreduce(d, &S[4], 2);
+			d.check(s3d_vecaxpy(ctx, &g, ratio(1.0, &S[4], &S[5]), p[k].dev(), x.dev_rw()), "s3d_vecaxpy");
+			// res -= alpha q_k with ||res||^2 fused
+			d.check(s3d_vecwaxpby(ctx, &g, imm(1.0), res.dev(), ratio(-1.0, &S[4], &S[5]), q[k].dev(), res.dev_rw(), &S[3]), "s3d_vecwaxpby");
+			allreduce(d, &S[3], 1);
+			loop.test(&S[3], &S[0], sparams.rtol, INT_MAX, S3D_CONV_STRICT);
+			if (k == north - 1) break;
+			// keep (q_k,q_k) for the Gram-Schmidt coefficients of later directions
+			d.check(s3d_scalar_op(ctx, 3, &QQ[k], &S[5], &S[5], nullptr, nullptr, 1, 1.0, nullptr), "s3d_scalar_op");
+			{ TimedPrec t(d); prec->apply(res, z); }
+			z.exchange_halo();
+			d.check(s3d_spmv(ctx, &g, A.dev(), z.dev(), q[k + 1].dev_w(), nullptr, nullptr, 0, nullptr, nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+			d.check(s3d_vecassign(ctx, &g, z.dev(), p[k + 1].dev_rw()), "s3d_vecassign");
+			// beta_i = -(q_new,q_i)/(q_i,q_i), i <= k, then p_new += sum beta_i p_i, q_new += sum beta_i q_i
+			for (int base = 0; base <= k; base += 32) {
+				const int n = std::min(32, k + 1 - base);
+				const double *qs[32];
+				for (int l = 0; l < n; l++) qs[l] = q[base + l].dev();
+				d.check(s3d_vec_multi_dot(ctx, &g, n, qs, q[k + 1].dev(), &DOT[base]), "s3d_vec_multi_dot");
+				allreduce(d, &DOT[base], n);
+			}
+			for (int base = 0; base <= k; base += 32) {
+				const int n = std::min(32, k + 1 - base);
+				const double *qs[32], *ps[32];
+				for (int l = 0; l < n; l++) { qs[l] = q[base + l].dev(); ps[l] = p[base + l].dev(); }
+				d.check(s3d_scalar_op(ctx, 0, &BETA[base], &DOT[base], &QQ[base], nullptr, nullptr, n, -1.0, nullptr), "s3d_scalar_op");
+				d.check(s3d_vec_multi_axpy(ctx, &g, n, &BETA[base], ps, p[k + 1].dev_rw()), "s3d_vec_multi_axpy");
+				d.check(s3d_vec_multi_axpy(ctx, &g, n, &BETA[base], qs, q[k + 1].dev_rw()), "s3d_vec_multi_axpy");
+			}
+		}
+		code = loop.poll(iterations);
+	}
+	d.check(s3d_ctx_set_gate(ctx, nullptr), "s3d_ctx_set_gate");
+	const SolveInfo info = finish(d, &S[3], &S[0], sparams.rtol, iterations, code, 0);
+	d.release(S);
+	return info;
+}
+
+// ------------------------------------------------------------------ CG (new)
+
+CG::CG(const SMat &lhs, SolverBase *const precond, const SolveParams params) : SolverBase(lhs, precond), sparams(params) {}
+
+void CG::updateOperator() { if (prec) prec->updateOperator(); }
+
+SolveInfo CG::apply(const SVec &b, SVec &x) const
+{
+	if (b.m != x.m || b.m != A.m) throw std::runtime_error("All vectors and matrix should be defined over the same mesh!");
+	const Device &d = Device::get();
+	s3d_ctx *ctx = d.ctx();
+	const s3d_grid &g = A.grid();
+	const bool jacobi = dynamic_cast<const JacobiPreconditioner *>(prec) != nullptr;
+	SVec r(A.m), p(A.m), q(A.m);
+	SVec z;
+	if (!jacobi) z.init(A.m);
+	// scalars: [0] (b,b)  [1..2] SpMV reductions: (p,Ap), -  [3,4] and [5,6]: ping-pong pairs {(r,r), (r,z)}
+	double *S = d.scalars(8);
+	DeviceLoop loop(sparams.maxiter + 1, 10, history);
+
+	d.check(s3d_nrm2sq(ctx, &g, b.dev(), &S[0]), "s3d_nrm2sq");
+	allreduce(d, &S[0], 1);
+	x.exchange_halo();
+	d.check(s3d_spmv(ctx, &g, A.dev(), x.dev(), r.dev_w(), b.dev(), nullptr, 1, &S[4], nullptr, S3D_SPMV_AUTO), "s3d_spmv");   // (r,r) -> S[5]
+	allreduce(d, &S[5], 1);
+	loop.test(&S[5], &S[0], sparams.rtol, sparams.maxiter, S3D_CONV_INITIAL);
+	loop.gate();
+	// z = M^-1 r, p = z, (r,z) -> S[6]  (the "previous" pair of iteration 0 is {5,6})
+	if (jacobi) {
+		{ TimedPrec t(d); prec->apply(r, p); }
+		d.check(s3d_dot(ctx, &g, r.dev(), p.dev(), &S[6]), "s3d_dot");
+	} else {
+		{ TimedPrec t(d); prec->apply(r, z); }
+		d.check(s3d_vecassign(ctx, &g, z.dev(), p.dev_rw()), "s3d_vecassign");
+		d.check(s3d_dot(ctx, &g, r.dev(), z.dev(), &S[6]), "s3d_dot");
+	}
+	allreduce(d, &S[6], 1);
+
+	int iterations = 0;
+	int code = loop.poll(iterations);
+	const int batch = batch_size(g, 200);
+	long it = 0;
+	const double *rr_final = &S[5];
+	while (!code) {
+		for (int i = 0; i < batch; i++, it++) {
+			double *cur = (it % 2 == 0) ? &S[3] : &S[5];    // this iteration's {(r,r), (r,z)}
+			double *prev = (it % 2 == 0) ? &S[5] : &S[3];   // the previous iteration's pair
+			p.exchange_halo();
+			d.check(s3d_spmv(ctx, &g, A.dev(), p.dev(), q.dev_w(), nullptr, p.dev(), 0, &S[1], nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+			allreduce(d, &S[1], 1);
+			// x += alpha p, r -= alpha q, alpha = (r,z)/(p,Ap); fused (r,r) [and (r, r/diag)]
+			d.check(s3d_cg_update(ctx, &g, ratio(1.0, &prev[1], &S[1]), p.dev(), q.dev(), x.dev_rw(), r.dev_rw(),
+			                      jacobi ? A.dev() : nullptr, cur, nullptr), "s3d_cg_update");
+			allreduce(d, cur, 2);
+			loop.test(&cur[0], &S[0], sparams.rtol, sparams.maxiter, 0);
+			if (jacobi) {
+				d.check(s3d_cg_direction_jacobi(ctx, &g, ratio(1.0, &cur[1], &prev[1]), A.dev(), r.dev(), p.dev_rw(), nullptr), "s3d_cg_direction_jacobi");
+			} else {
+				{ TimedPrec t(d); prec->apply(r, z); }
+				d.check(s3d_dot(ctx, &g, r.dev(), z.dev(), &cur[1]), "s3d_dot");
+				allreduce(d, &cur[1], 1);
+				d.check(s3d_vecaxpby(ctx, &g, imm(1.0), z.dev(), ratio(1.0, &cur[1], &prev[1]), p.dev_rw()), "s3d_vecaxpby");
+			}
+		}
+		code = loop.poll(iterations);
+	}
+	d.check(s3d_ctx_set_gate(ctx, nullptr), "s3d_ctx_set_gate");
+	// the residual norm of the last COUNTED iteration lives in the pair that iteration wrote
+	if (iterations > 0) rr_final = ((iterations - 1) % 2 == 0) ? &S[3] : &S[5];
+	const SolveInfo info = finish(d, rr_final, &S[0], sparams.rtol, iterations, code, 0);
+	d.release(S);
+	return info;
+}
+
+// ------------------------------------------------------------------ BiCGSTAB (new)
+
+BiCGSTAB::BiCGSTAB(const SMat &lhs, SolverBase *const precond, const SolveParams params) : SolverBase(lhs, precond), sparams(params) {}
+
+void BiCGSTAB::updateOperator() { if (prec) prec->updateOperator(); }
+
+SolveInfo BiCGSTAB::apply(const SVec &b, SVec &x) const
+{
+	if (b.m != x.m || b.m != A.m) throw std::runtime_error("All vectors and matrix should be defined over the same mesh!");
+	const Device &d = Device::get();
+	s3d_ctx *ctx = d.ctx();
+	const s3d_grid &g = A.grid();
+	SVec r(A.m), rhat(A.m), p(A.m), v(A.m), s(A.m), t(A.m), ph(A.m), sh(A.m);
+	// scalars: [0] (b,b)  [1,2] (rhat,v),-  [3,4] (t,s),(t,t)  [5,6] / [7,8] ping-pong {(r,r), (rhat,r)}
+	//          [9] alpha  [10] omega  [11] beta
+	double *S = d.scalars(12);
+	DeviceLoop loop(sparams.maxiter + 1, 10, history);
+
+	d.check(s3d_nrm2sq(ctx, &g, b.dev(), &S[0]), "s3d_nrm2sq");
+	allreduce(d, &S[0], 1);
+	x.exchange_halo();
+	d.check(s3d_spmv(ctx, &g, A.dev(), x.dev(), r.dev_w(), b.dev(), nullptr, 1, &S[6], nullptr, S3D_SPMV_AUTO), "s3d_spmv");   // (r,r) -> S[7]
+	allreduce(d, &S[7], 1);
+	d.check(s3d_vecassign(ctx, &g, r.dev(), rhat.dev_rw()), "s3d_vecassign");
+	// rho_0 = (rhat, r) = (r,r): place it where iteration 0 expects "the previous pair's (rhat,r)" = S[8]
+	d.check(s3d_dot(ctx, &g, rhat.dev(), r.dev(), &S[8]), "s3d_dot");
+	allreduce(d, &S[8], 1);
+	loop.test(&S[7], &S[0], sparams.rtol, sparams.maxiter, S3D_CONV_INITIAL);
+	loop.gate();
+
+	int iterations = 0;
+	int code = loop.poll(iterations);
+	const int batch = batch_size(g, 400);
+	long it = 0;
+	while (!code) {
+		for (int i = 0; i < batch; i++, it++) {
+			double *cur = (it % 2 == 0) ? &S[5] : &S[7];
+			double *prev = (it % 2 == 0) ? &S[7] : &S[5];
+			if (it == 0) {
+				d.check(s3d_vecassign(ctx, &g, r.dev(), p.dev_rw()), "s3d_vecassign");
+			} else {
+				// beta = (rho_new/rho_old)(alpha/omega); rho_new = prev[1], rho_old = cur[1] (written two iterations ago)
+				d.check(s3d_scalar_op(ctx, 1, &S[11], &prev[1], &cur[1], &S[9], &S[10], 1, 1.0, loop.stop()), "s3d_scalar_op");
+				d.check(s3d_bicg_direction(ctx, &g, ratio(1.0, &S[11], nullptr), ratio(1.0, &S[10], nullptr), r.dev(), v.dev(), p.dev_rw(), nullptr), "s3d_bicg_direction");
+			}
+			{ TimedPrec tp(d); prec->apply(p, ph); }
+			ph.exchange_halo();
+			d.check(s3d_spmv(ctx, &g, A.dev(), ph.dev(), v.dev_w(), nullptr, rhat.dev(), 0, &S[1], nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+			allreduce(d, &S[1], 1);
+			d.check(s3d_scalar_op(ctx, 2, &S[9], &prev[1], &S[1], nullptr, nullptr, 1, 1.0, loop.stop()), "s3d_scalar_op");   // alpha = rho/(rhat,v)
+			d.check(s3d_vecwaxpby(ctx, &g, imm(1.0), r.dev(), ratio(-1.0, &S[9], nullptr), v.dev(), s.dev_rw(), nullptr), "s3d_vecwaxpby");
+			{ TimedPrec tp(d); prec->apply(s, sh); }
+			sh.exchange_halo();
+			d.check(s3d_spmv(ctx, &g, A.dev(), sh.dev(), t.dev_w(), nullptr, s.dev(), 1, &S[3], nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+			allreduce(d, &S[3], 2);
+			d.check(s3d_scalar_op(ctx, 2, &S[10], &S[3], &S[4], nullptr, nullptr, 1, 1.0, loop.stop()), "s3d_scalar_op");    // omega = (t,s)/(t,t)
+			d.check(s3d_bicg_update(ctx, &g, ratio(1.0, &S[9], nullptr), ph.dev(), ratio(1.0, &S[10], nullptr), sh.dev(), s.dev(), t.dev(),
+			                        rhat.dev(), x.dev_rw(), r.dev_rw(), cur, nullptr), "s3d_bicg_update");
+			allreduce(d, cur, 2);
+			loop.test(&cur[0], &S[0], sparams.rtol, sparams.maxiter, 0);
+		}
+		code = loop.poll(iterations);
+	}
+	d.check(s3d_ctx_set_gate(ctx, nullptr), "s3d_ctx_set_gate");
+	const double *rr_final = &S[7];
+	if (iterations > 0) rr_final = ((iterations - 1) % 2 == 0) ? &S[5] : &S[7];
+	const SolveInfo info = finish(d, rr_final, &S[0], sparams.rtol, iterations, code, 0);
+	d.release(S);
+	return info;
+}
+
+// ------------------------------------------------------------------ factory (solverfactory.cpp:14-100)
+
+SolverBase *createSolver(const SMat &lhs)
+{
+	const bool talk = Device::get().rank() == 0;
+	const std::string tlsolver = petscoptions_get_string("-s3d_ksp_type", 20);
+	std::string precstr = "none";
+	if (s3d::options_has("-s3d_pc_type")) precstr = petscoptions_get_string("-s3d_pc_type", 30);
+	else if (talk) std::printf("No preconditioner\n");
+
+	SolveParams params;
+	params.rtol = petscoptions_get_real("-ksp_rtol");
+	params.maxiter = petscoptions_get_int("-ksp_max_it");
+	params.restart = 30;
+	if (s3d::options_has("-ksp_restart")) params.restart = petscoptions_get_int("-ksp_restart");
+	else if (talk && tlsolver == "gcr") std::printf(" No KSP restart specified, using 30.\n");
+
+	SolverBase *prec = nullptr;
+	if (precstr == "jacobi") {
+		if (talk) std::printf("  Using Jacobi preconditioner\n");
+		prec = new JacobiPreconditioner(lhs);
+	} else if (precstr == "sgs") {
+		if (talk) std::printf("  Using SGS preconditioner\n");
+		PreconParams pp;
+		pp.nbuildsweeps = 0;
+		pp.napplysweeps = petscoptions_get_int("-s3d_pc_apply_sweeps");
+		pp.thread_chunk_size = petscoptions_get_int("-s3d_thread_chunk_size");
+		pp.threadedbuild = false;
+		pp.threadedapply = s3d::options_has("-s3d_pc_use_threaded_apply") ? petscoptions_get_bool("-s3d_pc_use_threaded_apply") : true;
+		prec = new SGS_preconditioner(lhs, pp);
+	} else if (precstr == "strilu") {
+		throw std::runtime_error("createSolver: the StrILU preconditioner is outside this build's scope (SURVEY.md 8f)");
+	} else {
+		prec = new NoSolver(lhs);
+		if (talk) std::printf("WARNING: createSolver: Using no preconditioner\n");
+	}
+
+	SolverBase *solver = nullptr;
+	if (tlsolver == "richardson") {
+		if (talk) std::printf("  Using Richardson solver\n");
+		solver = new Richardson(lhs, prec, params);
+	} else if (tlsolver == "gcr") {
+		if (talk) std::printf("  Using GCR solver\n");
+		solver = new GCR(lhs, prec, params);
+	} else if (tlsolver == "cg") {
+		if (talk) std::printf("  Using CG solver\n");
+		solver = new CG(lhs, prec, params);
+	} else if (tlsolver == "bcgs" || tlsolver == "bicgstab") {
+		if (talk) std::printf("  Using BiCGSTAB solver\n");
+		solver = new BiCGSTAB(lhs, prec, params);
+	} else {
+		delete prec;
+		throw std::runtime_error("Need a valid solver option!");
+	}
+	return solver;
+}

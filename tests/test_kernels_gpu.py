@@ -1,0 +1,340 @@
+"""GPU parity tests proper: every kernel of libs3d_cuda.so, called through the C ABI, against the
+CPU oracle (oracle/s3d_oracle.c, pinned to the reference) on the same seeded inputs, plus the
+golden fixtures generated from the reference itself (tests/golden/).
+
+Tolerances: SpMV, Jacobi, SGS(lexicographic), assembly and vector updates are computed with the
+reference's rounding sequence (no FMA contraction) and must be BIT-EXACT; reductions sum in a
+different (deterministic) order and must agree to 1e-13 relative; north_star's bound is 1e-12."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cport
+from struct3d_b200 import capi
+from tests.util import V1, V2, ghosts_untouched, golden_vec, problem, rand_vec, real, relerr
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+# reference MatVec sizes (test/matvectest.cpp: 18^3 -> 36^3 -> 72^3), ragged/odd shapes, tiny and thin grids
+SHAPES = [(18, 18, 18), (36, 36, 36), (72, 72, 72), (20, 14, 18), (19, 23, 11), (3, 3, 3), (4, 9, 3), (131, 7, 5), (67, 66, 35)]
+VARIANTS = [capi.SPMV_PAIR, capi.SPMV_MARCH, capi.SPMV_NAIVE]
+
+
+def grid_of(m):
+    nx, ny, nz = m.n
+    return capi.make_grid(nx, ny, nz)
+
+
+@pytest.mark.parametrize("npdim", SHAPES)
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("pde", ["poisson", "convdiff"])
+def test_spmv_apply_bit_exact(ctx, npdim, variant, pde):
+    m, A = problem(npdim, "chebyshev" if npdim[0] % 2 else "uniform", pde, V1, 0.1)
+    g = grid_of(m)
+    x = rand_vec(m, 1)
+    dA, dx, dy = ctx.mat_from(g, A), ctx.vec_from(g, x), ctx.vec_alloc(g)
+    ctx.spmv(g, dA, dx, dy, variant=variant)
+    y = ctx.vec_download(g, dy)
+    ref = cport.apply(m, A, x)
+    assert np.array_equal(y, ref), f"max diff {np.abs(y - ref).max()}"
+    assert ghosts_untouched(y)
+    for p in (dA, dx, dy):
+        ctx.free(p)
+
+
+@pytest.mark.parametrize("npdim", SHAPES[:6])
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_spmv_apply_res_and_fused_dots(ctx, npdim, variant):
+    m, A = problem(npdim, "uniform", "convdiff", V2, 0.05)
+    g = grid_of(m)
+    x, b, w = rand_vec(m, 2), rand_vec(m, 3), rand_vec(m, 4)
+    dA, dx, db, dw, dy = ctx.mat_from(g, A), ctx.vec_from(g, x), ctx.vec_from(g, b), ctx.vec_from(g, w), ctx.vec_alloc(g)
+    red = ctx.scalars_alloc(2)
+    ctx.spmv(g, dA, dx, dy, b=db, w=dw, want_yy=True, red=red, variant=variant)
+    y = ctx.vec_download(g, dy)
+    ref = cport.apply_res(m, A, b, x)
+    assert np.array_equal(y, ref)
+    wy, yy = ctx.scalars(red, 2)
+    assert abs(wy - cport.inner_vector_l2(m, w, ref)) <= 1e-13 * np.linalg.norm(w) * np.linalg.norm(ref)
+    assert abs(yy - cport.inner_vector_l2(m, ref, ref)) <= 1e-13 * yy
+    # CG's (p, Ap): w aliases x
+    ctx.spmv(g, dA, dx, dy, w=dx, red=red, variant=variant)
+    ax = cport.apply(m, A, x)
+    assert abs(ctx.scalars(red, 1)[0] - cport.inner_vector_l2(m, x, ax)) <= 1e-13 * np.linalg.norm(x) * np.linalg.norm(ax)
+    # reductions are deterministic: the same launch gives the same bits
+    a1 = ctx.scalars(red, 1)[0]
+    ctx.spmv(g, dA, dx, dy, w=dx, red=red, variant=variant)
+    assert ctx.scalars(red, 1)[0] == a1
+    for p in (dA, dx, db, dw, dy, red):
+        ctx.free(p)
+
+
+def test_spmv_stop_gate(ctx):
+    m, A = problem((12, 12, 12))
+    g = grid_of(m)
+    x = rand_vec(m, 5)
+    dA, dx, dy = ctx.mat_from(g, A), ctx.vec_from(g, x), ctx.vec_alloc(g)
+    stop = ctx.ints_alloc(1)
+    ctx.spmv(g, dA, dx, dy, stop=stop)
+    assert np.array_equal(ctx.vec_download(g, dy), cport.apply(m, A, x))
+    ctx.vecset(g, 7.0, dy)
+    # use converge_test to raise the flag on the device: rr = 0 <= rtol
+    rr = ctx.scalars_alloc(2)
+    ctx.scalars_set(rr, [0.0, 1.0])
+    iters = ctx.ints_alloc(1)
+    ctx.converge_test(rr, rr + 8, 1e-6, 10, capi.CONV_INITIAL, stop, iters)
+    assert ctx.ints(stop)[0] == 1
+    ctx.spmv(g, dA, dx, dy, stop=stop)
+    assert np.all(real(ctx.vec_download(g, dy)) == 7.0), "a stopped launch must not write"
+
+
+@pytest.mark.parametrize("npdim", [(18, 18, 18), (19, 23, 11), (3, 3, 3), (131, 7, 5)])
+def test_blas1(ctx, npdim):
+    m, A = problem(npdim)
+    g = grid_of(m)
+    x, y = rand_vec(m, 10), rand_vec(m, 11)
+    # ghosts of y non-zero on purpose: real-point-only operations must not touch them
+    yg = rand_vec(m, 12, ghosts_zero=False)
+    dx, dy, dyg, dw = ctx.vec_from(g, x), ctx.vec_from(g, y), ctx.vec_from(g, yg), ctx.vec_alloc(g)
+
+    ref = y.copy(); cport.vecaxpy(m, 0.37, x, ref)
+    ctx.vecaxpy(g, 0.37, dx, dy)
+    assert np.array_equal(ctx.vec_download(g, dy), ref)
+
+    ref = yg.copy(); cport.vecassign(m, x, ref)
+    ctx.vecassign(g, dx, dyg)
+    assert np.array_equal(ctx.vec_download(g, dyg), ref)          # ghosts of yg preserved
+    ref2 = ref.copy(); cport.vecset(m, -2.5, ref2)
+    ctx.vecset(g, -2.5, dyg)
+    assert np.array_equal(ctx.vec_download(g, dyg), ref2)
+    ctx.veccopy_all(g, dx, dyg)
+    assert np.array_equal(ctx.vec_download(g, dyg), x)
+
+    assert abs(ctx.dot(g, dx, dy) - cport.inner_vector_l2(m, x, ctx.vec_download(g, dy))) <= 1e-13 * np.linalg.norm(x) * np.linalg.norm(y) * 2
+    assert abs(ctx.nrm2(g, dx) - cport.norm_vector_l2(m, x)) <= 1e-13 * np.linalg.norm(x)
+    red = ctx.scalars_alloc(4)
+    ctx.normL2sq_dev(g, m.coords, dx, red)
+    assert abs(np.sqrt(ctx.scalars(red)[0]) - cport.norm_L2(m, x)) <= 1e-13 * cport.norm_L2(m, x)
+
+    # w = a x + b y with fused norm; y = a x + b y; y = x + b y
+    yh = ctx.vec_download(g, dy)
+    ctx.vecwaxpby(g, 1.0, dx, -0.25, dy, dw, red)
+    ref = x.copy(); cport.vecaxpy(m, -0.25, yh, ref)
+    w = ctx.vec_download(g, dw)
+    assert np.array_equal(real(w), real(ref))
+    assert abs(ctx.scalars(red)[0] - cport.inner_vector_l2(m, ref, ref)) <= 1e-13 * cport.inner_vector_l2(m, ref, ref)
+    ctx.vecaxpby(g, 1.0, dx, 0.5, dy)     # y = x + 0.5 y
+    ref = x.copy(); cport.vecaxpy(m, 0.5, yh, ref)
+    assert np.array_equal(real(ctx.vec_download(g, dy)), real(ref))
+
+    # multi-axpy (one pass == the reference's n passes, same order) and multi-dot
+    xs = [rand_vec(m, 20 + l) for l in range(5)]
+    dxs = [ctx.vec_from(g, v) for v in xs]
+    a = np.array([0.3, -1.2, 0.01, 2.0, -0.7])
+    da = ctx.scalars_alloc(5); ctx.scalars_set(da, a)
+    y0 = ctx.vec_download(g, dy)
+    ref = y0.copy(); cport.vec_multi_axpy(m, a, xs, ref)
+    ctx.vec_multi_axpy(g, da, dxs, dy)
+    assert np.array_equal(ctx.vec_download(g, dy), ref)
+    red8 = ctx.scalars_alloc(8)
+    ctx.vec_multi_dot(g, dxs, dy, red8)
+    got = ctx.scalars(red8, 5)
+    for l in range(5):
+        want = cport.inner_vector_l2(m, xs[l], ref)
+        assert abs(got[l] - want) <= 1e-13 * np.linalg.norm(xs[l]) * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("npdim", [(18, 18, 18), (19, 23, 11), (4, 9, 3)])
+def test_device_scalars(ctx, npdim):
+    """axpy with alpha = -(num/den) taken from device memory equals the host-scalar result bitwise."""
+    m, _ = problem(npdim)
+    g = grid_of(m)
+    x, y = rand_vec(m, 30), rand_vec(m, 31)
+    dx, dy = ctx.vec_from(g, x), ctx.vec_from(g, y)
+    s = ctx.scalars_alloc(2); ctx.scalars_set(s, [3.0, 7.0])
+    ctx.vecaxpy(g, capi.scalar(-1.0, s, s + 8), dx, dy)
+    ref = y.copy(); cport.vecaxpy(m, -(3.0 / 7.0), x, ref)
+    assert np.array_equal(ctx.vec_download(g, dy), ref)
+
+
+@pytest.mark.parametrize("npdim", [(18, 18, 18), (19, 23, 11), (3, 3, 3), (36, 20, 28)])
+@pytest.mark.parametrize("pde", ["poisson", "convdiff"])
+def test_jacobi_and_sgs(ctx, npdim, pde):
+    m, A = problem(npdim, "chebyshev", pde, V1, 0.1)
+    g = grid_of(m)
+    r = rand_vec(m, 40)
+    dA, dr, dz, dy = ctx.mat_from(g, A), ctx.vec_from(g, r), ctx.vec_alloc(g), ctx.vec_alloc(g)
+    ctx.jacobi_apply(g, dA, dr, dz)
+    assert np.array_equal(ctx.vec_download(g, dz), cport.jacobi_apply(m, A, r))
+    dinv = ctx.scalars_alloc(int(g.cstride))
+    ctx.sgs_setup(g, dA, dinv)
+    di = cport.sgs_setup(m, A)
+    ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_LEXICOGRAPHIC, 1)
+    z = ctx.vec_download(g, dz)
+    ref = cport.sgs_like_apply(m, A, di, r, 1)
+    assert np.array_equal(z, ref), f"lexicographic SGS max diff {np.abs(z - ref).max()}"
+    ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_REDBLACK, 1)
+    z = ctx.vec_download(g, dz)
+    ref = cport.sgs_redblack_apply(m, A, di, r)
+    assert np.array_equal(z, ref), f"red-black SGS max diff {np.abs(z - ref).max()}"
+    assert ghosts_untouched(z)
+
+
+@pytest.mark.parametrize("npdim,grid", [((18, 18, 18), "uniform"), ((16, 16, 16), "chebyshev"), ((19, 23, 11), "chebyshev"), ((3, 5, 4), "uniform")])
+def test_assembly_bit_exact(ctx, npdim, grid):
+    m = cport.Mesh(npdim, grid=grid)
+    g = grid_of(m)
+    dA = ctx.mat_alloc(g)
+    ctx.assemble_poisson(g, m.coords, dA)
+    assert np.array_equal(ctx.mat_download(g, dA), cport.lhs(m, "poisson"))
+    for vel, mu in ((V1, 0.1), (V2, 0.05), ((0.0, -1.0, 2.0), 1.0)):
+        ctx.assemble_convdiff(g, m.coords, vel, mu, dA)
+        assert np.array_equal(ctx.mat_download(g, dA), cport.lhs(m, "convdiff", vel, mu)), (vel, mu)
+    # uniform Poisson closed form (test/nativevectorassemblytest.cpp:117-123): diag 6/dx^2, off -1/dx^2 within 100 eps
+    if grid == "uniform" and npdim[0] == npdim[1] == npdim[2]:
+        ctx.assemble_poisson(g, m.coords, dA)
+        A = ctx.mat_download(g, dA)
+        dx = m.coords[0][2] - m.coords[0][1]
+        assert np.all(np.abs(A[3] - 6.0 / dx**2) <= 100 * np.finfo(float).eps * 6.0 / dx**2 + 100 * np.finfo(float).eps)
+        for s in (0, 1, 2, 4, 5, 6):
+            assert np.all(np.abs(A[s] + 1.0 / dx**2) <= 100 * np.finfo(float).eps * (1.0 / dx**2) + 100 * np.finfo(float).eps)
+
+
+def _tables(m, pde, func, vel, mu):
+    """Separable tables with the reference's rounding sequence folded into the X table."""
+    PI = 3.141592653589793238
+    cx, cy, cz = m.coords
+    if func == "test_rhs":
+        return [np.sin(PI * cx)], [np.sin(PI * cy)], [np.sin(PI * cz)]
+    s = [np.sin(2 * PI * c) for c in (cx, cy, cz)]
+    c = [np.cos(2 * PI * c_) for c_ in (cx, cy, cz)]
+    if func == "manufactured_solution":
+        return [s[0]], [s[1]], [s[2]]
+    if pde == "poisson":
+        return [12 * PI * PI * s[0]], [s[1]], [s[2]]
+    tx, ty, tz = [mu * 12 * PI * PI * s[0]], [s[1]], [s[2]]
+    for d in range(3):
+        f = [c[e] if e == d else s[e] for e in range(3)]
+        tx.append(2 * PI * vel[d] * f[0]); ty.append(f[1]); tz.append(f[2])
+    return tx, ty, tz
+
+
+@pytest.mark.parametrize("npdim,grid", [((18, 18, 18), "uniform"), ((19, 23, 11), "chebyshev")])
+def test_rhs_separable_bit_exact(ctx, npdim, grid):
+    m = cport.Mesh(npdim, grid=grid)
+    g = grid_of(m)
+    df = ctx.vec_alloc(g)
+    for pde, func in (("poisson", "test_rhs"), ("poisson", "manufactured_solution"), ("poisson", "manufactured_rhs"), ("convdiff", "manufactured_rhs")):
+        tx, ty, tz = _tables(m, pde, func, V1, 0.1)
+        ctx.assemble_rhs_separable(g, np.stack(tx), np.stack(ty), np.stack(tz), df)
+        got = ctx.vec_download(g, df)
+        ref = cport.grid_function(m, pde, func, V1, 0.1)
+        assert np.array_equal(got, ref), (pde, func, np.abs(got - ref).max())
+        assert ghosts_untouched(got)
+
+
+def test_fused_cg_and_bicg_steps(ctx):
+    m, A = problem((20, 14, 18), "uniform", "poisson")
+    g = grid_of(m)
+    p, q, x, r = (rand_vec(m, 50 + i) for i in range(4))
+    dA = ctx.mat_from(g, A)
+    dp, dq, dx, dr = (ctx.vec_from(g, v) for v in (p, q, x, r))
+    red = ctx.scalars_alloc(4)
+    s = ctx.scalars_alloc(2); ctx.scalars_set(s, [2.0, 5.0])
+    alpha = 2.0 / 5.0
+    ctx.cg_update(g, capi.scalar(1.0, s, s + 8), dp, dq, dx, dr, dA, red)
+    xr, rr_ = x.copy(), r.copy()
+    cport.vecaxpy(m, alpha, p, xr); cport.vecaxpy(m, -alpha, q, rr_)
+    assert np.array_equal(ctx.vec_download(g, dx), xr) and np.array_equal(ctx.vec_download(g, dr), rr_)
+    got = ctx.scalars(red, 2)
+    z = cport.jacobi_apply(m, A, rr_)
+    assert abs(got[0] - cport.inner_vector_l2(m, rr_, rr_)) <= 1e-13 * got[0]
+    assert abs(got[1] - cport.inner_vector_l2(m, rr_, z)) <= 1e-13 * abs(got[1])
+    # p = r/diag + beta p
+    ctx.cg_direction_jacobi(g, capi.scalar(0.75), dA, dr, dp)
+    pref = z.copy(); cport.vecaxpy(m, 0.75, p, pref)
+    assert np.array_equal(real(ctx.vec_download(g, dp)), real(pref))
+    # BiCGSTAB direction and update
+    v = rand_vec(m, 60); dv = ctx.vec_from(g, v)
+    pn = ctx.vec_download(g, dp)
+    ctx.bicg_direction(g, capi.scalar(0.3), capi.scalar(1.7), dr, dv, dp)
+    t = pn.copy(); cport.vecaxpy(m, -1.7, v, t)
+    ref = rr_.copy(); cport.vecaxpy(m, 0.3, t, ref)
+    assert np.array_equal(real(ctx.vec_download(g, dp)), real(ref))
+    ph, sh, sv, tv, rh = (rand_vec(m, 70 + i) for i in range(5))
+    dph, dsh, dsv, dtv, drh = (ctx.vec_from(g, u) for u in (ph, sh, sv, tv, rh))
+    ctx.bicg_update(g, capi.scalar(0.4), dph, capi.scalar(-0.9), dsh, dsv, dtv, drh, dx, dr, red)
+    xref = xr.copy(); cport.vecaxpy(m, 0.4, ph, xref); cport.vecaxpy(m, -0.9, sh, xref)
+    rref = sv.copy(); cport.vecaxpy(m, 0.9, tv, rref)
+    assert np.array_equal(real(ctx.vec_download(g, dx)), real(xref)) and np.array_equal(real(ctx.vec_download(g, dr)), real(rref))
+    got = ctx.scalars(red, 2)
+    assert abs(got[0] - cport.inner_vector_l2(m, rref, rref)) <= 1e-13 * got[0]
+    assert abs(got[1] - cport.inner_vector_l2(m, rh, rref)) <= 1e-13 * np.linalg.norm(rh) * np.linalg.norm(rref)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "fields_*.npz"))))
+def test_against_reference_fixtures(ctx, path):
+    """Golden vectors produced by the REAL reference (oracle/make_golden.py): coefficients, y = Ax,
+    b - Ax, Jacobi, sequential SGS, axpy, norms."""
+    G = np.load(path)
+    npdim = tuple(int(v) for v in G["npdim"])
+    g = capi.make_grid(npdim[0] - 2, npdim[1] - 2, npdim[2] - 2)
+    coords = (G["cx"], G["cy"], G["cz"])
+    dA = ctx.mat_alloc(g)
+    if str(G["pde"]) == "poisson":
+        ctx.assemble_poisson(g, coords, dA)
+    else:
+        ctx.assemble_convdiff(g, coords, G["vel"], float(G["mu"]), dA)
+    assert np.array_equal(ctx.mat_download(g, dA), G["A"])
+    dx, db, dy, dz, ds = ctx.vec_from(g, G["x"]), ctx.vec_from(g, G["manufactured_rhs"]), ctx.vec_alloc(g), ctx.vec_alloc(g), ctx.vec_alloc(g)
+    ctx.spmv(g, dA, dx, dy)
+    assert np.array_equal(ctx.vec_download(g, dy), G["Ax"])
+    ctx.spmv(g, dA, dx, dy, b=db)
+    assert np.array_equal(ctx.vec_download(g, dy), G["b_minus_Ax"])
+    ctx.jacobi_apply(g, dA, db, dz)
+    assert np.array_equal(ctx.vec_download(g, dz), G["jacobi_b"])
+    dinv = ctx.scalars_alloc(int(g.cstride))
+    ctx.sgs_setup(g, dA, dinv)
+    ctx.sgs_apply(g, dA, dinv, db, dz, ds, capi.SGS_LEXICOGRAPHIC, 1)
+    assert np.array_equal(ctx.vec_download(g, dz), G["sgs_b"])
+    ctx.vecassign(g, db, dy)
+    ctx.vecaxpy(g, 0.37, dx, dy)
+    assert np.array_equal(real(ctx.vec_download(g, dy)), real(G["b_plus_037x"]))
+    assert abs(ctx.dot(g, dx, db) - float(G["dot_x_b"])) <= 1e-13 * np.linalg.norm(G["x"]) * np.linalg.norm(G["manufactured_rhs"])
+    assert abs(ctx.nrm2(g, dx) - float(G["norm_x"])) <= 1e-13 * float(G["norm_x"])
+    red = ctx.scalars_alloc(1)
+    ctx.normL2sq_dev(g, coords, dx, red)
+    assert abs(np.sqrt(ctx.scalars(red)[0]) - float(G["normL2_x"])) <= 1e-13 * float(G["normL2_x"])
+
+
+@pytest.mark.parametrize("n", [258, 514])
+def test_spmv_full_size_properties(ctx, n):
+    """At BASELINE sizes the oracle is too slow to run per test; use size-independent properties:
+    (1) ||A*1||_2 known answers from the reference, (2) linearity,
+    (3) apply and apply_res are consistent (test/matvectest.cpp:71), (4) all variants agree bitwise."""
+    m = cport.Mesh((n, n, n))
+    g = grid_of(m)
+    dA = ctx.mat_alloc(g)
+    ctx.assemble_poisson(g, m.coords, dA)
+    dx, dy, dy2, db = (ctx.vec_alloc(g) for _ in range(4))
+    ctx.vecset(g, 1.0, dx)
+    ctx.spmv(g, dA, dx, dy)
+    known = {258: 10434905.903215431, 514: 82834297.872071102}[n]
+    assert abs(ctx.nrm2(g, dy) - known) <= 1e-12 * known
+    x = golden_vec(m)
+    ctx.vec_upload(g, dx, x)
+    ctx.spmv(g, dA, dx, dy, variant=capi.SPMV_MARCH)
+    ctx.spmv(g, dA, dx, dy2, variant=capi.SPMV_NAIVE)
+    ctx.vecaxpy(g, -1.0, dy, dy2)
+    assert ctx.nrm2(g, dy2) == 0.0, "MARCH and NAIVE variants must agree bitwise"
+    # apply_res consistency: (b - Ax) + Ax - b == 0 to rounding
+    ctx.vecset(g, 0.25, db)
+    ctx.spmv(g, dA, dx, dy2, b=db)
+    ctx.vecaxpy(g, 1.0, dy, dy2)
+    ctx.vecaxpy(g, -1.0, db, dy2)
+    assert ctx.nrm2(g, dy2) <= 1e-12 * ctx.nrm2(g, dy)
+    for p in (dA, dx, dy, dy2, db):
+        ctx.free(p)
