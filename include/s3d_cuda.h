@@ -97,8 +97,9 @@ int64_t s3d_ctx_launch_count(const s3d_ctx *ctx);
 int  s3d_timer_start(s3d_ctx *ctx);
 int  s3d_timer_stop_ms(s3d_ctx *ctx, double *ms);
 
-/* kernel tuning knobs for sweeps ("spmv_by" in {4,8,16}, "spmv_kchunk" >= 0 where 0 = automatic,
- * "spmv_variant" = what S3D_SPMV_AUTO resolves to) */
+/* kernel tuning knobs for sweeps: "spmv_kchunk" (planes per march, 0 = automatic), "spmv_minb" (resident blocks per
+ * SM the march kernel is compiled for: 0 auto, 3, 4, 6), "spmv_hints" (evict-first hints on/off for the PAIR/NAIVE
+ * variants), "spmv_variant" (what S3D_SPMV_AUTO resolves to) */
 int  s3d_tune_set(s3d_ctx *ctx, const char *key, int value);
 
 /* Replaces the size arithmetic of SVec::SVec / SMat::SMat (matvec.cpp:8-57).  nz is the local slab. */
@@ -175,6 +176,7 @@ int  s3d_jacobi_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const do
 /* SGS_preconditioner::updateOperator (s3d_sgspreconditioners.cpp:122-135): dinv = 1/diag, matrix-compact layout (cstride doubles) */
 int  s3d_sgs_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, double *d_dinv);
 #define S3D_SGS_LEXICOGRAPHIC 0  /* the reference's ordering, executed as a tile-level dataflow wavefront: same arithmetic */
+#define S3D_SGS_LEXICOGRAPHIC_PLANES 2  /* same result, one launch per hyperplane i+j+k (slow; kept for cross-checks) */
 #define S3D_SGS_REDBLACK      1  /* two-colour ordering: four fully parallel half-sweeps (changes the iteration) */
 /* SGS_like_preconditioner::apply (s3d_sgspreconditioners.cpp:14-115): z = (D+U)^-1 D (D+L)^-1 r.
  * d_y: scratch vector (vlen doubles); it is re-zeroed by the call like the reference's temporary. */

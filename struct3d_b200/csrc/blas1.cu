@@ -349,7 +349,36 @@ static int multi_dot_n(s3d_ctx *ctx, const s3d_grid *g, int n, const double *con
 	return S3D_OK;
 }
 
+// sums partials[b*nr + r] over b in a fixed order with one block
+__global__ void __launch_bounds__(1024) final_reduce_kernel(const double *__restrict__ partials, unsigned nblocks, int nr,
+                                                            double *out, const int *stop)
+{
+	if (s3d_stopped(stop)) return;
+	__shared__ double sm[32];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	for (int r = 0; r < nr; r++) {
+		double s = 0.0;
+		for (unsigned b = tid; b < nblocks; b += 1024) s += partials[(size_t)b * nr + r];
+		s = warp_sum(s);
+		__syncthreads();
+		if (lane == 0) sm[warp] = s;
+		__syncthreads();
+		if (warp == 0) {
+			double v = sm[lane];
+			v = warp_sum(v);
+			if (lane == 0) out[r] = v;
+		}
+	}
+}
+
 }  // namespace
+
+int s3d_final_reduce(s3d_ctx *ctx, int nr, unsigned nblocks, double *out)
+{
+	final_reduce_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->partials, nblocks, nr, out, ctx->gate);
+	S3D_LAUNCHED(ctx);
+	return S3D_OK;
+}
 
 extern "C" {
 

@@ -26,6 +26,10 @@ struct s3d_ctx {
 	// SGS dataflow bookkeeping (tile completion flags + work ticket)
 	int *sgs_flags = nullptr;
 	size_t sgs_flags_cap = 0;
+	int sgs_epoch = 0;
+	int sgs_sleep_ns = 0;
+	int *sgs_order = nullptr;     // tile dispatch order (hyperplane-sorted), cached per tile-grid shape
+	int sgs_order_dims[3] = {0, 0, 0};
 	// device-side gate applied to every launch that does not bring its own stop flag
 	const int *gate = nullptr;
 	// timing
@@ -89,9 +93,13 @@ static inline GridDev to_dev(const s3d_grid *g)
 
 struct RedOut {
 	double *partials;
-	unsigned *ticket;
-	double *out;     // device scalars receiving the final sums (may be null: no reduction requested)
+	unsigned *ticket;   // null: write the per-block partials only; a separate final_reduce launch adds them up
+	double *out;        // device scalars receiving the final sums (may be null: no reduction requested)
 };
+
+// second stage as its own launch, for kernels with very many blocks (a per-block ticket atomic on one
+// address serialises in L2: 262k blocks cost ~1 ms).  Same fixed summation order: deterministic.
+int s3d_final_reduce(s3d_ctx *ctx, int nr, unsigned nblocks, double *out);
 
 #ifdef __CUDACC__
 
@@ -117,7 +125,7 @@ __device__ __forceinline__ double warp_sum(double v)
 // Stage 2: the block that draws the last ticket adds the partials in a fixed order.
 // The result depends only on the launch geometry, never on scheduling: deterministic.
 // Every thread of every block must call this (it contains __syncthreads).
-template <int NR>
+template <int NR, bool PARTIALS_ONLY = false>
 __device__ __forceinline__ void grid_reduce(double (&acc)[NR], const RedOut &ro)
 {
 	__shared__ double sm[NR][32];
@@ -142,6 +150,7 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[NR], const RedOut &ro)
 			if (lane == 0) ro.partials[(size_t)bid * NR + r] = v;
 		}
 	}
+	if (PARTIALS_ONLY || ro.ticket == nullptr) return;   // stage 2 is a separate launch (s3d_final_reduce)
 	if (tid == 0) {
 		__threadfence();
 		const unsigned t = atomicAdd(ro.ticket, 1u);

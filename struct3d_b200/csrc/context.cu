@@ -143,7 +143,7 @@ int s3d_ctx_destroy(s3d_ctx *ctx)
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
 	cudaFree(ctx->partials); cudaFree(ctx->ticket); cudaFree(ctx->tab); cudaFree(ctx->red_tmp);
-	cudaFree(ctx->sgs_flags);
+	cudaFree(ctx->sgs_flags); cudaFree(ctx->sgs_order);
 	cudaFreeHost(ctx->h_pinned);
 	cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

@@ -8,12 +8,14 @@
 //      i+j+k = const are independent once the previous hyperplane is done, and each point evaluates the
 //      very same expression, so the result equals the sequential sweep bit for bit (same roundings:
 //      __dmul_rn/__dsub_rn, no FMA contraction).  The iteration count of any solver using it therefore
-//      equals the reference's.  (Round-1 implementation: one launch per hyperplane; the tile-level
-//      dataflow version is the next kernel, see DESIGN.md.)
+//      equals the reference's.  Implemented as a tile-level DATAFLOW kernel (below); the one-launch-per-
+//      hyperplane version is kept as S3D_SGS_LEXICOGRAPHIC_PLANES for cross-checking.
 //
 //  S3D_SGS_REDBLACK       the same product M = (D+L) D^-1 (D+U) with the unknowns ordered red-then-black
 //      ((i+j+k) parity).  Every half-sweep is fully parallel: three streaming launches, no dependencies.
 //      It changes the iteration (different M), which is why it is an option and not the default.
+#include <algorithm>
+#include <vector>
 #include "common.cuh"
 
 namespace {
@@ -56,6 +58,198 @@ sgs_bwd_plane_kernel(const GridDev g, const double *__restrict__ A, const double
 	s = __dadd_rn(s, __dmul_rn(A[c + 6 * g.cstride], z[v + g.vplane]));
 	z[v] = __dsub_rn(y[v], __dmul_rn(dinv[c], s));
 }
+
+
+// ---------------------------------------------------------------- lexicographic, tile-level dataflow (exact, fast)
+//
+// The grid is cut into tiles of 32 x 8 x 8 points.  A tile can be swept as soon as its three predecessor
+// tiles (i-1, j-1, k-1 for the forward sweep; +1 for the backward sweep) are complete, so tiles on a tile-
+// hyperplane run concurrently: at 256^3 that is 32768 tiles, ~120 in flight on average, ~460 at 512^3.
+//   - persistent blocks draw tickets from a counter; ticket t maps to the t-th tile in HYPERPLANE order
+//     (sorted by ci+cj+ck; reversed for the backward sweep), so the ~300 resident blocks always hold a
+//     whole wavefront of mutually independent tiles (lexicographic dispatch was measured 35x slower: its
+//     window spans one k-plane of tiles, of which only a diagonal is independent).  A tile only ever waits
+//     on tiles with SMALLER tickets, whose owners are already running: no co-residency assumption, no deadlock;
+//   - completion flags carry an epoch number (no clearing between sweeps); a block publishes its tile with
+//     store -> __syncthreads -> __threadfence -> flag, a waiter spins on the flag and fences before loading
+//     the halo values with ld.cg (L2): y lines never straddle tiles (rows are 128-byte aligned, tiles are 32
+//     points wide), so a line read after the flag is complete and final;
+//   - inside a tile the local hyperplanes h = li + lj + lk are swept by 64 threads, one per (j,k) pencil (see
+//     the kernel); the five per-point inputs of the tile are staged through shared memory with cp.async
+//     and the results leave through it, so every global access is a coalesced 16-byte transfer;
+//   - every point evaluates the reference's expression with the reference's roundings, so the result is
+//     bit-identical to the sequential sweep.
+constexpr int SGS_TI = 32, SGS_TJ = 8, SGS_TK = 8;
+constexpr int SGS_TILE = SGS_TI * SGS_TJ * SGS_TK;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+	const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+struct SgsFlow {
+	int *flags;        // one per tile: epoch of the last sweep that completed it
+	const int *order;  // dispatch order: tile numbers sorted by tile hyperplane ci+cj+ck (then lexicographically)
+	unsigned *ticket;  // work counter, zeroed before every launch
+	int epoch;
+	int ntx, nty, ntz;
+	int sleep_ns;      // 0: busy-spin on the flag
+	int debug;         // timing experiments only (results become wrong): 1 skip wavefront, 2 skip staging, 4 skip fences, 8 skip waits
+};
+
+// FWD: in0 = r,  c0,c1,c2 = A0,A1,A2, out = y      y = (r - A0 y[i-1] - A1 y[j-1] - A2 y[k-1]) * dinv
+// BWD: in0 = y,  c0,c1,c2 = A4,A5,A6, out = z      z = y - dinv * (A4 z[i+1] + A5 z[j+1] + A6 z[k+1])
+//
+// Thread mapping (measured: the first version gave every POINT COLUMN a thread, 256 threads per tile, and was
+// issue-bound -- 8 warps executing the step body 46 times with <= 8 lanes active, 13.8 ms at 512^3).
+// Now the 64 threads of a block are the 8 x 8 (j,k) PENCILS of the tile and each marches along i:
+// at local step h the thread of pencil (lj,lk) computes point li = h - lj - lk.  Its i-neighbour is its own
+// previous value (a register), its j- and k-neighbours are the previous step's values of the adjacent
+// pencils (a double-buffered 10 x 10 array in shared memory); one 64-thread barrier per step, every lane
+// busy for 32 of the 46 steps.
+constexpr int SGS_NT = SGS_TJ * SGS_TK;   // 64 threads
+
+template <bool FWD>
+__global__ void __launch_bounds__(SGS_NT)
+sgs_dataflow_kernel(const GridDev g, const double *__restrict__ in0, const double *__restrict__ c0,
+                    const double *__restrict__ c1, const double *__restrict__ c2, const double *__restrict__ dinv,
+                    double *out, const SgsFlow f, const int *stop)
+{
+	if (s3d_stopped(stop)) return;
+	extern __shared__ __align__(16) double smem[];
+	double *s_in = smem;                       // [TK][TJ][TI] each; s_in is overwritten with the results
+	double *s_c0 = s_in + SGS_TILE;
+	double *s_c1 = s_c0 + SGS_TILE;
+	double *s_c2 = s_c1 + SGS_TILE;
+	double *s_dv = s_c2 + SGS_TILE;
+	double *s_hj = s_dv + SGS_TILE;            // [TK][TI] the j-neighbour row of the adjacent tile (or ghost row)
+	double *s_hk = s_hj + SGS_TK * SGS_TI;     // [TJ][TI] the k-neighbour row of the adjacent tile (or ghost plane)
+	double *s_w = s_hk + SGS_TJ * SGS_TI;      // [2][TK+2][TJ+2] last value of every pencil, double-buffered
+	__shared__ int s_tile;
+	constexpr int WP = SGS_TJ + 2, WPL = (SGS_TK + 2) * WP;
+
+	const int tid = threadIdx.x;
+	const int lj = tid >> 3, lk = tid & 7;
+	const int ntiles = f.ntx * f.nty * f.ntz;
+
+	for (;;) {
+		__syncthreads();                        // previous tile fully consumed before s_tile / smem are reused
+		if (tid == 0) s_tile = (int)atomicAdd(f.ticket, 1u);
+		__syncthreads();
+		const int ticket = s_tile;
+		if (ticket >= ntiles) return;
+		const int tile = f.order[FWD ? ticket : ntiles - 1 - ticket];
+		const int ci = tile % f.ntx, cj = (tile / f.ntx) % f.nty, ck = tile / (f.ntx * f.nty);
+		const int i0 = ci * SGS_TI, j0 = cj * SGS_TJ, k0 = ck * SGS_TK;
+		const int ti = min(SGS_TI, g.nx - i0), tj = min(SGS_TJ, g.ny - j0), tk = min(SGS_TK, g.nz - k0);
+		const long long vtile = g.voff + (long long)k0 * g.vplane + (long long)j0 * g.vpitch + i0;
+		const long long ctile = (long long)k0 * g.cplane + (long long)j0 * g.cpitch + i0;
+
+		// stage the tile's five inputs (coalesced 16-byte cp.async; rows are 128-byte aligned)
+		for (int c = tid; c < SGS_TK * SGS_TJ * (SGS_TI / 2) && !(f.debug & 2); c += SGS_NT) {
+			const int i2 = c % (SGS_TI / 2), row = c / (SGS_TI / 2);
+			const int rj = row % SGS_TJ, rk = row / SGS_TJ;
+			if (rk < tk && rj < tj && i0 + 2 * i2 < g.cpitch) {
+				const long long cv = ctile + (long long)rk * g.cplane + (long long)rj * g.cpitch + 2 * i2;
+				const long long vv = vtile + (long long)rk * g.vplane + (long long)rj * g.vpitch + 2 * i2;
+				const int so = (rk * SGS_TJ + rj) * SGS_TI + 2 * i2;
+				cp_async16(s_in + so, in0 + vv);
+				cp_async16(s_c0 + so, c0 + cv);
+				cp_async16(s_c1 + so, c1 + cv);
+				cp_async16(s_c2 + so, c2 + cv);
+				cp_async16(s_dv + so, dinv + cv);
+			}
+		}
+		// wait for the three predecessor tiles (the loads above do not depend on them)
+		if (tid < 3) {
+			int pred = -1;
+			if (FWD) {
+				if (tid == 0 && ci > 0) pred = tile - 1;
+				if (tid == 1 && cj > 0) pred = tile - f.ntx;
+				if (tid == 2 && ck > 0) pred = tile - f.ntx * f.nty;
+			} else {
+				if (tid == 0 && ci < f.ntx - 1) pred = tile + 1;
+				if (tid == 1 && cj < f.nty - 1) pred = tile + f.ntx;
+				if (tid == 2 && ck < f.ntz - 1) pred = tile + f.ntx * f.nty;
+			}
+			if (pred >= 0 && !(f.debug & 8)) {
+				const volatile int *fl = f.flags + pred;
+				while (*fl != f.epoch) { }
+			}
+			if (!(f.debug & 4)) __threadfence();
+		}
+		__syncthreads();
+		// halo rows of `out` from the neighbouring tiles / ghost layer, straight from L2 (ld.cg):
+		//   j-halo: row j0-1 (FWD) or j0+tj (BWD) for every level;  k-halo: plane k0-1 (FWD) or k0+tk (BWD) for every row
+		const int dn = FWD ? -1 : 1;
+		for (int c = tid; c < SGS_TK * SGS_TI; c += SGS_NT) {
+			const int i = c % SGS_TI, q = c / SGS_TI;
+			if (q < tk && i < ti) s_hj[c] = __ldcg(out + vtile + (long long)q * g.vplane + (long long)(FWD ? -1 : tj) * g.vpitch + i);
+		}
+		for (int c = tid; c < SGS_TJ * SGS_TI; c += SGS_NT) {
+			const int i = c % SGS_TI, q = c / SGS_TI;
+			if (q < tj && i < ti) s_hk[c] = __ldcg(out + vtile + (long long)(FWD ? -1 : tk) * g.vplane + (long long)q * g.vpitch + i);
+		}
+		const bool active = (lj < tj) && (lk < tk);
+		// logical position of this pencil in the sweep order
+		const int b = FWD ? lj : tj - 1 - lj, cc = FWD ? lk : tk - 1 - lk;
+		double wi = 0.0;                         // the i-neighbour: first the adjacent tile's / ghost value, then our own last value
+		if (active) wi = __ldcg(out + vtile + (long long)lk * g.vplane + (long long)lj * g.vpitch + (FWD ? -1 : ti));
+		cp_async_wait_all();
+		__syncthreads();
+
+		const int nsteps = (f.debug & 1) ? 0 : ti + tj + tk - 2;
+		const int rowbase = (lk * SGS_TJ + lj) * SGS_TI;
+		const int wslot = (lk + 1) * WP + (lj + 1);
+		for (int h = 0; h < nsteps; h++) {
+			const int c = h - b - cc;                           // logical i-position of this pencil at step h
+			if (active && c >= 0 && c < ti) {
+				const int li = FWD ? c : ti - 1 - c;
+				const double *prev = s_w + ((h + 1) & 1) * WPL;
+				const double wj = (b == 0) ? s_hj[lk * SGS_TI + li] : prev[wslot + dn];
+				const double wk = (cc == 0) ? s_hk[lj * SGS_TI + li] : prev[wslot + dn * WP];
+				const int so = rowbase + li;
+				double val;
+				if (FWD) {
+					double t = __dsub_rn(s_in[so], __dmul_rn(s_c0[so], wi));
+					t = __dsub_rn(t, __dmul_rn(s_c1[so], wj));
+					t = __dsub_rn(t, __dmul_rn(s_c2[so], wk));
+					val = __dmul_rn(t, s_dv[so]);
+				} else {
+					double t = __dmul_rn(s_c0[so], wi);
+					t = __dadd_rn(t, __dmul_rn(s_c1[so], wj));
+					t = __dadd_rn(t, __dmul_rn(s_c2[so], wk));
+					val = __dsub_rn(s_in[so], __dmul_rn(s_dv[so], t));
+				}
+				wi = val;
+				s_w[(h & 1) * WPL + wslot] = val;
+				s_in[so] = val;                                   // results replace the staged input
+			}
+			__syncthreads();
+		}
+		// results back to global, coalesced 16-byte stores (odd row lengths: the last element alone)
+		for (int c = tid; c < SGS_TK * SGS_TJ * (SGS_TI / 2); c += SGS_NT) {
+			const int i2 = c % (SGS_TI / 2), row = c / (SGS_TI / 2);
+			const int rj = row % SGS_TJ, rk = row / SGS_TJ;
+			if (rk < tk && rj < tj && 2 * i2 < ti) {
+				const int so = (rk * SGS_TJ + rj) * SGS_TI + 2 * i2;
+				double *dst = out + vtile + (long long)rk * g.vplane + (long long)rj * g.vpitch + 2 * i2;
+				if (2 * i2 + 1 < ti) st2(dst, make_double2(s_in[so], s_in[so + 1]));
+				else *dst = s_in[so];
+			}
+		}
+		if (!(f.debug & 4)) __threadfence();
+		__syncthreads();
+		if (tid == 0) {
+			if (!(f.debug & 4)) __threadfence();
+			*(volatile int *)(f.flags + tile) = f.epoch;
+		}
+	}
+}
+
+constexpr size_t SGS_SMEM = (5 * SGS_TILE + (SGS_TK + SGS_TJ) * SGS_TI + 2 * (SGS_TK + 2) * (SGS_TJ + 2)) * sizeof(double);
 
 // ---------------------------------------------------------------- red-black
 
@@ -141,12 +335,72 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		S3D_LAUNCHED(ctx);
 		return S3D_OK;
 	}
-	if (ordering != S3D_SGS_LEXICOGRAPHIC) return s3d_fail(ctx, S3D_ERR_ARG, "unknown SGS ordering %d", ordering);
+	if (ordering != S3D_SGS_LEXICOGRAPHIC && ordering != S3D_SGS_LEXICOGRAPHIC_PLANES)
+		return s3d_fail(ctx, S3D_ERR_ARG, "unknown SGS ordering %d", ordering);
 	if (g->nranks > 1)
 		return s3d_fail(ctx, S3D_ERR_ARG, "lexicographic SGS serialises across z-slabs; use S3D_SGS_REDBLACK on a decomposed grid");
 	// the scratch vector's real entries are all overwritten and its ghosts stay zero (they are never
 	// written), so the per-call zero fill of the reference (s3d_sgspreconditioners.cpp:25-28) is implicit.
 	// Sequential sweeps are idempotent, so nsweeps > 1 repeats identical work; do one.
+	if (ordering == S3D_SGS_LEXICOGRAPHIC) {
+		SgsFlow f;
+		f.ntx = (g->nx + SGS_TI - 1) / SGS_TI; f.nty = (g->ny + SGS_TJ - 1) / SGS_TJ; f.ntz = (g->nz + SGS_TK - 1) / SGS_TK;
+		const size_t ntiles = (size_t)f.ntx * f.nty * f.ntz;
+		if (ctx->sgs_flags_cap < ntiles + 1) {
+			S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			if (ctx->sgs_flags) S3D_CUDA(ctx, cudaFree(ctx->sgs_flags));
+			ctx->sgs_flags = nullptr; ctx->sgs_flags_cap = 0;
+			S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_flags, (ntiles + 1) * sizeof(int)));
+			S3D_CUDA(ctx, cudaMemsetAsync(ctx->sgs_flags, 0, (ntiles + 1) * sizeof(int), ctx->stream));
+			ctx->sgs_flags_cap = ntiles + 1;
+			ctx->sgs_epoch = 0;
+		}
+		static bool configured = false;
+		static int blocks_per_sm = 1;
+		if (!configured) {
+			S3D_CUDA(ctx, cudaFuncSetAttribute(sgs_dataflow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SGS_SMEM));
+			S3D_CUDA(ctx, cudaFuncSetAttribute(sgs_dataflow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SGS_SMEM));
+			S3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, sgs_dataflow_kernel<true>, SGS_NT, SGS_SMEM));
+			if (blocks_per_sm < 1) blocks_per_sm = 1;
+			configured = true;
+		}
+		if (ctx->sgs_order_dims[0] != f.ntx || ctx->sgs_order_dims[1] != f.nty || ctx->sgs_order_dims[2] != f.ntz) {
+			// counting sort of the tiles by hyperplane
+			const int nd = f.ntx + f.nty + f.ntz - 2;
+			std::vector<int> start(nd + 1, 0), order(ntiles);
+			for (int ck = 0; ck < f.ntz; ck++)
+				for (int cj = 0; cj < f.nty; cj++)
+					for (int ci = 0; ci < f.ntx; ci++) start[ci + cj + ck + 1]++;
+			for (int d = 0; d < nd; d++) start[d + 1] += start[d];
+			for (int ck = 0; ck < f.ntz; ck++)
+				for (int cj = 0; cj < f.nty; cj++)
+					for (int ci = 0; ci < f.ntx; ci++) order[start[ci + cj + ck]++] = (ck * f.nty + cj) * f.ntx + ci;
+			S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			if (ctx->sgs_order) S3D_CUDA(ctx, cudaFree(ctx->sgs_order));
+			ctx->sgs_order = nullptr;
+			S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_order, ntiles * sizeof(int)));
+			S3D_CUDA(ctx, cudaMemcpy(ctx->sgs_order, order.data(), ntiles * sizeof(int), cudaMemcpyHostToDevice));
+			ctx->sgs_order_dims[0] = f.ntx; ctx->sgs_order_dims[1] = f.nty; ctx->sgs_order_dims[2] = f.ntz;
+		}
+		f.flags = ctx->sgs_flags;
+		f.order = ctx->sgs_order;
+		f.sleep_ns = 0;
+		f.debug = ctx->sgs_sleep_ns;   // reuses the tuning slot: debug bit mask
+		f.ticket = reinterpret_cast<unsigned *>(ctx->sgs_flags + ntiles);   // the slot after the last flag
+		const unsigned nblocks = (unsigned)std::min<size_t>(ntiles, (size_t)ctx->sm_count * blocks_per_sm);
+		dim3 block(SGS_NT);
+		const long long cs = g->cstride;
+		f.epoch = ++ctx->sgs_epoch;
+		S3D_CUDA(ctx, cudaMemsetAsync(f.ticket, 0, sizeof(unsigned), ctx->stream));
+		sgs_dataflow_kernel<true><<<nblocks, block, SGS_SMEM, ctx->stream>>>(gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, ctx->gate);
+		S3D_LAUNCHED(ctx);
+		f.epoch = ++ctx->sgs_epoch;
+		S3D_CUDA(ctx, cudaMemsetAsync(f.ticket, 0, sizeof(unsigned), ctx->stream));
+		sgs_dataflow_kernel<false><<<nblocks, block, SGS_SMEM, ctx->stream>>>(gd, d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f, ctx->gate);
+		S3D_LAUNCHED(ctx);
+		return S3D_OK;
+	}
+	// S3D_SGS_LEXICOGRAPHIC_PLANES: one launch per global hyperplane (the first correct version)
 	dim3 block(32, 8);
 	dim3 grid((g->ny + 31) / 32, (g->nz + 7) / 8);
 	const int hmax = g->nx + g->ny + g->nz - 3;

@@ -20,7 +20,7 @@
 
 namespace {
 
-struct Tune { int by = 8; int kchunk = 0; int variant = S3D_SPMV_PAIR; };
+struct Tune { int kchunk = 0; int variant = S3D_SPMV_MARCH; int hints = 1; int minb = 0; };
 Tune g_tune;
 
 __device__ __forceinline__ double stencil7(double a0, double a1, double a2, double a3, double a4, double a5, double a6,
@@ -37,8 +37,10 @@ __device__ __forceinline__ double stencil7(double a0, double a1, double a2, doub
 }
 
 // grid: (ceil(nx/64), ceil(ny/BY), ceil(nz/kchunk)); block: (32, BY)
-template <int BY, bool RES, bool DOTW, bool DOTYY>
-__global__ void __launch_bounds__(32 * BY)
+// The fused reductions only do stage 1 (per-block partials) in this kernel; the fixed-order sum over blocks
+// is the separate s3d_final_reduce launch.  Inlining stage 2 here cost 102 registers (2 blocks/SM).
+template <int BY, int MINB, bool RES, bool DOTW, bool DOTYY>
+__global__ void __launch_bounds__(32 * BY, MINB)
 spmv_march_kernel(const GridDev g, const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ y,
                   const double *__restrict__ b, const double *__restrict__ w, const RedOut ro, const int *stop,
                   const int kchunk)
@@ -67,7 +69,7 @@ spmv_march_kernel(const GridDev g, const double *__restrict__ A, const double *_
 
 		double2 xm = ld2(xp - g.vplane);
 		double2 xc = ld2(xp);
-		for (int k = kbeg; k < kend; ++k) {
+		auto plane = [&]() {
 			// the seven coefficient streams: read once, evict-first
 			const double2 a0 = ld_stream2(ap);
 			const double2 a1 = ld_stream2(ap + cs);
@@ -106,9 +108,15 @@ spmv_march_kernel(const GridDev g, const double *__restrict__ A, const double *_
 			xp += g.vplane; yp += g.vplane; ap += g.cplane;
 			if (RES) bp += g.vplane;
 			if (DOTW) wp += g.vplane;
+		};
+		if constexpr (DOTW || DOTYY) {
+#pragma unroll 1   // unrolled, the fused-reduction forms take >100 registers
+			for (int k = kbeg; k < kend; ++k) plane();
+		} else {
+			for (int k = kbeg; k < kend; ++k) plane();
 		}
 	}
-	if (DOTW || DOTYY) grid_reduce<2>(acc, ro);
+	if (DOTW || DOTYY) grid_reduce<2, true>(acc, ro);
 }
 
 
@@ -121,7 +129,7 @@ spmv_march_kernel(const GridDev g, const double *__restrict__ A, const double *_
 template <bool RES, bool DOTW, bool DOTYY>
 __global__ void __launch_bounds__(256)
 spmv_pair_kernel(const GridDev g, const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ y,
-                 const double *__restrict__ b, const double *__restrict__ w, const RedOut ro, const int *stop)
+                 const double *__restrict__ b, const double *__restrict__ w, const RedOut ro, const int *stop, const int hints)
 {
 	if (s3d_stopped(stop)) return;
 	const int lane = threadIdx.x;
@@ -139,13 +147,13 @@ spmv_pair_kernel(const GridDev g, const double *__restrict__ A, const double *__
 		const double *xp = x + voffs;
 		const double *ap = A + (long long)k * g.cplane + (long long)j * g.cpitch + i0;
 		const long long cs = g.cstride;
-		const double2 a0 = ld_stream2(ap);
-		const double2 a1 = ld_stream2(ap + cs);
-		const double2 a2 = ld_stream2(ap + 2 * cs);
-		const double2 a3 = ld_stream2(ap + 3 * cs);
-		const double2 a4 = ld_stream2(ap + 4 * cs);
-		const double2 a5 = ld_stream2(ap + 5 * cs);
-		const double2 a6 = ld_stream2(ap + 6 * cs);
+		const double2 a0 = hints ? ld_stream2(ap) : ld2(ap);
+		const double2 a1 = hints ? ld_stream2(ap + cs) : ld2(ap + cs);
+		const double2 a2 = hints ? ld_stream2(ap + 2 * cs) : ld2(ap + 2 * cs);
+		const double2 a3 = hints ? ld_stream2(ap + 3 * cs) : ld2(ap + 3 * cs);
+		const double2 a4 = hints ? ld_stream2(ap + 4 * cs) : ld2(ap + 4 * cs);
+		const double2 a5 = hints ? ld_stream2(ap + 5 * cs) : ld2(ap + 5 * cs);
+		const double2 a6 = hints ? ld_stream2(ap + 6 * cs) : ld2(ap + 6 * cs);
 		const double2 xc = ld2(xp);
 		const double2 xjm = ld2(xp - g.vpitch);
 		const double2 xjp = ld2(xp + g.vpitch);
@@ -160,7 +168,7 @@ spmv_pair_kernel(const GridDev g, const double *__restrict__ A, const double *__
 		double y0 = stencil7(a0.x, a1.x, a2.x, a3.x, a4.x, a5.x, a6.x, xl, xjm.x, xkm.x, xc.x, xc.y, xjp.x, xkp.x);
 		double y1 = stencil7(a0.y, a1.y, a2.y, a3.y, a4.y, a5.y, a6.y, xc.x, xjm.y, xkm.y, xc.y, xr, xjp.y, xkp.y);
 		if (RES) { y0 = __dsub_rn(bv.x, y0); y1 = __dsub_rn(bv.y, y1); }
-		if (pair) st_stream2(y + voffs, make_double2(y0, y1));
+		if (pair) { if (hints) st_stream2(y + voffs, make_double2(y0, y1)); else st2(y + voffs, make_double2(y0, y1)); }
 		else y[voffs] = y0;
 		if (DOTW) {
 			const double2 wv = (w == x) ? xc : ld2(w + voffs);
@@ -172,14 +180,14 @@ spmv_pair_kernel(const GridDev g, const double *__restrict__ A, const double *__
 			if (pair) acc[1] += y1 * y1;
 		}
 	}
-	if (DOTW || DOTYY) grid_reduce<2>(acc, ro);
+	if (DOTW || DOTYY) grid_reduce<2, true>(acc, ro);
 }
 
 // The first correct version: one thread per point, all neighbours straight from global memory.
 template <bool RES, bool DOTW, bool DOTYY>
 __global__ void __launch_bounds__(256)
 spmv_naive_kernel(const GridDev g, const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ y,
-                  const double *__restrict__ b, const double *__restrict__ w, const RedOut ro, const int *stop)
+                  const double *__restrict__ b, const double *__restrict__ w, const RedOut ro, const int *stop, const int hints)
 {
 	if (s3d_stopped(stop)) return;
 	const int i = blockIdx.x * 64 + threadIdx.x;
@@ -189,19 +197,20 @@ spmv_naive_kernel(const GridDev g, const double *__restrict__ A, const double *_
 	if (i < g.nx && j < g.ny) {
 		const long long v = g.voff + (long long)k * g.vplane + (long long)j * g.vpitch + i;
 		const long long c = (long long)k * g.cplane + (long long)j * g.cpitch + i;
-		double s = stencil7(ld_stream(A + c), ld_stream(A + c + g.cstride), ld_stream(A + c + 2 * g.cstride),
-		                    ld_stream(A + c + 3 * g.cstride), ld_stream(A + c + 4 * g.cstride),
-		                    ld_stream(A + c + 5 * g.cstride), ld_stream(A + c + 6 * g.cstride),
+		double a[7];
+#pragma unroll
+		for (int q = 0; q < 7; q++) a[q] = hints ? ld_stream(A + c + q * g.cstride) : A[c + q * g.cstride];
+		double s = stencil7(a[0], a[1], a[2], a[3], a[4], a[5], a[6],
 		                    x[v - 1], x[v - g.vpitch], x[v - g.vplane], x[v], x[v + 1], x[v + g.vpitch], x[v + g.vplane]);
 		if (RES) s = __dsub_rn(ld_stream(b + v), s);
-		__stcs(y + v, s);
+		if (hints) __stcs(y + v, s); else y[v] = s;
 		if (DOTW) acc[0] = w[v] * s;
 		if (DOTYY) acc[1] = s * s;
 	}
-	if (DOTW || DOTYY) grid_reduce<2>(acc, ro);
+	if (DOTW || DOTYY) grid_reduce<2, true>(acc, ro);
 }
 
-template <int BY>
+template <int BY, int MINB>
 int launch_march(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *x, double *y, const double *b,
                  const double *w, bool yy, double *d_red, const int *stop, int kchunk)
 {
@@ -213,8 +222,8 @@ int launch_march(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double 
 		const int rc = s3d_ensure_partials(ctx, (size_t)grid.x * grid.y * grid.z * 2);
 		if (rc != S3D_OK) return rc;
 	}
-	RedOut ro{ctx->partials, ctx->ticket, d_red};
-#define GO(RES, DW, DY) spmv_march_kernel<BY, RES, DW, DY><<<grid, block, 0, ctx->stream>>>(gd, A, x, y, b, w, ro, stop, kchunk)
+	RedOut ro{ctx->partials, nullptr, d_red};
+#define GO(RES, DW, DY) spmv_march_kernel<BY, MINB, RES, DW, DY><<<grid, block, 0, ctx->stream>>>(gd, A, x, y, b, w, ro, stop, kchunk)
 	const int sel = (b ? 4 : 0) | (w ? 2 : 0) | (yy ? 1 : 0);
 	switch (sel) {
 	case 0: GO(false, false, false); break;
@@ -228,6 +237,7 @@ int launch_march(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double 
 	}
 #undef GO
 	S3D_LAUNCHED(ctx);
+	if (red) return s3d_final_reduce(ctx, 2, grid.x * grid.y * grid.z, d_red);
 	return S3D_OK;
 }
 
@@ -242,8 +252,8 @@ int launch_naive(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double 
 		const int rc = s3d_ensure_partials(ctx, (size_t)grid.x * grid.y * grid.z * 2);
 		if (rc != S3D_OK) return rc;
 	}
-	RedOut ro{ctx->partials, ctx->ticket, d_red};
-#define GO(RES, DW, DY) spmv_naive_kernel<RES, DW, DY><<<grid, block, 0, ctx->stream>>>(gd, A, x, y, b, w, ro, stop)
+	RedOut ro{ctx->partials, nullptr, d_red};   // very many blocks: partials only, summed by s3d_final_reduce
+#define GO(RES, DW, DY) spmv_naive_kernel<RES, DW, DY><<<grid, block, 0, ctx->stream>>>(gd, A, x, y, b, w, ro, stop, g_tune.hints)
 	const int sel = (b ? 4 : 0) | (w ? 2 : 0) | (yy ? 1 : 0);
 	switch (sel) {
 	case 0: GO(false, false, false); break;
@@ -257,6 +267,7 @@ int launch_naive(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double 
 	}
 #undef GO
 	S3D_LAUNCHED(ctx);
+	if (red) return s3d_final_reduce(ctx, 2, grid.x * grid.y * grid.z, d_red);
 	return S3D_OK;
 }
 
@@ -272,8 +283,8 @@ int launch_pair(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *
 		const int rc = s3d_ensure_partials(ctx, (size_t)grid.x * grid.y * grid.z * 2);
 		if (rc != S3D_OK) return rc;
 	}
-	RedOut ro{ctx->partials, ctx->ticket, d_red};
-#define GO(RES, DW, DY) spmv_pair_kernel<RES, DW, DY><<<grid, block, 0, ctx->stream>>>(gd, A, x, y, b, w, ro, stop)
+	RedOut ro{ctx->partials, nullptr, d_red};   // very many blocks: partials only, summed by s3d_final_reduce
+#define GO(RES, DW, DY) spmv_pair_kernel<RES, DW, DY><<<grid, block, 0, ctx->stream>>>(gd, A, x, y, b, w, ro, stop, g_tune.hints)
 	const int sel = (b ? 4 : 0) | (w ? 2 : 0) | (yy ? 1 : 0);
 	switch (sel) {
 	case 0: GO(false, false, false); break;
@@ -287,22 +298,19 @@ int launch_pair(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *
 	}
 #undef GO
 	S3D_LAUNCHED(ctx);
+	if (red) return s3d_final_reduce(ctx, 2, grid.x * grid.y * grid.z, d_red);
 	return S3D_OK;
 }
 
-// z-chunk length: long marches amortise the two extra x-planes a chunk re-reads (2/kchunk of 8 B/pt),
-// but the grid still has to cover the 148 SMs several times over.
-int pick_kchunk(const s3d_ctx *ctx, const s3d_grid *g, int by)
+// z-chunk length and occupancy, from the in-run sweep on B200 (profiles/sweep_r1e.md): the SHORTEST march wins
+// (2 planes: 7074 GB/s at 512^3, 7106 at 1024^3; 8 planes 6993/6800; 32 planes 6640) because parallelism and
+// bytes in flight matter more than saving the k-neighbour loads, which hit L2 anyway; compiling for 3 blocks/SM
+// (<= 80 registers, all loads of a plane in flight) beats 6 blocks/SM by ~0.3%.  The fused-reduction forms use
+// 4 planes so the per-block reduction is amortised over 8 points per thread.
+int pick_kchunk(const s3d_ctx *, const s3d_grid *g, bool fused)
 {
 	if (g_tune.kchunk > 0) return min(g_tune.kchunk, g->nz);
-	const long long tiles = (long long)((g->nx + 63) / 64) * ((g->ny + by - 1) / by);
-	const long long want = (long long)ctx->sm_count * 16;   // ~4 resident blocks per SM, ~4 waves
-	long long nchunks = (want + tiles - 1) / tiles;
-	if (nchunks < 1) nchunks = 1;
-	int kc = (int)((g->nz + nchunks - 1) / nchunks);
-	if (kc < 16) kc = 16;
-	if (kc > g->nz) kc = g->nz;
-	return kc;
+	return min(fused ? 4 : 2, g->nz);
 }
 
 }  // namespace
@@ -315,10 +323,12 @@ extern "C" {
 int s3d_tune_set(s3d_ctx *ctx, const char *key, int value)
 {
 	if (!key) return S3D_ERR_ARG;
-	if (!strcmp(key, "spmv_by")) {
-		S3D_REQUIRE(ctx, value == 4 || value == 8 || value == 16, "spmv_by must be 4, 8 or 16");
-		g_tune.by = value;
+	if (!strcmp(key, "spmv_minb")) {
+		S3D_REQUIRE(ctx, value == 0 || value == 3 || value == 4 || value == 6, "spmv_minb must be 0 (auto), 3, 4 or 6");
+		g_tune.minb = value;
 	} else if (!strcmp(key, "spmv_kchunk")) g_tune.kchunk = value;
+	else if (!strcmp(key, "spmv_hints")) g_tune.hints = value;
+	else if (!strcmp(key, "sgs_sleep_ns")) ctx->sgs_sleep_ns = value;
 	else if (!strcmp(key, "spmv_variant")) {
 		S3D_REQUIRE(ctx, value >= S3D_SPMV_MARCH && value <= S3D_SPMV_PAIR, "unknown SpMV variant");
 		g_tune.variant = value;
@@ -337,11 +347,14 @@ int s3d_spmv(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_x
 	if (!d_stop) d_stop = ctx->gate;
 	switch (variant) {
 	case S3D_SPMV_MARCH: {
-		const int by = g_tune.by;
-		const int kc = pick_kchunk(ctx, g, by);
-		if (by == 4) return launch_march<4>(ctx, g, A, d_x, d_y, d_b, d_w, want_yy != 0, d_red, d_stop, kc);
-		if (by == 16) return launch_march<16>(ctx, g, A, d_x, d_y, d_b, d_w, want_yy != 0, d_red, d_stop, kc);
-		return launch_march<8>(ctx, g, A, d_x, d_y, d_b, d_w, want_yy != 0, d_red, d_stop, kc);
+		const bool yy = want_yy != 0;
+		const int kc = pick_kchunk(ctx, g, d_w != nullptr || yy);
+		// resident blocks per SM the kernel is compiled for: 6 (<= 40 registers), 4 (<= 64) or 3 (<= 80)
+		int minb = g_tune.minb;
+		if (minb == 0) minb = 3;
+		if (minb >= 6) return launch_march<8, 6>(ctx, g, A, d_x, d_y, d_b, d_w, yy, d_red, d_stop, kc);
+		if (minb >= 4) return launch_march<8, 4>(ctx, g, A, d_x, d_y, d_b, d_w, yy, d_red, d_stop, kc);
+		return launch_march<8, 3>(ctx, g, A, d_x, d_y, d_b, d_w, yy, d_red, d_stop, kc);
 	}
 	case S3D_SPMV_PAIR:
 		return launch_pair(ctx, g, A, d_x, d_y, d_b, d_w, want_yy != 0, d_red, d_stop);

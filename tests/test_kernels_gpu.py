@@ -160,7 +160,8 @@ def test_device_scalars(ctx, npdim):
     assert np.array_equal(ctx.vec_download(g, dy), ref)
 
 
-@pytest.mark.parametrize("npdim", [(18, 18, 18), (19, 23, 11), (3, 3, 3), (36, 20, 28)])
+# sizes chosen to hit full tiles (32x8x8), ragged tile edges in every direction, and grids smaller than one tile
+@pytest.mark.parametrize("npdim", [(18, 18, 18), (19, 23, 11), (3, 3, 3), (36, 20, 28), (34, 10, 10), (67, 19, 27), (99, 12, 9)])
 @pytest.mark.parametrize("pde", ["poisson", "convdiff"])
 def test_jacobi_and_sgs(ctx, npdim, pde):
     m, A = problem(npdim, "chebyshev", pde, V1, 0.1)
@@ -175,7 +176,14 @@ def test_jacobi_and_sgs(ctx, npdim, pde):
     ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_LEXICOGRAPHIC, 1)
     z = ctx.vec_download(g, dz)
     ref = cport.sgs_like_apply(m, A, di, r, 1)
-    assert np.array_equal(z, ref), f"lexicographic SGS max diff {np.abs(z - ref).max()}"
+    assert np.array_equal(z, ref), f"lexicographic (dataflow) SGS max diff {np.abs(z - ref).max()}"
+    assert ghosts_untouched(z)
+    ctx.vecset(g, 9.0, dz)
+    ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_LEXICOGRAPHIC, 3)      # sweeps > 1 are idempotent
+    assert np.array_equal(ctx.vec_download(g, dz), ref)
+    ctx.vecset(g, -9.0, dz)
+    ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_LEXICOGRAPHIC_PLANES, 1)
+    assert np.array_equal(ctx.vec_download(g, dz), ref), "per-hyperplane SGS differs"
     ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_REDBLACK, 1)
     z = ctx.vec_download(g, dz)
     ref = cport.sgs_redblack_apply(m, A, di, r)
@@ -308,6 +316,29 @@ def test_against_reference_fixtures(ctx, path):
     red = ctx.scalars_alloc(1)
     ctx.normL2sq_dev(g, coords, dx, red)
     assert abs(np.sqrt(ctx.scalars(red)[0]) - float(G["normL2_x"])) <= 1e-13 * float(G["normL2_x"])
+
+
+@pytest.mark.parametrize("n", [130, 258])
+def test_sgs_dataflow_full_size(ctx, n):
+    """At sizes where the CPU oracle is slow: the dataflow kernel must equal the per-hyperplane kernel bitwise
+    (both are pinned to the oracle at small sizes), repeatedly (no stale flags between epochs), and M z = r must
+    hold: r - (D+L) D^-1 (D+U) z == 0 is checked through A: for SGS, A = M - L D^-1 U, so only equality is used."""
+    m = cport.Mesh((n, n, n))
+    g = grid_of(m)
+    dA = ctx.mat_alloc(g)
+    ctx.assemble_convdiff(g, m.coords, V1, 0.1, dA)
+    dr, dz, dz2, dy = (ctx.vec_alloc(g) for _ in range(4))
+    ctx.vec_upload(g, dr, golden_vec(m))
+    dinv = ctx.scalars_alloc(int(g.cstride))
+    ctx.sgs_setup(g, dA, dinv)
+    ctx.sgs_apply(g, dA, dinv, dr, dz2, dy, capi.SGS_LEXICOGRAPHIC_PLANES, 1)
+    for rep in range(3):
+        ctx.vecset(g, float(rep), dz)
+        ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_LEXICOGRAPHIC, 1)
+        ctx.vecaxpy(g, -1.0, dz2, dz)
+        assert ctx.nrm2(g, dz) == 0.0, f"dataflow SGS differs from the hyperplane SGS (rep {rep})"
+    for p in (dA, dr, dz, dz2, dy, dinv):
+        ctx.free(p)
 
 
 @pytest.mark.parametrize("n", [258, 514])

@@ -69,23 +69,23 @@ def main():
         ctx.vecset(g, 0.5, x); ctx.vecset(g, 0.25, b); ctx.vecset(g, 0.1, p); ctx.vecset(g, 0.2, q); ctx.vecset(g, 0.3, r)
         red = ctx.scalars_alloc(8)
         ctx.sync()
-        ctx.tune("spmv_by", 8); ctx.tune("spmv_kchunk", 0)
-        rec(n, "spmv march(auto)", 72, timeit(ctx, lambda: ctx.spmv(g, dA, x, y, variant=capi.SPMV_MARCH), reps))
-        rec(n, "spmv naive", 72, timeit(ctx, lambda: ctx.spmv(g, dA, x, y, variant=capi.SPMV_NAIVE), reps))
-        try:
-            rec(n, "spmv tma", 72, timeit(ctx, lambda: ctx.spmv(g, dA, x, y, variant=capi.SPMV_TMA), reps))
-        except capi.S3dError as e:
-            print("  (tma variant unavailable:", str(e)[:80], ")")
-        rec(n, "spmv march res (b-Ax)+yy", 80, timeit(ctx, lambda: ctx.spmv(g, dA, x, y, b=b, want_yy=True, red=red), reps))
-        rec(n, "spmv march +(x,Ax)", 72, timeit(ctx, lambda: ctx.spmv(g, dA, x, y, w=x, red=red), reps))
-        if a.full:
-            for by in (4, 8, 16):
-                for kc in (8, 16, 32, 64, 128, n):
-                    if kc > n:
-                        continue
-                    ctx.tune("spmv_by", by); ctx.tune("spmv_kchunk", kc)
-                    rec(n, f"spmv march by={by} kchunk={kc}", 72, timeit(ctx, lambda: ctx.spmv(g, dA, x, y, variant=capi.SPMV_MARCH), reps), by=by, kchunk=kc)
-            ctx.tune("spmv_by", 8); ctx.tune("spmv_kchunk", 0)
+        ctx.tune("spmv_kchunk", 0); ctx.tune("spmv_minb", 0)
+        for rnd in range(2 if a.full else 1):
+            rec(n, "spmv auto (march k8)", 72, timeit(ctx, lambda: ctx.spmv(g, dA, x, y), reps), round=rnd)
+            rec(n, "spmv naive", 72, timeit(ctx, lambda: ctx.spmv(g, dA, x, y, variant=capi.SPMV_NAIVE), reps), round=rnd)
+            rec(n, "spmv pair", 72, timeit(ctx, lambda: ctx.spmv(g, dA, x, y, variant=capi.SPMV_PAIR), reps), round=rnd)
+            rec(n, "spmv auto res (b-Ax)+yy", 80, timeit(ctx, lambda: ctx.spmv(g, dA, x, y, b=b, want_yy=True, red=red), reps), round=rnd)
+            rec(n, "spmv auto +(x,Ax)", 72, timeit(ctx, lambda: ctx.spmv(g, dA, x, y, w=x, red=red), reps), round=rnd)
+            if a.full:
+                for minb in (3, 4, 6):
+                    for kc in (2, 4, 8, 16, 32):
+                        ctx.tune("spmv_minb", minb); ctx.tune("spmv_kchunk", kc)
+                        rec(n, f"spmv march minb={minb} kchunk={kc}", 72, timeit(ctx, lambda: ctx.spmv(g, dA, x, y, variant=capi.SPMV_MARCH), reps), minb=minb, kchunk=kc, round=rnd)
+                for minb in (3, 4):
+                    for kc in (4, 8, 16):
+                        ctx.tune("spmv_minb", minb); ctx.tune("spmv_kchunk", kc)
+                        rec(n, f"spmv march +(x,Ax) minb={minb} kchunk={kc}", 72, timeit(ctx, lambda: ctx.spmv(g, dA, x, y, w=x, red=red, variant=capi.SPMV_MARCH), reps), minb=minb, kchunk=kc, round=rnd)
+                ctx.tune("spmv_kchunk", 0); ctx.tune("spmv_minb", 0)
         one = capi.scalar(1e-3)
         rec(n, "vecaxpy", 24, timeit(ctx, lambda: ctx.vecaxpy(g, one, x, y), reps))
         rec(n, "vecassign", 16, timeit(ctx, lambda: ctx.vecassign(g, x, y), reps))
@@ -96,12 +96,13 @@ def main():
         rec(n, "cg_update (x,r,+2 dots, jacobi)", 56, timeit(ctx, lambda: ctx.cg_update(g, one, p, q, x, r, dA, red), reps))
         rec(n, "cg_direction_jacobi", 32, timeit(ctx, lambda: ctx.cg_direction_jacobi(g, one, dA, r, p), reps))
         rec(n, "assemble_poisson", 56, timeit(ctx, lambda: ctx.assemble_poisson(g, uniform_coords(n), dA), max(3, reps // 4)))
-        if n <= 256:
+        if n <= 512:
             dinv = ctx.scalars_alloc(int(g.cstride))
             ctx.sgs_setup(g, dA, dinv)
             rec(n, "sgs_apply red-black", 96, timeit(ctx, lambda: ctx.sgs_apply(g, dA, dinv, r, y, q, capi.SGS_REDBLACK, 1), max(3, reps // 4)))
+            rec(n, "sgs_apply lexicographic (dataflow)", 96, timeit(ctx, lambda: ctx.sgs_apply(g, dA, dinv, r, y, q, capi.SGS_LEXICOGRAPHIC, 1), max(3, reps // 4)))
             if n <= 128:
-                rec(n, "sgs_apply lexicographic(wavefront)", 96, timeit(ctx, lambda: ctx.sgs_apply(g, dA, dinv, r, y, q, capi.SGS_LEXICOGRAPHIC, 1), 3, warm=1))
+                rec(n, "sgs_apply lexicographic (per-plane launches)", 96, timeit(ctx, lambda: ctx.sgs_apply(g, dA, dinv, r, y, q, capi.SGS_LEXICOGRAPHIC_PLANES, 1), 3, warm=1))
             ctx.free(dinv)
         for v in vs:
             ctx.free(v)
