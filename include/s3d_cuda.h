@@ -165,8 +165,11 @@ int  s3d_normL2sq(s3d_ctx *ctx, const s3d_grid *g, const double *h_cx, const dou
 /* blocking conveniences returning the reference's values (sqrt applied where the reference applies it) */
 int  s3d_dot_host(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, const double *d_y, double *h_out);
 int  s3d_nrm2_host(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, double *h_out);
-/* sum-allreduce n device scalars across the z-slab ranks (no-op for one rank) */
-int  s3d_allreduce_sum(s3d_ctx *ctx, double *d_s, int n);
+/* sum-allreduce n device scalars across the z-slab ranks: d_global[i] = sum over ranks of d_local[i].
+ * Out of place on purpose: kernels write d_local, consumers read d_global, so a repeated call with an unchanged
+ * d_local (what happens once the device-side gate has stopped the kernels) is idempotent.  One rank: a copy
+ * (nothing at all when d_local == d_global). */
+int  s3d_allreduce_sum(s3d_ctx *ctx, const double *d_local, double *d_global, int n);
 
 /* ------------------------------------------------------------------ preconditioners */
 

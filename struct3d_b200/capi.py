@@ -55,7 +55,7 @@ _SIGS = {
     "s3d_dot": [_P, _G, _vp, _vp, _vp], "s3d_nrm2sq": [_P, _G, _vp, _vp],
     "s3d_normL2sq": [_P, _G, _vp, _vp, _vp, _vp, _vp],
     "s3d_dot_host": [_P, _G, _vp, _vp, _dp], "s3d_nrm2_host": [_P, _G, _vp, _dp],
-    "s3d_allreduce_sum": [_P, _vp, _I],
+    "s3d_allreduce_sum": [_P, _vp, _vp, _I],
     "s3d_jacobi_apply": [_P, _G, _vp, _vp, _vp], "s3d_sgs_setup": [_P, _G, _vp, _vp],
     "s3d_sgs_apply": [_P, _G, _vp, _vp, _vp, _vp, _vp, _I, _I],
     "s3d_cg_update": [_P, _G, Scalar, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -308,8 +308,8 @@ class Context:
         cs = [np.ascontiguousarray(c, dtype=np.float64) for c in coords]
         self.call("s3d_normL2sq", C.byref(g), _ptr(cs[0]), _ptr(cs[1]), _ptr(cs[2]), _ptr(x), _ptr(red))
 
-    def allreduce_sum(self, d, n):
-        self.call("s3d_allreduce_sum", _ptr(d), n)
+    def allreduce_sum(self, d_local, d_global, n):
+        self.call("s3d_allreduce_sum", _ptr(d_local), _ptr(d_global), n)
 
     def jacobi_apply(self, g, A, r, z):
         self.call("s3d_jacobi_apply", C.byref(g), _ptr(A), _ptr(r), _ptr(z))

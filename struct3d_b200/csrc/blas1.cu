@@ -480,16 +480,16 @@ int s3d_normL2sq(s3d_ctx *ctx, const s3d_grid *g, const double *h_cx, const doub
 int s3d_dot_host(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, const double *d_y, double *h_out)
 {
 	int rc = s3d_dot(ctx, g, d_x, d_y, ctx->red_tmp);
-	if (rc == S3D_OK) rc = s3d_allreduce_sum(ctx, ctx->red_tmp, 1);
-	if (rc == S3D_OK) rc = s3d_scalars_download(ctx, ctx->red_tmp, 1, h_out);
+	if (rc == S3D_OK) rc = s3d_allreduce_sum(ctx, ctx->red_tmp, ctx->red_tmp + 32, 1);
+	if (rc == S3D_OK) rc = s3d_scalars_download(ctx, ctx->red_tmp + 32, 1, h_out);
 	return rc;
 }
 
 int s3d_nrm2_host(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, double *h_out)
 {
 	int rc = s3d_nrm2sq(ctx, g, d_x, ctx->red_tmp);
-	if (rc == S3D_OK) rc = s3d_allreduce_sum(ctx, ctx->red_tmp, 1);
-	if (rc == S3D_OK) rc = s3d_scalars_download(ctx, ctx->red_tmp, 1, h_out);
+	if (rc == S3D_OK) rc = s3d_allreduce_sum(ctx, ctx->red_tmp, ctx->red_tmp + 32, 1);
+	if (rc == S3D_OK) rc = s3d_scalars_download(ctx, ctx->red_tmp + 32, 1, h_out);
 	if (rc == S3D_OK) *h_out = sqrt(*h_out);
 	return rc;
 }

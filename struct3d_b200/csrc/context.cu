@@ -435,11 +435,16 @@ int s3d_halo_exchange(s3d_ctx *ctx, const s3d_grid *g, double *d_x)
 	return S3D_OK;
 }
 
-int s3d_allreduce_sum(s3d_ctx *ctx, double *d_s, int n)
+int s3d_allreduce_sum(s3d_ctx *ctx, const double *d_local, double *d_global, int n)
 {
-	if (ctx->nranks == 1) return S3D_OK;
+	S3D_REQUIRE(ctx, d_local && d_global && n > 0, "bad argument");
+	if (ctx->nranks == 1) {
+		if (d_local != d_global)
+			S3D_CUDA(ctx, cudaMemcpyAsync(d_global, d_local, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+		return S3D_OK;
+	}
 	if (!ctx->comm) return s3d_fail(ctx, S3D_ERR_STATE, "allreduce needs s3d_comm_init");
-	S3D_NCCL(ctx, g_nccl.AllReduce(d_s, d_s, n, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+	S3D_NCCL(ctx, g_nccl.AllReduce(d_local, d_global, n, ncclDouble, ncclSum, ctx->comm, ctx->stream));
 	return S3D_OK;
 }
 

@@ -198,12 +198,12 @@ void vec_multi_axpy(const int numvecs, const sreal *const a, const SVec *const x
 sreal norm_L2(const SVec &x)
 {
 	const Device &d = Device::get();
-	double *red = d.scalars(1);
+	double *red = d.scalars(2);
 	const sreal *const *c = x.m->pointer_coords();
 	d.check(s3d_normL2sq(d.ctx(), &x.grid(), c[0], c[1], c[2], x.dev(), red), "s3d_normL2sq");
-	d.check(s3d_allreduce_sum(d.ctx(), red, 1), "s3d_allreduce_sum");
+	d.check(s3d_allreduce_sum(d.ctx(), red, red + 1, 1), "s3d_allreduce_sum");
 	sreal v = 0;
-	d.check(s3d_scalars_download(d.ctx(), red, 1, &v), "s3d_scalars_download");
+	d.check(s3d_scalars_download(d.ctx(), red + 1, 1, &v), "s3d_scalars_download");
 	d.release(red);
 	return std::sqrt(v);
 }

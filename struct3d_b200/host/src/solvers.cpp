@@ -83,10 +83,29 @@ int batch_size(const s3d_grid &g, double bytes_per_point_per_iter)
 	return std::max(1, std::min(64, b));
 }
 
-void allreduce(const Device &d, double *s, int n)
-{
-	if (d.nranks() > 1) d.check(s3d_allreduce_sum(d.ctx(), s, n), "s3d_allreduce_sum");
-}
+// Device scalars of a solver loop.  Kernels write their reductions into the LOCAL copy (`loc`), the
+// allreduce sums them into the GLOBAL copy (`S`, what every consumer reads).  Out of place, so that once the
+// device-side gate has turned the kernels into no-ops a further allreduce just reproduces the same global
+// value (an in-place NCCL sum would keep multiplying it by the rank count).  One rank: both are the same memory.
+struct Scalars {
+	const Device &d;
+	double *S;      // global values
+	long off;       // loc(i) = S + off + i
+	Scalars(const Device &dev, int n) : d(dev), S(dev.scalars(2 * n)), off(dev.nranks() > 1 ? n : 0) {}
+	~Scalars() { s3d_free(d.ctx(), S); }
+	double *loc(int i) const { return S + off + i; }
+	double *glob(int i) const { return S + i; }
+	void allreduce(int i, int n) const
+	{
+		if (off) d.check(s3d_allreduce_sum(d.ctx(), loc(i), glob(i), n), "s3d_allreduce_sum");
+	}
+	// for slots addressed through a pointer into S (ping-pong pairs)
+	double *loc_of(double *g) const { return g + off; }
+	void allreduce_at(double *g, int n) const
+	{
+		if (off) d.check(s3d_allreduce_sum(d.ctx(), g + off, g, n), "s3d_allreduce_sum");
+	}
+};
 
 SolveInfo finish(const Device &d, const double *rr, const double *bb, double rtol, int iterations, int stopcode, int phase_slot)
 {
@@ -196,15 +215,16 @@ SolveInfo Richardson::apply(const SVec &b, SVec &x) const
 	s3d_ctx *ctx = d.ctx();
 	const s3d_grid &g = A.grid();
 	SVec res(A.m), dx(A.m);
-	double *S = d.scalars(4);   // [0] (b,b)  [1] unused  [2] (r,r)
+	Scalars sc(d, 4);   // [0] (b,b)  [1] unused  [2] (r,r)
+	double *S = sc.S;
 	DeviceLoop loop(sparams.maxiter + 1, 10, history);
 
-	d.check(s3d_nrm2sq(ctx, &g, b.dev(), &S[0]), "s3d_nrm2sq");
-	allreduce(d, &S[0], 1);
+	d.check(s3d_nrm2sq(ctx, &g, b.dev(), sc.loc(0)), "s3d_nrm2sq");
+	sc.allreduce(0, 1);
 	auto residual = [&]() {
 		x.exchange_halo();
-		d.check(s3d_spmv(ctx, &g, A.dev(), x.dev(), res.dev_w(), b.dev(), nullptr, 1, &S[1], nullptr, S3D_SPMV_AUTO), "s3d_spmv");
-		allreduce(d, &S[2], 1);
+		d.check(s3d_spmv(ctx, &g, A.dev(), x.dev(), res.dev_w(), b.dev(), nullptr, 1, sc.loc(1), nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+		sc.allreduce(2, 1);
 	};
 	residual();
 	loop.test(&S[2], &S[0], sparams.rtol, sparams.maxiter, S3D_CONV_INITIAL);
@@ -223,7 +243,6 @@ SolveInfo Richardson::apply(const SVec &b, SVec &x) const
 	}
 	d.check(s3d_ctx_set_gate(ctx, nullptr), "s3d_ctx_set_gate");
 	const SolveInfo info = finish(d, &S[2], &S[0], sparams.rtol, iterations, code, 0);
-	d.release(S);
 	return info;
 }
 
@@ -246,12 +265,13 @@ SolveInfo GCR::apply(const SVec &b, SVec &x) const
 
 	// scalars: [0] (b,b)  [1..2] spmv reductions  [3] (res,res)  [4..5] (res,q_k),(q_k,q_k)
 	//          QQ[i] = (q_i,q_i) cached (the reference recomputes the identical value)   DOT[i] = (q_new,q_i)   BETA[i]
-	double *S = d.scalars(8 + 3 * north);
+	Scalars sc(d, 8 + 3 * north);
+	double *S = sc.S;
 	double *QQ = S + 8, *DOT = QQ + north, *BETA = DOT + north;
 	DeviceLoop loop(sparams.maxiter + north + 1, 5, history);
 
-	d.check(s3d_nrm2sq(ctx, &g, b.dev(), &S[0]), "s3d_nrm2sq");
-	allreduce(d, &S[0], 1);
+	d.check(s3d_nrm2sq(ctx, &g, b.dev(), sc.loc(0)), "s3d_nrm2sq");
+	sc.allreduce(0, 1);
 	// before the first update the reference's resnorm is 1.0 and is never tested: give the final-result
 	// slot a defined value in case maxiter == 0
 	{ const double one = 1.0; d.check(s3d_scalars_upload(ctx, &S[3], 1, &one), "s3d_scalars_upload"); }
@@ -267,12 +287,12 @@ SolveInfo GCR::apply(const SVec &b, SVec &x) const
 		for (int k = 0; k < north; k++) {
 			// alpha = (res,q_k)/(q_k,q_k): one pass over q_k
 			const double *two[2] = {res.dev(), q[k].dev()};
-			d.check(s3d_vec_multi_dot(ctx, &g, 2, two, q[k].dev(), &S[4]), "s3d_vec_multi_dot");
-			allreduce(d, &S[4], 2);
+			d.check(s3d_vec_multi_dot(ctx, &g, 2, two, q[k].dev(), sc.loc(4)), "s3d_vec_multi_dot");
+			sc.allreduce(4, 2);
 			d.check(s3d_vecaxpy(ctx, &g, ratio(1.0, &S[4], &S[5]), p[k].dev(), x.dev_rw()), "s3d_vecaxpy");
 			// res -= alpha q_k with ||res||^2 fused
-			d.check(s3d_vecwaxpby(ctx, &g, imm(1.0), res.dev(), ratio(-1.0, &S[4], &S[5]), q[k].dev(), res.dev_rw(), &S[3]), "s3d_vecwaxpby");
-			allreduce(d, &S[3], 1);
+			d.check(s3d_vecwaxpby(ctx, &g, imm(1.0), res.dev(), ratio(-1.0, &S[4], &S[5]), q[k].dev(), res.dev_rw(), sc.loc(3)), "s3d_vecwaxpby");
+			sc.allreduce(3, 1);
 			loop.test(&S[3], &S[0], sparams.rtol, INT_MAX, S3D_CONV_STRICT);
 			if (k == north - 1) break;
 			// keep (q_k,q_k) for the Gram-Schmidt coefficients of later directions
@@ -286,8 +306,8 @@ SolveInfo GCR::apply(const SVec &b, SVec &x) const
 				const int n = std::min(32, k + 1 - base);
 				const double *qs[32];
 				for (int l = 0; l < n; l++) qs[l] = q[base + l].dev();
-				d.check(s3d_vec_multi_dot(ctx, &g, n, qs, q[k + 1].dev(), &DOT[base]), "s3d_vec_multi_dot");
-				allreduce(d, &DOT[base], n);
+				d.check(s3d_vec_multi_dot(ctx, &g, n, qs, q[k + 1].dev(), sc.loc_of(&DOT[base])), "s3d_vec_multi_dot");
+				sc.allreduce_at(&DOT[base], n);
 			}
 			for (int base = 0; base <= k; base += 32) {
 				const int n = std::min(32, k + 1 - base);
@@ -302,7 +322,6 @@ SolveInfo GCR::apply(const SVec &b, SVec &x) const
 	}
 	d.check(s3d_ctx_set_gate(ctx, nullptr), "s3d_ctx_set_gate");
 	const SolveInfo info = finish(d, &S[3], &S[0], sparams.rtol, iterations, code, 0);
-	d.release(S);
 	return info;
 }
 
@@ -323,26 +342,27 @@ SolveInfo CG::apply(const SVec &b, SVec &x) const
 	SVec z;
 	if (!jacobi) z.init(A.m);
 	// scalars: [0] (b,b)  [1..2] SpMV reductions: (p,Ap), -  [3,4] and [5,6]: ping-pong pairs {(r,r), (r,z)}
-	double *S = d.scalars(8);
+	Scalars sc(d, 8);
+	double *S = sc.S;
 	DeviceLoop loop(sparams.maxiter + 1, 10, history);
 
-	d.check(s3d_nrm2sq(ctx, &g, b.dev(), &S[0]), "s3d_nrm2sq");
-	allreduce(d, &S[0], 1);
+	d.check(s3d_nrm2sq(ctx, &g, b.dev(), sc.loc(0)), "s3d_nrm2sq");
+	sc.allreduce(0, 1);
 	x.exchange_halo();
-	d.check(s3d_spmv(ctx, &g, A.dev(), x.dev(), r.dev_w(), b.dev(), nullptr, 1, &S[4], nullptr, S3D_SPMV_AUTO), "s3d_spmv");   // (r,r) -> S[5]
-	allreduce(d, &S[5], 1);
+	d.check(s3d_spmv(ctx, &g, A.dev(), x.dev(), r.dev_w(), b.dev(), nullptr, 1, sc.loc(4), nullptr, S3D_SPMV_AUTO), "s3d_spmv");   // (r,r) -> S[5]
+	sc.allreduce(5, 1);
 	loop.test(&S[5], &S[0], sparams.rtol, sparams.maxiter, S3D_CONV_INITIAL);
 	loop.gate();
 	// z = M^-1 r, p = z, (r,z) -> S[6]  (the "previous" pair of iteration 0 is {5,6})
 	if (jacobi) {
 		{ TimedPrec t(d); prec->apply(r, p); }
-		d.check(s3d_dot(ctx, &g, r.dev(), p.dev(), &S[6]), "s3d_dot");
+		d.check(s3d_dot(ctx, &g, r.dev(), p.dev(), sc.loc(6)), "s3d_dot");
 	} else {
 		{ TimedPrec t(d); prec->apply(r, z); }
 		d.check(s3d_vecassign(ctx, &g, z.dev(), p.dev_rw()), "s3d_vecassign");
-		d.check(s3d_dot(ctx, &g, r.dev(), z.dev(), &S[6]), "s3d_dot");
+		d.check(s3d_dot(ctx, &g, r.dev(), z.dev(), sc.loc(6)), "s3d_dot");
 	}
-	allreduce(d, &S[6], 1);
+	sc.allreduce(6, 1);
 
 	int iterations = 0;
 	int code = loop.poll(iterations);
@@ -354,19 +374,19 @@ SolveInfo CG::apply(const SVec &b, SVec &x) const
 			double *cur = (it % 2 == 0) ? &S[3] : &S[5];    // this iteration's {(r,r), (r,z)}
 			double *prev = (it % 2 == 0) ? &S[5] : &S[3];   // the previous iteration's pair
 			p.exchange_halo();
-			d.check(s3d_spmv(ctx, &g, A.dev(), p.dev(), q.dev_w(), nullptr, p.dev(), 0, &S[1], nullptr, S3D_SPMV_AUTO), "s3d_spmv");
-			allreduce(d, &S[1], 1);
+			d.check(s3d_spmv(ctx, &g, A.dev(), p.dev(), q.dev_w(), nullptr, p.dev(), 0, sc.loc(1), nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+			sc.allreduce(1, 1);
 			// x += alpha p, r -= alpha q, alpha = (r,z)/(p,Ap); fused (r,r) [and (r, r/diag)]
 			d.check(s3d_cg_update(ctx, &g, ratio(1.0, &prev[1], &S[1]), p.dev(), q.dev(), x.dev_rw(), r.dev_rw(),
-			                      jacobi ? A.dev() : nullptr, cur, nullptr), "s3d_cg_update");
-			allreduce(d, cur, 2);
+			                      jacobi ? A.dev() : nullptr, sc.loc_of(cur), nullptr), "s3d_cg_update");
+			sc.allreduce_at(cur, 2);
 			loop.test(&cur[0], &S[0], sparams.rtol, sparams.maxiter, 0);
 			if (jacobi) {
 				d.check(s3d_cg_direction_jacobi(ctx, &g, ratio(1.0, &cur[1], &prev[1]), A.dev(), r.dev(), p.dev_rw(), nullptr), "s3d_cg_direction_jacobi");
 			} else {
 				{ TimedPrec t(d); prec->apply(r, z); }
-				d.check(s3d_dot(ctx, &g, r.dev(), z.dev(), &cur[1]), "s3d_dot");
-				allreduce(d, &cur[1], 1);
+				d.check(s3d_dot(ctx, &g, r.dev(), z.dev(), sc.loc_of(&cur[1])), "s3d_dot");
+				sc.allreduce_at(&cur[1], 1);
 				d.check(s3d_vecaxpby(ctx, &g, imm(1.0), z.dev(), ratio(1.0, &cur[1], &prev[1]), p.dev_rw()), "s3d_vecaxpby");
 			}
 		}
@@ -376,7 +396,6 @@ SolveInfo CG::apply(const SVec &b, SVec &x) const
 	// the residual norm of the last COUNTED iteration lives in the pair that iteration wrote
 	if (iterations > 0) rr_final = ((iterations - 1) % 2 == 0) ? &S[3] : &S[5];
 	const SolveInfo info = finish(d, rr_final, &S[0], sparams.rtol, iterations, code, 0);
-	d.release(S);
 	return info;
 }
 
@@ -395,18 +414,19 @@ SolveInfo BiCGSTAB::apply(const SVec &b, SVec &x) const
 	SVec r(A.m), rhat(A.m), p(A.m), v(A.m), s(A.m), t(A.m), ph(A.m), sh(A.m);
 	// scalars: [0] (b,b)  [1,2] (rhat,v),-  [3,4] (t,s),(t,t)  [5,6] / [7,8] ping-pong {(r,r), (rhat,r)}
 	//          [9] alpha  [10] omega  [11] beta
-	double *S = d.scalars(12);
+	Scalars sc(d, 12);
+	double *S = sc.S;
 	DeviceLoop loop(sparams.maxiter + 1, 10, history);
 
-	d.check(s3d_nrm2sq(ctx, &g, b.dev(), &S[0]), "s3d_nrm2sq");
-	allreduce(d, &S[0], 1);
+	d.check(s3d_nrm2sq(ctx, &g, b.dev(), sc.loc(0)), "s3d_nrm2sq");
+	sc.allreduce(0, 1);
 	x.exchange_halo();
-	d.check(s3d_spmv(ctx, &g, A.dev(), x.dev(), r.dev_w(), b.dev(), nullptr, 1, &S[6], nullptr, S3D_SPMV_AUTO), "s3d_spmv");   // (r,r) -> S[7]
-	allreduce(d, &S[7], 1);
+	d.check(s3d_spmv(ctx, &g, A.dev(), x.dev(), r.dev_w(), b.dev(), nullptr, 1, sc.loc(6), nullptr, S3D_SPMV_AUTO), "s3d_spmv");   // (r,r) -> S[7]
+	sc.allreduce(7, 1);
 	d.check(s3d_vecassign(ctx, &g, r.dev(), rhat.dev_rw()), "s3d_vecassign");
 	// rho_0 = (rhat, r) = (r,r): place it where iteration 0 expects "the previous pair's (rhat,r)" = S[8]
-	d.check(s3d_dot(ctx, &g, rhat.dev(), r.dev(), &S[8]), "s3d_dot");
-	allreduce(d, &S[8], 1);
+	d.check(s3d_dot(ctx, &g, rhat.dev(), r.dev(), sc.loc(8)), "s3d_dot");
+	sc.allreduce(8, 1);
 	loop.test(&S[7], &S[0], sparams.rtol, sparams.maxiter, S3D_CONV_INITIAL);
 	loop.gate();
 
@@ -427,18 +447,18 @@ SolveInfo BiCGSTAB::apply(const SVec &b, SVec &x) const
 			}
 			{ TimedPrec tp(d); prec->apply(p, ph); }
 			ph.exchange_halo();
-			d.check(s3d_spmv(ctx, &g, A.dev(), ph.dev(), v.dev_w(), nullptr, rhat.dev(), 0, &S[1], nullptr, S3D_SPMV_AUTO), "s3d_spmv");
-			allreduce(d, &S[1], 1);
+			d.check(s3d_spmv(ctx, &g, A.dev(), ph.dev(), v.dev_w(), nullptr, rhat.dev(), 0, sc.loc(1), nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+			sc.allreduce(1, 1);
 			d.check(s3d_scalar_op(ctx, 2, &S[9], &prev[1], &S[1], nullptr, nullptr, 1, 1.0, loop.stop()), "s3d_scalar_op");   // alpha = rho/(rhat,v)
 			d.check(s3d_vecwaxpby(ctx, &g, imm(1.0), r.dev(), ratio(-1.0, &S[9], nullptr), v.dev(), s.dev_rw(), nullptr), "s3d_vecwaxpby");
 			{ TimedPrec tp(d); prec->apply(s, sh); }
 			sh.exchange_halo();
-			d.check(s3d_spmv(ctx, &g, A.dev(), sh.dev(), t.dev_w(), nullptr, s.dev(), 1, &S[3], nullptr, S3D_SPMV_AUTO), "s3d_spmv");
-			allreduce(d, &S[3], 2);
+			d.check(s3d_spmv(ctx, &g, A.dev(), sh.dev(), t.dev_w(), nullptr, s.dev(), 1, sc.loc(3), nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+			sc.allreduce(3, 2);
 			d.check(s3d_scalar_op(ctx, 2, &S[10], &S[3], &S[4], nullptr, nullptr, 1, 1.0, loop.stop()), "s3d_scalar_op");    // omega = (t,s)/(t,t)
 			d.check(s3d_bicg_update(ctx, &g, ratio(1.0, &S[9], nullptr), ph.dev(), ratio(1.0, &S[10], nullptr), sh.dev(), s.dev(), t.dev(),
-			                        rhat.dev(), x.dev_rw(), r.dev_rw(), cur, nullptr), "s3d_bicg_update");
-			allreduce(d, cur, 2);
+			                        rhat.dev(), x.dev_rw(), r.dev_rw(), sc.loc_of(cur), nullptr), "s3d_bicg_update");
+			sc.allreduce_at(cur, 2);
 			loop.test(&cur[0], &S[0], sparams.rtol, sparams.maxiter, 0);
 		}
 		code = loop.poll(iterations);
@@ -447,7 +467,6 @@ SolveInfo BiCGSTAB::apply(const SVec &b, SVec &x) const
 	const double *rr_final = &S[7];
 	if (iterations > 0) rr_final = ((iterations - 1) % 2 == 0) ? &S[5] : &S[7];
 	const SolveInfo info = finish(d, rr_final, &S[0], sparams.rtol, iterations, code, 0);
-	d.release(S);
 	return info;
 }
 
