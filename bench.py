@@ -227,10 +227,10 @@ def run_ours(a):
     achieved = BYTES_SPMV * N_local / (ms_kernel * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("spmv_pair_512", {}).get("dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("spmv_march_512", {}).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "spmv_pair_kernel<false,false,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "spmv_march_kernel<BY=8,MINB=3,plain> (2-plane z-march, 2 points/thread)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": BYTES_SPMV * N_local, "avg_launch_ms": ms_kernel}
 

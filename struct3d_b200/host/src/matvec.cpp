@@ -95,9 +95,7 @@ SMat::SMat(const SMat &o) : m{o.m}, start{0}, nghost{1}, sz(o.sz)
 	const Device &d = Device::get();
 	d.check(s3d_mat_alloc(d.ctx(), &grid(), &d_), "s3d_mat_alloc");
 	bind_views();
-	// same-layout device copy: reuse the ghost-inclusive vector copy on a fake "vector" of the right length is
-	// not possible (different length), so go through the scalar download/upload-free path: a plain cudaMemcpy
-	// is not in the C ABI; copy stencil by stencil through the host mirror instead (matrices are copied rarely).
+	// matrices are copied rarely: go stencil by stencil through the host mirror
 	std::vector<sreal> tmp(compact_len(grid()));
 	for (int s = 0; s < NSTENCIL; s++) {
 		o.vals[s].copy_to(tmp.data());
