@@ -141,6 +141,13 @@ int  s3d_host_free(s3d_ctx *ctx, void *h_ptr);
 int  s3d_spmv(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_x, double *d_y,
               const double *d_b, const double *d_w, int want_yy, double *d_red, const int *d_stop, int variant);
 
+/* SMat::apply / apply_res for HOST vectors (the reference's SVec lives in host memory): y = A x, or b - A x with a device-resident
+ * d_b.  Pipelined in nchunks z-chunks (<= 0: 16) over three streams, so the upload of x, the kernel and the download of y overlap and
+ * the call runs at PCIe speed.  h_x / h_y: host SVec layout, pinned (s3d_host_alloc) for full speed; d_x / d_y: device vectors used
+ * as staging (d_y as allocated by s3d_vec_alloc: zero ghosts).  Single GPU; blocks until h_y is complete. */
+int  s3d_spmv_host(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *h_x, double *h_y, double *d_x, double *d_y,
+                   const double *d_b, int nchunks);
+
 /* ------------------------------------------------------------------ BLAS-1 (matvec.cpp:148-288), real points only */
 
 int  s3d_vecset(s3d_ctx *ctx, const s3d_grid *g, double a, double *d_x);                        /* vecset     :188 */
@@ -231,6 +238,11 @@ int  s3d_phase_total_ms(s3d_ctx *ctx, int slot, double *ms);
 int  s3d_ints_alloc(s3d_ctx *ctx, int n, int **d_out);
 int  s3d_ints_download(s3d_ctx *ctx, const int *d_s, int n, int *h_out);
 int  s3d_ints_zero(s3d_ctx *ctx, int *d_s, int n);
+/* Pipelined polling of device flags: `snapshot` enqueues an asynchronous copy of n (<= 8) device ints into pinned slot
+ * `slot` (0..7) and records an event; `snapshot_wait` spins on that event (no blocking driver wait) and returns the values.
+ * A host-driven loop snapshots after batch k, enqueues batch k+1, and only then waits for snapshot k. */
+int  s3d_ints_snapshot(s3d_ctx *ctx, const int *d_s, int n, int slot);
+int  s3d_ints_snapshot_wait(s3d_ctx *ctx, int slot, int n, int *h_out);
 
 /* ------------------------------------------------------------------ assembly (src/pde) */
 

@@ -47,6 +47,7 @@ _SIGS = {
     "s3d_scalars_download": [_P, _vp, _I, _vp], "s3d_scalars_upload": [_P, _vp, _I, _vp],
     "s3d_host_alloc": [_P, C.c_size_t, C.POINTER(_vp)], "s3d_host_free": [_P, _vp],
     "s3d_spmv": [_P, _G, _vp, _vp, _vp, _vp, _vp, _I, _vp, _vp, _I],
+    "s3d_spmv_host": [_P, _G, _vp, _vp, _vp, _vp, _vp, _vp, _I],
     "s3d_vecset": [_P, _G, _D, _vp], "s3d_vecassign": [_P, _G, _vp, _vp], "s3d_veccopy_all": [_P, _G, _vp, _vp],
     "s3d_vecaxpy": [_P, _G, Scalar, _vp, _vp], "s3d_vecaxpby": [_P, _G, Scalar, _vp, Scalar, _vp],
     "s3d_vecwaxpby": [_P, _G, Scalar, _vp, Scalar, _vp, _vp, _vp],
@@ -65,6 +66,7 @@ _SIGS = {
     "s3d_converge_test": [_P, _vp, _vp, _D, _I, _I, _vp, _vp, _vp],
     "s3d_scalar_op": [_P, _I, _vp, _vp, _vp, _vp, _vp, _I, _D, _vp],
     "s3d_ctx_set_gate": [_P, _vp], "s3d_phase_begin": [_P, _I], "s3d_phase_end": [_P, _I], "s3d_phase_total_ms": [_P, _I, _dp],
+    "s3d_ints_snapshot": [_P, _vp, _I, _I], "s3d_ints_snapshot_wait": [_P, _I, _I, _vp],
     "s3d_ints_alloc": [_P, _I, C.POINTER(_vp)], "s3d_ints_download": [_P, _vp, _I, _vp], "s3d_ints_zero": [_P, _vp, _I],
     "s3d_assemble_poisson": [_P, _G, _vp, _vp, _vp, _vp],
     "s3d_assemble_convdiff": [_P, _G, _vp, _vp, _vp, _vp, _D, _vp],
@@ -259,6 +261,10 @@ class Context:
     # --- kernels
     def spmv(self, g, A, x, y, b=None, w=None, want_yy=False, red=None, stop=None, variant=SPMV_AUTO):
         self.call("s3d_spmv", C.byref(g), _ptr(A), _ptr(x), _ptr(y), _ptr(b), _ptr(w), int(want_yy), _ptr(red), _ptr(stop), variant)
+
+    def spmv_host(self, g, A, h_x, h_y, d_x, d_y, d_b=None, nchunks=0):
+        """h_x / h_y: numpy arrays or raw host pointers in the SVec layout"""
+        self.call("s3d_spmv_host", C.byref(g), _ptr(A), _ptr(h_x), _ptr(h_y), _ptr(d_x), _ptr(d_y), _ptr(d_b), int(nchunks))
 
     def vecset(self, g, a, x):
         self.call("s3d_vecset", C.byref(g), float(a), _ptr(x))

@@ -34,6 +34,14 @@ struct s3d_ctx {
 	const int *gate = nullptr;
 	// timing
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	// pipelined host-buffer SpMV: copy streams and per-chunk events
+	cudaStream_t up_stream = nullptr, down_stream = nullptr;
+	double *stage = nullptr;       // device staging for contiguous host uploads (repacked into the padded layout on the device)
+	size_t stage_cap = 0;
+	int *h_slots = nullptr;        // 8 pinned slots of 8 ints for pipelined flag polling
+	cudaEvent_t slot_ev[8] = {};
+	cudaEvent_t *chunk_ev = nullptr;
+	int chunk_ev_cap = 0;
 	struct Phase { cudaEvent_t *ev = nullptr; int used = 0, cap = 0; };
 	Phase phase[4];
 	int64_t launches = 0;

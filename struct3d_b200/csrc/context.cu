@@ -143,9 +143,12 @@ int s3d_ctx_destroy(s3d_ctx *ctx)
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
 	cudaFree(ctx->partials); cudaFree(ctx->ticket); cudaFree(ctx->tab); cudaFree(ctx->red_tmp);
-	cudaFree(ctx->sgs_flags); cudaFree(ctx->sgs_order);
+	cudaFree(ctx->sgs_flags); cudaFree(ctx->sgs_order); cudaFree(ctx->stage);
 	cudaFreeHost(ctx->h_pinned);
+	if (ctx->h_slots) { cudaFreeHost(ctx->h_slots); for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->slot_ev[i]); }
 	cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+	if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
+	if (ctx->down_stream) cudaStreamDestroy(ctx->down_stream);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 	return S3D_OK;
@@ -297,6 +300,31 @@ int s3d_ints_download(s3d_ctx *ctx, const int *d_s, int n, int *h_out)
 	S3D_CUDA(ctx, cudaMemcpyAsync(pin, d_s, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
 	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	memcpy(h_out, pin, n * sizeof(int));
+	return S3D_OK;
+}
+
+int s3d_ints_snapshot(s3d_ctx *ctx, const int *d_s, int n, int slot)
+{
+	S3D_REQUIRE(ctx, d_s && n > 0 && n <= 8 && slot >= 0 && slot < 8, "bad argument");
+	if (!ctx->h_slots) {
+		S3D_CUDA(ctx, cudaMallocHost(&ctx->h_slots, 64 * sizeof(int)));
+		for (int i = 0; i < 8; i++) S3D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->slot_ev[i], cudaEventDisableTiming));
+	}
+	S3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_slots + 8 * slot, d_s, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	S3D_CUDA(ctx, cudaEventRecord(ctx->slot_ev[slot], ctx->stream));
+	return S3D_OK;
+}
+
+int s3d_ints_snapshot_wait(s3d_ctx *ctx, int slot, int n, int *h_out)
+{
+	S3D_REQUIRE(ctx, ctx->h_slots && h_out && n > 0 && n <= 8 && slot >= 0 && slot < 8, "bad argument");
+	// spin: a blocking driver wait costs milliseconds of wake-up latency on virtualised hosts
+	for (;;) {
+		const cudaError_t e = cudaEventQuery(ctx->slot_ev[slot]);
+		if (e == cudaSuccess) break;
+		if (e != cudaErrorNotReady) S3D_CUDA(ctx, e);
+	}
+	memcpy(h_out, ctx->h_slots + 8 * slot, n * sizeof(int));
 	return S3D_OK;
 }
 

@@ -53,12 +53,22 @@ struct DeviceLoop {
 	{
 		d.check(s3d_converge_test(ctx, rr, bb, rtol, maxiter, how, stop(), iters(), hist), "s3d_converge_test");
 	}
-	// blocks until everything enqueued so far has run; returns the stop code, fills the iteration count
-	int poll(int &iterations)
+	// Pipelined polling.  snapshot(s) enqueues an asynchronous copy of {stop, iterations} into pinned slot s;
+	// wait(s) spins until that copy has landed.  A loop snapshots after batch k, enqueues batch k+1 and only then
+	// waits for snapshot k: the GPU never idles while the host looks at the flags, and the host never sits in a
+	// blocking driver wait (measured: up to 2.8 ms of wake-up latency per poll on the virtualised GPU hosts).
+	// Batches enqueued after the stop flag rose are no-ops (the gate), so the state of snapshot k is final.
+	void snapshot(int slot) { d.check(s3d_ints_snapshot(ctx, flags, 2, slot), "s3d_ints_snapshot"); }
+	int wait(int slot, int &iterations)
 	{
 		int h[2] = {0, 0};
-		d.check(s3d_ints_download(ctx, flags, 2, h), "s3d_ints_download");
+		d.check(s3d_ints_snapshot_wait(ctx, slot, 2, h), "s3d_ints_snapshot_wait");
 		iterations = h[1];
+		return h[0];
+	}
+	// after the loop: fetch the residual history recorded on the device and print the reference's progress lines
+	void collect(int iterations)
+	{
 		const int have = std::min(iterations, hist_cap);
 		if (have > (int)history.size()) {
 			const int old = (int)history.size();
@@ -71,7 +81,6 @@ struct DeviceLoop {
 					std::printf("      Step %d: Rel res = %g\n", printed, history[printed]);
 					std::fflush(stdout);
 				}
-		return h[0];
 	}
 };
 
@@ -229,19 +238,23 @@ SolveInfo Richardson::apply(const SVec &b, SVec &x) const
 	residual();
 	loop.test(&S[2], &S[0], sparams.rtol, sparams.maxiter, S3D_CONV_INITIAL);
 	loop.gate();
-	int iterations = 0;
-	int code = loop.poll(iterations);
+	int iterations = 0, code = 0, cur = 0;
+	loop.snapshot(cur);
 	const int batch = batch_size(g, 200);
-	while (!code) {
+	for (;;) {
 		for (int i = 0; i < batch; i++) {
 			{ TimedPrec t(d); prec->apply(res, dx); }
 			d.check(s3d_vecaxpy(ctx, &g, imm(1.0), dx.dev(), x.dev_rw()), "s3d_vecaxpy");
 			residual();
 			loop.test(&S[2], &S[0], sparams.rtol, sparams.maxiter, 0);
 		}
-		code = loop.poll(iterations);
+		loop.snapshot(cur ^ 1);
+		code = loop.wait(cur, iterations);   // the state before the batch just enqueued
+		if (code) break;
+		cur ^= 1;
 	}
 	d.check(s3d_ctx_set_gate(ctx, nullptr), "s3d_ctx_set_gate");
+	loop.collect(iterations);
 	const SolveInfo info = finish(d, &S[2], &S[0], sparams.rtol, iterations, code, 0);
 	return info;
 }
@@ -277,8 +290,12 @@ SolveInfo GCR::apply(const SVec &b, SVec &x) const
 	{ const double one = 1.0; d.check(s3d_scalars_upload(ctx, &S[3], 1, &one), "s3d_scalars_upload"); }
 	loop.gate();
 
-	int iterations = 0, code = 0;
-	while (!code && iterations < sparams.maxiter) {
+	int iterations = 0, code = 0, cur = 0;
+	long steps_enqueued = 0;   // without convergence every cycle adds `north` steps: the host knows when maxiter is reached
+	loop.snapshot(cur);
+	for (;;) {
+		if (steps_enqueued >= sparams.maxiter) { code = loop.wait(cur, iterations); break; }
+		steps_enqueued += north;
 		x.exchange_halo();
 		d.check(s3d_spmv(ctx, &g, A.dev(), x.dev(), res.dev_w(), b.dev(), nullptr, 0, nullptr, nullptr, S3D_SPMV_AUTO), "s3d_spmv");
 		{ TimedPrec t(d); prec->apply(res, p[0]); }
@@ -318,9 +335,13 @@ SolveInfo GCR::apply(const SVec &b, SVec &x) const
 				d.check(s3d_vec_multi_axpy(ctx, &g, n, &BETA[base], qs, q[k + 1].dev_rw()), "s3d_vec_multi_axpy");
 			}
 		}
-		code = loop.poll(iterations);
+		loop.snapshot(cur ^ 1);
+		code = loop.wait(cur, iterations);
+		if (code) break;
+		cur ^= 1;
 	}
 	d.check(s3d_ctx_set_gate(ctx, nullptr), "s3d_ctx_set_gate");
+	loop.collect(iterations);
 	const SolveInfo info = finish(d, &S[3], &S[0], sparams.rtol, iterations, code, 0);
 	return info;
 }
@@ -364,12 +385,12 @@ SolveInfo CG::apply(const SVec &b, SVec &x) const
 	}
 	sc.allreduce(6, 1);
 
-	int iterations = 0;
-	int code = loop.poll(iterations);
+	int iterations = 0, code = 0, cur = 0;
+	loop.snapshot(cur);
 	const int batch = batch_size(g, 200);
 	long it = 0;
 	const double *rr_final = &S[5];
-	while (!code) {
+	for (;;) {
 		for (int i = 0; i < batch; i++, it++) {
 			double *cur = (it % 2 == 0) ? &S[3] : &S[5];    // this iteration's {(r,r), (r,z)}
 			double *prev = (it % 2 == 0) ? &S[5] : &S[3];   // the previous iteration's pair
@@ -390,9 +411,13 @@ SolveInfo CG::apply(const SVec &b, SVec &x) const
 				d.check(s3d_vecaxpby(ctx, &g, imm(1.0), z.dev(), ratio(1.0, &cur[1], &prev[1]), p.dev_rw()), "s3d_vecaxpby");
 			}
 		}
-		code = loop.poll(iterations);
+		loop.snapshot(cur ^ 1);
+		code = loop.wait(cur, iterations);
+		if (code) break;
+		cur ^= 1;
 	}
 	d.check(s3d_ctx_set_gate(ctx, nullptr), "s3d_ctx_set_gate");
+	loop.collect(iterations);
 	// the residual norm of the last COUNTED iteration lives in the pair that iteration wrote
 	if (iterations > 0) rr_final = ((iterations - 1) % 2 == 0) ? &S[3] : &S[5];
 	const SolveInfo info = finish(d, rr_final, &S[0], sparams.rtol, iterations, code, 0);
@@ -430,11 +455,11 @@ SolveInfo BiCGSTAB::apply(const SVec &b, SVec &x) const
 	loop.test(&S[7], &S[0], sparams.rtol, sparams.maxiter, S3D_CONV_INITIAL);
 	loop.gate();
 
-	int iterations = 0;
-	int code = loop.poll(iterations);
+	int iterations = 0, code = 0, cur = 0;
+	loop.snapshot(cur);
 	const int batch = batch_size(g, 400);
 	long it = 0;
-	while (!code) {
+	for (;;) {
 		for (int i = 0; i < batch; i++, it++) {
 			double *cur = (it % 2 == 0) ? &S[5] : &S[7];
 			double *prev = (it % 2 == 0) ? &S[7] : &S[5];
@@ -461,9 +486,13 @@ SolveInfo BiCGSTAB::apply(const SVec &b, SVec &x) const
 			sc.allreduce_at(cur, 2);
 			loop.test(&cur[0], &S[0], sparams.rtol, sparams.maxiter, 0);
 		}
-		code = loop.poll(iterations);
+		loop.snapshot(cur ^ 1);
+		code = loop.wait(cur, iterations);
+		if (code) break;
+		cur ^= 1;
 	}
 	d.check(s3d_ctx_set_gate(ctx, nullptr), "s3d_ctx_set_gate");
+	loop.collect(iterations);
 	const double *rr_final = &S[7];
 	if (iterations > 0) rr_final = ((iterations - 1) % 2 == 0) ? &S[5] : &S[7];
 	const SolveInfo info = finish(d, rr_final, &S[0], sparams.rtol, iterations, code, 0);

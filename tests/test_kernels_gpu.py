@@ -72,6 +72,23 @@ def test_spmv_apply_res_and_fused_dots(ctx, npdim, variant):
         ctx.free(p)
 
 
+@pytest.mark.parametrize("npdim,nchunks", [((20, 14, 18), 4), ((19, 23, 11), 9), ((36, 36, 36), 1), ((12, 12, 40), 0)])
+def test_spmv_host_buffers_pipelined(ctx, npdim, nchunks):
+    """SMat::apply for host vectors: chunked upload / multiply / download equals the resident path bit for bit."""
+    m, A = problem(npdim, "chebyshev", "convdiff", V1, 0.1)
+    g = grid_of(m)
+    x, b = rand_vec(m, 6), rand_vec(m, 7)
+    dA, dx, dy, db = ctx.mat_from(g, A), ctx.vec_alloc(g), ctx.vec_alloc(g), ctx.vec_from(g, b)
+    hy = np.full(m.vshape, 123.0)
+    ctx.spmv_host(g, dA, x, hy, dx, dy, nchunks=nchunks)
+    assert np.array_equal(hy, cport.apply(m, A, x))
+    hy[...] = -7.0
+    ctx.spmv_host(g, dA, x, hy, dx, dy, d_b=db, nchunks=nchunks)
+    assert np.array_equal(hy, cport.apply_res(m, A, b, x))
+    for p in (dA, dx, dy, db):
+        ctx.free(p)
+
+
 def test_spmv_stop_gate(ctx):
     m, A = problem((12, 12, 12))
     g = grid_of(m)
