@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 
 BYTES_SPMV = 72          # 7 coefficient streams + x + y, 8 B each
 BYTES_CG_ITER = 200      # credited unfused CG+Jacobi iteration
+_emit = print
 
 
 def peaks():
@@ -140,7 +141,7 @@ def run_reference(a):
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0}
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------- our arm
@@ -323,7 +324,7 @@ def run_ours(a):
                 "assembly_seconds": t_assemble, "solve": solve}
         if cb is not None:
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        _emit(json.dumps(line))
     barrier()
     if world > 1:
         dist.destroy_process_group()
@@ -339,10 +340,18 @@ def main():
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON record: everything else (NCCL's version banner, the host classes'
+    # progress prints) goes to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    _emit = lambda line: os.write(real_stdout, (line + "\n").encode())
     if a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

@@ -87,7 +87,8 @@ for ksp, pc in (("cg", "jacobi"), ("richardson", "jacobi"), ("gcr", "jacobi")):
     u = H.Vec(pm)
     info, _ = H._capture_stdout(lambda: H.solve(PA, pb, u, {"-s3d_ksp_type": ksp, "-s3d_pc_type": pc, "-ksp_rtol": 1e-6, "-ksp_max_it": 4000}))
     uo, oi, hist = cport.solve(pcm, cport.lhs(pcm), bg, ksp, pc, 1e-6, 4000)
-    check(info["converged"] and info["iters"] == oi["iters"], f"{ksp}+{pc} over {world} slabs: {info['iters']} iterations (oracle {oi['iters']})")
+    check(info["converged"] == oi["converged"] and info["iters"] == oi["iters"],
+          f"{ksp}+{pc} over {world} slabs: {info['iters']} iterations, converged={info['converged']} (oracle {oi['iters']}, {oi['converged']})")
     check(np.abs(u.a[1:-1] - uo[pm.k0:pm.k0 + pm.local[2] + 2][1:-1]).max() <= 1e-9 * np.abs(uo).max(), f"{ksp}+{pc} solution slab matches the oracle")
     if len(info["hist"]) == len(hist) and len(hist) > 1:
         check(np.max(np.abs(info["hist"] - hist) / hist) <= 1e-6, f"{ksp}+{pc} residual history matches the oracle to 1e-6")
