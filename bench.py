@@ -287,6 +287,35 @@ def run_ours(a):
                                       "ms_per_iter": dt * 1e3 / max(1, info["iters"]),
                                       "credited_gbs": BYTES_CG_ITER * N_total * info["iters"] / dt / 1e9, "moved_bytes_per_point_iter": 160}
         del s, u, b
+        # north_star's scaling target: CG+Jacobi Poisson on a FIXED 1024^3 grid (strong scaling over the z-slabs),
+        # a fixed number of iterations so that every N does the same work; the driver/judge derives the efficiency
+        if a.strong > 0 and a.strong >= world:
+            ns = a.strong
+            del y
+            ms_, _ = H._capture_stdout(lambda: H.Mesh((ns + 2, ns + 2, ns + 2)))
+            As = pde.lhs(ms_)
+            bs_, us_ = H.Vec(ms_), H.Vec(ms_)
+            nzs = ms_.local[2]
+            chunk = np.zeros((nzs + 2, ns + 2, ns + 2))
+            chunk[1:-1, 1:-1, 1:-1] = golden_field(ns * ns * nzs, (nzs, ns, ns))   # any non-eigenvector field will do for timing
+            bs_.set(chunk)
+            del chunk
+            its = a.strong_iters
+            H.set_options({"-s3d_ksp_type": "cg", "-s3d_pc_type": "jacobi", "-ksp_rtol": 1e-300, "-ksp_max_it": its})
+            (ss, _) = H._capture_stdout(lambda: H.Solver(As))
+            ss.update()
+            H._capture_stdout(lambda: ss.apply(bs_, us_))       # warm-up solve
+            H.vecset(0.0, us_)
+            barrier()
+            t0 = time.perf_counter()
+            infos, _ = H._capture_stdout(lambda: ss.apply(bs_, us_))
+            H.sync()
+            dts = max_over_ranks(time.perf_counter() - t0)
+            solve["cg_jacobi_poisson_strong"] = {"grid_total": f"{ns}^3", "grid_per_gpu": f"{ns}x{ns}x{nzs}", "iters": infos["iters"], "seconds": dts,
+                                                 "ms_per_iter": dts * 1e3 / max(1, infos["iters"]), "scaling": "strong",
+                                                 "credited_gbs": BYTES_CG_ITER * float(ns) ** 3 * infos["iters"] / dts / 1e9,
+                                                 "note": "fixed iteration count (rtol disabled) so every GPU count does identical work"}
+            del ss, us_, bs_, As
         if world == 1 and n >= 256:
             m2, _ = H._capture_stdout(lambda: H.Mesh((258, 258, 258)))
             p2, _ = H._capture_stdout(lambda: H.Pde("convdiff", (0.577350269189626, 0.7, 0.3), 0.1))
@@ -337,6 +366,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=512, help="unknowns per axis (per GPU along z)")
+    ap.add_argument("--strong", type=int, default=1024, help="grid size of the strong-scaling CG block (0 disables)")
+    ap.add_argument("--strong-iters", type=int, default=40)
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
