@@ -99,7 +99,7 @@ int  s3d_timer_stop_ms(s3d_ctx *ctx, double *ms);
 
 /* kernel tuning knobs for sweeps: "spmv_kchunk" (planes per march, 0 = automatic), "spmv_minb" (resident blocks per
  * SM the march kernel is compiled for: 0 auto, 3, 4, 6), "spmv_hints" (evict-first hints on/off for the PAIR/NAIVE
- * variants), "spmv_variant" (what S3D_SPMV_AUTO resolves to) */
+ * variants), "spmv_variant" (what S3D_SPMV_AUTO resolves to), "halo_overlap" (0 = exchange first, then multiply) */
 int  s3d_tune_set(s3d_ctx *ctx, const char *key, int value);
 
 /* Replaces the size arithmetic of SVec::SVec / SMat::SMat (matvec.cpp:8-57).  nz is the local slab. */
@@ -140,6 +140,12 @@ int  s3d_host_free(s3d_ctx *ctx, void *h_ptr);
  * In a z-slab decomposition the caller must have exchanged x's halo planes first (s3d_halo_exchange). */
 int  s3d_spmv(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_x, double *d_y,
               const double *d_b, const double *d_w, int want_yy, double *d_red, const int *d_stop, int variant);
+
+/* SMat::apply / apply_res on a z-slab in ONE call: the one-plane halo exchange of x (NCCL, on a second stream) overlapped with
+ * the multiply of the interior planes; the two boundary planes follow once the halos have landed; fused reductions as in s3d_spmv.
+ * Writes the ghost planes of d_x.  One rank: identical to s3d_spmv. */
+int  s3d_spmv_exchange(s3d_ctx *ctx, const s3d_grid *g, const double *A, double *d_x, double *d_y, const double *d_b,
+                       const double *d_w, int want_yy, double *d_red, const int *d_stop);
 
 /* SMat::apply / apply_res for HOST vectors (the reference's SVec lives in host memory): y = A x, or b - A x with a device-resident
  * d_b.  Pipelined in nchunks z-chunks (<= 0: 16) over three streams, so the upload of x, the kernel and the download of y overlap and

@@ -47,6 +47,7 @@ _SIGS = {
     "s3d_scalars_download": [_P, _vp, _I, _vp], "s3d_scalars_upload": [_P, _vp, _I, _vp],
     "s3d_host_alloc": [_P, C.c_size_t, C.POINTER(_vp)], "s3d_host_free": [_P, _vp],
     "s3d_spmv": [_P, _G, _vp, _vp, _vp, _vp, _vp, _I, _vp, _vp, _I],
+    "s3d_spmv_exchange": [_P, _G, _vp, _vp, _vp, _vp, _vp, _I, _vp, _vp],
     "s3d_spmv_host": [_P, _G, _vp, _vp, _vp, _vp, _vp, _vp, _I],
     "s3d_vecset": [_P, _G, _D, _vp], "s3d_vecassign": [_P, _G, _vp, _vp], "s3d_veccopy_all": [_P, _G, _vp, _vp],
     "s3d_vecaxpy": [_P, _G, Scalar, _vp, _vp], "s3d_vecaxpby": [_P, _G, Scalar, _vp, Scalar, _vp],

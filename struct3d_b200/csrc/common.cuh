@@ -36,6 +36,12 @@ struct s3d_ctx {
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	// pipelined host-buffer SpMV: copy streams and per-chunk events
 	cudaStream_t up_stream = nullptr, down_stream = nullptr;
+	// split SpMV launches that share one reduction (overlapped halo exchange): partials are appended, summed once at the end
+	bool no_overlap = false;
+	bool red_defer = false;
+	size_t red_blocks = 0;
+	cudaStream_t comm_stream = nullptr;   // NCCL halo traffic, concurrent with the interior SpMV
+	cudaEvent_t comm_ev[2] = {};
 	double *stage = nullptr;       // device staging for contiguous host uploads (repacked into the padded layout on the device)
 	size_t stage_cap = 0;
 	int *h_slots = nullptr;        // 8 pinned slots of 8 ints for pipelined flag polling

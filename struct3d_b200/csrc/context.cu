@@ -147,6 +147,7 @@ int s3d_ctx_destroy(s3d_ctx *ctx)
 	cudaFreeHost(ctx->h_pinned);
 	if (ctx->h_slots) { cudaFreeHost(ctx->h_slots); for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->slot_ev[i]); }
 	cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+	if (ctx->comm_stream) { cudaStreamDestroy(ctx->comm_stream); cudaEventDestroy(ctx->comm_ev[0]); cudaEventDestroy(ctx->comm_ev[1]); }
 	if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
 	if (ctx->down_stream) cudaStreamDestroy(ctx->down_stream);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

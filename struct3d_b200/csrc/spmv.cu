@@ -218,11 +218,13 @@ int launch_march(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double 
 	dim3 block(32, BY);
 	dim3 grid((g->nx + 63) / 64, (g->ny + BY - 1) / BY, (g->nz + kchunk - 1) / kchunk);
 	const bool red = (w != nullptr) || yy;
+	const size_t nblk = (size_t)grid.x * grid.y * grid.z;
+	const size_t first = ctx->red_defer ? ctx->red_blocks : 0;   // deferred mode: append behind earlier launches' partials
 	if (red) {
-		const int rc = s3d_ensure_partials(ctx, (size_t)grid.x * grid.y * grid.z * 2);
+		const int rc = s3d_ensure_partials(ctx, (first + nblk) * 2 + 256);   // + room for s3d_final_reduce's second level
 		if (rc != S3D_OK) return rc;
 	}
-	RedOut ro{ctx->partials, nullptr, d_red};
+	RedOut ro{ctx->partials + first * 2, nullptr, d_red};
 #define GO(RES, DW, DY) spmv_march_kernel<BY, MINB, RES, DW, DY><<<grid, block, 0, ctx->stream>>>(gd, A, x, y, b, w, ro, stop, kchunk)
 	const int sel = (b ? 4 : 0) | (w ? 2 : 0) | (yy ? 1 : 0);
 	switch (sel) {
@@ -237,7 +239,8 @@ int launch_march(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double 
 	}
 #undef GO
 	S3D_LAUNCHED(ctx);
-	if (red) return s3d_final_reduce(ctx, 2, grid.x * grid.y * grid.z, d_red);
+	if (red && ctx->red_defer) { ctx->red_blocks += nblk; return S3D_OK; }
+	if (red) return s3d_final_reduce(ctx, 2, (unsigned)nblk, d_red);
 	return S3D_OK;
 }
 
@@ -248,11 +251,13 @@ int launch_naive(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double 
 	dim3 block(64, 4);
 	dim3 grid((g->nx + 63) / 64, (g->ny + 3) / 4, g->nz);
 	const bool red = (w != nullptr) || yy;
+	const size_t nblk = (size_t)grid.x * grid.y * grid.z;
+	const size_t first = ctx->red_defer ? ctx->red_blocks : 0;   // deferred mode: append behind earlier launches' partials
 	if (red) {
-		const int rc = s3d_ensure_partials(ctx, (size_t)grid.x * grid.y * grid.z * 2);
+		const int rc = s3d_ensure_partials(ctx, (first + nblk) * 2 + 256);   // + room for s3d_final_reduce's second level
 		if (rc != S3D_OK) return rc;
 	}
-	RedOut ro{ctx->partials, nullptr, d_red};   // very many blocks: partials only, summed by s3d_final_reduce
+	RedOut ro{ctx->partials + first * 2, nullptr, d_red};   // very many blocks: partials only, summed by s3d_final_reduce
 #define GO(RES, DW, DY) spmv_naive_kernel<RES, DW, DY><<<grid, block, 0, ctx->stream>>>(gd, A, x, y, b, w, ro, stop, g_tune.hints)
 	const int sel = (b ? 4 : 0) | (w ? 2 : 0) | (yy ? 1 : 0);
 	switch (sel) {
@@ -267,7 +272,8 @@ int launch_naive(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double 
 	}
 #undef GO
 	S3D_LAUNCHED(ctx);
-	if (red) return s3d_final_reduce(ctx, 2, grid.x * grid.y * grid.z, d_red);
+	if (red && ctx->red_defer) { ctx->red_blocks += nblk; return S3D_OK; }
+	if (red) return s3d_final_reduce(ctx, 2, (unsigned)nblk, d_red);
 	return S3D_OK;
 }
 
@@ -280,7 +286,7 @@ int launch_pair(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *
 	dim3 grid((g->nx + 63) / 64, (g->ny + 7) / 8, g->nz);
 	const bool red = (w != nullptr) || yy;
 	if (red) {
-		const int rc = s3d_ensure_partials(ctx, (size_t)grid.x * grid.y * grid.z * 2);
+		const int rc = s3d_ensure_partials(ctx, (size_t)grid.x * grid.y * grid.z * 2 + 256);   // + room for s3d_final_reduce's second level
 		if (rc != S3D_OK) return rc;
 	}
 	RedOut ro{ctx->partials, nullptr, d_red};   // very many blocks: partials only, summed by s3d_final_reduce
@@ -329,6 +335,7 @@ int s3d_tune_set(s3d_ctx *ctx, const char *key, int value)
 	} else if (!strcmp(key, "spmv_kchunk")) g_tune.kchunk = value;
 	else if (!strcmp(key, "spmv_hints")) g_tune.hints = value;
 	else if (!strcmp(key, "sgs_sleep_ns")) ctx->sgs_sleep_ns = value;
+	else if (!strcmp(key, "halo_overlap")) ctx->no_overlap = (value == 0);
 	else if (!strcmp(key, "spmv_variant")) {
 		S3D_REQUIRE(ctx, value >= S3D_SPMV_MARCH && value <= S3D_SPMV_PAIR, "unknown SpMV variant");
 		g_tune.variant = value;
@@ -365,6 +372,59 @@ int s3d_spmv(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_x
 	default:
 		return s3d_fail(ctx, S3D_ERR_ARG, "unknown SpMV variant %d", variant);
 	}
+}
+
+// SMat::apply / apply_res on a z-slab: the halo exchange and the multiply in one call, overlapped.
+//   comm stream : NCCL send/recv of the two boundary planes of x (starts when x is ready on the compute stream)
+//   compute     : the interior planes [1, nz-1), which need no halo, run meanwhile; then, once the halos have landed,
+//                 the two boundary planes.  The fused reductions of the three launches share one final sum.
+// One rank (or a slab too thin to split): plain s3d_spmv.  Only the MARCH variant is split.
+int s3d_spmv_exchange(s3d_ctx *ctx, const s3d_grid *g, const double *A, double *d_x, double *d_y, const double *d_b,
+                      const double *d_w, int want_yy, double *d_red, const int *d_stop)
+{
+	S3D_REQUIRE(ctx, g && A && d_x && d_y, "null argument");
+	if (g->nranks == 1) return s3d_spmv(ctx, g, A, d_x, d_y, d_b, d_w, want_yy, d_red, d_stop, S3D_SPMV_AUTO);
+	if (g->nz < 3 || g_tune.variant != S3D_SPMV_MARCH || ctx->no_overlap) {
+		const int rc = s3d_halo_exchange(ctx, g, d_x);
+		if (rc != S3D_OK) return rc;
+		return s3d_spmv(ctx, g, A, d_x, d_y, d_b, d_w, want_yy, d_red, d_stop, S3D_SPMV_AUTO);
+	}
+	if (!ctx->comm_stream) {
+		S3D_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+		S3D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->comm_ev[0], cudaEventDisableTiming));
+		S3D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->comm_ev[1], cudaEventDisableTiming));
+	}
+	// 1. halo exchange on the comm stream, after everything already enqueued on the compute stream (x is final there)
+	S3D_CUDA(ctx, cudaEventRecord(ctx->comm_ev[0], ctx->stream));
+	S3D_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->comm_ev[0], 0));
+	cudaStream_t compute = ctx->stream;
+	ctx->stream = ctx->comm_stream;
+	int rc = s3d_halo_exchange(ctx, g, d_x);
+	ctx->stream = compute;
+	if (rc != S3D_OK) return rc;
+	S3D_CUDA(ctx, cudaEventRecord(ctx->comm_ev[1], ctx->comm_stream));
+	// 2. interior planes meanwhile; 3. boundary planes after the halos
+	const bool red = (d_w != nullptr) || want_yy;
+	ctx->red_defer = red;
+	ctx->red_blocks = 0;
+	auto part = [&](int k0, int nzp) -> int {
+		s3d_grid sub = *g;
+		sub.nz = nzp;
+		const size_t vo = (size_t)k0 * g->vplane, co = (size_t)k0 * g->cplane;
+		return s3d_spmv(ctx, &sub, A + co, d_x + vo, d_y + vo, d_b ? d_b + vo : nullptr, d_w ? d_w + vo : nullptr, want_yy, d_red, d_stop,
+		                S3D_SPMV_MARCH);
+	};
+	rc = part(1, g->nz - 2);
+	if (rc == S3D_OK) {
+		cudaError_t e = cudaStreamWaitEvent(ctx->stream, ctx->comm_ev[1], 0);
+		if (e != cudaSuccess) { ctx->red_defer = false; S3D_CUDA(ctx, e); }
+		rc = part(0, 1);
+	}
+	if (rc == S3D_OK) rc = part(g->nz - 1, 1);
+	ctx->red_defer = false;
+	if (rc != S3D_OK) return rc;
+	if (red) return s3d_final_reduce(ctx, 2, (unsigned)ctx->red_blocks, d_red);
+	return S3D_OK;
 }
 
 // y = A x (or b - A x with a device-resident b) for HOST vectors, pipelined in z-chunks: chunk c+1 of x is on its way up

@@ -34,6 +34,8 @@ struct SVec
 	const double *dev() const { vals.device_will_read(); return d_; }
 	double *dev_rw() { vals.device_will_read(); vals.device_wrote(); return d_; }
 	double *dev_w() { vals.device_will_read(); vals.device_wrote(); return d_; }
+	/// device pointer for a kernel that reads the vector AND refreshes its z-ghost planes (halo exchange)
+	double *dev_halo() const { vals.device_will_read(); if (s3d::Device::get().nranks() > 1) vals.device_wrote(); return d_; }
 	const s3d_grid &grid() const { return m->device_grid(); }
 	/// make ghost planes k=-1 / k=nz current with the z-neighbours' data (no-op on one rank)
 	void exchange_halo() const;

@@ -45,6 +45,11 @@ protected:
 	const SMat &A;
 	SolverBase *const prec;
 	mutable std::vector<sreal> history;
+	/// Work vectors of apply(), allocated on first use and kept for the life of the solver (the reference
+	/// allocates them inside every apply(); on the GPU a cudaMalloc/cudaFree pair per vector per solve costs
+	/// far more than the solve's first iterations).  Consequence: apply() is not re-entrant per object.
+	SVec &work(size_t i) const;
+	mutable std::vector<SVec *> workspace;
 };
 
 /// Identity: copies b into x, ghosts included.

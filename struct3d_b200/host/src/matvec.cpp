@@ -140,8 +140,7 @@ void SMat::apply(const SVec &x, SVec &y) const
 	if (x.m != y.m) throw std::runtime_error("Both vectors should be defined over the same mesh!");
 	assert(x.nghost == 1);
 	const Device &d = Device::get();
-	x.exchange_halo();
-	d.check(s3d_spmv(d.ctx(), &grid(), dev(), x.dev(), y.dev_w(), nullptr, nullptr, 0, nullptr, nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+	d.check(s3d_spmv_exchange(d.ctx(), &grid(), dev(), x.dev_halo(), y.dev_w(), nullptr, nullptr, 0, nullptr, nullptr), "s3d_spmv_exchange");
 }
 
 void SMat::apply_res(const SVec &b, const SVec &x, SVec &y) const
@@ -150,8 +149,7 @@ void SMat::apply_res(const SVec &b, const SVec &x, SVec &y) const
 		throw std::runtime_error("All vectors and matrix should be defined over the same mesh!");
 	assert(x.nghost == 1);
 	const Device &d = Device::get();
-	x.exchange_halo();
-	d.check(s3d_spmv(d.ctx(), &grid(), dev(), x.dev(), y.dev_w(), b.dev(), nullptr, 0, nullptr, nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+	d.check(s3d_spmv_exchange(d.ctx(), &grid(), dev(), x.dev_halo(), y.dev_w(), b.dev(), nullptr, 0, nullptr, nullptr), "s3d_spmv_exchange");
 }
 
 // ------------------------------------------------------------------ free functions

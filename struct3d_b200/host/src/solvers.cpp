@@ -144,7 +144,18 @@ struct TimedPrec {   // brackets a preconditioner application with the GPU stopw
 
 SolverBase::SolverBase(const SMat &lhs, SolverBase *const precond) : A(lhs), prec{precond} {}
 
-SolverBase::~SolverBase() { delete prec; }
+SolverBase::~SolverBase()
+{
+	for (SVec *w : workspace) delete w;
+	delete prec;
+}
+
+SVec &SolverBase::work(size_t i) const
+{
+	if (workspace.size() <= i) workspace.resize(i + 1, nullptr);
+	if (!workspace[i]) workspace[i] = new SVec(A.m);   // zero-filled, ghosts included; every use overwrites the real points
+	return *workspace[i];
+}
 
 NoSolver::NoSolver(const SMat &lhs, SolverBase *const) : SolverBase(lhs, nullptr) {}
 
@@ -223,7 +234,7 @@ SolveInfo Richardson::apply(const SVec &b, SVec &x) const
 	const Device &d = Device::get();
 	s3d_ctx *ctx = d.ctx();
 	const s3d_grid &g = A.grid();
-	SVec res(A.m), dx(A.m);
+	SVec &res = work(0), &dx = work(1);
 	Scalars sc(d, 4);   // [0] (b,b)  [1] unused  [2] (r,r)
 	double *S = sc.S;
 	DeviceLoop loop(sparams.maxiter + 1, 10, history);
@@ -231,8 +242,7 @@ SolveInfo Richardson::apply(const SVec &b, SVec &x) const
 	d.check(s3d_nrm2sq(ctx, &g, b.dev(), sc.loc(0)), "s3d_nrm2sq");
 	sc.allreduce(0, 1);
 	auto residual = [&]() {
-		x.exchange_halo();
-		d.check(s3d_spmv(ctx, &g, A.dev(), x.dev(), res.dev_w(), b.dev(), nullptr, 1, sc.loc(1), nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+		d.check(s3d_spmv_exchange(ctx, &g, A.dev(), x.dev_halo(), res.dev_w(), b.dev(), nullptr, 1, sc.loc(1), nullptr), "s3d_spmv_exchange");
 		sc.allreduce(2, 1);
 	};
 	residual();
@@ -272,9 +282,10 @@ SolveInfo GCR::apply(const SVec &b, SVec &x) const
 	s3d_ctx *ctx = d.ctx();
 	const s3d_grid &g = A.grid();
 	const int north = std::max(1, sparams.restart);
-	SVec res(A.m), z(A.m);
-	std::vector<SVec> p(north), q(north);
-	for (int i = 0; i < north; i++) { p[i].init(A.m); q[i].init(A.m); }
+	SVec &res = work(0), &z = work(1);
+	std::vector<SVec *> pp(north), qq(north);
+	for (int i = 0; i < north; i++) { pp[i] = &work(2 + 2 * i); qq[i] = &work(3 + 2 * i); }
+	struct Ref { std::vector<SVec *> &v; SVec &operator[](int i) const { return *v[i]; } } p{pp}, q{qq};
 
 	// scalars: [0] (b,b)  [1..2] spmv reductions  [3] (res,res)  [4..5] (res,q_k),(q_k,q_k)
 	//          QQ[i] = (q_i,q_i) cached (the reference recomputes the identical value)   DOT[i] = (q_new,q_i)   BETA[i]
@@ -296,11 +307,9 @@ SolveInfo GCR::apply(const SVec &b, SVec &x) const
 	for (;;) {
 		if (steps_enqueued >= sparams.maxiter) { code = loop.wait(cur, iterations); break; }
 		steps_enqueued += north;
-		x.exchange_halo();
-		d.check(s3d_spmv(ctx, &g, A.dev(), x.dev(), res.dev_w(), b.dev(), nullptr, 0, nullptr, nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+		d.check(s3d_spmv_exchange(ctx, &g, A.dev(), x.dev_halo(), res.dev_w(), b.dev(), nullptr, 0, nullptr, nullptr), "s3d_spmv_exchange");
 		{ TimedPrec t(d); prec->apply(res, p[0]); }
-		p[0].exchange_halo();
-		d.check(s3d_spmv(ctx, &g, A.dev(), p[0].dev(), q[0].dev_w(), nullptr, nullptr, 0, nullptr, nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+		d.check(s3d_spmv_exchange(ctx, &g, A.dev(), p[0].dev_halo(), q[0].dev_w(), nullptr, nullptr, 0, nullptr, nullptr), "s3d_spmv_exchange");
 		for (int k = 0; k < north; k++) {
 			// alpha = (res,q_k)/(q_k,q_k): one pass over q_k
 			const double *two[2] = {res.dev(), q[k].dev()};
@@ -315,8 +324,7 @@ SolveInfo GCR::apply(const SVec &b, SVec &x) const
 			// keep (q_k,q_k) for the Gram-Schmidt coefficients of later directions
 			d.check(s3d_scalar_op(ctx, 3, &QQ[k], &S[5], &S[5], nullptr, nullptr, 1, 1.0, nullptr), "s3d_scalar_op");
 			{ TimedPrec t(d); prec->apply(res, z); }
-			z.exchange_halo();
-			d.check(s3d_spmv(ctx, &g, A.dev(), z.dev(), q[k + 1].dev_w(), nullptr, nullptr, 0, nullptr, nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+			d.check(s3d_spmv_exchange(ctx, &g, A.dev(), z.dev_halo(), q[k + 1].dev_w(), nullptr, nullptr, 0, nullptr, nullptr), "s3d_spmv_exchange");
 			d.check(s3d_vecassign(ctx, &g, z.dev(), p[k + 1].dev_rw()), "s3d_vecassign");
 			// beta_i = -(q_new,q_i)/(q_i,q_i), i <= k, then p_new += sum beta_i p_i, q_new += sum beta_i q_i
 			for (int base = 0; base <= k; base += 32) {
@@ -359,9 +367,8 @@ SolveInfo CG::apply(const SVec &b, SVec &x) const
 	s3d_ctx *ctx = d.ctx();
 	const s3d_grid &g = A.grid();
 	const bool jacobi = dynamic_cast<const JacobiPreconditioner *>(prec) != nullptr;
-	SVec r(A.m), p(A.m), q(A.m);
-	SVec z;
-	if (!jacobi) z.init(A.m);
+	SVec &r = work(0), &p = work(1), &q = work(2);
+	SVec &z = jacobi ? work(0) : work(3);   // unused with Jacobi (folded into the kernels)
 	// scalars: [0] (b,b)  [1..2] SpMV reductions: (p,Ap), -  [3,4] and [5,6]: ping-pong pairs {(r,r), (r,z)}
 	Scalars sc(d, 8);
 	double *S = sc.S;
@@ -369,8 +376,7 @@ SolveInfo CG::apply(const SVec &b, SVec &x) const
 
 	d.check(s3d_nrm2sq(ctx, &g, b.dev(), sc.loc(0)), "s3d_nrm2sq");
 	sc.allreduce(0, 1);
-	x.exchange_halo();
-	d.check(s3d_spmv(ctx, &g, A.dev(), x.dev(), r.dev_w(), b.dev(), nullptr, 1, sc.loc(4), nullptr, S3D_SPMV_AUTO), "s3d_spmv");   // (r,r) -> S[5]
+	d.check(s3d_spmv_exchange(ctx, &g, A.dev(), x.dev_halo(), r.dev_w(), b.dev(), nullptr, 1, sc.loc(4), nullptr), "s3d_spmv_exchange");   // (r,r) -> S[5]
 	sc.allreduce(5, 1);
 	loop.test(&S[5], &S[0], sparams.rtol, sparams.maxiter, S3D_CONV_INITIAL);
 	loop.gate();
@@ -394,8 +400,7 @@ SolveInfo CG::apply(const SVec &b, SVec &x) const
 		for (int i = 0; i < batch; i++, it++) {
 			double *cur = (it % 2 == 0) ? &S[3] : &S[5];    // this iteration's {(r,r), (r,z)}
 			double *prev = (it % 2 == 0) ? &S[5] : &S[3];   // the previous iteration's pair
-			p.exchange_halo();
-			d.check(s3d_spmv(ctx, &g, A.dev(), p.dev(), q.dev_w(), nullptr, p.dev(), 0, sc.loc(1), nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+			d.check(s3d_spmv_exchange(ctx, &g, A.dev(), p.dev_halo(), q.dev_w(), nullptr, p.dev(), 0, sc.loc(1), nullptr), "s3d_spmv_exchange");
 			sc.allreduce(1, 1);
 			// x += alpha p, r -= alpha q, alpha = (r,z)/(p,Ap); fused (r,r) [and (r, r/diag)]
 			d.check(s3d_cg_update(ctx, &g, ratio(1.0, &prev[1], &S[1]), p.dev(), q.dev(), x.dev_rw(), r.dev_rw(),
@@ -436,7 +441,7 @@ SolveInfo BiCGSTAB::apply(const SVec &b, SVec &x) const
 	const Device &d = Device::get();
 	s3d_ctx *ctx = d.ctx();
 	const s3d_grid &g = A.grid();
-	SVec r(A.m), rhat(A.m), p(A.m), v(A.m), s(A.m), t(A.m), ph(A.m), sh(A.m);
+	SVec &r = work(0), &rhat = work(1), &p = work(2), &v = work(3), &s = work(4), &t = work(5), &ph = work(6), &sh = work(7);
 	// scalars: [0] (b,b)  [1,2] (rhat,v),-  [3,4] (t,s),(t,t)  [5,6] / [7,8] ping-pong {(r,r), (rhat,r)}
 	//          [9] alpha  [10] omega  [11] beta
 	Scalars sc(d, 12);
@@ -445,8 +450,7 @@ SolveInfo BiCGSTAB::apply(const SVec &b, SVec &x) const
 
 	d.check(s3d_nrm2sq(ctx, &g, b.dev(), sc.loc(0)), "s3d_nrm2sq");
 	sc.allreduce(0, 1);
-	x.exchange_halo();
-	d.check(s3d_spmv(ctx, &g, A.dev(), x.dev(), r.dev_w(), b.dev(), nullptr, 1, sc.loc(6), nullptr, S3D_SPMV_AUTO), "s3d_spmv");   // (r,r) -> S[7]
+	d.check(s3d_spmv_exchange(ctx, &g, A.dev(), x.dev_halo(), r.dev_w(), b.dev(), nullptr, 1, sc.loc(6), nullptr), "s3d_spmv_exchange");   // (r,r) -> S[7]
 	sc.allreduce(7, 1);
 	d.check(s3d_vecassign(ctx, &g, r.dev(), rhat.dev_rw()), "s3d_vecassign");
 	// rho_0 = (rhat, r) = (r,r): place it where iteration 0 expects "the previous pair's (rhat,r)" = S[8]
@@ -471,14 +475,12 @@ SolveInfo BiCGSTAB::apply(const SVec &b, SVec &x) const
 				d.check(s3d_bicg_direction(ctx, &g, ratio(1.0, &S[11], nullptr), ratio(1.0, &S[10], nullptr), r.dev(), v.dev(), p.dev_rw(), nullptr), "s3d_bicg_direction");
 			}
 			{ TimedPrec tp(d); prec->apply(p, ph); }
-			ph.exchange_halo();
-			d.check(s3d_spmv(ctx, &g, A.dev(), ph.dev(), v.dev_w(), nullptr, rhat.dev(), 0, sc.loc(1), nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+			d.check(s3d_spmv_exchange(ctx, &g, A.dev(), ph.dev_halo(), v.dev_w(), nullptr, rhat.dev(), 0, sc.loc(1), nullptr), "s3d_spmv_exchange");
 			sc.allreduce(1, 1);
 			d.check(s3d_scalar_op(ctx, 2, &S[9], &prev[1], &S[1], nullptr, nullptr, 1, 1.0, loop.stop()), "s3d_scalar_op");   // alpha = rho/(rhat,v)
 			d.check(s3d_vecwaxpby(ctx, &g, imm(1.0), r.dev(), ratio(-1.0, &S[9], nullptr), v.dev(), s.dev_rw(), nullptr), "s3d_vecwaxpby");
 			{ TimedPrec tp(d); prec->apply(s, sh); }
-			sh.exchange_halo();
-			d.check(s3d_spmv(ctx, &g, A.dev(), sh.dev(), t.dev_w(), nullptr, s.dev(), 1, sc.loc(3), nullptr, S3D_SPMV_AUTO), "s3d_spmv");
+			d.check(s3d_spmv_exchange(ctx, &g, A.dev(), sh.dev_halo(), t.dev_w(), nullptr, s.dev(), 1, sc.loc(3), nullptr), "s3d_spmv_exchange");
 			sc.allreduce(3, 2);
 			d.check(s3d_scalar_op(ctx, 2, &S[10], &S[3], &S[4], nullptr, nullptr, 1, 1.0, loop.stop()), "s3d_scalar_op");    // omega = (t,s)/(t,t)
 			d.check(s3d_bicg_update(ctx, &g, ratio(1.0, &S[9], nullptr), ph.dev(), ratio(1.0, &S[10], nullptr), sh.dev(), s.dev(), t.dev(),
