@@ -166,6 +166,7 @@ def run_ours(a):
     hostapi.init(local, rank, world, nccl_id)
     ctx = capi.Context.from_handle(hostapi.cuda_ctx())
     H = hostapi
+    ctx.tune("halo_overlap", a.halo_overlap)
 
     def barrier():
         H.sync()
@@ -373,6 +374,7 @@ def main():
     ap.add_argument("--size", type=int, default=512, help="unknowns per axis (per GPU along z)")
     ap.add_argument("--strong", type=int, default=1024, help="grid size of the strong-scaling CG block (0 disables)")
     ap.add_argument("--strong-iters", type=int, default=40)
+    ap.add_argument("--halo-overlap", type=int, default=0, help="0: exchange halos first, then multiply (A/B switch)")
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()

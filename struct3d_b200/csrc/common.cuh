@@ -37,7 +37,7 @@ struct s3d_ctx {
 	// pipelined host-buffer SpMV: copy streams and per-chunk events
 	cudaStream_t up_stream = nullptr, down_stream = nullptr;
 	// split SpMV launches that share one reduction (overlapped halo exchange): partials are appended, summed once at the end
-	bool no_overlap = false;
+	bool no_overlap = true;        // measured on 2 and 8 B200s: overlapping the NCCL halo exchange with the interior SpMV gains nothing (r1), so it is opt-in
 	bool red_defer = false;
 	size_t red_blocks = 0;
 	cudaStream_t comm_stream = nullptr;   // NCCL halo traffic, concurrent with the interior SpMV

@@ -405,6 +405,13 @@ int s3d_spmv_exchange(s3d_ctx *ctx, const s3d_grid *g, const double *A, double *
 	S3D_CUDA(ctx, cudaEventRecord(ctx->comm_ev[1], ctx->comm_stream));
 	// 2. interior planes meanwhile; 3. boundary planes after the halos
 	const bool red = (d_w != nullptr) || want_yy;
+	if (red) {
+		// size the partials buffer for all three launches up front: a reallocation between them would lose partials
+		const int kc = pick_kchunk(ctx, g, true);
+		const size_t tiles = (size_t)((g->nx + 63) / 64) * ((g->ny + 7) / 8);
+		rc = s3d_ensure_partials(ctx, tiles * ((g->nz + kc - 1) / kc + 3) * 2 + 256);
+		if (rc != S3D_OK) return rc;
+	}
 	ctx->red_defer = red;
 	ctx->red_blocks = 0;
 	auto part = [&](int k0, int nzp) -> int {
