@@ -191,6 +191,9 @@ int  s3d_jacobi_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const do
 
 /* SGS_preconditioner::updateOperator (s3d_sgspreconditioners.cpp:122-135): dinv = 1/diag, matrix-compact layout (cstride doubles) */
 int  s3d_sgs_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, double *d_dinv);
+/* StrILU_preconditioner::updateOperator, sequential build (s3d_ilu.cpp:17-64): dinv = 1 / (ILU(0) diagonal); use with s3d_sgs_apply.
+ * nbuildsweeps > 1 is idempotent for the sequential build and is treated as 1; 0 gives 1/diag.  Single GPU. */
+int  s3d_strilu_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuildsweeps, double *d_dinv);
 #define S3D_SGS_LEXICOGRAPHIC 0  /* the reference's ordering, executed as a tile-level dataflow wavefront: same arithmetic */
 #define S3D_SGS_LEXICOGRAPHIC_PLANES 2  /* same result, one launch per hyperplane i+j+k (slow; kept for cross-checks) */
 #define S3D_SGS_REDBLACK      1  /* two-colour ordering: four fully parallel half-sweeps (changes the iteration) */

@@ -111,12 +111,17 @@ struct SgsFlow {
 // busy for 32 of the 46 steps.
 constexpr int SGS_NT = SGS_TJ * SGS_TK;   // 64 threads
 
-template <bool FWD>
+// MODE 0: forward SGS sweep, 1: backward SGS sweep, 2: StrILU diagonal recurrence (forward order)
+//   d = ((A3 - P0/d[i-1]) - P1/d[j-1]) - P2/d[k-1]   with P0 = A0*A4[i-1] etc. precomputed (zero where there is no neighbour),
+//   reference: StrILU_preconditioner::updateOperatorWithBranchingInLoop, src/linalg/s3d_ilu.cpp:34-57.
+template <int MODE>
 __global__ void __launch_bounds__(SGS_NT)
 sgs_dataflow_kernel(const GridDev g, const double *__restrict__ in0, const double *__restrict__ c0,
                     const double *__restrict__ c1, const double *__restrict__ c2, const double *__restrict__ dinv,
                     double *out, const SgsFlow f, const int *stop)
 {
+	constexpr bool FWD = (MODE != 1);
+	constexpr bool ILU = (MODE == 2);
 	if (s3d_stopped(stop)) return;
 	extern __shared__ __align__(16) double smem[];
 	double *s_in = smem;                       // [TK][TJ][TI] each; s_in is overwritten with the results
@@ -155,11 +160,11 @@ sgs_dataflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 				const long long cv = ctile + (long long)rk * g.cplane + (long long)rj * g.cpitch + 2 * i2;
 				const long long vv = vtile + (long long)rk * g.vplane + (long long)rj * g.vpitch + 2 * i2;
 				const int so = (rk * SGS_TJ + rj) * SGS_TI + 2 * i2;
-				cp_async16(s_in + so, in0 + vv);
+				cp_async16(s_in + so, in0 + (ILU ? cv : vv));   // the ILU recurrence starts from the diagonal (coefficient layout)
 				cp_async16(s_c0 + so, c0 + cv);
 				cp_async16(s_c1 + so, c1 + cv);
 				cp_async16(s_c2 + so, c2 + cv);
-				cp_async16(s_dv + so, dinv + cv);
+				if (!ILU) cp_async16(s_dv + so, dinv + cv);
 			}
 		}
 		// wait for the three predecessor tiles (the loads above do not depend on them)
@@ -212,7 +217,11 @@ sgs_dataflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 				const double wk = (cc == 0) ? s_hk[lj * SGS_TI + li] : prev[wslot + dn * WP];
 				const int so = rowbase + li;
 				double val;
-				if (FWD) {
+				if (ILU) {
+					double t = __dsub_rn(s_in[so], __ddiv_rn(s_c0[so], wi));
+					t = __dsub_rn(t, __ddiv_rn(s_c1[so], wj));
+					val = __dsub_rn(t, __ddiv_rn(s_c2[so], wk));
+				} else if (FWD) {
 					double t = __dsub_rn(s_in[so], __dmul_rn(s_c0[so], wi));
 					t = __dsub_rn(t, __dmul_rn(s_c1[so], wj));
 					t = __dsub_rn(t, __dmul_rn(s_c2[so], wk));
@@ -301,6 +310,39 @@ sgs_rb_kernel(const GridDev g, int k0, const double *__restrict__ A, const doubl
 	}
 }
 
+// StrILU helpers.  products: P_s[c] = A_s[c] * A_{s+4}[neighbour], zero where the neighbour does not exist (the reference's
+// `if(i > 0)` branches, s3d_ilu.cpp:45-56); fill: every entry (ghosts included) of a vector-layout array;
+// invert: dinv[c] = 1 / d[v].
+__global__ void __launch_bounds__(256)
+ilu_products_kernel(const GridDev g, const double *__restrict__ A, double *__restrict__ P)
+{
+	const unsigned total = (unsigned)g.nx * (unsigned)g.ny * (unsigned)g.nz;
+	for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < total; it += gridDim.x * blockDim.x) {
+		const int i = it % g.nx, j = (it / g.nx) % g.ny, k = it / (g.nx * g.ny);
+		const long long c = (long long)k * g.cplane + (long long)j * g.cpitch + i;
+		const long long cs = g.cstride;
+		P[c] = (i > 0) ? __dmul_rn(A[c], A[4 * cs + c - 1]) : 0.0;
+		P[cs + c] = (j > 0) ? __dmul_rn(A[cs + c], A[5 * cs + c - g.cpitch]) : 0.0;
+		P[2 * cs + c] = (k > 0) ? __dmul_rn(A[2 * cs + c], A[6 * cs + c - g.cplane]) : 0.0;
+	}
+}
+
+__global__ void __launch_bounds__(256) fill_all_kernel(double *p, long long n, double v)
+{
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+__global__ void __launch_bounds__(256)
+ilu_invert_kernel(const GridDev g, const double *__restrict__ d, double *__restrict__ dinv)
+{
+	const unsigned total = (unsigned)g.nx * (unsigned)g.ny * (unsigned)g.nz;
+	for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < total; it += gridDim.x * blockDim.x) {
+		const int i = it % g.nx, j = (it / g.nx) % g.ny, k = it / (g.nx * g.ny);
+		dinv[(long long)k * g.cplane + (long long)j * g.cpitch + i] =
+		    __ddiv_rn(1.0, d[g.voff + (long long)k * g.vplane + (long long)j * g.vpitch + i]);
+	}
+}
+
 unsigned ew_blocks(const s3d_ctx *ctx, const s3d_grid *g)
 {
 	const unsigned long long total = (unsigned long long)((g->nx + 1) / 2) * g->ny * g->nz;
@@ -308,6 +350,57 @@ unsigned ew_blocks(const s3d_ctx *ctx, const s3d_grid *g)
 	const unsigned long long cap = (unsigned long long)ctx->sm_count * 16;
 	if (b > cap) b = cap;
 	return (unsigned)(b < 1 ? 1 : b);
+}
+
+// flags / dispatch table / occupancy for the dataflow kernels; returns the number of persistent blocks
+int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblocks)
+{
+	f.ntx = (g->nx + SGS_TI - 1) / SGS_TI; f.nty = (g->ny + SGS_TJ - 1) / SGS_TJ; f.ntz = (g->nz + SGS_TK - 1) / SGS_TK;
+	const size_t ntiles = (size_t)f.ntx * f.nty * f.ntz;
+	if (ctx->sgs_flags_cap < ntiles + 1) {
+		S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		if (ctx->sgs_flags) S3D_CUDA(ctx, cudaFree(ctx->sgs_flags));
+		ctx->sgs_flags = nullptr; ctx->sgs_flags_cap = 0;
+		S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_flags, (ntiles + 1) * sizeof(int)));
+		S3D_CUDA(ctx, cudaMemsetAsync(ctx->sgs_flags, 0, (ntiles + 1) * sizeof(int), ctx->stream));
+		ctx->sgs_flags_cap = ntiles + 1;
+		ctx->sgs_epoch = 0;
+	}
+	static bool configured = false;
+	static int blocks_per_sm = 1;
+	if (!configured) {
+		S3D_CUDA(ctx, cudaFuncSetAttribute(sgs_dataflow_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SGS_SMEM));
+		S3D_CUDA(ctx, cudaFuncSetAttribute(sgs_dataflow_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SGS_SMEM));
+		S3D_CUDA(ctx, cudaFuncSetAttribute(sgs_dataflow_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SGS_SMEM));
+		S3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, sgs_dataflow_kernel<0>, SGS_NT, SGS_SMEM));
+		if (blocks_per_sm < 1) blocks_per_sm = 1;
+		configured = true;
+	}
+	if (ctx->sgs_order_dims[0] != f.ntx || ctx->sgs_order_dims[1] != f.nty || ctx->sgs_order_dims[2] != f.ntz) {
+		// counting sort of the tiles by hyperplane
+		const int nd = f.ntx + f.nty + f.ntz - 2;
+		std::vector<int> start(nd + 1, 0), order(ntiles);
+		for (int ck = 0; ck < f.ntz; ck++)
+			for (int cj = 0; cj < f.nty; cj++)
+				for (int ci = 0; ci < f.ntx; ci++) start[ci + cj + ck + 1]++;
+		for (int d = 0; d < nd; d++) start[d + 1] += start[d];
+		for (int ck = 0; ck < f.ntz; ck++)
+			for (int cj = 0; cj < f.nty; cj++)
+				for (int ci = 0; ci < f.ntx; ci++) order[start[ci + cj + ck]++] = (ck * f.nty + cj) * f.ntx + ci;
+		S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		if (ctx->sgs_order) S3D_CUDA(ctx, cudaFree(ctx->sgs_order));
+		ctx->sgs_order = nullptr;
+		S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_order, ntiles * sizeof(int)));
+		S3D_CUDA(ctx, cudaMemcpy(ctx->sgs_order, order.data(), ntiles * sizeof(int), cudaMemcpyHostToDevice));
+		ctx->sgs_order_dims[0] = f.ntx; ctx->sgs_order_dims[1] = f.nty; ctx->sgs_order_dims[2] = f.ntz;
+	}
+	f.flags = ctx->sgs_flags;
+	f.order = ctx->sgs_order;
+	f.sleep_ns = 0;
+	f.debug = ctx->sgs_sleep_ns;   // reuses the tuning slot: debug bit mask
+	f.ticket = reinterpret_cast<unsigned *>(ctx->sgs_flags + ntiles);   // the slot after the last flag
+	nblocks = (unsigned)std::min<size_t>(ntiles, (size_t)ctx->sm_count * blocks_per_sm);
+	return S3D_OK;
 }
 
 }  // namespace
@@ -344,59 +437,18 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 	// Sequential sweeps are idempotent, so nsweeps > 1 repeats identical work; do one.
 	if (ordering == S3D_SGS_LEXICOGRAPHIC) {
 		SgsFlow f;
-		f.ntx = (g->nx + SGS_TI - 1) / SGS_TI; f.nty = (g->ny + SGS_TJ - 1) / SGS_TJ; f.ntz = (g->nz + SGS_TK - 1) / SGS_TK;
-		const size_t ntiles = (size_t)f.ntx * f.nty * f.ntz;
-		if (ctx->sgs_flags_cap < ntiles + 1) {
-			S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-			if (ctx->sgs_flags) S3D_CUDA(ctx, cudaFree(ctx->sgs_flags));
-			ctx->sgs_flags = nullptr; ctx->sgs_flags_cap = 0;
-			S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_flags, (ntiles + 1) * sizeof(int)));
-			S3D_CUDA(ctx, cudaMemsetAsync(ctx->sgs_flags, 0, (ntiles + 1) * sizeof(int), ctx->stream));
-			ctx->sgs_flags_cap = ntiles + 1;
-			ctx->sgs_epoch = 0;
-		}
-		static bool configured = false;
-		static int blocks_per_sm = 1;
-		if (!configured) {
-			S3D_CUDA(ctx, cudaFuncSetAttribute(sgs_dataflow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SGS_SMEM));
-			S3D_CUDA(ctx, cudaFuncSetAttribute(sgs_dataflow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SGS_SMEM));
-			S3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, sgs_dataflow_kernel<true>, SGS_NT, SGS_SMEM));
-			if (blocks_per_sm < 1) blocks_per_sm = 1;
-			configured = true;
-		}
-		if (ctx->sgs_order_dims[0] != f.ntx || ctx->sgs_order_dims[1] != f.nty || ctx->sgs_order_dims[2] != f.ntz) {
-			// counting sort of the tiles by hyperplane
-			const int nd = f.ntx + f.nty + f.ntz - 2;
-			std::vector<int> start(nd + 1, 0), order(ntiles);
-			for (int ck = 0; ck < f.ntz; ck++)
-				for (int cj = 0; cj < f.nty; cj++)
-					for (int ci = 0; ci < f.ntx; ci++) start[ci + cj + ck + 1]++;
-			for (int d = 0; d < nd; d++) start[d + 1] += start[d];
-			for (int ck = 0; ck < f.ntz; ck++)
-				for (int cj = 0; cj < f.nty; cj++)
-					for (int ci = 0; ci < f.ntx; ci++) order[start[ci + cj + ck]++] = (ck * f.nty + cj) * f.ntx + ci;
-			S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-			if (ctx->sgs_order) S3D_CUDA(ctx, cudaFree(ctx->sgs_order));
-			ctx->sgs_order = nullptr;
-			S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_order, ntiles * sizeof(int)));
-			S3D_CUDA(ctx, cudaMemcpy(ctx->sgs_order, order.data(), ntiles * sizeof(int), cudaMemcpyHostToDevice));
-			ctx->sgs_order_dims[0] = f.ntx; ctx->sgs_order_dims[1] = f.nty; ctx->sgs_order_dims[2] = f.ntz;
-		}
-		f.flags = ctx->sgs_flags;
-		f.order = ctx->sgs_order;
-		f.sleep_ns = 0;
-		f.debug = ctx->sgs_sleep_ns;   // reuses the tuning slot: debug bit mask
-		f.ticket = reinterpret_cast<unsigned *>(ctx->sgs_flags + ntiles);   // the slot after the last flag
-		const unsigned nblocks = (unsigned)std::min<size_t>(ntiles, (size_t)ctx->sm_count * blocks_per_sm);
+		unsigned nblocks = 0;
+		const int rcp = sgs_flow_prepare(ctx, g, f, nblocks);
+		if (rcp != S3D_OK) return rcp;
 		dim3 block(SGS_NT);
 		const long long cs = g->cstride;
 		f.epoch = ++ctx->sgs_epoch;
 		S3D_CUDA(ctx, cudaMemsetAsync(f.ticket, 0, sizeof(unsigned), ctx->stream));
-		sgs_dataflow_kernel<true><<<nblocks, block, SGS_SMEM, ctx->stream>>>(gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, ctx->gate);
+		sgs_dataflow_kernel<0><<<nblocks, block, SGS_SMEM, ctx->stream>>>(gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, ctx->gate);
 		S3D_LAUNCHED(ctx);
 		f.epoch = ++ctx->sgs_epoch;
 		S3D_CUDA(ctx, cudaMemsetAsync(f.ticket, 0, sizeof(unsigned), ctx->stream));
-		sgs_dataflow_kernel<false><<<nblocks, block, SGS_SMEM, ctx->stream>>>(gd, d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f, ctx->gate);
+		sgs_dataflow_kernel<1><<<nblocks, block, SGS_SMEM, ctx->stream>>>(gd, d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f, ctx->gate);
 		S3D_LAUNCHED(ctx);
 		return S3D_OK;
 	}
@@ -414,6 +466,47 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 	}
 	S3D_CUDA(ctx, cudaGetLastError());
 	return S3D_OK;
+}
+
+// StrILU_preconditioner::updateOperator (src/linalg/s3d_ilu.cpp:17-64), sequential build: the ILU(0) diagonal of the 7-point
+// matrix, d_ijk = A3 - A0*A4[i-1]/d[i-1] - A1*A5[j-1]/d[j-1] - A2*A6[k-1]/d[k-1], then dinv = 1/d.  A lexicographic sweep computes
+// the exact fixed point, so further build sweeps reproduce it (they are skipped); 0 sweeps gives dinv = 1/diag like the reference.
+// The result feeds s3d_sgs_apply (same (D+L) D^-1 (D+U) application, SGS_like_preconditioner::apply).
+int s3d_strilu_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuildsweeps, double *d_dinv)
+{
+	S3D_REQUIRE(ctx, g && A && d_dinv && nbuildsweeps >= 0, "bad argument");
+	if (g->nranks > 1) return s3d_fail(ctx, S3D_ERR_ARG, "the StrILU recurrence is lexicographic over the whole grid; it is not available on a decomposed grid");
+	if (nbuildsweeps == 0) return s3d_sgs_setup(ctx, g, A, d_dinv);
+	const GridDev gd = to_dev(g);
+	double *P = nullptr, *D = nullptr;
+	S3D_CUDA(ctx, cudaMalloc(&P, 3 * (size_t)g->cstride * sizeof(double)));
+	cudaError_t e = cudaMalloc(&D, (size_t)g->vlen * sizeof(double));
+	if (e != cudaSuccess) { cudaFree(P); S3D_CUDA(ctx, e); }
+	const unsigned nb = (unsigned)std::min<long long>(((long long)g->nx * g->ny * g->nz + 255) / 256, (long long)ctx->sm_count * 16);
+	ilu_products_kernel<<<nb, 256, 0, ctx->stream>>>(gd, A, P);
+	ctx->launches++;
+	fill_all_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(D, g->vlen, 1.0);   // ghosts = 1 so that 0/d stays 0 at the boundary
+	ctx->launches++;
+	SgsFlow f;
+	unsigned nblocks = 0;
+	int rc = sgs_flow_prepare(ctx, g, f, nblocks);
+	if (rc == S3D_OK) {
+		f.epoch = ++ctx->sgs_epoch;
+		e = cudaMemsetAsync(f.ticket, 0, sizeof(unsigned), ctx->stream);
+		if (e == cudaSuccess) {
+			sgs_dataflow_kernel<2><<<nblocks, SGS_NT, SGS_SMEM, ctx->stream>>>(gd, A + 3 * (size_t)g->cstride, P, P + g->cstride, P + 2 * (size_t)g->cstride,
+			                                                                      nullptr, D, f, nullptr);
+			ctx->launches++;
+			ilu_invert_kernel<<<nb, 256, 0, ctx->stream>>>(gd, D, d_dinv);
+			ctx->launches++;
+			e = cudaGetLastError();
+		}
+		if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+		if (e != cudaSuccess) rc = s3d_fail(ctx, S3D_ERR_CUDA, "s3d_strilu_setup: %s", cudaGetErrorString(e));
+	}
+	cudaFree(P);
+	cudaFree(D);
+	return rc;
 }
 
 }  // extern "C"

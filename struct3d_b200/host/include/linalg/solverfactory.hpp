@@ -5,7 +5,7 @@
 #include "s3d_solverbase.hpp"
 
 /// Options (same keys as the reference's .perc files): -s3d_ksp_type {richardson|gcr|cg|bcgs},
-/// -s3d_pc_type {jacobi|sgs|none}, -ksp_rtol, -ksp_max_it, [-ksp_restart 30], and for sgs
+/// -s3d_pc_type {jacobi|sgs|strilu|none}, -ksp_rtol, -ksp_max_it, [-ksp_restart 30], and for sgs
 /// -s3d_pc_apply_sweeps, -s3d_thread_chunk_size, [-s3d_pc_use_threaded_apply], [-s3d_sgs_ordering].
 /// Throws std::runtime_error("Need a valid solver option!") for an unknown solver and
 /// NonExistentPetscOpion for a missing mandatory key.  The caller owns the result.

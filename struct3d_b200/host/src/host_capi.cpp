@@ -2,6 +2,7 @@
 #include <vector>
 #include "case.hpp"
 #include "common_utils.hpp"
+#include "linalg/s3d_ilu.hpp"
 #include "linalg/s3d_jacobi.hpp"
 #include "linalg/s3d_sgspreconditioners.hpp"
 #include "linalg/solverfactory.hpp"
@@ -207,6 +208,7 @@ void *s3dh_prec_create(void *A, const char *pc, int applysweeps, int buildsweeps
 	SolverBase *p = nullptr;
 	if (s == "jacobi") p = new JacobiPreconditioner(M(A));
 	else if (s == "sgs") p = new SGS_preconditioner(M(A), pp);
+	else if (s == "strilu") p = new StrILU_preconditioner(M(A), pp);
 	else if (s == "none") p = new NoSolver(M(A));
 	else throw std::runtime_error("unknown preconditioner");
 	p->updateOperator();

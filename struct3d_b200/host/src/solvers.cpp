@@ -12,6 +12,7 @@
 #include <cstring>
 #include "common_utils.hpp"
 #include "linalg/s3d_gcr.hpp"
+#include "linalg/s3d_ilu.hpp"
 #include "linalg/s3d_jacobi.hpp"
 #include "linalg/s3d_krylov.hpp"
 #include "linalg/s3d_sgspreconditioners.hpp"
@@ -219,6 +220,14 @@ void SGS_preconditioner::updateOperator()
 {
 	const Device &d = Device::get();
 	d.check(s3d_sgs_setup(d.ctx(), &A.grid(), A.dev(), diaginv), "s3d_sgs_setup");
+}
+
+StrILU_preconditioner::StrILU_preconditioner(const SMat &lhs, const PreconParams parms) : SGS_like_preconditioner(lhs, parms) {}
+
+void StrILU_preconditioner::updateOperator()
+{
+	const Device &d = Device::get();
+	d.check(s3d_strilu_setup(d.ctx(), &A.grid(), A.dev(), params.nbuildsweeps, diaginv), "s3d_strilu_setup");
 }
 
 // ------------------------------------------------------------------ Richardson (s3d_solverbase.cpp:45-80)
@@ -532,7 +541,14 @@ SolverBase *createSolver(const SMat &lhs)
 		pp.threadedapply = s3d::options_has("-s3d_pc_use_threaded_apply") ? petscoptions_get_bool("-s3d_pc_use_threaded_apply") : true;
 		prec = new SGS_preconditioner(lhs, pp);
 	} else if (precstr == "strilu") {
-		throw std::runtime_error("createSolver: the StrILU preconditioner is outside this build's scope (SURVEY.md 8f)");
+		if (talk) std::printf("  Using StrILU preconditioner\n");
+		PreconParams pp;
+		pp.nbuildsweeps = petscoptions_get_int("-s3d_pc_build_sweeps");
+		pp.napplysweeps = petscoptions_get_int("-s3d_pc_apply_sweeps");
+		pp.thread_chunk_size = petscoptions_get_int("-s3d_thread_chunk_size");
+		pp.threadedbuild = s3d::options_has("-s3d_pc_use_threaded_build") ? petscoptions_get_bool("-s3d_pc_use_threaded_build") : true;
+		pp.threadedapply = s3d::options_has("-s3d_pc_use_threaded_apply") ? petscoptions_get_bool("-s3d_pc_use_threaded_apply") : true;
+		prec = new StrILU_preconditioner(lhs, pp);
 	} else {
 		prec = new NoSolver(lhs);
 		if (talk) std::printf("WARNING: createSolver: Using no preconditioner\n");

@@ -53,7 +53,7 @@ def _setup(H, rec):
     return m, P, A, b
 
 
-RUNS = [r for r in SOLVES["solves"] if r["pc"] in ("jacobi", "sgs", "none")]
+RUNS = [r for r in SOLVES["solves"] if r["pc"] in ("jacobi", "sgs", "strilu", "none")]
 
 
 @pytest.mark.parametrize("rec", RUNS, ids=lambda r: f"{r['case']}-{r['ksp']}-{r['pc']}")
@@ -262,6 +262,8 @@ def test_zero_rhs_and_nosolver(H):
     ["testmatvec", os.path.join(INPUT, "poisson_conv.control")],
     ["gridconv", os.path.join(INPUT, "poisson_conv.control"), "-options_file", os.path.join(INPUT, "cg_jacobi.perc")],
     ["gridconv", os.path.join(INPUT, "convdiff_conv.control"), "-options_file", os.path.join(INPUT, "bcgs_sgs.perc"), "-ksp_rtol", "1e-8"],
+    ["gridconv", os.path.join(INPUT, "poisson_conv.control"), "-options_file", os.path.join(INPUT, "richardson_strilu.perc")],
+    ["gridconv", os.path.join(INPUT, "convdiff_conv.control"), "-options_file", os.path.join(INPUT, "richardson_strilu.perc")],
     ["runcase", os.path.join(INPUT, "convdiff64.control"), "-options_file", os.path.join(INPUT, "richardson_sgs.perc")],
     ["runcase", os.path.join(INPUT, "poisson16_cheb.control"), "-options_file", os.path.join(INPUT, "gcr_jacobi.perc")],
 ])

@@ -201,6 +201,13 @@ def test_jacobi_and_sgs(ctx, npdim, pde):
     ctx.vecset(g, -9.0, dz)
     ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_LEXICOGRAPHIC_PLANES, 1)
     assert np.array_equal(ctx.vec_download(g, dz), ref), "per-hyperplane SGS differs"
+    # StrILU: the ILU(0) diagonal (same dataflow kernel, divisions) and its application
+    dinv2 = ctx.scalars_alloc(int(g.cstride))
+    for sweeps in (1, 3, 0):
+        ctx.strilu_setup(g, dA, sweeps, dinv2)
+        want = cport.strilu_setup(m, A, sweeps)
+        ctx.sgs_apply(g, dA, dinv2, dr, dz, dy, capi.SGS_LEXICOGRAPHIC, 1)
+        assert np.array_equal(ctx.vec_download(g, dz), cport.sgs_like_apply(m, A, want, r, 1)), f"StrILU({sweeps} build sweeps) differs"
     ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_REDBLACK, 1)
     z = ctx.vec_download(g, dz)
     ref = cport.sgs_redblack_apply(m, A, di, r)
@@ -325,6 +332,9 @@ def test_against_reference_fixtures(ctx, path):
     ctx.sgs_setup(g, dA, dinv)
     ctx.sgs_apply(g, dA, dinv, db, dz, ds, capi.SGS_LEXICOGRAPHIC, 1)
     assert np.array_equal(ctx.vec_download(g, dz), G["sgs_b"])
+    ctx.strilu_setup(g, dA, 1, dinv)
+    ctx.sgs_apply(g, dA, dinv, db, dz, ds, capi.SGS_LEXICOGRAPHIC, 1)
+    assert np.array_equal(ctx.vec_download(g, dz), G["strilu_b"])
     ctx.vecassign(g, db, dy)
     ctx.vecaxpy(g, 0.37, dx, dy)
     assert np.array_equal(real(ctx.vec_download(g, dy)), real(G["b_plus_037x"]))
