@@ -262,6 +262,10 @@ int  s3d_assemble_poisson(s3d_ctx *ctx, const s3d_grid *g, const double *h_cx, c
 /* PDEBase::computeLHS + ConvDiff::lhsmat_kernel (convdiff.cpp:48-88): mu * diffusion, then first-order upwind */
 int  s3d_assemble_convdiff(s3d_ctx *ctx, const s3d_grid *g, const double *h_cx, const double *h_cy,
                            const double *h_cz, const double vel[3], double mu, double *A);
+/* PDEBase::computeLHS + ConvDiffCirc::lhsmat_kernel (convdiff_circular.cpp:59-102): mu * diffusion plus upwinding
+ * with the rotational velocity (2y(1-x^2), -2x(1-y^2), sin(pi z)), reproduced as the reference has it. */
+int  s3d_assemble_convdiff_circ(s3d_ctx *ctx, const s3d_grid *g, const double *h_cx, const double *h_cy,
+                                const double *h_cz, double mu, double *A);
 /* PDEBase::computeVector for separable functions f = sum_t X_t(x_i) Y_t(y_j) Z_t(z_k)  (pdebase.cpp:50-72):
  * h_tx: nterms*(nx+2) host table, h_ty: nterms*(ny+2), h_tz: nterms*(nz_global+2), row t = term t, evaluated
  * at the grid coordinates (boundary entries unused).  Each term is ((X*Y)*Z), terms are added in order.

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 PC = {"none": 0, "jacobi": 1, "sgs": 2, "strilu": 3}
-PDE = {"poisson": 0, "convdiff": 1}
+PDE = {"poisson": 0, "convdiff": 1, "convdiff_circular": 2}
 FUNC = {"test_rhs": 0, "manufactured_solution": 1, "manufactured_rhs": 2}
 
 _dp = C.POINTER(C.c_double)
@@ -103,6 +103,8 @@ def lhs(mesh, pde="poisson", vel=(0, 0, 0), mu=0.0):
     A = np.zeros(mesh.mshape)
     if pde == "poisson":
         lib().orc_lhs_poisson(_np(mesh.npdim), *mesh._c(), _d(A))
+    elif pde == "convdiff_circular":
+        lib().orc_lhs_convdiff_circ(_np(mesh.npdim), *mesh._c(), C.c_double(mu), _d(A))
     else:
         lib().orc_lhs_convdiff(_np(mesh.npdim), *mesh._c(), _a3(vel), C.c_double(mu), _d(A))
     return A

@@ -89,7 +89,10 @@ class Vec:
         self.mesh = mesh
         self.h_ = _vp(handle if handle is not None else lib().refs_vec_create(mesh.h_))
         n = lib().refs_vec_len(self.h_)
-        self.a = np.ctypeslib.as_array(lib().refs_vec_data(self.h_), shape=(n,)).reshape(mesh.vshape)
+        # the view must keep this object (and with it the C++ SVec) alive: `P.vector(m, w).a` is a common pattern
+        buf = (C.c_double * n).from_address(C.addressof(lib().refs_vec_data(self.h_).contents))
+        buf._owner = self
+        self.a = np.frombuffer(buf, dtype=np.float64).reshape(mesh.vshape)
 
     def __del__(self):
         try:
@@ -105,7 +108,11 @@ class Mat:
         self.mesh = mesh
         self.h_ = _vp(handle if handle is not None else lib().refs_mat_create(mesh.h_))
         n = lib().refs_mat_len(self.h_)
-        self.a = [np.ctypeslib.as_array(lib().refs_mat_data(self.h_, s), shape=(n,)).reshape(mesh.mshape) for s in range(7)]
+        self.a = []
+        for s in range(7):
+            buf = (C.c_double * n).from_address(C.addressof(lib().refs_mat_data(self.h_, s).contents))
+            buf._owner = self
+            self.a.append(np.frombuffer(buf, dtype=np.float64).reshape(mesh.mshape))
 
     def stacked(self):
         return np.stack(self.a)

@@ -124,6 +124,37 @@ void orc_lhs_convdiff(const int npdim[3], const double *cx, const double *cy, co
 	}
 }
 
+/* src/pde/convdiff_circular.cpp:20-27 */
+static void circ_velocity(const double r[3], double v[3])
+{
+	v[0] = 2 * r[1] * (1.0 - r[0] * r[0]);
+	v[1] = -2 * r[0] * (1.0 - r[1] * r[1]);
+	v[2] = sin(ORC_PI * r[2]);
+}
+
+/* src/pde/pdebase.cpp:123-150 + src/pde/convdiff_circular.cpp:59-102 (reproduced as it is, including the reference's own
+ * "TODO: Correct convection part": bmag is not applied to the matrix, and b_d == 0 takes the FIRST branch here). */
+void orc_lhs_convdiff_circ(const int npdim[3], const double *cx, const double *cy, const double *cz, double mu, double *A)
+{
+	DIMS;
+	FOR_REAL {
+		double drm[3], drp[3], drs[3], v[7], b[3];
+		spacings(cx, i, &drm[0], &drp[0], &drs[0]);
+		spacings(cy, j, &drm[1], &drp[1], &drs[1]);
+		spacings(cz, k, &drm[2], &drp[2], &drs[2]);
+		diffusion_row(drm, drp, drs, v);
+		for (int s = 0; s < 7; s++) v[s] *= mu;
+		const double r[3] = {cx[i], cy[j], cz[k]};
+		circ_velocity(r, b);
+		for (int d = 0; d < 3; d++) {
+			if (b[d] >= 0) { v[d] -= b[d] / drm[d]; v[3] += b[d] / drm[d]; }
+			else           { v[d + 4] += b[d] / drp[d]; v[3] -= b[d] / drp[d]; }
+		}
+		const i64 q = RI(i - 1, j - 1, k - 1);
+		for (int s = 0; s < 7; s++) A[s * N + q] = v[s];
+	}
+}
+
 /* the source / solution functions: src/pde/poisson.cpp:15-26, src/pde/convdiff.cpp:20-46 */
 static double eval_function(int pde, int func, const double b[3], double mu, const double r[3])
 {
@@ -134,6 +165,16 @@ static double eval_function(int pde, int func, const double b[3], double mu, con
 	if (pde == ORC_PDE_POISSON)
 		return 12 * ORC_PI * ORC_PI * sin(2 * ORC_PI * r[0]) * sin(2 * ORC_PI * r[1]) * sin(2 * ORC_PI * r[2]);
 	double val = mu * 12 * ORC_PI * ORC_PI * sin(2 * ORC_PI * r[0]) * sin(2 * ORC_PI * r[1]) * sin(2 * ORC_PI * r[2]);
+	if (pde == ORC_PDE_CONVDIFF_CIRC) {   /* src/pde/convdiff_circular.cpp:37-49; b[0] carries bmag */
+		double vel[3];
+		circ_velocity(r, vel);
+		for (int d = 0; d < 3; d++) {
+			double term = 2 * ORC_PI * b[0] * vel[d];
+			for (int e = 0; e < 3; e++) term *= (d == e) ? cos(2 * ORC_PI * r[e]) : sin(2 * ORC_PI * r[e]);
+			val += term;
+		}
+		return val;
+	}
 	for (int d = 0; d < 3; d++) {
 		double term = 2 * ORC_PI * b[d];
 		for (int e = 0; e < 3; e++) term *= (d == e) ? cos(2 * ORC_PI * r[e]) : sin(2 * ORC_PI * r[e]);

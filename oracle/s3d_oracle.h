@@ -24,7 +24,7 @@ extern "C" {
 #endif
 
 enum { ORC_PC_NONE = 0, ORC_PC_JACOBI = 1, ORC_PC_SGS = 2, ORC_PC_STRILU = 3 };
-enum { ORC_PDE_POISSON = 0, ORC_PDE_CONVDIFF = 1 };
+enum { ORC_PDE_POISSON = 0, ORC_PDE_CONVDIFF = 1, ORC_PDE_CONVDIFF_CIRC = 2 };
 enum { ORC_F_TEST_RHS = 0, ORC_F_MANUFACTURED_SOLUTION = 1, ORC_F_MANUFACTURED_RHS = 2 };
 
 typedef struct {
@@ -49,6 +49,7 @@ double orc_mesh_h(const int npdim[3], const double *cx, const double *cy, const 
 void   orc_lhs_poisson(const int npdim[3], const double *cx, const double *cy, const double *cz, double *A);
 void   orc_lhs_convdiff(const int npdim[3], const double *cx, const double *cy, const double *cz,
                         const double b[3], double mu, double *A);
+void   orc_lhs_convdiff_circ(const int npdim[3], const double *cx, const double *cy, const double *cz, double mu, double *A);
 int    orc_grid_function(const int npdim[3], const double *cx, const double *cy, const double *cz,
                          int pde, int func, const double b[3], double mu, const double bvals[6], double *f);
 

@@ -71,6 +71,7 @@ _SIGS = {
     "s3d_ints_alloc": [_P, _I, C.POINTER(_vp)], "s3d_ints_download": [_P, _vp, _I, _vp], "s3d_ints_zero": [_P, _vp, _I],
     "s3d_assemble_poisson": [_P, _G, _vp, _vp, _vp, _vp],
     "s3d_assemble_convdiff": [_P, _G, _vp, _vp, _vp, _vp, _D, _vp],
+    "s3d_assemble_convdiff_circ": [_P, _G, _vp, _vp, _vp, _D, _vp],
     "s3d_assemble_rhs_separable": [_P, _G, _I, _vp, _vp, _vp, _vp, _vp],
     "s3d_comm_unique_id": [_vp], "s3d_comm_init": [_P, _I, _I, _vp], "s3d_comm_destroy": [_P],
     "s3d_halo_exchange": [_P, _G, _vp],
@@ -360,6 +361,10 @@ class Context:
         cs = [np.ascontiguousarray(c, dtype=np.float64) for c in coords]
         v = np.ascontiguousarray(vel, dtype=np.float64)
         self.call("s3d_assemble_convdiff", C.byref(g), _ptr(cs[0]), _ptr(cs[1]), _ptr(cs[2]), _ptr(v), float(mu), _ptr(A))
+
+    def assemble_convdiff_circ(self, g, coords, mu, A):
+        cs = [np.ascontiguousarray(c, dtype=np.float64) for c in coords]
+        self.call("s3d_assemble_convdiff_circ", C.byref(g), _ptr(cs[0]), _ptr(cs[1]), _ptr(cs[2]), float(mu), _ptr(A))
 
     def assemble_rhs_separable(self, g, tx, ty, tz, f, face=None):
         tx, ty, tz = [np.ascontiguousarray(t, dtype=np.float64) for t in (tx, ty, tz)]

@@ -6,6 +6,8 @@
 // (11.8 s at 512^3).  Each coefficient depends on ONE axis index only, so a
 // tiny kernel first builds per-axis tables with exactly the reference's rounding sequence, and a
 // streaming kernel then writes the 7 arrays: 56 B/point of pure, 128-bit coalesced stores.
+#include <cmath>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -18,7 +20,7 @@ struct AxisTab { const double *lo, *up, *dg, *ad; };
 
 // c: device copy of the axis coordinates incl. boundary points; real index m <-> coordinate index m+1+shift
 __global__ void axis_table_kernel(const double *c, int n, int shift, double bvel, double mu, int convdiff,
-                                  double *lo, double *up, double *dg, double *ad)
+                                  double *lo, double *up, double *dg, double *ad, double *o_drm, double *o_drp)
 {
 	const int m = blockIdx.x * blockDim.x + threadIdx.x;
 	if (m >= n) return;
@@ -31,7 +33,11 @@ __global__ void axis_table_kernel(const double *c, int n, int shift, double bvel
 	double u = __ddiv_rn(-1.0, __dmul_rn(__dmul_rn(drp, 0.5), drs));
 	const double d = __dmul_rn(__ddiv_rn(2.0, drs), __dadd_rn(__ddiv_rn(1.0, drp), __ddiv_rn(1.0, drm)));
 	double a = 0.0;
-	if (convdiff) {
+	if (o_drm) { o_drm[m] = drm; o_drp[m] = drp; }
+	if (convdiff == 2) {   // point-dependent velocity (ConvDiffCirc): only the mu scaling is separable
+		l = __dmul_rn(l, mu);
+		u = __dmul_rn(u, mu);
+	} else if (convdiff) {
 		// convdiff.cpp:74-87: all seven entries times mu, then first-order upwinding (b == 0 takes the else branch)
 		l = __dmul_rn(l, mu);
 		u = __dmul_rn(u, mu);
@@ -84,6 +90,47 @@ fill_stencil_kernel(const GridDev g, const AxisTab tx, const AxisTab ty, const A
 			if (np == 2) st_stream2(p, make_double2(v[s][0], v[s][1]));
 			else *p = v[s][0];
 		}
+	}
+}
+
+// ConvDiffCirc (reference src/pde/convdiff_circular.cpp:59-102): mu * diffusion from the per-axis tables, then first-order upwinding
+// with the point-dependent velocity b = (2y(1-x^2), -2x(1-y^2), sin(pi z)); b_d >= 0 takes the backward difference.  Reproduced as the
+// reference has it (its own TODO notes the convection part is not final; bmag does not enter the matrix).  sin(pi z_k) comes from a host
+// libm table so the coefficients are bit-identical to the reference's.
+struct CircTab { const double *x, *y, *sinz; const double *drm[3], *drp[3]; };
+
+__global__ void __launch_bounds__(256)
+fill_stencil_circ_kernel(const GridDev g, const AxisTab tx, const AxisTab ty, const AxisTab tz, const CircTab ct, double mu,
+                         double *__restrict__ A)
+{
+	const unsigned total = (unsigned)g.nx * (unsigned)g.ny * (unsigned)g.nz;
+	for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < total; it += gridDim.x * blockDim.x) {
+		const int i = it % g.nx, j = (it / g.nx) % g.ny, k = it / (g.nx * g.ny);
+		double v[7];
+		v[0] = __ldg(tx.lo + i); v[1] = __ldg(ty.lo + j); v[2] = __ldg(tz.lo + k);
+		v[4] = __ldg(tx.up + i); v[5] = __ldg(ty.up + j); v[6] = __ldg(tz.up + k);
+		v[3] = __dmul_rn(__dadd_rn(__dadd_rn(__ldg(tx.dg + i), __ldg(ty.dg + j)), __ldg(tz.dg + k)), mu);
+		const double x = __ldg(ct.x + i), y = __ldg(ct.y + j);
+		double b[3];
+		b[0] = __dmul_rn(__dmul_rn(2.0, y), __dsub_rn(1.0, __dmul_rn(x, x)));
+		b[1] = __dmul_rn(__dmul_rn(-2.0, x), __dsub_rn(1.0, __dmul_rn(y, y)));
+		b[2] = __ldg(ct.sinz + k);
+		const int idx[3] = {i, j, k};
+#pragma unroll
+		for (int d = 0; d < 3; d++) {
+			if (b[d] >= 0) {
+				const double t = __ddiv_rn(b[d], __ldg(ct.drm[d] + idx[d]));
+				v[d] = __dsub_rn(v[d], t);
+				v[3] = __dadd_rn(v[3], t);
+			} else {
+				const double t = __ddiv_rn(b[d], __ldg(ct.drp[d] + idx[d]));
+				v[d + 4] = __dadd_rn(v[d + 4], t);
+				v[3] = __dsub_rn(v[3], t);
+			}
+		}
+		const long long c = (long long)k * g.cplane + (long long)j * g.cpitch + i;
+#pragma unroll
+		for (int s = 0; s < 7; s++) A[(long long)s * g.cstride + c] = v[s];
 	}
 }
 
@@ -152,7 +199,7 @@ int assemble(s3d_ctx *ctx, const s3d_grid *g, const double *h_cx, const double *
 		double *lo = p, *up = p + n[d], *dg = p + 2 * n[d], *ad = p + 3 * n[d];
 		p += 4 * (size_t)n[d];
 		const int shift = (d == 2) ? g->k0 : 0;
-		axis_table_kernel<<<(n[d] + 127) / 128, 128, 0, ctx->stream>>>(dc, n[d], shift, vel ? vel[d] : 0.0, mu, convdiff, lo, up, dg, ad);
+		axis_table_kernel<<<(n[d] + 127) / 128, 128, 0, ctx->stream>>>(dc, n[d], shift, vel ? vel[d] : 0.0, mu, convdiff, lo, up, dg, ad, nullptr, nullptr);
 		S3D_LAUNCHED(ctx);
 		T[d] = AxisTab{lo, up, dg, ad};
 	}
@@ -163,9 +210,60 @@ int assemble(s3d_ctx *ctx, const s3d_grid *g, const double *h_cx, const double *
 	return S3D_OK;
 }
 
+int assemble_circ(s3d_ctx *ctx, const s3d_grid *g, const double *h_cx, const double *h_cy, const double *h_cz, double mu, double *A)
+{
+	S3D_REQUIRE(ctx, g && h_cx && h_cy && h_cz && A, "null argument");
+	const int n[3] = {g->nx, g->ny, g->nz};
+	const int ncoord[3] = {g->nx + 2, g->ny + 2, g->nz_global + 2};
+	const double *hc[3] = {h_cx, h_cy, h_cz};
+	size_t need = 0;
+	for (int d = 0; d < 3; d++) need += (size_t)ncoord[d] + 6 * (size_t)n[d];
+	need += (size_t)n[2];
+	const int rc = s3d_ensure_tab(ctx, need);
+	if (rc != S3D_OK) return rc;
+	AxisTab T[3];
+	CircTab ct;
+	double *p = ctx->tab;
+	const double *dcoord[3];
+	for (int d = 0; d < 3; d++) {
+		double *dc = p; p += ncoord[d];
+		dcoord[d] = dc;
+		S3D_CUDA(ctx, cudaMemcpyAsync(dc, hc[d], ncoord[d] * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+		double *lo = p, *up = p + n[d], *dg = p + 2 * n[d], *ad = p + 3 * n[d], *drm = p + 4 * n[d], *drp = p + 5 * n[d];
+		p += 6 * (size_t)n[d];
+		const int shift = (d == 2) ? g->k0 : 0;
+		axis_table_kernel<<<(n[d] + 127) / 128, 128, 0, ctx->stream>>>(dc, n[d], shift, 0.0, mu, 2, lo, up, dg, ad, drm, drp);
+		S3D_LAUNCHED(ctx);
+		T[d] = AxisTab{lo, up, dg, ad};
+		ct.drm[d] = drm; ct.drp[d] = drp;
+	}
+	// sin(pi z) on the host (libm), for this rank's planes
+	double *hs = (double *)malloc(sizeof(double) * n[2]);
+	for (int k = 0; k < n[2]; k++) hs[k] = sin(3.141592653589793238 * h_cz[g->k0 + k + 1]);
+	double *dsin = p;
+	cudaError_t e = cudaMemcpyAsync(dsin, hs, n[2] * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	free(hs);
+	S3D_CUDA(ctx, e);
+	ct.x = dcoord[0] + 1; ct.y = dcoord[1] + 1; ct.sinz = dsin;   // real index m <-> coordinate index m + 1
+	const unsigned long long total = (unsigned long long)g->nx * g->ny * g->nz;
+	unsigned long long nb = (total + 255) / 256;
+	if (nb > (unsigned long long)ctx->sm_count * 16) nb = (unsigned long long)ctx->sm_count * 16;
+	fill_stencil_circ_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(to_dev(g), T[0], T[1], T[2], ct, mu, A);
+	S3D_LAUNCHED(ctx);
+	return S3D_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+int s3d_assemble_convdiff_circ(s3d_ctx *ctx, const s3d_grid *g, const double *h_cx, const double *h_cy, const double *h_cz,
+                               double mu, double *A)
+{
+	return assemble_circ(ctx, g, h_cx, h_cy, h_cz, mu, A);
+}
+
 
 int s3d_assemble_poisson(s3d_ctx *ctx, const s3d_grid *g, const double *h_cx, const double *h_cy, const double *h_cz,
                          double *A)

@@ -5,8 +5,8 @@
 #include "case.hpp"
 #include "pdebase.hpp"
 
-/// "poisson" or "convdiff"; anything else prints a message and aborts, like the reference.
-/// ("convdiff_circular" is out of this path's scope, SURVEY.md 8f: it also aborts, with its own message.)
+/// "poisson", "convdiff" or "convdiff_circular" (vel[0] carries the velocity magnitude); anything else prints a message
+/// and aborts, like the reference.
 PDEBase *construct_pde(const CaseData &cdata);
 
 #endif

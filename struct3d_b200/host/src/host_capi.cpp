@@ -95,7 +95,7 @@ void *s3dh_pde_create(const char *type, const double vel[3], double mu, const in
 	TRY
 	CaseData c;
 	c.pdetype = type;
-	if (c.pdetype != "poisson" && c.pdetype != "convdiff") throw std::runtime_error("PDE type not recognized!");
+	if (c.pdetype != "poisson" && c.pdetype != "convdiff" && c.pdetype != "convdiff_circular") throw std::runtime_error("PDE type not recognized!");
 	for (int i = 0; i < 3; i++) c.vel[i] = vel[i];
 	c.diffcoeff = mu;
 	for (int i = 0; i < 6; i++) { c.btypes[i] = dirichlet[i] ? S3D_DIRICHLET : S3D_EXTRAPOLATION; c.bvals[i] = bvals[i]; }

@@ -2,6 +2,7 @@
 // (reference: src/pde/pdebase.cpp:50-72,123-150, poisson.cpp, convdiff.cpp, pdefactory.cpp).
 #include "common_utils.hpp"
 #include "pde/convdiff.hpp"
+#include "pde/convdiff_circular.hpp"
 #include "pde/pdefactory.hpp"
 #include "pde/poisson.hpp"
 
@@ -178,13 +179,64 @@ void ConvDiff::assemble_lhs(const CartMesh *const m, SMat &A) const
 // the reference's boundary terms for this PDE are commented out (convdiff.cpp:96-121): none
 bool ConvDiff::boundary_terms(const CartMesh *const, sreal[6]) const { return false; }
 
+// ------------------------------------------------------------------ ConvDiffCirc
+
+ConvDiffCirc::ConvDiffCirc(const std::array<BCType, 6> &bc_types, const std::array<sreal, 6> &bc_vals, const sreal advel, const sreal diffc)
+	: PDEBase(bc_types, bc_vals), mu{diffc}, bmag(advel)
+{
+	if (Device::get().rank() == 0) std::printf("ConvDiff: Using |b| = %f, mu = %f.\n", bmag, mu);
+}
+
+std::array<sreal, NDIM> ConvDiffCirc::advectionVel(const sreal r[NDIM])
+{
+	std::array<sreal, NDIM> v;
+	v[0] = 2 * r[1] * (1.0 - r[0] * r[0]);
+	v[1] = -2 * r[0] * (1.0 - r[1] * r[1]);
+	v[2] = std::sin(PI * r[2]);
+	return v;
+}
+
+std::array<GridFunction, 2> ConvDiffCirc::manufactured_solution() const
+{
+	const sreal munum = mu, bmagnum = bmag;
+	auto s2 = [](sreal x) { return std::sin(2 * PI * x); };
+	GridFunction u([](const sreal r[NDIM]) { return std::sin(2 * PI * r[0]) * std::sin(2 * PI * r[1]) * std::sin(2 * PI * r[2]); },
+	               {{s2, s2, s2}});
+	GridFunction f([munum, bmagnum](const sreal r[NDIM]) {
+		sreal val = munum * 12 * PI * PI * std::sin(2 * PI * r[0]) * std::sin(2 * PI * r[1]) * std::sin(2 * PI * r[2]);
+		const std::array<sreal, NDIM> vel = ConvDiffCirc::advectionVel(r);
+		for (int i = 0; i < NDIM; i++) {
+			sreal term = 2 * PI * bmagnum * vel[i];
+			for (int j = 0; j < NDIM; j++) term *= (i == j) ? std::cos(2 * PI * r[j]) : std::sin(2 * PI * r[j]);
+			val += term;
+		}
+		return val;
+	});
+	return {u, f};
+}
+
+GridFunction ConvDiffCirc::test_rhs() const
+{
+	auto s1 = [](sreal x) { return std::sin(PI * x); };
+	return GridFunction([](const sreal r[NDIM]) { return std::sin(PI * r[0]) * std::sin(PI * r[1]) * std::sin(PI * r[2]); }, {{s1, s1, s1}});
+}
+
+void ConvDiffCirc::assemble_lhs(const CartMesh *const m, SMat &A) const
+{
+	const Device &d = Device::get();
+	const sreal *const *c = m->pointer_coords();
+	d.check(s3d_assemble_convdiff_circ(d.ctx(), &m->device_grid(), c[0], c[1], c[2], mu, A.dev_w()), "s3d_assemble_convdiff_circ");
+}
+
+bool ConvDiffCirc::boundary_terms(const CartMesh *const, sreal[6]) const { return false; }   // "TODO: Add BC" in the reference: none
+
 // ------------------------------------------------------------------ factory
 
 PDEBase *construct_pde(const CaseData &cdata)
 {
 	if (cdata.pdetype == "poisson") return new Poisson(cdata.btypes, cdata.bvals);
 	if (cdata.pdetype == "convdiff") return new ConvDiff(cdata.btypes, cdata.bvals, cdata.vel, cdata.diffcoeff);
-	if (cdata.pdetype == "convdiff_circular") std::printf("PDE type convdiff_circular is outside this build's scope!\n");
-	else std::printf("PDE type not recognized!\n");
+	if (cdata.pdetype == "convdiff_circular") return new ConvDiffCirc(cdata.btypes, cdata.bvals, cdata.vel[0], cdata.diffcoeff);
+	std::printf("PDE type not recognized!\n");
 	std::abort();
 }

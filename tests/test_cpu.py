@@ -124,6 +124,18 @@ def test_redblack_sgs_is_the_same_operator_reordered():
 
 
 @pytest.mark.skipif(not refshim.available(), reason="oracle/_ref not built (no /root/reference here)")
+def test_oracle_convdiff_circular_matches_live_reference():
+    """the rotational-velocity operator, reproduced as the reference has it."""
+    refshim.set_num_threads(1)
+    for npdim, grid in (((14, 11, 9), "chebyshev"), ((12, 12, 12), "uniform")):
+        m, rm = cport.Mesh(npdim, grid=grid), refshim.Mesh(npdim, grid=grid)
+        P = refshim.Pde("convdiff_circular", (1.3, 0, 0), 0.07)
+        assert np.array_equal(cport.lhs(m, "convdiff_circular", (1.3, 0, 0), 0.07), P.lhs(rm).stacked())
+        for w in ("test_rhs", "manufactured_solution", "manufactured_rhs"):
+            assert np.array_equal(cport.grid_function(m, "convdiff_circular", w, (1.3, 0, 0), 0.07), P.vector(rm, w).a)
+
+
+@pytest.mark.skipif(not refshim.available(), reason="oracle/_ref not built (no /root/reference here)")
 def test_oracle_matches_live_reference():
     """Where the compiled reference is present, re-pin the restatement against it on a fresh case."""
     refshim.set_num_threads(1)

@@ -135,7 +135,7 @@ def test_assembly_like_reference_test(H):
     for npdim, grid in (((12, 12, 12), "uniform"), ((13, 9, 11), "chebyshev")):
         m = H.Mesh(npdim, grid=grid)
         cm = cport.Mesh(npdim, grid=grid)
-        for pde, vel, mu in (("poisson", (0, 0, 0), 0.0), ("convdiff", V1, 0.1)):
+        for pde, vel, mu in (("poisson", (0, 0, 0), 0.0), ("convdiff", V1, 0.1), ("convdiff_circular", (1.3, 0, 0), 0.07)):
             P = H.Pde(pde, vel, mu)
             for which in ("test_rhs", "manufactured_solution", "manufactured_rhs"):
                 f = P.vector(m, which).a
@@ -264,6 +264,7 @@ def test_zero_rhs_and_nosolver(H):
     ["gridconv", os.path.join(INPUT, "convdiff_conv.control"), "-options_file", os.path.join(INPUT, "bcgs_sgs.perc"), "-ksp_rtol", "1e-8"],
     ["gridconv", os.path.join(INPUT, "poisson_conv.control"), "-options_file", os.path.join(INPUT, "richardson_strilu.perc")],
     ["gridconv", os.path.join(INPUT, "convdiff_conv.control"), "-options_file", os.path.join(INPUT, "richardson_strilu.perc")],
+    ["gridconv", os.path.join(INPUT, "cdcirc_conv.control"), "-options_file", os.path.join(INPUT, "richardson_strilu.perc")],
     ["runcase", os.path.join(INPUT, "convdiff64.control"), "-options_file", os.path.join(INPUT, "richardson_sgs.perc")],
     ["runcase", os.path.join(INPUT, "poisson16_cheb.control"), "-options_file", os.path.join(INPUT, "gcr_jacobi.perc")],
 ])

@@ -225,6 +225,9 @@ def test_assembly_bit_exact(ctx, npdim, grid):
     for vel, mu in ((V1, 0.1), (V2, 0.05), ((0.0, -1.0, 2.0), 1.0)):
         ctx.assemble_convdiff(g, m.coords, vel, mu, dA)
         assert np.array_equal(ctx.mat_download(g, dA), cport.lhs(m, "convdiff", vel, mu)), (vel, mu)
+    for mu in (0.07, 1.0):
+        ctx.assemble_convdiff_circ(g, m.coords, mu, dA)
+        assert np.array_equal(ctx.mat_download(g, dA), cport.lhs(m, "convdiff_circular", (1.0, 0, 0), mu)), ("circ", mu)
     # uniform Poisson closed form (test/nativevectorassemblytest.cpp:117-123): diag 6/dx^2, off -1/dx^2 within 100 eps
     if grid == "uniform" and npdim[0] == npdim[1] == npdim[2]:
         ctx.assemble_poisson(g, m.coords, dA)
