@@ -326,7 +326,9 @@ def run_ours(a):
             m2, _ = H._capture_stdout(lambda: H.Mesh((258, 258, 258)))
             p2, _ = H._capture_stdout(lambda: H.Pde("convdiff", (0.577350269189626, 0.7, 0.3), 0.1))
             A2, b2, u2 = p2.lhs(m2), p2.vector(m2, "manufactured_rhs"), H.Vec(m2)
-            for pc, extra in (("sgs", {"-s3d_sgs_ordering": "lexicographic"}), ("sgs", {"-s3d_sgs_ordering": "redblack"}), ("jacobi", {})):
+            for pc, extra in (("sgs", {"-s3d_sgs_ordering": "lexicographic"}), ("sgs", {"-s3d_sgs_ordering": "redblack"}),
+                              ("sgs", {"-s3d_sgs_ordering": "sweeps", "-s3d_pc_apply_sweeps": 2}),
+                              ("sgs", {"-s3d_sgs_ordering": "sweeps", "-s3d_pc_apply_sweeps": 4}), ("jacobi", {})):
                 o = {"-s3d_ksp_type": "bcgs", "-s3d_pc_type": pc, "-ksp_rtol": 1e-6, "-ksp_max_it": 5000, "-s3d_pc_apply_sweeps": 1,
                      "-s3d_thread_chunk_size": 1024, "-s3d_pc_use_threaded_apply": "false"}
                 o.update(extra)
@@ -339,7 +341,7 @@ def run_ours(a):
                 i2, _ = H._capture_stdout(lambda: s2.apply(b2, u2))
                 H.sync()
                 dt2 = time.perf_counter() - t0
-                key = "bicgstab_" + pc + ("_" + extra["-s3d_sgs_ordering"] if extra else "") + "_convdiff256"
+                key = "bicgstab_" + pc + ("_" + extra["-s3d_sgs_ordering"] if extra else "") + (str(extra["-s3d_pc_apply_sweeps"]) if "-s3d_pc_apply_sweeps" in extra else "") + "_convdiff256"
                 solve[key] = {"seconds": dt2, "iters": i2["iters"], "converged": i2["converged"], "precapply_seconds": i2["precapplywtime"]}
                 del s2
             del A2, b2, u2

@@ -196,7 +196,9 @@ int  s3d_sgs_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, double *d_d
 int  s3d_strilu_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuildsweeps, double *d_dinv);
 #define S3D_SGS_LEXICOGRAPHIC 0  /* the reference's ordering, executed as a tile-level dataflow wavefront: same arithmetic */
 #define S3D_SGS_LEXICOGRAPHIC_PLANES 2  /* same result, one launch per hyperplane i+j+k (slow; kept for cross-checks) */
-#define S3D_SGS_REDBLACK      1  /* two-colour ordering: four fully parallel half-sweeps (changes the iteration) */
+#define S3D_SGS_REDBLACK      1
+#define S3D_SGS_JACOBI_SWEEPS 3  /* nsweeps synchronous Jacobi sweeps per triangular factor: the deterministic counterpart of the
+                                  * reference's asynchronous threaded sweeps (threadedapply = true); exact for nsweeps >= nx+ny+nz-2 */  /* two-colour ordering: four fully parallel half-sweeps (changes the iteration) */
 /* SGS_like_preconditioner::apply (s3d_sgspreconditioners.cpp:14-115): z = (D+U)^-1 D (D+L)^-1 r.
  * d_y: scratch vector (vlen doubles); it is re-zeroed by the call like the reference's temporary. */
 int  s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_dinv,

@@ -187,6 +187,12 @@ def sgs_like_apply(mesh, A, diaginv, r, nsweeps=1):
     return z
 
 
+def sgs_jacobi_sweeps_apply(mesh, A, diaginv, r, nsweeps):
+    z = mesh.zeros()
+    lib().orc_sgs_jacobi_sweeps_apply(_np(mesh.npdim), _d(A), _d(diaginv), int(nsweeps), _d(r), _d(z))
+    return z
+
+
 def sgs_redblack_apply(mesh, A, diaginv, r):
     z = mesh.zeros()
     lib().orc_sgs_redblack_apply(_np(mesh.npdim), _d(A), _d(diaginv), _d(r), _d(z))

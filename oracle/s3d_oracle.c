@@ -395,6 +395,43 @@ void orc_sgs_like_apply(const int npdim[3], const double *A, const double *diagi
 	free(y);
 }
 
+/* Synchronous multi-sweep variant of the same apply: every sweep recomputes ALL points from the previous sweep's values
+ * (Jacobi iterations on the two triangular systems, starting from zero):
+ *   forward  y <- dinv (r - A0 y[i-1] - A1 y[j-1] - A2 y[k-1]),   backward  z <- y - dinv (A4 z[i+1] + A5 z[j+1] + A6 z[k+1]).
+ * This is the deterministic counterpart of the reference's ASYNCHRONOUS threaded sweeps (s3d_sgspreconditioners.cpp:32-112 with
+ * threadedapply = true, napplysweeps = n), which update in place with no ordering between threads.  After nx+ny+nz-2 sweeps it
+ * equals the sequential sweep exactly. */
+void orc_sgs_jacobi_sweeps_apply(const int npdim[3], const double *A, const double *diaginv, int nsweeps,
+                                 const double *r, double *z)
+{
+	DIMS;
+	const size_t G = (size_t)np0 * np1 * np2;
+	double *y0 = (double *)calloc(G, sizeof(double)), *y1 = (double *)calloc(G, sizeof(double));
+	double *z0 = (double *)calloc(G, sizeof(double));
+	for (int swp = 0; swp < nsweeps; swp++) {
+		FOR_REAL {
+			const i64 q = RI(i - 1, j - 1, k - 1);
+			double t = r[GI(i, j, k)] - A[0 * N + q] * y0[GI(i - 1, j, k)] - A[1 * N + q] * y0[GI(i, j - 1, k)]
+			         - A[2 * N + q] * y0[GI(i, j, k - 1)];
+			y1[GI(i, j, k)] = t * diaginv[q];
+		}
+		double *tmp = y0; y0 = y1; y1 = tmp;
+	}
+	/* y0 holds the forward result; reuse y1 / z0 as the backward ping-pong pair */
+	memset(y1, 0, G * sizeof(double));
+	for (int swp = 0; swp < nsweeps; swp++) {
+		FOR_REAL {
+			const i64 q = RI(i - 1, j - 1, k - 1);
+			z0[GI(i, j, k)] = y0[GI(i, j, k)]
+			    - diaginv[q] * (A[4 * N + q] * y1[GI(i + 1, j, k)] + A[5 * N + q] * y1[GI(i, j + 1, k)]
+			                    + A[6 * N + q] * y1[GI(i, j, k + 1)]);
+		}
+		double *tmp = z0; z0 = y1; y1 = tmp;
+	}
+	FOR_REAL z[GI(i, j, k)] = y1[GI(i, j, k)];
+	free(y0); free(y1); free(z0);
+}
+
 /* NOT in the reference.  The same M = (D+L) D^-1 (D+U) product, but with the unknowns ordered
  * red ((i+j+k) even, 1-based) before black.  Every neighbour of a red point is black and vice
  * versa, so under that ordering L couples black rows to all six red neighbours and U couples red

@@ -72,6 +72,10 @@ void   orc_sgs_setup(const int npdim[3], const double *A, double *diaginv);
 void   orc_strilu_setup(const int npdim[3], const double *A, int nbuildsweeps, double *diaginv);
 void   orc_sgs_like_apply(const int npdim[3], const double *A, const double *diaginv, int nsweeps,
                           const double *r, double *z);
+/* synchronous Jacobi sweeps on the two triangular systems: NOT in the reference as such; the deterministic counterpart of its
+ * asynchronous threaded sweeps, used to pin the GPU's S3D_SGS_JACOBI_SWEEPS ordering. */
+void   orc_sgs_jacobi_sweeps_apply(const int npdim[3], const double *A, const double *diaginv, int nsweeps,
+                                   const double *r, double *z);
 /* red-black (2-colour) variant of the same M = (D+L) D^-1 (D+U) sweeps: NOT in the reference; it is
  * the CPU statement of the multicolour ordering the GPU path offers, used to pin that kernel. */
 void   orc_sgs_redblack_apply(const int npdim[3], const double *A, const double *diaginv,

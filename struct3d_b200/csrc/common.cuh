@@ -26,6 +26,9 @@ struct s3d_ctx {
 	// SGS dataflow bookkeeping (tile completion flags + work ticket)
 	int *sgs_flags = nullptr;
 	size_t sgs_flags_cap = 0;
+	double *sweep_buf = nullptr;   // second ping-pong vector of the Jacobi-sweeps SGS
+	size_t sweep_buf_cap = 0;
+	int sweep_buf_dims[3] = {0, 0, 0};
 	int sgs_epoch = 0;
 	int sgs_sleep_ns = 0;
 	int *sgs_order = nullptr;     // tile dispatch order (hyperplane-sorted), cached per tile-grid shape

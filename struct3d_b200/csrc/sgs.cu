@@ -343,6 +343,55 @@ ilu_invert_kernel(const GridDev g, const double *__restrict__ d, double *__restr
 	}
 }
 
+// ---------------------------------------------------------------- synchronous Jacobi sweeps on the triangular systems
+//
+// The reference's threaded apply (threadedapply = true, napplysweeps = n) runs n asynchronous, unordered in-place sweeps per
+// triangular factor.  Its deterministic GPU counterpart: n SYNCHRONOUS sweeps, each a fully parallel streaming pass that
+// recomputes every point from the previous sweep's values (ping-pong buffers), starting from zero.  One sweep is Jacobi; the
+// result converges to the exact lexicographic solve as n grows (bit-identical from n = nx+ny+nz-2 on).  48 B/point per sweep.
+// PHASE 0: out = dinv (r - A0 in[i-1] - A1 in[j-1] - A2 in[k-1])      PHASE 1: out = y - dinv (A4 in[i+1] + A5 in[j+1] + A6 in[k+1])
+// first: the previous iterate is zero (skip its loads).
+template <int PHASE>
+__global__ void __launch_bounds__(256)
+sgs_sweep_kernel(const GridDev g, const double *__restrict__ A, const double *__restrict__ dinv, const double *__restrict__ rhs,
+                 const double *__restrict__ in, double *__restrict__ out, int first, const int *stop)
+{
+	if (s3d_stopped(stop)) return;
+	const unsigned nx2 = (unsigned)(g.nx + 1) >> 1;
+	const unsigned total = nx2 * (unsigned)g.ny * (unsigned)g.nz;
+	const long long cs = g.cstride;
+	const int o = PHASE == 0 ? 0 : 4;
+	for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < total; it += gridDim.x * blockDim.x) {
+		const unsigned row = it / nx2;
+		const int i = 2 * (int)(it - row * nx2);
+		const int k = (int)(row / (unsigned)g.ny);
+		const int j = (int)(row - (unsigned)k * (unsigned)g.ny);
+		const long long v = g.voff + (long long)k * g.vplane + (long long)j * g.vpitch + i;
+		const long long c = (long long)k * g.cplane + (long long)j * g.cpitch + i;
+		const int np = (i + 1 < g.nx) ? 2 : 1;
+		const long long di = PHASE == 0 ? -1 : 1, dj = PHASE == 0 ? -(long long)g.vpitch : g.vpitch, dk = PHASE == 0 ? -g.vplane : g.vplane;
+		double res[2];
+		for (int e = 0; e < np; e++) {
+			const double ni = first ? 0.0 : in[v + e + di], nj = first ? 0.0 : in[v + e + dj], nk = first ? 0.0 : in[v + e + dk];
+			const double a0 = ld_stream(A + (o + 0) * cs + c + e), a1 = ld_stream(A + (o + 1) * cs + c + e), a2 = ld_stream(A + (o + 2) * cs + c + e);
+			const double dv = dinv[c + e], b = rhs[v + e];
+			if (PHASE == 0) {
+				double t = __dsub_rn(b, __dmul_rn(a0, ni));
+				t = __dsub_rn(t, __dmul_rn(a1, nj));
+				t = __dsub_rn(t, __dmul_rn(a2, nk));
+				res[e] = __dmul_rn(t, dv);
+			} else {
+				double t = __dmul_rn(a0, ni);
+				t = __dadd_rn(t, __dmul_rn(a1, nj));
+				t = __dadd_rn(t, __dmul_rn(a2, nk));
+				res[e] = __dsub_rn(b, __dmul_rn(dv, t));
+			}
+		}
+		if (np == 2) st2(out + v, make_double2(res[0], res[1]));
+		else out[v] = res[0];
+	}
+}
+
 unsigned ew_blocks(const s3d_ctx *ctx, const s3d_grid *g)
 {
 	const unsigned long long total = (unsigned long long)((g->nx + 1) / 2) * g->ny * g->nz;
@@ -426,6 +475,41 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		if (rc != S3D_OK) return rc;
 		sgs_rb_kernel<2><<<nb, 256, 0, ctx->stream>>>(gd, g->k0, A, d_dinv, d_r, d_y, d_z, ctx->gate);
 		S3D_LAUNCHED(ctx);
+		return S3D_OK;
+	}
+	if (ordering == S3D_SGS_JACOBI_SWEEPS) {
+		// forward: ping-pong between d_y and d_z, ending in d_y; backward: ping-pong between d_z and the context's sweep buffer
+		const unsigned nb = ew_blocks(ctx, g);
+		if (ctx->sweep_buf_cap < (size_t)g->vlen) {
+			S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			if (ctx->sweep_buf) S3D_CUDA(ctx, cudaFree(ctx->sweep_buf));
+			ctx->sweep_buf = nullptr; ctx->sweep_buf_cap = 0;
+			S3D_CUDA(ctx, cudaMalloc(&ctx->sweep_buf, (size_t)g->vlen * sizeof(double)));
+			S3D_CUDA(ctx, cudaMemsetAsync(ctx->sweep_buf, 0, (size_t)g->vlen * sizeof(double), ctx->stream));   // ghosts stay zero
+			ctx->sweep_buf_cap = (size_t)g->vlen;
+			ctx->sweep_buf_dims[0] = g->nx; ctx->sweep_buf_dims[1] = g->ny; ctx->sweep_buf_dims[2] = g->nz;
+		} else if (ctx->sweep_buf_dims[0] != g->nx || ctx->sweep_buf_dims[1] != g->ny || ctx->sweep_buf_dims[2] != g->nz) {
+			// another grid shape: what are ghost positions now may hold old real values
+			S3D_CUDA(ctx, cudaMemsetAsync(ctx->sweep_buf, 0, (size_t)g->vlen * sizeof(double), ctx->stream));
+			ctx->sweep_buf_dims[0] = g->nx; ctx->sweep_buf_dims[1] = g->ny; ctx->sweep_buf_dims[2] = g->nz;
+		}
+		double *w = ctx->sweep_buf;
+		// choose the starting buffer so that the last forward sweep lands in d_y
+		double *cur = (nsweeps % 2 == 1) ? d_y : w, *oth = (nsweeps % 2 == 1) ? w : d_y;
+		for (int swp = 0; swp < nsweeps; swp++) {
+			if (swp > 0) { const int rc = s3d_halo_exchange(ctx, g, oth); if (rc != S3D_OK) return rc; }
+			sgs_sweep_kernel<0><<<nb, 256, 0, ctx->stream>>>(gd, A, d_dinv, d_r, oth, cur, swp == 0, ctx->gate);
+			S3D_LAUNCHED(ctx);
+			double *t = cur; cur = oth; oth = t;
+		}
+		// now `oth` == d_y holds the forward result
+		cur = (nsweeps % 2 == 1) ? d_z : w; oth = (nsweeps % 2 == 1) ? w : d_z;
+		for (int swp = 0; swp < nsweeps; swp++) {
+			if (swp > 0) { const int rc = s3d_halo_exchange(ctx, g, oth); if (rc != S3D_OK) return rc; }
+			sgs_sweep_kernel<1><<<nb, 256, 0, ctx->stream>>>(gd, A, d_dinv, d_y, oth, cur, swp == 0, ctx->gate);
+			S3D_LAUNCHED(ctx);
+			double *t = cur; cur = oth; oth = t;
+		}
 		return S3D_OK;
 	}
 	if (ordering != S3D_SGS_LEXICOGRAPHIC && ordering != S3D_SGS_LEXICOGRAPHIC_PLANES)

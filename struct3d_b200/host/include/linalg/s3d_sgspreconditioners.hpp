@@ -11,7 +11,8 @@ public:
 	~SGS_like_preconditioner();
 	/// z = (D+U)^-1 D (D+L)^-1 r.  Ordering: lexicographic wavefront (bit-identical to the reference's
 	/// sequential sweep) unless params.threadedapply selects the red-black multicolour ordering, or the
-	/// option -s3d_sgs_ordering {lexicographic|redblack} says otherwise.
+	/// option -s3d_sgs_ordering {lexicographic|redblack|sweeps} says otherwise (sweeps: params.napplysweeps synchronous Jacobi
+	/// sweeps per triangular factor, the deterministic counterpart of the reference's asynchronous threaded sweeps).
 	SolveInfo apply(const SVec &r, SVec &z) const;
 	/// S3D_SGS_LEXICOGRAPHIC or S3D_SGS_REDBLACK
 	int ordering() const { return order; }

@@ -192,7 +192,8 @@ SGS_like_preconditioner::SGS_like_preconditioner(const SMat &lhs, const PreconPa
 		const std::string o = petscoptions_get_string("-s3d_sgs_ordering", 40);
 		if (o == "redblack" || o == "multicolour" || o == "multicolor") order = S3D_SGS_REDBLACK;
 		else if (o == "lexicographic") order = S3D_SGS_LEXICOGRAPHIC;
-		else throw std::runtime_error("-s3d_sgs_ordering must be lexicographic or redblack");
+		else if (o == "sweeps" || o == "jacobi_sweeps" || o == "async") order = S3D_SGS_JACOBI_SWEEPS;
+		else throw std::runtime_error("-s3d_sgs_ordering must be lexicographic, redblack or sweeps");
 	}
 	if (d.nranks() > 1 && order == S3D_SGS_LEXICOGRAPHIC) {
 		if (d.rank() == 0) std::printf(" WARNING: SGS: lexicographic sweeps serialise across z-slabs; using the red-black ordering.\n");

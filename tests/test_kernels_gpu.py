@@ -201,6 +201,12 @@ def test_jacobi_and_sgs(ctx, npdim, pde):
     ctx.vecset(g, -9.0, dz)
     ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_LEXICOGRAPHIC_PLANES, 1)
     assert np.array_equal(ctx.vec_download(g, dz), ref), "per-hyperplane SGS differs"
+    # synchronous Jacobi sweeps: equal to the oracle's statement sweep for sweep, and to the exact sweep once n >= nx+ny+nz-2
+    nx, ny, nz = m.n
+    for n in (1, 2, 3, nx + ny + nz - 2, nx + ny + nz - 1):
+        ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_JACOBI_SWEEPS, n)
+        assert np.array_equal(ctx.vec_download(g, dz), cport.sgs_jacobi_sweeps_apply(m, A, di, r, n)), f"{n} Jacobi sweeps differ"
+    assert np.array_equal(ctx.vec_download(g, dz), cport.sgs_like_apply(m, A, di, r, 1)), "enough sweeps must reproduce the exact solve"
     # StrILU: the ILU(0) diagonal (same dataflow kernel, divisions) and its application
     dinv2 = ctx.scalars_alloc(int(g.cstride))
     for sweeps in (1, 3, 0):
