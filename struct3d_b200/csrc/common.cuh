@@ -26,11 +26,17 @@ struct s3d_ctx {
 	// SGS dataflow bookkeeping (tile completion flags + work ticket)
 	int *sgs_flags = nullptr;
 	size_t sgs_flags_cap = 0;
+	double *sgs_iface = nullptr;  // per tile: the 64 values of its last i-column (what the next tile along i needs)
+	size_t sgs_iface_cap = 0;
 	double *sweep_buf = nullptr;   // second ping-pong vector of the Jacobi-sweeps SGS
 	size_t sweep_buf_cap = 0;
 	int sweep_buf_dims[3] = {0, 0, 0};
 	int sgs_epoch = 0;
 	int sgs_sleep_ns = 0;
+	int sgs_variant = 0;        // 0: warp-per-tile dataflow kernel, 1: block-per-tile kernel (r1's first version)
+	int sgs_warps_per_sm = 0;   // 0: as many as fit
+	long long *sgs_prof = nullptr;   // timing experiments: per-phase cycle sums of the warp kernel (tuning key sgs_profile)
+	int sgs_tile_i = 0;         // warp kernel: tile length along i, 16 (default) or 32
 	int *sgs_order = nullptr;     // tile dispatch order (hyperplane-sorted), cached per tile-grid shape
 	int sgs_order_dims[3] = {0, 0, 0};
 	// device-side gate applied to every launch that does not bring its own stop flag

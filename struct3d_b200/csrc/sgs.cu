@@ -91,11 +91,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 struct SgsFlow {
 	int *flags;        // one per tile: epoch of the last sweep that completed it
+	double *iface;     // warp kernel: [tile][64] the tile's last i-column, indexed by logical pencil b*8+c
 	const int *order;  // dispatch order: tile numbers sorted by tile hyperplane ci+cj+ck (then lexicographically)
 	unsigned *ticket;  // work counter, zeroed before every launch
 	int epoch;
 	int ntx, nty, ntz;
 	int sleep_ns;      // 0: busy-spin on the flag
+	long long *prof;   // optional per-phase cycle accumulators (warp kernel; timing experiments only)
 	int debug;         // timing experiments only (results become wrong): 1 skip wavefront, 2 skip staging, 4 skip fences, 8 skip waits
 };
 
@@ -260,6 +262,299 @@ sgs_dataflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 
 constexpr size_t SGS_SMEM = (5 * SGS_TILE + (SGS_TK + SGS_TJ) * SGS_TI + 2 * (SGS_TK + 2) * (SGS_TJ + 2)) * sizeof(double);
 
+// ---------------------------------------------------------------- warp-per-tile dataflow (the default)
+//
+// Same tiles, flags, dispatch order and arithmetic as sgs_dataflow_kernel, but ONE WARP owns a tile and nothing is
+// block-wide.  What was measured on the way (profiles/r1_sgs_phases.md):
+//   * the block version runs load -> wait -> sweep -> store one after the other behind block barriers, ~16 us per tile;
+//   * a lone warp is bound by instruction ISSUE, not by the fp64 chain (dmul/dadd 8.5 cycles, 64-bit shuffle 28): a first
+//     warp version that streamed its operands through per-lane cp.async rings spent ~130 instructions = 650-800 cycles per
+//     step on ring indexing, divergent bodies and copy issue.  So the step loop below is branch-free and ~50 instructions.
+// Design:
+//   - a lane owns TWO adjacent (j,k) pencils of the 32 x 8 x 8 tile (logical b = 2m, 2m+1; c = lane & 7) and marches along i;
+//     the two points it computes in a step lie on one hyperplane, so the two chains interleave (ILP 2 inside one warp);
+//   - neighbour values travel by warp shuffle: the j-neighbour of pencil 2m is lane-8's pencil 2m+1 one step ago, the
+//     j-neighbour of pencil 2m+1 is the lane's own previous value, the k-neighbours come from lane-1; no barrier;
+//   - the inputs of the tile arrive by cp.async.bulk (one 256-byte row per copy, completion on an mbarrier) while the warp waits
+//     for its predecessors.  Row rho(pencil) of a stream sits at rho*34 doubles with rho chosen so that the lanes of a half-warp,
+//     each at its own skewed i, hit 16 different banks; pencil 2m+1 is row rho+8, so ONE shared pointer, advanced by one
+//     element per step, addresses all ten operands with immediate offsets;
+//   - every lane evaluates every step (out-of-range steps read padding and are not committed), results leave with plain
+//     stores as they are produced, and only a fence + flag store remain after the last step.
+// tile length along i is a template parameter TI (16 or 32); a staged row has stride TI+2 doubles (16-byte aligned, == 2 mod 16)
+constexpr int SGW_PAD = 32;                // slack around the staged block: out-of-range steps read (and discard) it
+constexpr size_t sgw_smem(int na, int ti) { return (size_t)(3 * SGW_PAD + na * 64 * (ti + 2) + 16 * (ti + 2)) * sizeof(double) + 16; }
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned a, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned a, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned a, unsigned parity)
+{
+	unsigned ok;
+	asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+	return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned mbar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+	int v;
+	asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ double2 ldcg2(const double *p)
+{
+	double2 v;
+	asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+	return v;
+}
+
+template <int MODE, int TI>
+__global__ void __launch_bounds__(32)
+sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const double *__restrict__ c0,
+                    const double *__restrict__ c1, const double *__restrict__ c2, const double *__restrict__ dinv,
+                    double *out, const SgsFlow f, const int *stop)
+{
+	constexpr bool FWD = (MODE != 1);
+	constexpr bool ILU = (MODE == 2);
+	constexpr int NA = ILU ? 4 : 5;
+	constexpr int DIR = FWD ? 1 : -1;
+	constexpr int R = TI + 2, ASZ = 64 * R;
+	constexpr int CH = TI / 2;                               // 16-byte chunks per row
+	constexpr int RM = (R % 16 == 2) ? 5 : 1;                // row numbering multiplier: R = 2 (mod 16) -> 5, R = 10 (mod 16) -> 1
+	static_assert(R % 16 == 2 || R % 16 == 10, "row stride must be 2 or 10 modulo 16");
+	constexpr unsigned FULL = 0xffffffffu;
+	if (s3d_stopped(stop)) return;
+	extern __shared__ __align__(16) double smem[];
+	double *s_a = smem + SGW_PAD;                             // [stream][row rho][R]
+	double *s_hj = s_a + NA * ASZ + SGW_PAD;                  // [c][R]  j-neighbour rows of the adjacent tile / ghost row
+	double *s_hk = s_hj + 8 * R;                              // [b][R]  k-neighbour rows of the adjacent tile / ghost plane
+
+	const int lane = threadIdx.x;
+	const int m = lane >> 3, cc = lane & 7;
+	const int b0 = 2 * m, b1 = 2 * m + 1;                     // logical (sweep-order) j positions of the two pencils
+	const int s0 = b0 + cc;                                   // step at which pencil 0 starts; pencil 1 starts one later
+	// bank-conflict-free row numbering (see above): rho mod 8 = (5m + 2(c>>1)) mod 8, eight pencils share a residue
+	const int rho0 = 8 * ((m >> 1) * 4 + (cc & 1) * 2) + ((RM * m + 2 * (cc >> 1)) & 7);
+	const int ntiles = f.ntx * f.nty * f.ntz;
+	const int nwarps = gridDim.x;
+
+	// stage a tile's input rows: 16-byte cp.async, a half-warp (TI = 32) or quarter-warp (TI = 16) per row.  Issued for the NEXT
+	// tile as soon as the sweep of the current one is over, so the copies fly while the warp publishes and then waits.
+	auto stage = [&](int t) {
+		const int ci = t % f.ntx, cj = (t / f.ntx) % f.nty, ck = t / (f.ntx * f.nty);
+		const int i0 = ci * TI, j0 = cj * SGS_TJ, k0 = ck * SGS_TK;
+		const int tj = min(SGS_TJ, g.ny - j0), tk = min(SGS_TK, g.nz - k0);
+		const long long vtile = g.voff + (long long)k0 * g.vplane + (long long)j0 * g.vpitch + i0;
+		const long long ctile = (long long)k0 * g.cplane + (long long)j0 * g.cpitch + i0;
+		__syncwarp();                                           // the last tile's reads of the staging area come first
+#pragma unroll
+		for (int u = 0; u < 64 * CH / 32; u++) {
+			const int q = lane + 32 * u, i2 = q % CH, row = q / CH, rb = row >> 3, rc = row & 7;   // row of logical pencil (rb, rc), chunk i2
+			if (rb < tj && rc < tk && i0 + 2 * i2 < g.cpitch) {
+				const int rho = 8 * ((rb >> 2) * 4 + (rc & 1) * 2 + (rb & 1)) + ((RM * (rb >> 1) + 2 * (rc >> 1)) & 7);
+				const int pj = FWD ? rb : tj - 1 - rb, pk = FWD ? rc : tk - 1 - rc;
+				const long long cv = ctile + (long long)pk * g.cplane + (long long)pj * g.cpitch + 2 * i2;
+				const long long vv = vtile + (long long)pk * g.vplane + (long long)pj * g.vpitch + 2 * i2;
+				double *dst = s_a + rho * R + 2 * i2;
+				cp_async16(dst, in0 + (ILU ? cv : vv));
+				cp_async16(dst + ASZ, c0 + cv);
+				cp_async16(dst + 2 * ASZ, c1 + cv);
+				cp_async16(dst + 3 * ASZ, c2 + cv);
+				if (!ILU) cp_async16(dst + 4 * ASZ, dinv + cv);
+			}
+		}
+	};
+
+	int ticket = blockIdx.x;                                  // the first ticket is the warp's own number, later ones come from the counter
+	int tile = (ticket < ntiles) ? f.order[FWD ? ticket : ntiles - 1 - ticket] : -1;
+	if (tile >= 0) stage(tile);
+	while (tile >= 0) {
+		long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0;
+		if (f.prof) tp0 = clock64();
+		const int ci = tile % f.ntx, cj = (tile / f.ntx) % f.nty, ck = tile / (f.ntx * f.nty);
+		const int i0 = ci * TI, j0 = cj * SGS_TJ, k0 = ck * SGS_TK;
+		const int ti = min(TI, g.nx - i0), tj = min(SGS_TJ, g.ny - j0), tk = min(SGS_TK, g.nz - k0);
+		const long long vtile = g.voff + (long long)k0 * g.vplane + (long long)j0 * g.vpitch + i0;
+		const long long ctile = (long long)k0 * g.cplane + (long long)j0 * g.cpitch + i0;
+		const bool act0 = (b0 < tj) && (cc < tk), act1 = (b1 < tj) && (cc < tk);
+		const int lk = FWD ? cc : tk - 1 - cc;
+		const int lj0 = FWD ? b0 : tj - 1 - b0, lj1 = FWD ? b1 : tj - 1 - b1;
+		const long long cv0 = ctile + (long long)lk * g.cplane + (long long)lj0 * g.cpitch;
+		const long long cv1 = ctile + (long long)lk * g.cplane + (long long)lj1 * g.cpitch;
+		const long long vv0 = vtile + (long long)lk * g.vplane + (long long)lj0 * g.vpitch;
+		const long long vv1 = vtile + (long long)lk * g.vplane + (long long)lj1 * g.vpitch;
+
+		// where the halo comes from (addresses only; the loads follow the wait): rows 0..7 are the j-halo (row j0-1 / j0+tj at
+		// level c), rows 8..15 the k-halo (plane k0-1 / k0+tk at row b), then the two i-neighbours of the lane's pencils
+		constexpr int NH = 16 * CH / 32;                        // halo chunks per lane
+		const double *hp[NH];
+#pragma unroll
+		for (int u = 0; u < NH; u++) {
+			const int q = lane + 32 * u, row = q / CH, i2 = q % CH, r = row & 7;
+			hp[u] = nullptr;
+			if (2 * i2 < ti) {
+				if (row < 8) {
+					if (r < tk) hp[u] = out + vtile + (long long)(FWD ? r : tk - 1 - r) * g.vplane + (long long)(FWD ? -1 : tj) * g.vpitch + 2 * i2;
+				} else {
+					if (r < tj) hp[u] = out + vtile + (long long)(FWD ? -1 : tk) * g.vplane + (long long)(FWD ? r : tj - 1 - r) * g.vpitch + 2 * i2;
+				}
+			}
+		}
+		const bool iedge = FWD ? (ci == 0) : (ci == f.ntx - 1);    // no tile there: the ghost column of `out`
+		const double *box = f.iface + (long long)(FWD ? tile - 1 : tile + 1) * 64;
+		const double *wp0 = !act0 ? nullptr : iedge ? out + vv0 + (FWD ? -1 : ti) : box + b0 * 8 + cc;
+		const double *wp1 = !act1 ? nullptr : iedge ? out + vv1 + (FWD ? -1 : ti) : box + b1 * 8 + cc;
+		// ---- wait for the three predecessor tiles.  The poll is warp-uniform (vote): a loop that only three lanes
+		//      run leaves the warp split afterwards and every shuffle of the sweep then takes the divergent slow path
+		//      (measured: 1640 instead of 154 cycles per step).
+		{
+			int pred = -1;
+			if (FWD) {
+				if (lane == 0 && ci > 0) pred = tile - 1;
+				if (lane == 1 && cj > 0) pred = tile - f.ntx;
+				if (lane == 2 && ck > 0) pred = tile - f.ntx * f.nty;
+			} else {
+				if (lane == 0 && ci < f.ntx - 1) pred = tile + 1;
+				if (lane == 1 && cj < f.nty - 1) pred = tile + f.ntx;
+				if (lane == 2 && ck < f.ntz - 1) pred = tile + f.ntx * f.nty;
+			}
+			bool done = (pred < 0) || (f.debug & 1);
+			for (;;) {
+				if (!done) done = (ld_acquire(f.flags + pred) == f.epoch);
+				if (__all_sync(FULL, done)) break;
+			}
+		}
+		__syncwarp();
+		if (f.prof) tp1 = clock64();
+		// we are about to be busy for a few microseconds: claim the next ticket now, look its tile up at the end
+		int nticket = 0, ntile = -1;
+		double last0 = 0.0, last1 = 0.0;                      // the lane's newest value of either pencil
+		if (lane == 0) nticket = (int)atomicAdd(f.ticket, 1u) + nwarps;
+		// ---- halo values (from L2): all loads first, then the stores
+		{
+			double2 hv[NH];
+#pragma unroll
+			for (int u = 0; u < NH; u++) hv[u] = hp[u] ? ldcg2(hp[u]) : make_double2(0.0, 0.0);
+			const double wi0 = wp0 ? __ldcg(wp0) : 0.0, wi1 = wp1 ? __ldcg(wp1) : 0.0;   // i-neighbours: the adjacent tile's last column / the ghost column
+#pragma unroll
+			for (int u = 0; u < NH; u++) {
+				const int q = lane + 32 * u, row = q / CH, i2 = q % CH;
+				*reinterpret_cast<double2 *>(s_hj + row * R + 2 * i2) = hv[u];
+			}
+			// the ticket is back by now: look the next tile up (the load completes during the sweep)
+			if (lane == 0) ntile = (nticket < ntiles) ? f.order[FWD ? nticket : ntiles - 1 - nticket] : -1;
+			cp_async_wait_all();
+			__syncwarp();
+			if (f.prof) tp2 = clock64();
+
+			// ---- the sweep: pencil 0 is at i-position u0 = h - s0 (li = u0 forward, ti-1-u0 backward), pencil 1 at u0 - 1
+			const int start = FWD ? -s0 : ti - 1 + s0;
+			double *pa = s_a + rho0 * R + start;                 // pencil 0 operand; pencil 1: + 8R - DIR
+			const double *phj = s_hj + cc * R + start;           // used by lanes with b0 == 0
+			const double *phk = s_hk + b0 * R + start;           // used by lanes with c == 0; pencil 1: + R - DIR
+			last0 = wi0; last1 = wi1;
+			const int nsteps = ti + tj + tk - 1;                 // pencil 1 of a lane runs one step behind pencil 0
+			constexpr int E1 = 8 * R - DIR;
+			const bool jhalo = (m == 0), khalo = (cc == 0);
+			// operands of the step are fetched one step ahead so that no shared-memory latency sits on the fp64 chain
+			double a_in = pa[0], a_c0 = pa[ASZ], a_c1 = pa[2 * ASZ], a_c2 = pa[3 * ASZ], a_dv = ILU ? 0.0 : pa[(NA - 1) * ASZ];
+			double b_in = pa[E1], b_c0 = pa[E1 + ASZ], b_c1 = pa[E1 + 2 * ASZ], b_c2 = pa[E1 + 3 * ASZ], b_dv = ILU ? 0.0 : pa[E1 + (NA - 1) * ASZ];
+			double hj0 = jhalo ? phj[0] : 0.0, hk0 = khalo ? phk[0] : 0.0, hk1 = khalo ? phk[R - DIR] : 0.0;
+#pragma unroll 2
+			for (int h = 0; h < nsteps; h++) {
+				const double shj = __shfl_up_sync(FULL, last1, 8);
+				const double shk0 = __shfl_up_sync(FULL, last0, 1);
+				const double shk1 = __shfl_up_sync(FULL, last1, 1);
+				pa += DIR; phj += DIR; phk += DIR;
+				const double n_a_in = pa[0], n_a_c0 = pa[ASZ], n_a_c1 = pa[2 * ASZ], n_a_c2 = pa[3 * ASZ], n_a_dv = ILU ? 0.0 : pa[(NA - 1) * ASZ];
+				const double n_b_in = pa[E1], n_b_c0 = pa[E1 + ASZ], n_b_c1 = pa[E1 + 2 * ASZ], n_b_c2 = pa[E1 + 3 * ASZ], n_b_dv = ILU ? 0.0 : pa[E1 + (NA - 1) * ASZ];
+				const double n_hj0 = jhalo ? phj[0] : 0.0, n_hk0 = khalo ? phk[0] : 0.0, n_hk1 = khalo ? phk[R - DIR] : 0.0;
+				const int u0 = h - s0;
+				const bool in0 = act0 && (unsigned)u0 < (unsigned)ti;
+				const bool in1 = act1 && (unsigned)(u0 - 1) < (unsigned)ti;
+				const double wj0 = jhalo ? hj0 : shj, wk0 = khalo ? hk0 : shk0, wk1 = khalo ? hk1 : shk1;
+				const double wj1 = last0;                          // pencil 2m of this lane, one step ago, same i
+				double v0, v1;
+				if (ILU) {
+					v0 = __dsub_rn(__dsub_rn(__dsub_rn(a_in, __ddiv_rn(a_c0, last0)), __ddiv_rn(a_c1, wj0)), __ddiv_rn(a_c2, wk0));
+					v1 = __dsub_rn(__dsub_rn(__dsub_rn(b_in, __ddiv_rn(b_c0, last1)), __ddiv_rn(b_c1, wj1)), __ddiv_rn(b_c2, wk1));
+				} else if (FWD) {
+					v0 = __dmul_rn(__dsub_rn(__dsub_rn(__dsub_rn(a_in, __dmul_rn(a_c0, last0)), __dmul_rn(a_c1, wj0)), __dmul_rn(a_c2, wk0)), a_dv);
+					v1 = __dmul_rn(__dsub_rn(__dsub_rn(__dsub_rn(b_in, __dmul_rn(b_c0, last1)), __dmul_rn(b_c1, wj1)), __dmul_rn(b_c2, wk1)), b_dv);
+				} else {
+					v0 = __dsub_rn(a_in, __dmul_rn(a_dv, __dadd_rn(__dadd_rn(__dmul_rn(a_c0, last0), __dmul_rn(a_c1, wj0)), __dmul_rn(a_c2, wk0))));
+					v1 = __dsub_rn(b_in, __dmul_rn(b_dv, __dadd_rn(__dadd_rn(__dmul_rn(b_c0, last1), __dmul_rn(b_c1, wj1)), __dmul_rn(b_c2, wk1))));
+				}
+				// results replace the staged input (pa already points one step ahead)
+				if (in0) { last0 = v0; pa[-DIR] = v0; }
+				if (in1) { last1 = v1; pa[E1 - DIR] = v1; }
+				a_in = n_a_in; a_c0 = n_a_c0; a_c1 = n_a_c1; a_c2 = n_a_c2; a_dv = n_a_dv;
+				b_in = n_b_in; b_c0 = n_b_c0; b_c1 = n_b_c1; b_c2 = n_b_c2; b_dv = n_b_dv;
+				hj0 = n_hj0; hk0 = n_hk0; hk1 = n_hk1;
+			}
+		}
+		// ---- publish: every lane's stores, then the flag.  With f.debug & 64 the next tile's copies are issued first (their issue
+		//      overlaps the drain of the stores the fence waits for) at the price of a later flag.
+		long long tpf = 0;
+		if (f.prof) tpf = clock64();
+		ntile = __shfl_sync(FULL, ntile, 0);
+		// What other tiles of this sweep need goes out first: the last i-column (to the tile's mailbox, straight from the registers),
+		// the rows of the last j and the last k (whole 128/256-byte rows of `out`); then the fence and the flag.  The other rows
+		// follow after the flag -- only later kernels read them.  Whole rows = full 32-byte sectors: an 8-byte store per point made
+		// L2 fetch the rest of each sector first (measured: 5000-cycle fences under load).
+		__syncwarp();
+		if (act0) f.iface[(long long)tile * 64 + b0 * 8 + cc] = last0;
+		if (act1) f.iface[(long long)tile * 64 + b1 * 8 + cc] = last1;
+		auto copy_row_chunk = [&](int rb, int rc, int i2) {
+			const int rho = 8 * ((rb >> 2) * 4 + (rc & 1) * 2 + (rb & 1)) + ((RM * (rb >> 1) + 2 * (rc >> 1)) & 7);
+			const int pj = FWD ? rb : tj - 1 - rb, pk = FWD ? rc : tk - 1 - rc;
+			double *dst = out + vtile + (long long)pk * g.vplane + (long long)pj * g.vpitch + 2 * i2;
+			const double2 v = *reinterpret_cast<const double2 *>(s_a + rho * R + 2 * i2);
+			if (2 * i2 + 1 < ti) *reinterpret_cast<double2 *>(dst) = v;
+			else *dst = v.x;
+		};
+		// face rows: 0..7 the last j (b = tj-1) at every c, 8..15 the last k (c = tk-1) at every b < tj-1
+#pragma unroll
+		for (int u = 0; u < 16 * CH / 32; u++) {
+			const int q = lane + 32 * u, i2 = q % CH, fr = q / CH;
+			const int rb = (fr < 8) ? tj - 1 : fr - 8, rc = (fr < 8) ? fr : tk - 1;
+			if (rc < tk && rb < tj && (fr < 8 || rb < tj - 1) && 2 * i2 < ti) copy_row_chunk(rb, rc, i2);
+		}
+		asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+		__syncwarp();
+		if (f.prof) tp3 = clock64();
+		if (lane == 0) {
+			*(volatile int *)(f.flags + tile) = f.epoch;
+			if (f.prof) {
+				const long long tp4 = clock64();
+				atomicAdd((unsigned long long *)f.prof + 0, (unsigned long long)(tp1 - tp0));   // staging issue + flag wait
+				atomicAdd((unsigned long long *)f.prof + 1, (unsigned long long)(tp2 - tp1));   // ticket + halo rows + copy completion
+				atomicAdd((unsigned long long *)f.prof + 2, (unsigned long long)(tpf - tp2));   // sweep loop
+				atomicAdd((unsigned long long *)f.prof + 3, (unsigned long long)(tp4 - tpf));   // fence + flag
+				atomicAdd((unsigned long long *)f.prof + 4, 1ull);
+				atomicAdd((unsigned long long *)f.prof + 5, (unsigned long long)(ti + tj + tk - 1));
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < 64 * CH / 32; u++) {
+			const int q = lane + 32 * u, i2 = q % CH, row = q / CH, rb = row >> 3, rc = row & 7;
+			if (rb < tj - 1 && rc < tk - 1 && 2 * i2 < ti) copy_row_chunk(rb, rc, i2);
+		}
+		if (ntile >= 0) stage(ntile);
+		tile = ntile;
+	}
+}
+
 // ---------------------------------------------------------------- red-black
 
 // phase 0: y_R = r_R dinv                       (red:   (i+j+k) even in the reference's 1-based indices = odd+... see parity())
@@ -401,10 +696,32 @@ unsigned ew_blocks(const s3d_ctx *ctx, const s3d_grid *g)
 	return (unsigned)(b < 1 ? 1 : b);
 }
 
+inline int sgw_tile_i(const s3d_ctx *ctx) { return (ctx->sgs_tile_i == 32 || ctx->sgs_tile_i == 8) ? ctx->sgs_tile_i : 16; }
+
+template <int MODE, typename... Args> void sgw_launch(s3d_ctx *ctx, unsigned nblocks, Args... args)
+{
+	constexpr int NA = (MODE == 2) ? 4 : 5;
+	if (sgw_tile_i(ctx) == 32) sgs_warpflow_kernel<MODE, 32><<<nblocks, 32, sgw_smem(NA, 32), ctx->stream>>>(args...);
+	else if (sgw_tile_i(ctx) == 8) sgs_warpflow_kernel<MODE, 8><<<nblocks, 32, sgw_smem(NA, 8), ctx->stream>>>(args...);
+	else sgs_warpflow_kernel<MODE, 16><<<nblocks, 32, sgw_smem(NA, 16), ctx->stream>>>(args...);
+}
+
+template <int TI> int sgw_configure()
+{
+	cudaFuncSetAttribute(sgs_warpflow_kernel<0, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sgw_smem(5, TI));
+	cudaFuncSetAttribute(sgs_warpflow_kernel<1, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sgw_smem(5, TI));
+	cudaFuncSetAttribute(sgs_warpflow_kernel<2, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sgw_smem(4, TI));
+	int a = 1, b = 1;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sgs_warpflow_kernel<0, TI>, 32, sgw_smem(5, TI));
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sgs_warpflow_kernel<1, TI>, 32, sgw_smem(5, TI));
+	return std::max(1, std::min(a, b));
+}
+
 // flags / dispatch table / occupancy for the dataflow kernels; returns the number of persistent blocks
 int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblocks)
 {
-	f.ntx = (g->nx + SGS_TI - 1) / SGS_TI; f.nty = (g->ny + SGS_TJ - 1) / SGS_TJ; f.ntz = (g->nz + SGS_TK - 1) / SGS_TK;
+	const int tile_i = (ctx->sgs_variant == 0) ? sgw_tile_i(ctx) : SGS_TI;
+	f.ntx = (g->nx + tile_i - 1) / tile_i; f.nty = (g->ny + SGS_TJ - 1) / SGS_TJ; f.ntz = (g->nz + SGS_TK - 1) / SGS_TK;
 	const size_t ntiles = (size_t)f.ntx * f.nty * f.ntz;
 	if (ctx->sgs_flags_cap < ntiles + 1) {
 		S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -442,12 +759,41 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 		S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_order, ntiles * sizeof(int)));
 		S3D_CUDA(ctx, cudaMemcpy(ctx->sgs_order, order.data(), ntiles * sizeof(int), cudaMemcpyHostToDevice));
 		ctx->sgs_order_dims[0] = f.ntx; ctx->sgs_order_dims[1] = f.nty; ctx->sgs_order_dims[2] = f.ntz;
+		// another tiling: the old ticket slot now is a flag; start the epochs over
+		S3D_CUDA(ctx, cudaMemsetAsync(ctx->sgs_flags, 0, ctx->sgs_flags_cap * sizeof(int), ctx->stream));
+		ctx->sgs_epoch = 0;
 	}
 	f.flags = ctx->sgs_flags;
+	f.iface = ctx->sgs_iface;
 	f.order = ctx->sgs_order;
 	f.sleep_ns = 0;
 	f.debug = ctx->sgs_sleep_ns;   // reuses the tuning slot: debug bit mask
+	f.prof = ctx->sgs_prof;
 	f.ticket = reinterpret_cast<unsigned *>(ctx->sgs_flags + ntiles);   // the slot after the last flag
+	if (ctx->sgs_variant == 0) {
+		if (ctx->sgs_iface_cap < ntiles * 64) {
+			S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			if (ctx->sgs_iface) S3D_CUDA(ctx, cudaFree(ctx->sgs_iface));
+			ctx->sgs_iface = nullptr; ctx->sgs_iface_cap = 0;
+			S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_iface, ntiles * 64 * sizeof(double)));
+			ctx->sgs_iface_cap = ntiles * 64;
+		}
+		f.iface = ctx->sgs_iface;
+		static bool wconfigured = false;
+		static int warps_per_sm16 = 1, warps_per_sm32 = 1, warps_per_sm8 = 1;
+		if (!wconfigured) {
+			warps_per_sm8 = sgw_configure<8>();
+			warps_per_sm16 = sgw_configure<16>();
+			warps_per_sm32 = sgw_configure<32>();
+			S3D_CUDA(ctx, cudaGetLastError());
+			wconfigured = true;
+		}
+		int wps = (sgw_tile_i(ctx) == 32) ? warps_per_sm32 : (sgw_tile_i(ctx) == 8) ? warps_per_sm8 : warps_per_sm16;
+		if (ctx->sgs_warps_per_sm > 0) wps = std::min(wps, ctx->sgs_warps_per_sm);
+		if (wps < 1) wps = 1;
+		nblocks = (unsigned)std::min<size_t>(ntiles, (size_t)ctx->sm_count * wps);
+		return S3D_OK;
+	}
 	nblocks = (unsigned)std::min<size_t>(ntiles, (size_t)ctx->sm_count * blocks_per_sm);
 	return S3D_OK;
 }
@@ -528,11 +874,17 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		const long long cs = g->cstride;
 		f.epoch = ++ctx->sgs_epoch;
 		S3D_CUDA(ctx, cudaMemsetAsync(f.ticket, 0, sizeof(unsigned), ctx->stream));
-		sgs_dataflow_kernel<0><<<nblocks, block, SGS_SMEM, ctx->stream>>>(gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, ctx->gate);
+		if (ctx->sgs_variant == 0)
+			sgw_launch<0>(ctx, nblocks, gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, (const int *)ctx->gate);
+		else
+			sgs_dataflow_kernel<0><<<nblocks, block, SGS_SMEM, ctx->stream>>>(gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, ctx->gate);
 		S3D_LAUNCHED(ctx);
 		f.epoch = ++ctx->sgs_epoch;
 		S3D_CUDA(ctx, cudaMemsetAsync(f.ticket, 0, sizeof(unsigned), ctx->stream));
-		sgs_dataflow_kernel<1><<<nblocks, block, SGS_SMEM, ctx->stream>>>(gd, d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f, ctx->gate);
+		if (ctx->sgs_variant == 0)
+			sgw_launch<1>(ctx, nblocks, gd, (const double *)d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f, (const int *)ctx->gate);
+		else
+			sgs_dataflow_kernel<1><<<nblocks, block, SGS_SMEM, ctx->stream>>>(gd, d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f, ctx->gate);
 		S3D_LAUNCHED(ctx);
 		return S3D_OK;
 	}
@@ -578,8 +930,12 @@ int s3d_strilu_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuil
 		f.epoch = ++ctx->sgs_epoch;
 		e = cudaMemsetAsync(f.ticket, 0, sizeof(unsigned), ctx->stream);
 		if (e == cudaSuccess) {
-			sgs_dataflow_kernel<2><<<nblocks, SGS_NT, SGS_SMEM, ctx->stream>>>(gd, A + 3 * (size_t)g->cstride, P, P + g->cstride, P + 2 * (size_t)g->cstride,
-			                                                                      nullptr, D, f, nullptr);
+			if (ctx->sgs_variant == 0)
+				sgw_launch<2>(ctx, nblocks, gd, A + 3 * (size_t)g->cstride, (const double *)P, (const double *)(P + g->cstride),
+				              (const double *)(P + 2 * (size_t)g->cstride), (const double *)nullptr, D, f, (const int *)nullptr);
+			else
+				sgs_dataflow_kernel<2><<<nblocks, SGS_NT, SGS_SMEM, ctx->stream>>>(gd, A + 3 * (size_t)g->cstride, P, P + g->cstride, P + 2 * (size_t)g->cstride,
+				                                                                      nullptr, D, f, nullptr);
 			ctx->launches++;
 			ilu_invert_kernel<<<nb, 256, 0, ctx->stream>>>(gd, D, d_dinv);
 			ctx->launches++;

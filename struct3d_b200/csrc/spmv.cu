@@ -335,6 +335,25 @@ int s3d_tune_set(s3d_ctx *ctx, const char *key, int value)
 	} else if (!strcmp(key, "spmv_kchunk")) g_tune.kchunk = value;
 	else if (!strcmp(key, "spmv_hints")) g_tune.hints = value;
 	else if (!strcmp(key, "sgs_sleep_ns")) ctx->sgs_sleep_ns = value;
+	else if (!strcmp(key, "sgs_variant")) ctx->sgs_variant = value;
+	else if (!strcmp(key, "sgs_warps_per_sm")) ctx->sgs_warps_per_sm = value;
+	else if (!strcmp(key, "sgs_tile_i")) ctx->sgs_tile_i = value;
+	else if (!strcmp(key, "sgs_profile")) {
+		// 1: start accumulating per-phase cycles in the warp dataflow kernel; 0: print and stop (timing experiments only)
+		if (value && !ctx->sgs_prof) {
+			S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_prof, 8 * sizeof(long long)));
+			S3D_CUDA(ctx, cudaMemset(ctx->sgs_prof, 0, 8 * sizeof(long long)));
+		} else if (!value && ctx->sgs_prof) {
+			long long h[8];
+			S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			S3D_CUDA(ctx, cudaMemcpy(h, ctx->sgs_prof, sizeof h, cudaMemcpyDeviceToHost));
+			const double t = h[4] ? (double)h[4] : 1.0;
+			fprintf(stderr, "[sgs_profile] tiles %lld  cycles/tile: wait %.0f  halo %.0f  loop %.0f (%.1f per step)  publish %.0f\n", h[4], h[0] / t, h[1] / t,
+			        h[2] / t, h[5] ? (double)h[2] / h[5] : 0.0, h[3] / t);
+			S3D_CUDA(ctx, cudaFree(ctx->sgs_prof));
+			ctx->sgs_prof = nullptr;
+		}
+	}
 	else if (!strcmp(key, "halo_overlap")) ctx->no_overlap = (value == 0);
 	else if (!strcmp(key, "spmv_variant")) {
 		S3D_REQUIRE(ctx, value >= S3D_SPMV_MARCH && value <= S3D_SPMV_PAIR, "unknown SpMV variant");

@@ -1,23 +1,36 @@
 #!/usr/bin/env python
-"""Times the SGS dataflow kernel under different spin strategies / sizes."""
+"""Times the exact-lexicographic SGS apply: warp-per-tile (variant 0) against block-per-tile (variant 1), and warps per SM."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
 from struct3d_b200 import capi
 ctx = capi.Context(0)
-for n in (64, 256, 512):
+sizes = [int(a) for a in sys.argv[1:]] or [64, 128, 256, 512]
+for n in sizes:
     g = capi.make_grid(n, n, n)
     c = [-1.0 + 2.0 * np.arange(n + 2) / (n + 1)] * 3
     A = ctx.mat_alloc(g); ctx.assemble_convdiff(g, c, (0.577, 0.7, 0.3), 0.1, A)
-    r, z, y = (ctx.vec_alloc(g) for _ in range(3))
+    r, z, y, zr = (ctx.vec_alloc(g) for _ in range(4))
     ctx.vecset(g, 0.3, r)
     dinv = ctx.scalars_alloc(int(g.cstride)); ctx.sgs_setup(g, A, dinv)
-    for sl in (0, 1, 2, 4, 8, 1|8, 1|2|8, 1|2|4|8):
-        ctx.tune("sgs_sleep_ns", sl)
+    ctx.tune("sgs_variant", 1)
+    ctx.sgs_apply(g, A, dinv, r, zr, y, capi.SGS_LEXICOGRAPHIC, 1)
+    ref = ctx.vec_download(g, zr)
+    for variant, wps, depth, dbgv in ((1, 0, 0, 0), (0, 0, 32, 0), (0, 0, 16, 0), (0, 0, 8, 0)):
+        ctx.tune("sgs_variant", variant); ctx.tune("sgs_warps_per_sm", wps); ctx.tune("sgs_tile_i", depth)
+        ctx.tune("sgs_sleep_ns", dbgv)
         for _ in range(2): ctx.sgs_apply(g, A, dinv, r, z, y, capi.SGS_LEXICOGRAPHIC, 1)
+        same = np.array_equal(ctx.vec_download(g, z), ref)
         ctx.sync(); ctx.timer_start()
         for _ in range(5): ctx.sgs_apply(g, A, dinv, r, z, y, capi.SGS_LEXICOGRAPHIC, 1)
         ms = ctx.timer_stop_ms() / 5
-        print(f"{n:4d}^3 debug={sl:3d}  {ms:9.4f} ms   {96*n**3/ms/1e6:8.1f} GB/s(96B/pt)", flush=True)
-    for p in (A, r, z, y, dinv): ctx.free(p)
+        print(f"{n:4d}^3 variant={variant} warps/SM={wps} tile_i={depth} dbg={dbgv}  {ms:9.4f} ms   {96*n**3/ms/1e6:8.1f} GB/s(96B/pt)  bitwise_same={same}", flush=True)
+    ctx.tune("sgs_variant", 0); ctx.tune("sgs_warps_per_sm", 0); ctx.tune("sgs_tile_i", 0)
+    for dbg in (0,):
+        ctx.tune("sgs_sleep_ns", dbg)
+        ctx.tune("sgs_profile", 1)
+        ctx.sgs_apply(g, A, dinv, r, z, y, capi.SGS_LEXICOGRAPHIC, 1)
+        print("debug", dbg, file=sys.stderr, end=" ", flush=True); ctx.tune("sgs_profile", 0)
+    ctx.tune("sgs_sleep_ns", 0)
+    for p in (A, r, z, y, zr, dinv): ctx.free(p)
