@@ -264,47 +264,34 @@ constexpr size_t SGS_SMEM = (5 * SGS_TILE + (SGS_TK + SGS_TJ) * SGS_TI + 2 * (SG
 
 // ---------------------------------------------------------------- warp-per-tile dataflow (the default)
 //
-// Same tiles, flags, dispatch order and arithmetic as sgs_dataflow_kernel, but ONE WARP owns a tile and nothing is
-// block-wide.  What was measured on the way (profiles/r1_sgs_phases.md):
+// Same flags, dispatch order and arithmetic as sgs_dataflow_kernel, but ONE WARP owns a tile and nothing is block-wide.
+// What was measured on the way (profiles/r1_sgs_phases.md):
 //   * the block version runs load -> wait -> sweep -> store one after the other behind block barriers, ~16 us per tile;
-//   * a lone warp is bound by instruction ISSUE, not by the fp64 chain (dmul/dadd 8.5 cycles, 64-bit shuffle 28): a first
+//   * a lone warp is bound by instruction ISSUE, not by the fp64 chain (dmul/dadd 8.5 cycles, 64-bit shuffle 28 cycles): a first
 //     warp version that streamed its operands through per-lane cp.async rings spent ~130 instructions = 650-800 cycles per
-//     step on ring indexing, divergent bodies and copy issue.  So the step loop below is branch-free and ~50 instructions.
-// Design:
-//   - a lane owns TWO adjacent (j,k) pencils of the 32 x 8 x 8 tile (logical b = 2m, 2m+1; c = lane & 7) and marches along i;
-//     the two points it computes in a step lie on one hyperplane, so the two chains interleave (ILP 2 inside one warp);
-//   - neighbour values travel by warp shuffle: the j-neighbour of pencil 2m is lane-8's pencil 2m+1 one step ago, the
-//     j-neighbour of pencil 2m+1 is the lane's own previous value, the k-neighbours come from lane-1; no barrier;
-//   - the inputs of the tile arrive by cp.async.bulk (one 256-byte row per copy, completion on an mbarrier) while the warp waits
-//     for its predecessors.  Row rho(pencil) of a stream sits at rho*34 doubles with rho chosen so that the lanes of a half-warp,
-//     each at its own skewed i, hit 16 different banks; pencil 2m+1 is row rho+8, so ONE shared pointer, advanced by one
-//     element per step, addresses all ten operands with immediate offsets;
-//   - every lane evaluates every step (out-of-range steps read padding and are not committed), results leave with plain
-//     stores as they are produced, and only a fence + flag store remain after the last step.
-// tile length along i is a template parameter TI (16 or 32); a staged row has stride TI+2 doubles (16-byte aligned, == 2 mod 16)
+//     step on ring indexing, divergent bodies and copy issue; the step loop below is branch-free (~66 instructions for two points
+//     per lane, 135-150 cycles);
+//   * a poll loop run by three lanes leaves the warp split and every later shuffle takes the divergent slow path (1640 instead
+//     of 154 cycles per step): the poll is a warp-uniform vote;
+//   * cp.async.bulk per 256-byte row costs ~55 cycles of issue each (17600 cycles per tile); 16-byte cp.async by all lanes: 2500;
+//   * an 8-byte store per point makes L2 fetch the rest of each 32-byte sector and the fence that follows waits for it (5000
+//     cycles under load): results leave as whole rows.
+// Design (P = pencils per lane, tile = TI x 4P x 8 points):
+//   - lane (m, c) = (lane >> 3, lane & 7) owns the (j,k) pencils b = P m .. P m + P-1, c (logical = sweep-order positions) and
+//     marches along i; with P = 2 the two points it computes in a step lie on one hyperplane, so two chains interleave;
+//   - neighbour values travel by warp shuffle (j-neighbour: lane-8, or with P = 2 the lane's own other pencil; k-neighbour:
+//     lane-1); the tile's halo rows and its i-neighbour column come from L2 after the predecessors' flags;
+//   - the inputs of the tile are staged in shared memory with cp.async (issued for the NEXT tile right after the flag of the
+//     current one, so they fly during the wait).  Row rho(pencil) of a stream sits at rho*(TI+2) doubles with rho chosen so
+//     that the lanes of a half-warp, each at its own skewed i, hit 16 different banks; with P = 2 the second pencil is row rho+8,
+//     so ONE shared pointer, advanced by one element per step, addresses all operands with immediate offsets;
+//   - every lane evaluates every step (out-of-range steps read padding and are not committed); results overwrite the staged
+//     input and leave as whole rows: first what other tiles of this sweep need (the last i-column through a per-tile mailbox,
+//     the rows of the last j and the last k), then fence + flag, then the rest.
 constexpr int SGW_PAD = 32;                // slack around the staged block: out-of-range steps read (and discard) it
-constexpr size_t sgw_smem(int na, int ti) { return (size_t)(3 * SGW_PAD + na * 64 * (ti + 2) + 16 * (ti + 2)) * sizeof(double) + 16; }
+constexpr int SGW_TK = 8;
+constexpr size_t sgw_smem(int na, int ti, int p) { return (size_t)(3 * SGW_PAD + na * 32 * p * (ti + 2) + (8 + 4 * p) * (ti + 2)) * sizeof(double) + 16; }
 
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned a, unsigned count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
-	asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned a, unsigned bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned a, unsigned parity)
-{
-	unsigned ok;
-	asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-	return ok != 0;
-}
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned mbar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
-}
 __device__ __forceinline__ int ld_acquire(const int *p)
 {
 	int v;
@@ -318,7 +305,17 @@ __device__ __forceinline__ double2 ldcg2(const double *p)
 	return v;
 }
 
-template <int MODE, int TI>
+// bank-conflict-free row numbering for a row stride == 2 (mod 16) doubles: lane (m, c) at step h reads element h - s of its row,
+// s = b + c, so the bank (8-byte units) is (2 rho - s + h) mod 16; rho is chosen so that this is a bijection on each half-warp.
+// The backward sweep reads element ti-1 - (h - s): bank (2 rho + s - h + const), so it takes the negated low part.
+template <int P, bool FWD> __device__ __forceinline__ int sgw_row(int b, int c)
+{
+	const int lo = (P == 2) ? 5 * (b >> 1) + 2 * (c >> 1) : ((b + c + 1) >> 1) + (c >> 1) + 4 * (b & 1);
+	const int hi = (P == 2) ? (b >> 2) * 4 + (c & 1) * 2 + (b & 1) : 2 * (b & 1) + (c & 1);
+	return 8 * hi + ((FWD ? lo : -lo) & 7);
+}
+
+template <int MODE, int TI, int P>
 __global__ void __launch_bounds__(32)
 sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const double *__restrict__ c0,
                     const double *__restrict__ c1, const double *__restrict__ c2, const double *__restrict__ dinv,
@@ -328,10 +325,10 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 	constexpr bool ILU = (MODE == 2);
 	constexpr int NA = ILU ? 4 : 5;
 	constexpr int DIR = FWD ? 1 : -1;
-	constexpr int R = TI + 2, ASZ = 64 * R;
+	constexpr int TJ = 4 * P, TK = SGW_TK, NROWS = TJ * TK;
+	constexpr int R = TI + 2, ASZ = NROWS * R;
 	constexpr int CH = TI / 2;                               // 16-byte chunks per row
-	constexpr int RM = (R % 16 == 2) ? 5 : 1;                // row numbering multiplier: R = 2 (mod 16) -> 5, R = 10 (mod 16) -> 1
-	static_assert(R % 16 == 2 || R % 16 == 10, "row stride must be 2 or 10 modulo 16");
+	static_assert(R % 16 == 2, "row stride must be 2 modulo 16 (see sgw_row)");
 	constexpr unsigned FULL = 0xffffffffu;
 	if (s3d_stopped(stop)) return;
 	extern __shared__ __align__(16) double smem[];
@@ -341,31 +338,29 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 
 	const int lane = threadIdx.x;
 	const int m = lane >> 3, cc = lane & 7;
-	const int b0 = 2 * m, b1 = 2 * m + 1;                     // logical (sweep-order) j positions of the two pencils
+	const int b0 = P * m, b1 = P * m + 1;                     // logical (sweep-order) j positions of the lane's pencils (b1: P = 2)
 	const int s0 = b0 + cc;                                   // step at which pencil 0 starts; pencil 1 starts one later
-	// bank-conflict-free row numbering (see above): rho mod 8 = (5m + 2(c>>1)) mod 8, eight pencils share a residue
-	const int rho0 = 8 * ((m >> 1) * 4 + (cc & 1) * 2) + ((RM * m + 2 * (cc >> 1)) & 7);
+	const int rho0 = sgw_row<P, FWD>(b0, cc);                      // P = 2: pencil 1 is row rho0 + 8
 	const int ntiles = f.ntx * f.nty * f.ntz;
 	const int nwarps = gridDim.x;
 
-	// stage a tile's input rows: 16-byte cp.async, a half-warp (TI = 32) or quarter-warp (TI = 16) per row.  Issued for the NEXT
-	// tile as soon as the sweep of the current one is over, so the copies fly while the warp publishes and then waits.
+	// stage a tile's input rows: 16-byte cp.async, CH lanes per row.  Issued for the NEXT tile as soon as the flag of the current
+	// one is out, so the copies fly while the warp waits for the predecessors.
 	auto stage = [&](int t) {
 		const int ci = t % f.ntx, cj = (t / f.ntx) % f.nty, ck = t / (f.ntx * f.nty);
-		const int i0 = ci * TI, j0 = cj * SGS_TJ, k0 = ck * SGS_TK;
-		const int tj = min(SGS_TJ, g.ny - j0), tk = min(SGS_TK, g.nz - k0);
+		const int i0 = ci * TI, j0 = cj * TJ, k0 = ck * TK;
+		const int tj = min(TJ, g.ny - j0), tk = min(TK, g.nz - k0);
 		const long long vtile = g.voff + (long long)k0 * g.vplane + (long long)j0 * g.vpitch + i0;
 		const long long ctile = (long long)k0 * g.cplane + (long long)j0 * g.cpitch + i0;
 		__syncwarp();                                           // the last tile's reads of the staging area come first
 #pragma unroll
-		for (int u = 0; u < 64 * CH / 32; u++) {
+		for (int u = 0; u < NROWS * CH / 32; u++) {
 			const int q = lane + 32 * u, i2 = q % CH, row = q / CH, rb = row >> 3, rc = row & 7;   // row of logical pencil (rb, rc), chunk i2
 			if (rb < tj && rc < tk && i0 + 2 * i2 < g.cpitch) {
-				const int rho = 8 * ((rb >> 2) * 4 + (rc & 1) * 2 + (rb & 1)) + ((RM * (rb >> 1) + 2 * (rc >> 1)) & 7);
 				const int pj = FWD ? rb : tj - 1 - rb, pk = FWD ? rc : tk - 1 - rc;
 				const long long cv = ctile + (long long)pk * g.cplane + (long long)pj * g.cpitch + 2 * i2;
 				const long long vv = vtile + (long long)pk * g.vplane + (long long)pj * g.vpitch + 2 * i2;
-				double *dst = s_a + rho * R + 2 * i2;
+				double *dst = s_a + sgw_row<P, FWD>(rb, rc) * R + 2 * i2;
 				cp_async16(dst, in0 + (ILU ? cv : vv));
 				cp_async16(dst + ASZ, c0 + cv);
 				cp_async16(dst + 2 * ASZ, c1 + cv);
@@ -382,30 +377,28 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0;
 		if (f.prof) tp0 = clock64();
 		const int ci = tile % f.ntx, cj = (tile / f.ntx) % f.nty, ck = tile / (f.ntx * f.nty);
-		const int i0 = ci * TI, j0 = cj * SGS_TJ, k0 = ck * SGS_TK;
-		const int ti = min(TI, g.nx - i0), tj = min(SGS_TJ, g.ny - j0), tk = min(SGS_TK, g.nz - k0);
+		const int i0 = ci * TI, j0 = cj * TJ, k0 = ck * TK;
+		const int ti = min(TI, g.nx - i0), tj = min(TJ, g.ny - j0), tk = min(TK, g.nz - k0);
 		const long long vtile = g.voff + (long long)k0 * g.vplane + (long long)j0 * g.vpitch + i0;
-		const long long ctile = (long long)k0 * g.cplane + (long long)j0 * g.cpitch + i0;
-		const bool act0 = (b0 < tj) && (cc < tk), act1 = (b1 < tj) && (cc < tk);
+		const bool act0 = (b0 < tj) && (cc < tk), act1 = (P == 2) && (b1 < tj) && (cc < tk);
 		const int lk = FWD ? cc : tk - 1 - cc;
 		const int lj0 = FWD ? b0 : tj - 1 - b0, lj1 = FWD ? b1 : tj - 1 - b1;
-		const long long cv0 = ctile + (long long)lk * g.cplane + (long long)lj0 * g.cpitch;
-		const long long cv1 = ctile + (long long)lk * g.cplane + (long long)lj1 * g.cpitch;
 		const long long vv0 = vtile + (long long)lk * g.vplane + (long long)lj0 * g.vpitch;
 		const long long vv1 = vtile + (long long)lk * g.vplane + (long long)lj1 * g.vpitch;
 
 		// where the halo comes from (addresses only; the loads follow the wait): rows 0..7 are the j-halo (row j0-1 / j0+tj at
-		// level c), rows 8..15 the k-halo (plane k0-1 / k0+tk at row b), then the two i-neighbours of the lane's pencils
-		constexpr int NH = 16 * CH / 32;                        // halo chunks per lane
+		// level c), rows 8..8+TJ-1 the k-halo (plane k0-1 / k0+tk at row b), then the i-neighbours of the lane's pencils
+		constexpr int NH = (8 + TJ) * CH / 32;                  // halo chunks per lane
 		const double *hp[NH];
 #pragma unroll
 		for (int u = 0; u < NH; u++) {
-			const int q = lane + 32 * u, row = q / CH, i2 = q % CH, r = row & 7;
+			const int q = lane + 32 * u, row = q / CH, i2 = q % CH;
 			hp[u] = nullptr;
 			if (2 * i2 < ti) {
 				if (row < 8) {
-					if (r < tk) hp[u] = out + vtile + (long long)(FWD ? r : tk - 1 - r) * g.vplane + (long long)(FWD ? -1 : tj) * g.vpitch + 2 * i2;
+					if (row < tk) hp[u] = out + vtile + (long long)(FWD ? row : tk - 1 - row) * g.vplane + (long long)(FWD ? -1 : tj) * g.vpitch + 2 * i2;
 				} else {
+					const int r = row - 8;
 					if (r < tj) hp[u] = out + vtile + (long long)(FWD ? -1 : tk) * g.vplane + (long long)(FWD ? r : tj - 1 - r) * g.vpitch + 2 * i2;
 				}
 			}
@@ -414,9 +407,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		const double *box = f.iface + (long long)(FWD ? tile - 1 : tile + 1) * 64;
 		const double *wp0 = !act0 ? nullptr : iedge ? out + vv0 + (FWD ? -1 : ti) : box + b0 * 8 + cc;
 		const double *wp1 = !act1 ? nullptr : iedge ? out + vv1 + (FWD ? -1 : ti) : box + b1 * 8 + cc;
-		// ---- wait for the three predecessor tiles.  The poll is warp-uniform (vote): a loop that only three lanes
-		//      run leaves the warp split afterwards and every shuffle of the sweep then takes the divergent slow path
-		//      (measured: 1640 instead of 154 cycles per step).
+		// ---- wait for the three predecessor tiles (warp-uniform vote, see above)
 		{
 			int pred = -1;
 			if (FWD) {
@@ -436,7 +427,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		}
 		__syncwarp();
 		if (f.prof) tp1 = clock64();
-		// we are about to be busy for a few microseconds: claim the next ticket now, look its tile up at the end
+		// we are about to be busy for a few microseconds: claim the next ticket now, look its tile up before the sweep
 		int nticket = 0, ntile = -1;
 		double last0 = 0.0, last1 = 0.0;                      // the lane's newest value of either pencil
 		if (lane == 0) nticket = (int)atomicAdd(f.ticket, 1u) + nwarps;
@@ -463,69 +454,73 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 			const double *phj = s_hj + cc * R + start;           // used by lanes with b0 == 0
 			const double *phk = s_hk + b0 * R + start;           // used by lanes with c == 0; pencil 1: + R - DIR
 			last0 = wi0; last1 = wi1;
-			const int nsteps = ti + tj + tk - 1;                 // pencil 1 of a lane runs one step behind pencil 0
+			const int nsteps = ti + tj + tk - 2 + (P - 1);       // P = 2: pencil 1 of a lane runs one step behind pencil 0
 			constexpr int E1 = 8 * R - DIR;
 			const bool jhalo = (m == 0), khalo = (cc == 0);
 			// operands of the step are fetched one step ahead so that no shared-memory latency sits on the fp64 chain
 			double a_in = pa[0], a_c0 = pa[ASZ], a_c1 = pa[2 * ASZ], a_c2 = pa[3 * ASZ], a_dv = ILU ? 0.0 : pa[(NA - 1) * ASZ];
-			double b_in = pa[E1], b_c0 = pa[E1 + ASZ], b_c1 = pa[E1 + 2 * ASZ], b_c2 = pa[E1 + 3 * ASZ], b_dv = ILU ? 0.0 : pa[E1 + (NA - 1) * ASZ];
-			double hj0 = jhalo ? phj[0] : 0.0, hk0 = khalo ? phk[0] : 0.0, hk1 = khalo ? phk[R - DIR] : 0.0;
+			double hj0 = jhalo ? phj[0] : 0.0, hk0 = khalo ? phk[0] : 0.0;
+			double b_in = 0.0, b_c0 = 0.0, b_c1 = 0.0, b_c2 = 0.0, b_dv = 0.0, hk1 = 0.0;
+			if (P == 2) {
+				b_in = pa[E1]; b_c0 = pa[E1 + ASZ]; b_c1 = pa[E1 + 2 * ASZ]; b_c2 = pa[E1 + 3 * ASZ]; b_dv = ILU ? 0.0 : pa[E1 + (NA - 1) * ASZ];
+				hk1 = khalo ? phk[R - DIR] : 0.0;
+			}
 #pragma unroll 2
 			for (int h = 0; h < nsteps; h++) {
-				const double shj = __shfl_up_sync(FULL, last1, 8);
+				const double shj = __shfl_up_sync(FULL, P == 2 ? last1 : last0, 8);
 				const double shk0 = __shfl_up_sync(FULL, last0, 1);
-				const double shk1 = __shfl_up_sync(FULL, last1, 1);
+				double shk1 = 0.0;
+				if (P == 2) shk1 = __shfl_up_sync(FULL, last1, 1);
 				pa += DIR; phj += DIR; phk += DIR;
 				const double n_a_in = pa[0], n_a_c0 = pa[ASZ], n_a_c1 = pa[2 * ASZ], n_a_c2 = pa[3 * ASZ], n_a_dv = ILU ? 0.0 : pa[(NA - 1) * ASZ];
-				const double n_b_in = pa[E1], n_b_c0 = pa[E1 + ASZ], n_b_c1 = pa[E1 + 2 * ASZ], n_b_c2 = pa[E1 + 3 * ASZ], n_b_dv = ILU ? 0.0 : pa[E1 + (NA - 1) * ASZ];
-				const double n_hj0 = jhalo ? phj[0] : 0.0, n_hk0 = khalo ? phk[0] : 0.0, n_hk1 = khalo ? phk[R - DIR] : 0.0;
+				const double n_hj0 = jhalo ? phj[0] : 0.0, n_hk0 = khalo ? phk[0] : 0.0;
+				double n_b_in = 0.0, n_b_c0 = 0.0, n_b_c1 = 0.0, n_b_c2 = 0.0, n_b_dv = 0.0, n_hk1 = 0.0;
+				if (P == 2) {
+					n_b_in = pa[E1]; n_b_c0 = pa[E1 + ASZ]; n_b_c1 = pa[E1 + 2 * ASZ]; n_b_c2 = pa[E1 + 3 * ASZ]; n_b_dv = ILU ? 0.0 : pa[E1 + (NA - 1) * ASZ];
+					n_hk1 = khalo ? phk[R - DIR] : 0.0;
+				}
 				const int u0 = h - s0;
 				const bool in0 = act0 && (unsigned)u0 < (unsigned)ti;
 				const bool in1 = act1 && (unsigned)(u0 - 1) < (unsigned)ti;
 				const double wj0 = jhalo ? hj0 : shj, wk0 = khalo ? hk0 : shk0, wk1 = khalo ? hk1 : shk1;
 				const double wj1 = last0;                          // pencil 2m of this lane, one step ago, same i
-				double v0, v1;
+				double v0, v1 = 0.0;
 				if (ILU) {
 					v0 = __dsub_rn(__dsub_rn(__dsub_rn(a_in, __ddiv_rn(a_c0, last0)), __ddiv_rn(a_c1, wj0)), __ddiv_rn(a_c2, wk0));
-					v1 = __dsub_rn(__dsub_rn(__dsub_rn(b_in, __ddiv_rn(b_c0, last1)), __ddiv_rn(b_c1, wj1)), __ddiv_rn(b_c2, wk1));
+					if (P == 2) v1 = __dsub_rn(__dsub_rn(__dsub_rn(b_in, __ddiv_rn(b_c0, last1)), __ddiv_rn(b_c1, wj1)), __ddiv_rn(b_c2, wk1));
 				} else if (FWD) {
 					v0 = __dmul_rn(__dsub_rn(__dsub_rn(__dsub_rn(a_in, __dmul_rn(a_c0, last0)), __dmul_rn(a_c1, wj0)), __dmul_rn(a_c2, wk0)), a_dv);
-					v1 = __dmul_rn(__dsub_rn(__dsub_rn(__dsub_rn(b_in, __dmul_rn(b_c0, last1)), __dmul_rn(b_c1, wj1)), __dmul_rn(b_c2, wk1)), b_dv);
+					if (P == 2) v1 = __dmul_rn(__dsub_rn(__dsub_rn(__dsub_rn(b_in, __dmul_rn(b_c0, last1)), __dmul_rn(b_c1, wj1)), __dmul_rn(b_c2, wk1)), b_dv);
 				} else {
 					v0 = __dsub_rn(a_in, __dmul_rn(a_dv, __dadd_rn(__dadd_rn(__dmul_rn(a_c0, last0), __dmul_rn(a_c1, wj0)), __dmul_rn(a_c2, wk0))));
-					v1 = __dsub_rn(b_in, __dmul_rn(b_dv, __dadd_rn(__dadd_rn(__dmul_rn(b_c0, last1), __dmul_rn(b_c1, wj1)), __dmul_rn(b_c2, wk1))));
+					if (P == 2) v1 = __dsub_rn(b_in, __dmul_rn(b_dv, __dadd_rn(__dadd_rn(__dmul_rn(b_c0, last1), __dmul_rn(b_c1, wj1)), __dmul_rn(b_c2, wk1))));
 				}
 				// results replace the staged input (pa already points one step ahead)
 				if (in0) { last0 = v0; pa[-DIR] = v0; }
-				if (in1) { last1 = v1; pa[E1 - DIR] = v1; }
-				a_in = n_a_in; a_c0 = n_a_c0; a_c1 = n_a_c1; a_c2 = n_a_c2; a_dv = n_a_dv;
-				b_in = n_b_in; b_c0 = n_b_c0; b_c1 = n_b_c1; b_c2 = n_b_c2; b_dv = n_b_dv;
-				hj0 = n_hj0; hk0 = n_hk0; hk1 = n_hk1;
+				if (P == 2 && in1) { last1 = v1; pa[E1 - DIR] = v1; }
+				a_in = n_a_in; a_c0 = n_a_c0; a_c1 = n_a_c1; a_c2 = n_a_c2; a_dv = n_a_dv; hj0 = n_hj0; hk0 = n_hk0;
+				if (P == 2) { b_in = n_b_in; b_c0 = n_b_c0; b_c1 = n_b_c1; b_c2 = n_b_c2; b_dv = n_b_dv; hk1 = n_hk1; }
 			}
 		}
-		// ---- publish: every lane's stores, then the flag.  With f.debug & 64 the next tile's copies are issued first (their issue
-		//      overlaps the drain of the stores the fence waits for) at the price of a later flag.
+		// ---- publish.  What other tiles of this sweep need goes out first: the last i-column (to the tile's mailbox, straight from
+		//      the registers) and the rows of the last j and the last k (whole rows of `out`); then the fence and the flag.  The other
+		//      rows follow after the flag -- only later kernels read them.
 		long long tpf = 0;
 		if (f.prof) tpf = clock64();
 		ntile = __shfl_sync(FULL, ntile, 0);
-		// What other tiles of this sweep need goes out first: the last i-column (to the tile's mailbox, straight from the registers),
-		// the rows of the last j and the last k (whole 128/256-byte rows of `out`); then the fence and the flag.  The other rows
-		// follow after the flag -- only later kernels read them.  Whole rows = full 32-byte sectors: an 8-byte store per point made
-		// L2 fetch the rest of each sector first (measured: 5000-cycle fences under load).
 		__syncwarp();
 		if (act0) f.iface[(long long)tile * 64 + b0 * 8 + cc] = last0;
 		if (act1) f.iface[(long long)tile * 64 + b1 * 8 + cc] = last1;
 		auto copy_row_chunk = [&](int rb, int rc, int i2) {
-			const int rho = 8 * ((rb >> 2) * 4 + (rc & 1) * 2 + (rb & 1)) + ((RM * (rb >> 1) + 2 * (rc >> 1)) & 7);
 			const int pj = FWD ? rb : tj - 1 - rb, pk = FWD ? rc : tk - 1 - rc;
 			double *dst = out + vtile + (long long)pk * g.vplane + (long long)pj * g.vpitch + 2 * i2;
-			const double2 v = *reinterpret_cast<const double2 *>(s_a + rho * R + 2 * i2);
+			const double2 v = *reinterpret_cast<const double2 *>(s_a + sgw_row<P, FWD>(rb, rc) * R + 2 * i2);
 			if (2 * i2 + 1 < ti) *reinterpret_cast<double2 *>(dst) = v;
 			else *dst = v.x;
 		};
-		// face rows: 0..7 the last j (b = tj-1) at every c, 8..15 the last k (c = tk-1) at every b < tj-1
+		// face rows: 0..7 the last j (b = tj-1) at every c, then the last k (c = tk-1) at every b < tj-1
 #pragma unroll
-		for (int u = 0; u < 16 * CH / 32; u++) {
+		for (int u = 0; u < (8 + TJ) * CH / 32; u++) {
 			const int q = lane + 32 * u, i2 = q % CH, fr = q / CH;
 			const int rb = (fr < 8) ? tj - 1 : fr - 8, rc = (fr < 8) ? fr : tk - 1;
 			if (rc < tk && rb < tj && (fr < 8 || rb < tj - 1) && 2 * i2 < ti) copy_row_chunk(rb, rc, i2);
@@ -537,16 +532,16 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 			*(volatile int *)(f.flags + tile) = f.epoch;
 			if (f.prof) {
 				const long long tp4 = clock64();
-				atomicAdd((unsigned long long *)f.prof + 0, (unsigned long long)(tp1 - tp0));   // staging issue + flag wait
+				atomicAdd((unsigned long long *)f.prof + 0, (unsigned long long)(tp1 - tp0));   // flag wait
 				atomicAdd((unsigned long long *)f.prof + 1, (unsigned long long)(tp2 - tp1));   // ticket + halo rows + copy completion
 				atomicAdd((unsigned long long *)f.prof + 2, (unsigned long long)(tpf - tp2));   // sweep loop
-				atomicAdd((unsigned long long *)f.prof + 3, (unsigned long long)(tp4 - tpf));   // fence + flag
+				atomicAdd((unsigned long long *)f.prof + 3, (unsigned long long)(tp4 - tpf));   // face rows + fence + flag
 				atomicAdd((unsigned long long *)f.prof + 4, 1ull);
-				atomicAdd((unsigned long long *)f.prof + 5, (unsigned long long)(ti + tj + tk - 1));
+				atomicAdd((unsigned long long *)f.prof + 5, (unsigned long long)(ti + tj + tk - 2 + (P - 1)));
 			}
 		}
 #pragma unroll
-		for (int u = 0; u < 64 * CH / 32; u++) {
+		for (int u = 0; u < NROWS * CH / 32; u++) {
 			const int q = lane + 32 * u, i2 = q % CH, row = q / CH, rb = row >> 3, rc = row & 7;
 			if (rb < tj - 1 && rc < tk - 1 && 2 * i2 < ti) copy_row_chunk(rb, rc, i2);
 		}
@@ -696,24 +691,33 @@ unsigned ew_blocks(const s3d_ctx *ctx, const s3d_grid *g)
 	return (unsigned)(b < 1 ? 1 : b);
 }
 
-inline int sgw_tile_i(const s3d_ctx *ctx) { return (ctx->sgs_tile_i == 32 || ctx->sgs_tile_i == 8) ? ctx->sgs_tile_i : 16; }
-
-template <int MODE, typename... Args> void sgw_launch(s3d_ctx *ctx, unsigned nblocks, Args... args)
+inline int sgw_tile_i(const s3d_ctx *ctx) { return ctx->sgs_tile_i == 32 ? 32 : 16; }
+// pencils per lane: 2 (tile TI x 8 x 8) has the shorter dependency chain across the grid, 1 (tile TI x 4 x 8) twice as many tiles in
+// flight per SM.  Measured on B200 (profiles/r1_sgs_phases.md): 256^3 0.82 vs 1.01 ms, 512^3 3.73 vs 3.27 ms.
+inline int sgw_pencils(const s3d_ctx *ctx, const s3d_grid *g)
 {
-	constexpr int NA = (MODE == 2) ? 4 : 5;
-	if (sgw_tile_i(ctx) == 32) sgs_warpflow_kernel<MODE, 32><<<nblocks, 32, sgw_smem(NA, 32), ctx->stream>>>(args...);
-	else if (sgw_tile_i(ctx) == 8) sgs_warpflow_kernel<MODE, 8><<<nblocks, 32, sgw_smem(NA, 8), ctx->stream>>>(args...);
-	else sgs_warpflow_kernel<MODE, 16><<<nblocks, 32, sgw_smem(NA, 16), ctx->stream>>>(args...);
+	if (ctx->sgs_pencils == 1 || ctx->sgs_pencils == 2) return ctx->sgs_pencils;
+	return ((long long)g->nx * g->ny * g->nz >= (64ll << 20)) ? 1 : 2;
 }
 
-template <int TI> int sgw_configure()
+template <int MODE, typename... Args> void sgw_launch(s3d_ctx *ctx, const s3d_grid *g, unsigned nblocks, Args... args)
 {
-	cudaFuncSetAttribute(sgs_warpflow_kernel<0, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sgw_smem(5, TI));
-	cudaFuncSetAttribute(sgs_warpflow_kernel<1, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sgw_smem(5, TI));
-	cudaFuncSetAttribute(sgs_warpflow_kernel<2, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sgw_smem(4, TI));
+	constexpr int NA = (MODE == 2) ? 4 : 5;
+	const int ti = sgw_tile_i(ctx), p = sgw_pencils(ctx, g);
+	if (ti == 32 && p == 2) sgs_warpflow_kernel<MODE, 32, 2><<<nblocks, 32, sgw_smem(NA, 32, 2), ctx->stream>>>(args...);
+	else if (ti == 32) sgs_warpflow_kernel<MODE, 32, 1><<<nblocks, 32, sgw_smem(NA, 32, 1), ctx->stream>>>(args...);
+	else if (p == 2) sgs_warpflow_kernel<MODE, 16, 2><<<nblocks, 32, sgw_smem(NA, 16, 2), ctx->stream>>>(args...);
+	else sgs_warpflow_kernel<MODE, 16, 1><<<nblocks, 32, sgw_smem(NA, 16, 1), ctx->stream>>>(args...);
+}
+
+template <int TI, int P> int sgw_configure()
+{
+	cudaFuncSetAttribute(sgs_warpflow_kernel<0, TI, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sgw_smem(5, TI, P));
+	cudaFuncSetAttribute(sgs_warpflow_kernel<1, TI, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sgw_smem(5, TI, P));
+	cudaFuncSetAttribute(sgs_warpflow_kernel<2, TI, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sgw_smem(4, TI, P));
 	int a = 1, b = 1;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sgs_warpflow_kernel<0, TI>, 32, sgw_smem(5, TI));
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sgs_warpflow_kernel<1, TI>, 32, sgw_smem(5, TI));
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sgs_warpflow_kernel<0, TI, P>, 32, sgw_smem(5, TI, P));
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sgs_warpflow_kernel<1, TI, P>, 32, sgw_smem(5, TI, P));
 	return std::max(1, std::min(a, b));
 }
 
@@ -721,7 +725,8 @@ template <int TI> int sgw_configure()
 int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblocks)
 {
 	const int tile_i = (ctx->sgs_variant == 0) ? sgw_tile_i(ctx) : SGS_TI;
-	f.ntx = (g->nx + tile_i - 1) / tile_i; f.nty = (g->ny + SGS_TJ - 1) / SGS_TJ; f.ntz = (g->nz + SGS_TK - 1) / SGS_TK;
+	const int tile_j = (ctx->sgs_variant == 0) ? 4 * sgw_pencils(ctx, g) : SGS_TJ;
+	f.ntx = (g->nx + tile_i - 1) / tile_i; f.nty = (g->ny + tile_j - 1) / tile_j; f.ntz = (g->nz + SGS_TK - 1) / SGS_TK;
 	const size_t ntiles = (size_t)f.ntx * f.nty * f.ntz;
 	if (ctx->sgs_flags_cap < ntiles + 1) {
 		S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -780,15 +785,14 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 		}
 		f.iface = ctx->sgs_iface;
 		static bool wconfigured = false;
-		static int warps_per_sm16 = 1, warps_per_sm32 = 1, warps_per_sm8 = 1;
+		static int warps_per_sm[4] = {1, 1, 1, 1};   // [tile_i == 32][pencils == 2]
 		if (!wconfigured) {
-			warps_per_sm8 = sgw_configure<8>();
-			warps_per_sm16 = sgw_configure<16>();
-			warps_per_sm32 = sgw_configure<32>();
+			warps_per_sm[0] = sgw_configure<16, 1>(); warps_per_sm[1] = sgw_configure<16, 2>();
+			warps_per_sm[2] = sgw_configure<32, 1>(); warps_per_sm[3] = sgw_configure<32, 2>();
 			S3D_CUDA(ctx, cudaGetLastError());
 			wconfigured = true;
 		}
-		int wps = (sgw_tile_i(ctx) == 32) ? warps_per_sm32 : (sgw_tile_i(ctx) == 8) ? warps_per_sm8 : warps_per_sm16;
+		int wps = warps_per_sm[(sgw_tile_i(ctx) == 32 ? 2 : 0) + (sgw_pencils(ctx, g) == 2 ? 1 : 0)];
 		if (ctx->sgs_warps_per_sm > 0) wps = std::min(wps, ctx->sgs_warps_per_sm);
 		if (wps < 1) wps = 1;
 		nblocks = (unsigned)std::min<size_t>(ntiles, (size_t)ctx->sm_count * wps);
@@ -875,14 +879,14 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		f.epoch = ++ctx->sgs_epoch;
 		S3D_CUDA(ctx, cudaMemsetAsync(f.ticket, 0, sizeof(unsigned), ctx->stream));
 		if (ctx->sgs_variant == 0)
-			sgw_launch<0>(ctx, nblocks, gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, (const int *)ctx->gate);
+			sgw_launch<0>(ctx, g, nblocks, gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, (const int *)ctx->gate);
 		else
 			sgs_dataflow_kernel<0><<<nblocks, block, SGS_SMEM, ctx->stream>>>(gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, ctx->gate);
 		S3D_LAUNCHED(ctx);
 		f.epoch = ++ctx->sgs_epoch;
 		S3D_CUDA(ctx, cudaMemsetAsync(f.ticket, 0, sizeof(unsigned), ctx->stream));
 		if (ctx->sgs_variant == 0)
-			sgw_launch<1>(ctx, nblocks, gd, (const double *)d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f, (const int *)ctx->gate);
+			sgw_launch<1>(ctx, g, nblocks, gd, (const double *)d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f, (const int *)ctx->gate);
 		else
 			sgs_dataflow_kernel<1><<<nblocks, block, SGS_SMEM, ctx->stream>>>(gd, d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f, ctx->gate);
 		S3D_LAUNCHED(ctx);
@@ -931,7 +935,7 @@ int s3d_strilu_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuil
 		e = cudaMemsetAsync(f.ticket, 0, sizeof(unsigned), ctx->stream);
 		if (e == cudaSuccess) {
 			if (ctx->sgs_variant == 0)
-				sgw_launch<2>(ctx, nblocks, gd, A + 3 * (size_t)g->cstride, (const double *)P, (const double *)(P + g->cstride),
+				sgw_launch<2>(ctx, g, nblocks, gd, A + 3 * (size_t)g->cstride, (const double *)P, (const double *)(P + g->cstride),
 				              (const double *)(P + 2 * (size_t)g->cstride), (const double *)nullptr, D, f, (const int *)nullptr);
 			else
 				sgs_dataflow_kernel<2><<<nblocks, SGS_NT, SGS_SMEM, ctx->stream>>>(gd, A + 3 * (size_t)g->cstride, P, P + g->cstride, P + 2 * (size_t)g->cstride,

@@ -338,6 +338,7 @@ int s3d_tune_set(s3d_ctx *ctx, const char *key, int value)
 	else if (!strcmp(key, "sgs_variant")) ctx->sgs_variant = value;
 	else if (!strcmp(key, "sgs_warps_per_sm")) ctx->sgs_warps_per_sm = value;
 	else if (!strcmp(key, "sgs_tile_i")) ctx->sgs_tile_i = value;
+	else if (!strcmp(key, "sgs_pencils")) ctx->sgs_pencils = value;
 	else if (!strcmp(key, "sgs_profile")) {
 		// 1: start accumulating per-phase cycles in the warp dataflow kernel; 0: print and stop (timing experiments only)
 		if (value && !ctx->sgs_prof) {

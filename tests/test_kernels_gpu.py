@@ -221,6 +221,37 @@ def test_jacobi_and_sgs(ctx, npdim, pde):
     assert ghosts_untouched(z)
 
 
+# every build of the exact dataflow sweep: block-per-tile (variant 1), warp-per-tile (variant 0) with 16- or 32-long tiles and one
+# or two pencils per lane; full, ragged and sub-tile grids; forward/backward sweep and the StrILU recurrence
+@pytest.mark.parametrize("npdim", [(18, 18, 18), (35, 11, 20), (3, 3, 3), (50, 23, 14), (131, 9, 6), (21, 38, 27)])
+@pytest.mark.parametrize("variant,tile_i,pencils", [(1, 0, 0), (0, 16, 1), (0, 16, 2), (0, 32, 1), (0, 32, 2)])
+def test_sgs_dataflow_variants(ctx, npdim, variant, tile_i, pencils):
+    m, A = problem(npdim, "chebyshev", "convdiff", V1, 0.1)
+    g = grid_of(m)
+    r = rand_vec(m, 41)
+    dA, dr, dz, dy = ctx.mat_from(g, A), ctx.vec_from(g, r), ctx.vec_alloc(g), ctx.vec_alloc(g)
+    dinv = ctx.scalars_alloc(int(g.cstride))
+    try:
+        ctx.tune("sgs_variant", variant); ctx.tune("sgs_tile_i", tile_i); ctx.tune("sgs_pencils", pencils)
+        ctx.sgs_setup(g, dA, dinv)
+        di = cport.sgs_setup(m, A)
+        ref = cport.sgs_like_apply(m, A, di, r, 1)
+        for rep in range(2):                                    # twice: the flags of the first sweep must not satisfy the second
+            ctx.vecset(g, 3.0 + rep, dz)
+            ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_LEXICOGRAPHIC, 1)
+            z = ctx.vec_download(g, dz)
+            assert np.array_equal(z, ref), f"max diff {np.abs(z - ref).max()} (rep {rep})"
+            assert ghosts_untouched(z)
+        ctx.strilu_setup(g, dA, 1, dinv)
+        want = cport.strilu_setup(m, A, 1)
+        ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_LEXICOGRAPHIC, 1)
+        assert np.array_equal(ctx.vec_download(g, dz), cport.sgs_like_apply(m, A, want, r, 1)), "StrILU differs"
+    finally:
+        ctx.tune("sgs_variant", 0); ctx.tune("sgs_tile_i", 0); ctx.tune("sgs_pencils", 0)
+        for p_ in (dA, dr, dz, dy, dinv):
+            ctx.free(p_)
+
+
 @pytest.mark.parametrize("npdim,grid", [((18, 18, 18), "uniform"), ((16, 16, 16), "chebyshev"), ((19, 23, 11), "chebyshev"), ((3, 5, 4), "uniform")])
 def test_assembly_bit_exact(ctx, npdim, grid):
     m = cport.Mesh(npdim, grid=grid)
