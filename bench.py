@@ -144,6 +144,65 @@ def run_reference(a):
     _emit(json.dumps(line))
 
 
+# ---------------------------------------------------------------------------------------------- bandwidth sweep (BASELINE.json configs[4])
+
+def run_sweep(a):
+    """SpMV / axpy / dot bandwidth, 32^3 .. 1024^3 fp64: this library on cuda:0 (CUDA events) against the HBM roofline, and the
+    reference's CPU kernels (oracle/_ref, all host threads) on the same grids up to --sweep-cpu-max.  Writes a markdown table."""
+    from struct3d_b200 import capi
+    from oracle import refshim
+    sizes = [int(v) for v in a.sweep_sizes.split(",")]
+    peak, _src = peaks()
+    ctx = capi.Context(0)
+    rows = []
+    for n in sizes:
+        g = capi.make_grid(n, n, n)
+        coords = [-1.0 + 2.0 * np.arange(n + 2) / (n + 1)] * 3
+        dA = ctx.mat_alloc(g); ctx.assemble_poisson(g, coords, dA)
+        dx, dy = ctx.vec_alloc(g), ctx.vec_alloc(g)
+        ctx.vecset(g, 0.5, dx); ctx.vecset(g, 0.25, dy)
+        red = ctx.scalars_alloc(2)
+        reps = 20 if n >= 256 else 200
+        def t(fn):
+            for _ in range(3): fn()
+            ctx.sync(); ctx.timer_start()
+            for _ in range(reps): fn()
+            return ctx.timer_stop_ms() / reps
+        gpu = {"spmv": BYTES_SPMV * n ** 3 / t(lambda: ctx.spmv(g, dA, dx, dy)) / 1e6,
+               "axpy": 24 * n ** 3 / t(lambda: ctx.vecaxpy(g, 1e-9, dx, dy)) / 1e6,
+               "dot": 16 * n ** 3 / t(lambda: ctx.dot_dev(g, dx, dy, red)) / 1e6}
+        for p_ in (dA, dx, dy, red): ctx.free(p_)
+        cpu = {"spmv": None, "axpy": None, "dot": None}
+        cores = None
+        if refshim.available() and n <= a.sweep_cpu_max:
+            cores = refshim.num_threads()
+            m, _t = refshim._capture_stdout(lambda: refshim.Mesh((n + 2,) * 3))
+            A, x, y = refshim.Mat(m), refshim.Vec(m), refshim.Vec(m)
+            h2 = (2.0 / (n + 1)) ** 2
+            for s_ in range(7):
+                A.a[s_][...] = (6.0 if s_ == 3 else -1.0) / h2
+            x.a[1:-1, 1:-1, 1:-1] = 0.5; y.a[1:-1, 1:-1, 1:-1] = 0.25
+            r = 3 if n >= 256 else 20
+            cpu["spmv"] = BYTES_SPMV * n ** 3 / refshim.time_apply(A, x, y, r) / 1e9
+            cpu["axpy"] = 24 * n ** 3 / refshim.time_axpy(x, y, r) / 1e9
+            cpu["dot"] = 16 * n ** 3 / refshim.time_dot(x, y, r) / 1e9
+            del A, x, y, m
+        rows.append((n, gpu, cpu, cores))
+        print(f"[sweep] {n}^3 gpu {gpu} cpu {cpu}", file=sys.stderr, flush=True)
+    out = ["| grid | working set | SpMV GB/s (% of measured peak) | axpy GB/s (%) | dot GB/s (%) | reference CPU SpMV / axpy / dot GB/s (threads) |", "|---|---|---|---|---|---|"]
+    for n, gpu, cpu, cores in rows:
+        ws = (7 * 8 + 2 * 8) * n ** 3
+        note = "L2-resident" if ws < 100e6 else "streams from HBM"
+        cp = " / ".join("-" if cpu[k] is None else f"{cpu[k]:.1f}" for k in ("spmv", "axpy", "dot")) + (f" ({cores})" if cores else "")
+        out.append(f"| {n}^3 | {ws / 1e6:.1f} MB, {note} | " + " | ".join(f"{gpu[k]:.0f} ({100 * gpu[k] / peak:.0f} %)" for k in ("spmv", "axpy", "dot")) + f" | {cp} |")
+    text = "\n".join(out)
+    os.makedirs(os.path.dirname(a.sweep_out), exist_ok=True)
+    with open(a.sweep_out, "w") as fh:
+        fh.write(text + "\n")
+    print(text, file=sys.stderr)
+    _emit(json.dumps({"sweep": [{"n": n, "gpu_gbs": gpu, "cpu_gbs": cpu, "cpu_threads": cores} for n, gpu, cpu, cores in rows], "peak_gbs": peak}))
+
+
 # ---------------------------------------------------------------------------------------------- our arm
 
 def run_ours(a):
@@ -379,6 +438,10 @@ def main():
     ap.add_argument("--halo-overlap", type=int, default=0, help="0: exchange halos first, then multiply (A/B switch)")
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="bandwidth sweep over grid sizes instead of the bench line (BASELINE.json configs[4])")
+    ap.add_argument("--sweep-sizes", default="32,64,128,256,512,1024")
+    ap.add_argument("--sweep-cpu-max", type=int, default=512, help="largest grid the reference CPU kernels are timed on")
+    ap.add_argument("--sweep-out", default=os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpurun_out", "bw_sweep.md"))
     a = ap.parse_args()
     # stdout carries exactly ONE line, the JSON record: everything else (NCCL's version banner, the host classes'
     # progress prints) goes to stderr for the duration of the run
@@ -387,7 +450,9 @@ def main():
     os.dup2(2, 1)
     global _emit
     _emit = lambda line: os.write(real_stdout, (line + "\n").encode())
-    if a.impl == "reference":
+    if a.sweep:
+        run_sweep(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)
