@@ -246,6 +246,17 @@ int  s3d_ctx_set_gate(s3d_ctx *ctx, const int *d_stop);
 int  s3d_phase_begin(s3d_ctx *ctx, int slot);
 int  s3d_phase_end(s3d_ctx *ctx, int slot);
 int  s3d_phase_total_ms(s3d_ctx *ctx, int slot, double *ms);
+/* CUDA graphs for the host-driven loops (no counterpart in the reference, whose loops call their kernels directly,
+ * src/linalg/s3d_solverbase.cpp:45-80, s3d_gcr.cpp:14-86).  Between graph_begin and graph_end every s3d_* call that enqueues work on
+ * the context's stream is RECORDED instead of run; graph_launch replays the recording.  A batch of solver iterations qualifies because
+ * its coefficients, iteration counter, residual history index and stop flag all live in device memory.  Calls that allocate or
+ * synchronise (first-use scratch, downloads, s3d_phase_total_ms) must not be made inside a capture: run one batch eagerly first.
+ * s3d_phase_begin/end inside a capture are ignored.  s3d_ctx_launch_count counts a replay as the kernels it contains. */
+typedef struct s3d_graph s3d_graph;
+int  s3d_graph_begin(s3d_ctx *ctx);
+int  s3d_graph_end(s3d_ctx *ctx, s3d_graph **out);
+int  s3d_graph_launch(s3d_ctx *ctx, s3d_graph *g);
+int  s3d_graph_destroy(s3d_ctx *ctx, s3d_graph *g);
 int  s3d_ints_alloc(s3d_ctx *ctx, int n, int **d_out);
 int  s3d_ints_download(s3d_ctx *ctx, const int *d_s, int n, int *h_out);
 int  s3d_ints_zero(s3d_ctx *ctx, int *d_s, int n);

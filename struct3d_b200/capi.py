@@ -67,6 +67,7 @@ _SIGS = {
     "s3d_converge_test": [_P, _vp, _vp, _D, _I, _I, _vp, _vp, _vp],
     "s3d_scalar_op": [_P, _I, _vp, _vp, _vp, _vp, _vp, _I, _D, _vp],
     "s3d_ctx_set_gate": [_P, _vp], "s3d_phase_begin": [_P, _I], "s3d_phase_end": [_P, _I], "s3d_phase_total_ms": [_P, _I, _dp],
+    "s3d_graph_begin": [_P], "s3d_graph_end": [_P, C.POINTER(_vp)], "s3d_graph_launch": [_P, _vp], "s3d_graph_destroy": [_P, _vp],
     "s3d_ints_snapshot": [_P, _vp, _I, _I], "s3d_ints_snapshot_wait": [_P, _I, _I, _vp],
     "s3d_ints_alloc": [_P, _I, C.POINTER(_vp)], "s3d_ints_download": [_P, _vp, _I, _vp], "s3d_ints_zero": [_P, _vp, _I],
     "s3d_assemble_poisson": [_P, _G, _vp, _vp, _vp, _vp],
@@ -259,6 +260,21 @@ class Context:
 
     def tune(self, key, value):
         self.call("s3d_tune_set", key.encode(), int(value))
+
+    # --- CUDA graphs: record the calls between graph_begin and graph_end, replay them with graph_launch
+    def graph_begin(self):
+        self.call("s3d_graph_begin")
+
+    def graph_end(self):
+        h = _vp()
+        self.call("s3d_graph_end", C.byref(h))
+        return h.value
+
+    def graph_launch(self, h):
+        self.call("s3d_graph_launch", _vp(h))
+
+    def graph_destroy(self, h):
+        self.call("s3d_graph_destroy", _vp(h))
 
     # --- kernels
     def spmv(self, g, A, x, y, b=None, w=None, want_yy=False, red=None, stop=None, variant=SPMV_AUTO):

@@ -31,7 +31,9 @@ struct s3d_ctx {
 	double *sweep_buf = nullptr;   // second ping-pong vector of the Jacobi-sweeps SGS
 	size_t sweep_buf_cap = 0;
 	int sweep_buf_dims[3] = {0, 0, 0};
-	int sgs_epoch = 0;
+	int *sgs_ctl = nullptr;       // device: [0] ticket counter, [1] epoch of the running dataflow sweep
+	bool capturing = false;       // between s3d_graph_begin and s3d_graph_end
+	int64_t capture_launches0 = 0;
 	int sgs_sleep_ns = 0;
 	int sgs_variant = 0;        // 0: warp-per-tile dataflow kernel, 1: block-per-tile kernel (r1's first version)
 	int sgs_warps_per_sm = 0;   // 0: as many as fit

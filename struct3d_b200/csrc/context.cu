@@ -143,7 +143,7 @@ int s3d_ctx_destroy(s3d_ctx *ctx)
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
 	cudaFree(ctx->partials); cudaFree(ctx->ticket); cudaFree(ctx->tab); cudaFree(ctx->red_tmp);
-	cudaFree(ctx->sgs_flags); cudaFree(ctx->sgs_iface); cudaFree(ctx->sgs_order); cudaFree(ctx->sweep_buf); cudaFree(ctx->stage);
+	cudaFree(ctx->sgs_flags); cudaFree(ctx->sgs_ctl); cudaFree(ctx->sgs_iface); cudaFree(ctx->sgs_order); cudaFree(ctx->sweep_buf); cudaFree(ctx->stage);
 	cudaFreeHost(ctx->h_pinned);
 	if (ctx->h_slots) { cudaFreeHost(ctx->h_slots); for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->slot_ev[i]); }
 	cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
@@ -190,6 +190,7 @@ int s3d_ctx_set_gate(s3d_ctx *ctx, const int *d_stop)
 static int phase_record(s3d_ctx *ctx, int slot, int parity)
 {
 	S3D_REQUIRE(ctx, slot >= 0 && slot < 4, "phase slot out of range");
+	if (ctx->capturing) return S3D_OK;   // event pairs recorded into a graph cannot be timed: phases inside a capture are not attributed
 	s3d_ctx::Phase &p = ctx->phase[slot];
 	S3D_REQUIRE(ctx, (p.used & 1) == parity, "phase begin/end out of order");
 	if (p.used == p.cap) {
@@ -218,6 +219,60 @@ int s3d_phase_total_ms(s3d_ctx *ctx, int slot, double *ms)
 	}
 	p.used = 0;
 	*ms = total;
+	return S3D_OK;
+}
+
+// ------------------------------------------------------------------------------------ CUDA graphs
+// A solver iteration is a fixed sequence of launches whose scalars, iteration counter and stop flag all live on the device, so a
+// batch of iterations can be captured once and replayed: one cudaGraphLaunch instead of ~10 kernel launches per iteration.
+// Between begin and end every s3d_* call that enqueues work is recorded instead of run; calls that allocate or synchronise
+// (first-use buffers, downloads) must have happened before -- run one batch eagerly first.
+
+struct s3d_graph {
+	cudaGraphExec_t exec = nullptr;
+	int64_t kernels = 0;     // kernel launches one replay stands for
+};
+
+int s3d_graph_begin(s3d_ctx *ctx)
+{
+	S3D_REQUIRE(ctx, !ctx->capturing, "a graph capture is already open");
+	S3D_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+	ctx->capturing = true;
+	ctx->capture_launches0 = ctx->launches;
+	return S3D_OK;
+}
+
+int s3d_graph_end(s3d_ctx *ctx, s3d_graph **out)
+{
+	S3D_REQUIRE(ctx, ctx->capturing && out, "no graph capture is open");
+	cudaGraph_t graph = nullptr;
+	ctx->capturing = false;
+	const int64_t kernels = ctx->launches - ctx->capture_launches0;
+	ctx->launches = ctx->capture_launches0;      // nothing ran yet; replays are counted when they are launched
+	S3D_CUDA(ctx, cudaStreamEndCapture(ctx->stream, &graph));
+	s3d_graph *g = new s3d_graph;
+	const cudaError_t e = cudaGraphInstantiate(&g->exec, graph, 0);
+	cudaGraphDestroy(graph);
+	if (e != cudaSuccess) { delete g; S3D_CUDA(ctx, e); }
+	g->kernels = kernels;
+	*out = g;
+	return S3D_OK;
+}
+
+int s3d_graph_launch(s3d_ctx *ctx, s3d_graph *g)
+{
+	S3D_REQUIRE(ctx, g && g->exec, "null graph");
+	S3D_CUDA(ctx, cudaGraphLaunch(g->exec, ctx->stream));
+	ctx->launches += g->kernels;
+	return S3D_OK;
+}
+
+int s3d_graph_destroy(s3d_ctx *ctx, s3d_graph *g)
+{
+	if (!g) return S3D_OK;
+	if (g->exec) cudaGraphExecDestroy(g->exec);
+	delete g;
+	(void)ctx;
 	return S3D_OK;
 }
 

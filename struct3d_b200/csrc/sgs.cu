@@ -94,7 +94,7 @@ struct SgsFlow {
 	double *iface;     // warp kernel: [tile][64] the tile's last i-column, indexed by logical pencil b*8+c
 	const int *order;  // dispatch order: tile numbers sorted by tile hyperplane ci+cj+ck (then lexicographically)
 	unsigned *ticket;  // work counter, zeroed before every launch
-	int epoch;
+	const int *epoch_p; // device word holding the epoch of this sweep (bumped on the device, so a captured graph can be replayed)
 	int ntx, nty, ntz;
 	int sleep_ns;      // 0: busy-spin on the flag
 	long long *prof;   // optional per-phase cycle accumulators (warp kernel; timing experiments only)
@@ -125,6 +125,7 @@ sgs_dataflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 	constexpr bool FWD = (MODE != 1);
 	constexpr bool ILU = (MODE == 2);
 	if (s3d_stopped(stop)) return;
+	const int epoch = __ldcg(f.epoch_p);
 	extern __shared__ __align__(16) double smem[];
 	double *s_in = smem;                       // [TK][TJ][TI] each; s_in is overwritten with the results
 	double *s_c0 = s_in + SGS_TILE;
@@ -183,7 +184,7 @@ sgs_dataflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 			}
 			if (pred >= 0 && !(f.debug & 8)) {
 				const volatile int *fl = f.flags + pred;
-				while (*fl != f.epoch) { }
+				while (*fl != epoch) { }
 			}
 			if (!(f.debug & 4)) __threadfence();
 		}
@@ -255,7 +256,7 @@ sgs_dataflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		__syncthreads();
 		if (tid == 0) {
 			if (!(f.debug & 4)) __threadfence();
-			*(volatile int *)(f.flags + tile) = f.epoch;
+			*(volatile int *)(f.flags + tile) = epoch;
 		}
 	}
 }
@@ -331,6 +332,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 	static_assert(R % 16 == 2, "row stride must be 2 modulo 16 (see sgw_row)");
 	constexpr unsigned FULL = 0xffffffffu;
 	if (s3d_stopped(stop)) return;
+	const int epoch = __ldcg(f.epoch_p);
 	extern __shared__ __align__(16) double smem[];
 	double *s_a = smem + SGW_PAD;                             // [stream][row rho][R]
 	double *s_hj = s_a + NA * ASZ + SGW_PAD;                  // [c][R]  j-neighbour rows of the adjacent tile / ghost row
@@ -421,7 +423,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 			}
 			bool done = (pred < 0) || (f.debug & 1);
 			for (;;) {
-				if (!done) done = (ld_acquire(f.flags + pred) == f.epoch);
+				if (!done) done = (ld_acquire(f.flags + pred) == epoch);
 				if (__all_sync(FULL, done)) break;
 			}
 		}
@@ -529,7 +531,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		__syncwarp();
 		if (f.prof) tp3 = clock64();
 		if (lane == 0) {
-			*(volatile int *)(f.flags + tile) = f.epoch;
+			*(volatile int *)(f.flags + tile) = epoch;
 			if (f.prof) {
 				const long long tp4 = clock64();
 				atomicAdd((unsigned long long *)f.prof + 0, (unsigned long long)(tp1 - tp0));   // flag wait
@@ -721,6 +723,15 @@ template <int TI, int P> int sgw_configure()
 	return std::max(1, std::min(a, b));
 }
 
+// start of a dataflow sweep: rewind the ticket counter and move to the next epoch -- on the device, so that a captured CUDA graph
+// of a solver iteration can be replayed (a host-side epoch would be frozen into the graph)
+__global__ void sgs_begin_kernel(int *ctl, const int *stop)
+{
+	if (s3d_stopped(stop)) return;
+	ctl[0] = 0;
+	ctl[1] += 1;
+}
+
 // flags / dispatch table / occupancy for the dataflow kernels; returns the number of persistent blocks
 int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblocks)
 {
@@ -728,6 +739,10 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 	const int tile_j = (ctx->sgs_variant == 0) ? 4 * sgw_pencils(ctx, g) : SGS_TJ;
 	f.ntx = (g->nx + tile_i - 1) / tile_i; f.nty = (g->ny + tile_j - 1) / tile_j; f.ntz = (g->nz + SGS_TK - 1) / SGS_TK;
 	const size_t ntiles = (size_t)f.ntx * f.nty * f.ntz;
+	if (!ctx->sgs_ctl) {
+		S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_ctl, 2 * sizeof(int)));
+		S3D_CUDA(ctx, cudaMemsetAsync(ctx->sgs_ctl, 0, 2 * sizeof(int), ctx->stream));
+	}
 	if (ctx->sgs_flags_cap < ntiles + 1) {
 		S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 		if (ctx->sgs_flags) S3D_CUDA(ctx, cudaFree(ctx->sgs_flags));
@@ -735,7 +750,7 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 		S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_flags, (ntiles + 1) * sizeof(int)));
 		S3D_CUDA(ctx, cudaMemsetAsync(ctx->sgs_flags, 0, (ntiles + 1) * sizeof(int), ctx->stream));
 		ctx->sgs_flags_cap = ntiles + 1;
-		ctx->sgs_epoch = 0;
+		S3D_CUDA(ctx, cudaMemsetAsync(ctx->sgs_ctl, 0, 2 * sizeof(int), ctx->stream));
 	}
 	static bool configured = false;
 	static int blocks_per_sm = 1;
@@ -764,9 +779,9 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 		S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_order, ntiles * sizeof(int)));
 		S3D_CUDA(ctx, cudaMemcpy(ctx->sgs_order, order.data(), ntiles * sizeof(int), cudaMemcpyHostToDevice));
 		ctx->sgs_order_dims[0] = f.ntx; ctx->sgs_order_dims[1] = f.nty; ctx->sgs_order_dims[2] = f.ntz;
-		// another tiling: the old ticket slot now is a flag; start the epochs over
+		// another tiling: start the epochs over
 		S3D_CUDA(ctx, cudaMemsetAsync(ctx->sgs_flags, 0, ctx->sgs_flags_cap * sizeof(int), ctx->stream));
-		ctx->sgs_epoch = 0;
+		S3D_CUDA(ctx, cudaMemsetAsync(ctx->sgs_ctl, 0, 2 * sizeof(int), ctx->stream));
 	}
 	f.flags = ctx->sgs_flags;
 	f.iface = ctx->sgs_iface;
@@ -774,7 +789,8 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 	f.sleep_ns = 0;
 	f.debug = ctx->sgs_sleep_ns;   // reuses the tuning slot: debug bit mask
 	f.prof = ctx->sgs_prof;
-	f.ticket = reinterpret_cast<unsigned *>(ctx->sgs_flags + ntiles);   // the slot after the last flag
+	f.ticket = reinterpret_cast<unsigned *>(ctx->sgs_ctl);
+	f.epoch_p = ctx->sgs_ctl + 1;
 	if (ctx->sgs_variant == 0) {
 		if (ctx->sgs_iface_cap < ntiles * 64) {
 			S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -876,15 +892,15 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		if (rcp != S3D_OK) return rcp;
 		dim3 block(SGS_NT);
 		const long long cs = g->cstride;
-		f.epoch = ++ctx->sgs_epoch;
-		S3D_CUDA(ctx, cudaMemsetAsync(f.ticket, 0, sizeof(unsigned), ctx->stream));
+		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
+		S3D_LAUNCHED(ctx);
 		if (ctx->sgs_variant == 0)
 			sgw_launch<0>(ctx, g, nblocks, gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, (const int *)ctx->gate);
 		else
 			sgs_dataflow_kernel<0><<<nblocks, block, SGS_SMEM, ctx->stream>>>(gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, ctx->gate);
 		S3D_LAUNCHED(ctx);
-		f.epoch = ++ctx->sgs_epoch;
-		S3D_CUDA(ctx, cudaMemsetAsync(f.ticket, 0, sizeof(unsigned), ctx->stream));
+		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
+		S3D_LAUNCHED(ctx);
 		if (ctx->sgs_variant == 0)
 			sgw_launch<1>(ctx, g, nblocks, gd, (const double *)d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f, (const int *)ctx->gate);
 		else
@@ -931,8 +947,9 @@ int s3d_strilu_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuil
 	unsigned nblocks = 0;
 	int rc = sgs_flow_prepare(ctx, g, f, nblocks);
 	if (rc == S3D_OK) {
-		f.epoch = ++ctx->sgs_epoch;
-		e = cudaMemsetAsync(f.ticket, 0, sizeof(unsigned), ctx->stream);
+		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, nullptr);
+		ctx->launches++;
+		e = cudaGetLastError();
 		if (e == cudaSuccess) {
 			if (ctx->sgs_variant == 0)
 				sgw_launch<2>(ctx, g, nblocks, gd, A + 3 * (size_t)g->cstride, (const double *)P, (const double *)(P + g->cstride),

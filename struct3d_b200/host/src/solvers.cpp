@@ -25,6 +25,20 @@ namespace {
 s3d_scalar imm(double a) { return s3d_scalar{a, nullptr, nullptr}; }
 s3d_scalar ratio(double sign, const double *num, const double *den) { return s3d_scalar{sign, num, den}; }
 
+// CUDA graphs for the iteration batches: -s3d_cuda_graph on|off|auto (default auto = on for grids up to 4 Mi points on one GPU,
+// where an iteration is bound by launch latency rather than by HBM; measured in profiles/r1_graphs.md).
+bool g_time_phases = true;   // preconditioner stopwatch; off while batches are replayed from a graph (events cannot be timed there)
+
+bool want_graphs(const Device &d, const s3d_grid &g)
+{
+	if (d.nranks() > 1) return false;                       // the NCCL exchange stays outside captures
+	std::string v = "auto";
+	if (s3d::options_has("-s3d_cuda_graph")) v = petscoptions_get_string("-s3d_cuda_graph", 10);
+	if (v == "on" || v == "1" || v == "true") return true;
+	if (v == "off" || v == "0" || v == "false") return false;
+	return (long long)g.nx * g.ny * g.nz <= (4ll << 20);
+}
+
 // Device-side loop bookkeeping: stop flag, iteration counter, residual history.
 struct DeviceLoop {
 	const Device &d;
@@ -35,17 +49,42 @@ struct DeviceLoop {
 	int printed = 0;
 	int every;         // print "Step n: Rel res" every this many steps, like the reference
 	std::vector<sreal> &history;
+	bool use_graph = false;  // batches after the first are captured once and replayed
+	s3d_graph *graph = nullptr;
+	int nbatch = 0;
 
 	DeviceLoop(int cap, int print_every, std::vector<sreal> &out)
 		: d(Device::get()), ctx(d.ctx()), flags(d.ints(2)), hist(d.scalars(cap)), hist_cap(cap), every(print_every), history(out)
 	{
 		history.clear();
+		g_time_phases = true;
 	}
 	~DeviceLoop()
 	{
+		if (graph) s3d_graph_destroy(ctx, graph);
+		g_time_phases = true;
 		s3d_ctx_set_gate(ctx, nullptr);
 		s3d_free(ctx, flags);
 		s3d_free(ctx, hist);
+	}
+	void graphs(const s3d_grid &g)
+	{
+		use_graph = want_graphs(d, g);
+		g_time_phases = !use_graph;
+	}
+	// One batch of iterations.  `enqueue` must issue the same launches every time it is called from the second batch on (an even
+	// number of iterations when the loop ping-pongs its scalars).  The first batch runs eagerly (first-use allocations, the special
+	// first iteration), the second is captured and launched, later ones replay the capture.
+	template <class F> void batch(F &&enqueue)
+	{
+		const int index = nbatch++;
+		if (!use_graph || index == 0) { enqueue(); return; }
+		if (!graph) {
+			d.check(s3d_graph_begin(ctx), "s3d_graph_begin");
+			enqueue();
+			d.check(s3d_graph_end(ctx, &graph), "s3d_graph_end");
+		}
+		d.check(s3d_graph_launch(ctx, graph), "s3d_graph_launch");
 	}
 	int *stop() const { return flags; }
 	int *iters() const { return flags + 1; }
@@ -135,8 +174,8 @@ SolveInfo finish(const Device &d, const double *rr, const double *bb, double rto
 
 struct TimedPrec {   // brackets a preconditioner application with the GPU stopwatch (SolveInfo::precapplywtime)
 	const Device &d;
-	explicit TimedPrec(const Device &dev) : d(dev) { d.check(s3d_phase_begin(d.ctx(), 0), "s3d_phase_begin"); }
-	~TimedPrec() { s3d_phase_end(d.ctx(), 0); }
+	explicit TimedPrec(const Device &dev) : d(dev) { if (g_time_phases) d.check(s3d_phase_begin(d.ctx(), 0), "s3d_phase_begin"); }
+	~TimedPrec() { if (g_time_phases) s3d_phase_end(d.ctx(), 0); }
 };
 
 }  // namespace
@@ -261,13 +300,16 @@ SolveInfo Richardson::apply(const SVec &b, SVec &x) const
 	int iterations = 0, code = 0, cur = 0;
 	loop.snapshot(cur);
 	const int batch = batch_size(g, 200);
+	loop.graphs(g);
 	for (;;) {
-		for (int i = 0; i < batch; i++) {
-			{ TimedPrec t(d); prec->apply(res, dx); }
-			d.check(s3d_vecaxpy(ctx, &g, imm(1.0), dx.dev(), x.dev_rw()), "s3d_vecaxpy");
-			residual();
-			loop.test(&S[2], &S[0], sparams.rtol, sparams.maxiter, 0);
-		}
+		loop.batch([&]() {
+			for (int i = 0; i < batch; i++) {
+				{ TimedPrec t(d); prec->apply(res, dx); }
+				d.check(s3d_vecaxpy(ctx, &g, imm(1.0), dx.dev(), x.dev_rw()), "s3d_vecaxpy");
+				residual();
+				loop.test(&S[2], &S[0], sparams.rtol, sparams.maxiter, 0);
+			}
+		});
 		loop.snapshot(cur ^ 1);
 		code = loop.wait(cur, iterations);   // the state before the batch just enqueued
 		if (code) break;
@@ -403,10 +445,12 @@ SolveInfo CG::apply(const SVec &b, SVec &x) const
 
 	int iterations = 0, code = 0, cur = 0;
 	loop.snapshot(cur);
-	const int batch = batch_size(g, 200);
+	const int batch = 2 * ((batch_size(g, 200) + 1) / 2);   // even: the scalar pairs ping-pong, and a captured batch must end where it began
 	long it = 0;
 	const double *rr_final = &S[5];
+	loop.graphs(g);
 	for (;;) {
+		loop.batch([&]() {
 		for (int i = 0; i < batch; i++, it++) {
 			double *cur = (it % 2 == 0) ? &S[3] : &S[5];    // this iteration's {(r,r), (r,z)}
 			double *prev = (it % 2 == 0) ? &S[5] : &S[3];   // the previous iteration's pair
@@ -426,6 +470,7 @@ SolveInfo CG::apply(const SVec &b, SVec &x) const
 				d.check(s3d_vecaxpby(ctx, &g, imm(1.0), z.dev(), ratio(1.0, &cur[1], &prev[1]), p.dev_rw()), "s3d_vecaxpby");
 			}
 		}
+		});
 		loop.snapshot(cur ^ 1);
 		code = loop.wait(cur, iterations);
 		if (code) break;
@@ -471,9 +516,11 @@ SolveInfo BiCGSTAB::apply(const SVec &b, SVec &x) const
 
 	int iterations = 0, code = 0, cur = 0;
 	loop.snapshot(cur);
-	const int batch = batch_size(g, 400);
+	const int batch = 2 * ((batch_size(g, 400) + 1) / 2);   // even, see CG
 	long it = 0;
+	loop.graphs(g);
 	for (;;) {
+		loop.batch([&]() {
 		for (int i = 0; i < batch; i++, it++) {
 			double *cur = (it % 2 == 0) ? &S[5] : &S[7];
 			double *prev = (it % 2 == 0) ? &S[7] : &S[5];
@@ -498,6 +545,7 @@ SolveInfo BiCGSTAB::apply(const SVec &b, SVec &x) const
 			sc.allreduce_at(cur, 2);
 			loop.test(&cur[0], &S[0], sparams.rtol, sparams.maxiter, 0);
 		}
+		});
 		loop.snapshot(cur ^ 1);
 		code = loop.wait(cur, iterations);
 		if (code) break;

@@ -89,6 +89,33 @@ def test_solver_matches_reference_run(H, rec):
     assert ghosts_untouched(x.a)
 
 
+GRAPH_RUNS = [r for r in RUNS if (r["ksp"], r["pc"]) in (("cg", "jacobi"), ("cg", "sgs"), ("bcgs", "sgs"), ("bcgs", "jacobi"),
+                                                         ("richardson", "sgs"), ("richardson", "strilu"), ("gcr", "sgs"))][:14]
+
+
+@pytest.mark.parametrize("rec", GRAPH_RUNS, ids=lambda r: f"{r['case']}-{r['ksp']}-{r['pc']}")
+@pytest.mark.parametrize("ordering", ["lexicographic", "redblack", "sweeps"])
+def test_cuda_graph_replay_is_identical(H, rec, ordering):
+    """Iteration batches replayed from a captured CUDA graph must give bit-identical iterates, histories and counts to
+    the eagerly enqueued loop (same kernels, same order; only the launch mechanism differs)."""
+    if rec["pc"] not in ("sgs", "strilu") and ordering != "lexicographic":
+        pytest.skip("ordering only matters for the SGS-like preconditioners")
+    out = {}
+    for mode in ("off", "on"):
+        m, P, A, b = _setup(H, rec)
+        x = H.Vec(m)
+        extra = {"-s3d_cuda_graph": mode, "-s3d_sgs_ordering": ordering}
+        if ordering == "sweeps":
+            extra["-s3d_pc_apply_sweeps"] = 3
+        info = H.solve(A, b, x, _opts(rec, **extra), capture=True)
+        out[mode] = (info["iters"], info["converged"], np.array(info["hist"]), x.a.copy())
+    H.set_options({})
+    assert out["on"][0] == out["off"][0] and out["on"][1] == out["off"][1]
+    assert np.array_equal(out["on"][2], out["off"][2]), "residual histories differ between graph replay and eager launches"
+    assert np.array_equal(out["on"][3], out["off"][3]), "solutions differ between graph replay and eager launches"
+    assert out["on"][0] > 0
+
+
 @pytest.mark.parametrize("case", ["convdiff48", "convdiff64", "poisson26", "poisson64_test_rhs"])
 def test_redblack_sgs_iteration_gate(H, case):
     """north_star: multicolour SGS must reach the same final residual within 5% more iterations than
