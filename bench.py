@@ -203,6 +203,82 @@ def run_sweep(a):
     _emit(json.dumps({"sweep": [{"n": n, "gpu_gbs": gpu, "cpu_gbs": cpu, "cpu_threads": cores} for n, gpu, cpu, cores in rows], "peak_gbs": peak}))
 
 
+# ---------------------------------------------------------------------------------------------- solve comparison (SURVEY 8d "CPU baseline")
+
+def run_solves(a):
+    """Whole solves, createSolver -> updateOperator -> apply, on the reference's as-is cases and on the 256^3 benchmark cases: the
+    reference itself on the host cores (oracle/_ref; CG/BiCGSTAB = the harness loops over reference primitives, SGS sequential) beside
+    this library on cuda:0.  Same grids, same right-hand sides, same options; iteration counts must agree (BiCGSTAB within 5 %)."""
+    from struct3d_b200 import hostapi as H
+    from oracle import refshim as R
+    H.init(0)
+    V = (0.577350269189626, 0.7, 0.3)
+    cases = [("test/input/poisson.control as-is", (16, 16, 16), "chebyshev", "poisson", V, 0.0, "test_rhs", "richardson", "jacobi"),
+             ("test/input/poisson.control as-is", (16, 16, 16), "chebyshev", "poisson", V, 0.0, "test_rhs", "gcr", "jacobi"),
+             ("structsolvers/input/poisson.control", (26, 26, 26), "uniform", "poisson", V, 0.0, "manufactured_rhs", "richardson", "jacobi"),
+             ("structsolvers/input/convdiff.control", (48, 48, 48), "uniform", "convdiff", V, 0.1, "manufactured_rhs", "gcr", "jacobi"),
+             ("structsolvers/input/convdiff.control", (48, 48, 48), "uniform", "convdiff", V, 0.1, "manufactured_rhs", "richardson", "sgs"),
+             ("structsolvers/input/convdiff-large.control", (64, 64, 64), "uniform", "convdiff", V, 0.1, "manufactured_rhs", "gcr", "sgs"),
+             ("structsolvers/input/convdiff-large.control", (64, 64, 64), "uniform", "convdiff", V, 0.1, "manufactured_rhs", "gcr", "strilu"),
+             ("Poisson 64^3 (configs[0]), golden rhs", (66, 66, 66), "uniform", "poisson", V, 0.0, "golden", "cg", "jacobi"),
+             ("convection-diffusion 64^3", (66, 66, 66), "uniform", "convdiff", V, 0.1, "manufactured_rhs", "bcgs", "sgs")]
+    if a.solves_large:
+        n = a.solves_large + 2
+        cases += [(f"Poisson {a.solves_large}^3 (configs[1]), golden rhs", (n, n, n), "uniform", "poisson", V, 0.0, "golden", "cg", "jacobi"),
+                  (f"convection-diffusion {a.solves_large}^3 (configs[2])", (n, n, n), "uniform", "convdiff", V, 0.1, "manufactured_rhs", "bcgs", "sgs")]
+    cores = R.num_threads() if R.available() else 0
+    out = [f"| case | grid | solver | reference CPU: iterations, s ({cores} threads; SGS/StrILU sequential) | this library, 1 B200: iterations, s | speed-up |", "|---|---|---|---|---|---|"]
+    rows = []
+    for name, npd, grid, pde, vel, mu, rhs, ksp, pc in cases:
+        opts = {"-s3d_ksp_type": ksp, "-s3d_pc_type": pc, "-ksp_rtol": 1e-6, "-ksp_max_it": 5000, "-s3d_pc_apply_sweeps": 1, "-s3d_pc_build_sweeps": 1,
+                "-s3d_thread_chunk_size": 1024, "-s3d_pc_use_threaded_apply": "false", "-s3d_pc_use_threaded_build": "false", "-ksp_restart": 30}
+        nreal = tuple(v - 2 for v in npd)
+        gold = np.zeros(npd[::-1]); gold[1:-1, 1:-1, 1:-1] = golden_field(nreal[0] * nreal[1] * nreal[2], nreal[::-1])
+        # --- reference
+        ref = None
+        if R.available():
+            m, _ = R._capture_stdout(lambda: R.Mesh(npd, grid=grid))
+            P = R.Pde(pde, vel, mu)
+            (A, b), _ = R._capture_stdout(lambda: (P.lhs(m), P.vector(m, "test_rhs" if rhs == "golden" else rhs)))
+            if rhs == "golden":
+                b.a[...] = gold
+            x = R.Vec(m)
+            t0 = time.perf_counter()
+            if ksp in ("cg", "bcgs"):
+                pr = R.Prec(A, pc)
+                info, _h = R.harness(A, pr, b, x, "cg" if ksp == "cg" else "bicgstab", 1e-6, 5000)
+            else:
+                info = R.solve(A, b, x, opts)
+            ref = (info["iters"], time.perf_counter() - t0, info["converged"])
+            del A, b, x, P, m
+        # --- ours
+        m = H.Mesh(npd, grid=grid)
+        P = H.Pde(pde, vel, mu)
+        A = P.lhs(m)
+        if rhs == "golden":
+            b = H.Vec(m); b.set(gold)
+        else:
+            b = P.vector(m, rhs)
+        x = H.Vec(m)
+        H.set_options(opts)
+        sv = H.Solver(A); sv.update(); H.sync()
+        best, info = 1e30, None
+        for _ in range(2):
+            H.vecset(0.0, x)
+            t0 = time.perf_counter(); info = sv.apply(b, x); H.sync(); best = min(best, time.perf_counter() - t0)
+        del sv
+        rows.append({"case": name, "npdim": list(npd), "ksp": ksp, "pc": pc, "reference": ref, "ours": (info["iters"], best, info["converged"])})
+        r = "-" if ref is None else f"{ref[0]}, {ref[1]:.4f}"
+        sp = "-" if ref is None else f"{ref[1] / best:.1f}x"
+        out.append(f"| {name} | {nreal[0]}x{nreal[1]}x{nreal[2]} {grid} | {ksp} + {pc} | {r} | {info['iters']}, {best:.4f} | {sp} |")
+        print(out[-1], file=sys.stderr, flush=True)
+    text = "\n".join(out)
+    os.makedirs(os.path.dirname(a.solves_out), exist_ok=True)
+    with open(a.solves_out, "w") as fh:
+        fh.write(text + "\n")
+    _emit(json.dumps({"solves": rows, "cpu_threads": cores}))
+
+
 # ---------------------------------------------------------------------------------------------- our arm
 
 def run_ours(a):
@@ -438,6 +514,9 @@ def main():
     ap.add_argument("--halo-overlap", type=int, default=0, help="0: exchange halos first, then multiply (A/B switch)")
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--solves", action="store_true", help="whole solves: the reference on the host cores beside this library (SURVEY 8d)")
+    ap.add_argument("--solves-large", type=int, default=256, help="grid size of the two benchmark cases in --solves (0 = skip them)")
+    ap.add_argument("--solves-out", default=os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpurun_out", "solves.md"))
     ap.add_argument("--sweep", action="store_true", help="bandwidth sweep over grid sizes instead of the bench line (BASELINE.json configs[4])")
     ap.add_argument("--sweep-sizes", default="32,64,128,256,512,1024")
     ap.add_argument("--sweep-cpu-max", type=int, default=512, help="largest grid the reference CPU kernels are timed on")
@@ -452,6 +531,8 @@ def main():
     _emit = lambda line: os.write(real_stdout, (line + "\n").encode())
     if a.sweep:
         run_sweep(a)
+    elif a.solves:
+        run_solves(a)
     elif a.impl == "reference":
         run_reference(a)
     else:
