@@ -35,10 +35,8 @@ __device__ __forceinline__ Item make_item(const GridDev &g, unsigned it, unsigne
 	return t;
 }
 
-// Ops come in two shapes.  SPLIT ops expose load(item) -> registers and apply(item, registers, acc): the kernel
-// then issues the loads of TWO independent items before the first store, doubling the bytes each thread keeps
-// in flight (measured: copy/axpy sat at 90-92 % of the copy peak with one item in flight).  Plain ops are
-// called item by item.
+// Ops come in two shapes.  SPLIT ops expose load(item) -> registers and apply(item, registers, acc) and normally run in
+// ew_chunk_kernel below; plain ops are called item by item here.
 template <class Op>
 __global__ void __launch_bounds__(256) ew_kernel(const GridDev g, Op op, const RedOut ro, const int *stop)
 {
@@ -69,6 +67,42 @@ __global__ void __launch_bounds__(256) ew_kernel(const GridDev g, Op op, const R
 	if (Op::NR > 0) grid_reduce<NR>(acc, ro);
 }
 
+// The order the SPLIT ops run in: a block walks contiguous segments of 256*U items (U x 4 KB per stream) and issues the loads of all
+// U items of a segment before the first store.  Against the grid-stride order above (512^3, one B200, profiles/r1_ew_unroll.md):
+// copy 5749 -> 6258 GB/s, axpy 5945 -> 6545, waxpby 6119 -> 6536, cg_update 6214 -> 6578 with U = 8; the ops that divide
+// (Jacobi) lose at U = 8 (the division is a long subroutine) and take U = 4: 6217 -> 6448.  Each op names its U (Op::UNROLL);
+// the tuning key ew_unroll overrides it (2, 4, 8; -1 = the grid-stride kernel).
+template <class Op, int U>
+__global__ void __launch_bounds__(256) ew_chunk_kernel(const GridDev g, Op op, const RedOut ro, const int *stop)
+{
+	if (s3d_stopped(stop)) return;
+	constexpr int NR = Op::NR > 0 ? Op::NR : 1;
+	double acc[NR];
+#pragma unroll
+	for (int r = 0; r < NR; r++) acc[r] = 0.0;
+	op.prepare();
+	const unsigned nx2 = (unsigned)(g.nx + 1) >> 1;
+	const unsigned long long total = (unsigned long long)nx2 * (unsigned)g.ny * (unsigned)g.nz;
+	constexpr unsigned long long SEG = 256ull * U;
+	for (unsigned long long seg = blockIdx.x; seg * SEG < total; seg += gridDim.x) {
+		const unsigned long long base = seg * SEG + threadIdx.x;
+		Item t[U];
+		decltype(op.load(t[0])) r[U];
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			const unsigned long long it = base + 256ull * u;
+			t[u] = make_item(g, (unsigned)(it < total ? it : seg * SEG), nx2);
+			r[u] = op.load(t[u]);
+		}
+#pragma unroll
+		for (int u = 0; u < U; u++)
+			if (base + 256ull * u < total) op.apply(t[u], r[u], acc);
+	}
+	if (Op::NR > 0) grid_reduce<NR>(acc, ro);
+}
+
+int g_ew_unroll = 0;
+
 template <class Op>
 int run(s3d_ctx *ctx, const s3d_grid *g, const Op &op, double *d_red, const int *stop)
 {
@@ -84,6 +118,18 @@ int run(s3d_ctx *ctx, const s3d_grid *g, const Op &op, double *d_red, const int 
 		if (rc != S3D_OK) return rc;
 	}
 	RedOut ro{ctx->partials, ctx->ticket, d_red};
+	if constexpr (Op::SPLIT) {
+		const int U = (g_ew_unroll > 0) ? g_ew_unroll : (g_ew_unroll == 0 ? Op::UNROLL : 0);
+		if (U == 2 || U == 4 || U == 8) {
+			const long long segs = (long long)((total + 256ull * U - 1) / (256ull * U));
+			const unsigned nb = (unsigned)std::max<long long>(1, std::min<long long>(segs, blocks));
+			if (U == 2) ew_chunk_kernel<Op, 2><<<nb, 256, 0, ctx->stream>>>(to_dev(g), op, ro, stop ? stop : ctx->gate);
+			else if (U == 4) ew_chunk_kernel<Op, 4><<<nb, 256, 0, ctx->stream>>>(to_dev(g), op, ro, stop ? stop : ctx->gate);
+			else ew_chunk_kernel<Op, 8><<<nb, 256, 0, ctx->stream>>>(to_dev(g), op, ro, stop ? stop : ctx->gate);
+			S3D_LAUNCHED(ctx);
+			return S3D_OK;
+		}
+	}
 	ew_kernel<Op><<<(unsigned)blocks, 256, 0, ctx->stream>>>(to_dev(g), op, ro, stop ? stop : ctx->gate);
 	S3D_LAUNCHED(ctx);
 	return S3D_OK;
@@ -108,15 +154,18 @@ __device__ __forceinline__ double madd(double a, double x, double y) { return __
 
 struct OpSet {
 	static constexpr int NR = 0;
-	static constexpr bool SPLIT = false;
+	static constexpr bool SPLIT = true;
+	static constexpr int UNROLL = 8;
 	double a; double *x;
 	__device__ void prepare() {}
-	__device__ void operator()(const Item &t, double *) const { stp(x, t, make_double2(a, a)); }
+	__device__ char load(const Item &) const { return 0; }
+	__device__ void apply(const Item &t, const char &, double *) const { stp(x, t, make_double2(a, a)); }
 };
 
 struct OpCopy {
 	static constexpr int NR = 0;
 	static constexpr bool SPLIT = true;
+	static constexpr int UNROLL = 8;
 	const double *x; double *y;
 	__device__ void prepare() {}
 	__device__ double2 load(const Item &t) const { return ldp(x, t); }
@@ -131,6 +180,7 @@ struct Regs6 { double2 a, b, c, d, e, f; };
 struct OpAxpy {   // y += a x
 	static constexpr int NR = 0;
 	static constexpr bool SPLIT = true;
+	static constexpr int UNROLL = 8;
 	s3d_scalar sa; const double *x; double *y; double a;
 	__device__ void prepare() { a = s3d_sval(sa); }
 	__device__ Regs2 load(const Item &t) const { return Regs2{ldp(x, t), ldp(y, t)}; }
@@ -144,6 +194,7 @@ template <bool READY, bool NORM>
 struct OpWaxpby {   // w = a x + b y  [+ (w,w)]
 	static constexpr int NR = NORM ? 1 : 0;
 	static constexpr bool SPLIT = true;
+	static constexpr int UNROLL = 8;
 	s3d_scalar sa, sb; const double *x; const double *y; double *w; double a, b;
 	__device__ void prepare() { a = s3d_sval(sa); b = READY ? s3d_sval(sb) : 0.0; }
 	__device__ Regs2 load(const Item &t) const { return Regs2{ldp(x, t), READY ? ldp(y, t) : make_double2(0.0, 0.0)}; }
@@ -162,6 +213,7 @@ struct OpWaxpby {   // w = a x + b y  [+ (w,w)]
 struct OpXpby {   // y = x + b y   (CG direction update p = z + beta p: z + (beta*p), two roundings)
 	static constexpr int NR = 0;
 	static constexpr bool SPLIT = true;
+	static constexpr int UNROLL = 8;
 	s3d_scalar sb; const double *x; double *y; double b;
 	__device__ void prepare() { b = s3d_sval(sb); }
 	__device__ Regs2 load(const Item &t) const { return Regs2{ldp(x, t), ldp(y, t)}; }
@@ -214,6 +266,7 @@ struct OpMultiDot {   // acc[l] = (x_l, y)
 struct OpDot {
 	static constexpr int NR = 1;
 	static constexpr bool SPLIT = true;
+	static constexpr int UNROLL = 4;
 	const double *x, *y;
 	__device__ void prepare() {}
 	__device__ Regs2 load(const Item &t) const { return Regs2{ldp(x, t), ldp(y, t)}; }
@@ -223,6 +276,7 @@ struct OpDot {
 struct OpNrm2 {
 	static constexpr int NR = 1;
 	static constexpr bool SPLIT = true;
+	static constexpr int UNROLL = 8;
 	const double *x;
 	__device__ void prepare() {}
 	__device__ double2 load(const Item &t) const { return ldp(x, t); }
@@ -250,6 +304,7 @@ struct OpNormL2 {   // sum x^2 * vol, vol = 1/8 * wx[i] * wy[j] * wz[k]   (matve
 struct OpJacobi {   // z = r / diag(A)   (s3d_jacobi.cpp:17-26: a true division)
 	static constexpr int NR = 0;
 	static constexpr bool SPLIT = true;
+	static constexpr int UNROLL = 4;
 	const double *diag; const double *r; double *z;
 	__device__ void prepare() {}
 	__device__ Regs2 load(const Item &t) const { return Regs2{ldp(r, t), ldc(diag, t)}; }
@@ -263,6 +318,7 @@ template <bool JAC>
 struct OpCgUpdate {   // x += alpha p; r -= alpha q; (r,r); [ (r, r/diag) ]
 	static constexpr int NR = 2;
 	static constexpr bool SPLIT = true;
+	static constexpr int UNROLL = 8;
 	s3d_scalar salpha; const double *p, *q; double *x, *r; const double *diag; double alpha;
 	struct R { double2 p, q, x, r, d; };
 	__device__ void prepare() { alpha = s3d_sval(salpha); }
@@ -288,6 +344,7 @@ struct OpCgUpdate {   // x += alpha p; r -= alpha q; (r,r); [ (r, r/diag) ]
 struct OpCgDirJacobi {   // p = r/diag + beta p
 	static constexpr int NR = 0;
 	static constexpr bool SPLIT = true;
+	static constexpr int UNROLL = 4;
 	s3d_scalar sbeta; const double *diag; const double *r; double *p; double beta;
 	__device__ void prepare() { beta = s3d_sval(sbeta); }
 	__device__ Regs3 load(const Item &t) const { return Regs3{ldp(r, t), ldc(diag, t), ldp(p, t)}; }
@@ -300,6 +357,7 @@ struct OpCgDirJacobi {   // p = r/diag + beta p
 struct OpBicgDir {   // p = r + beta (p - omega v)
 	static constexpr int NR = 0;
 	static constexpr bool SPLIT = true;
+	static constexpr int UNROLL = 4;
 	s3d_scalar sbeta, somega; const double *r, *v; double *p; double beta, omega;
 	__device__ void prepare() { beta = s3d_sval(sbeta); omega = s3d_sval(somega); }
 	__device__ Regs3 load(const Item &t) const { return Regs3{ldp(r, t), ldp(v, t), ldp(p, t)}; }
@@ -313,6 +371,7 @@ struct OpBicgDir {   // p = r + beta (p - omega v)
 struct OpBicgUpdate {   // x += alpha ph + omega sh; r = s - omega t; (r,r); (rhat,r)
 	static constexpr int NR = 2;
 	static constexpr bool SPLIT = true;
+	static constexpr int UNROLL = 4;
 	s3d_scalar salpha, somega; const double *ph, *sh, *s, *tt, *rhat; double *x, *r; double alpha, omega;
 	__device__ void prepare() { alpha = s3d_sval(salpha); omega = s3d_sval(somega); }
 	__device__ Regs6 load(const Item &t) const { return Regs6{ldp(ph, t), ldp(sh, t), ldp(s, t), ldp(tt, t), ldp(rhat, t), ldp(x, t)}; }
@@ -421,6 +480,8 @@ int s3d_final_reduce(s3d_ctx *ctx, int nr, unsigned nblocks, double *out)
 }
 
 extern "C" {
+
+void s3d_internal_set_ew_unroll(int u) { g_ew_unroll = u; }
 
 int s3d_vecset(s3d_ctx *ctx, const s3d_grid *g, double a, double *d_x)
 {

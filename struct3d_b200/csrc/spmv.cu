@@ -324,6 +324,8 @@ int pick_kchunk(const s3d_ctx *, const s3d_grid *g, bool fused)
 int s3d_spmv_tma(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *x, double *y, const double *b,
                  const double *w, bool yy, double *d_red, const int *stop);
 
+extern "C" void s3d_internal_set_ew_unroll(int u);
+
 extern "C" {
 
 int s3d_tune_set(s3d_ctx *ctx, const char *key, int value)
@@ -337,6 +339,7 @@ int s3d_tune_set(s3d_ctx *ctx, const char *key, int value)
 	else if (!strcmp(key, "sgs_sleep_ns")) ctx->sgs_sleep_ns = value;
 	else if (!strcmp(key, "sgs_variant")) ctx->sgs_variant = value;
 	else if (!strcmp(key, "sgs_warps_per_sm")) ctx->sgs_warps_per_sm = value;
+	else if (!strcmp(key, "ew_unroll")) s3d_internal_set_ew_unroll(value);
 	else if (!strcmp(key, "sgs_tile_i")) ctx->sgs_tile_i = value;
 	else if (!strcmp(key, "sgs_pencils")) ctx->sgs_pencils = value;
 	else if (!strcmp(key, "sgs_profile")) {
