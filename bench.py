@@ -302,6 +302,7 @@ def run_ours(a):
     ctx = capi.Context.from_handle(hostapi.cuda_ctx())
     H = hostapi
     ctx.tune("halo_overlap", a.halo_overlap)
+    ctx.tune("halo_p2p", a.halo_p2p)
 
     def barrier():
         H.sync()
@@ -512,6 +513,7 @@ def main():
     ap.add_argument("--strong", type=int, default=1024, help="grid size of the strong-scaling CG block (0 disables)")
     ap.add_argument("--strong-iters", type=int, default=40)
     ap.add_argument("--halo-overlap", type=int, default=0, help="0: exchange halos first, then multiply (A/B switch)")
+    ap.add_argument("--halo-p2p", type=int, default=1, help="1: halo planes through peer-memory windows (CUDA IPC), 0: NCCL send/recv (A/B switch)")
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--solves", action="store_true", help="whole solves: the reference on the host cores beside this library (SURVEY 8d)")

@@ -65,6 +65,16 @@ struct s3d_ctx {
 	int64_t launches = 0;
 	// z-slab communicator
 	ncclComm_t comm = nullptr;
+	// peer-memory halo window (one process per GPU, neighbours' windows mapped through CUDA IPC); see context.cu
+	struct P2P {
+		int mode = 1;                 // tuning key halo_p2p: 1 = use peer memory when it can be set up, 0 = NCCL send/recv
+		bool ok = false;              // windows of the neighbours are mapped on every rank
+		double *win = nullptr;        // [32 doubles of header: 4 int flags][4 planes: (from below, from above) x parity]
+		size_t plane_cap = 0;         // doubles per plane slot
+		double *peer_lo = nullptr, *peer_hi = nullptr;   // the windows of rank-1 / rank+1 as mapped here
+		unsigned *ticket = nullptr;   // last-block election of the push kernel
+		int epoch = 0;
+	} p2p;
 	int rank = 0, nranks = 1;
 	char err[512] = "";
 };

@@ -493,6 +493,11 @@ int s3d_comm_init(s3d_ctx *ctx, int rank, int nranks, const void *idbytes)
 
 int s3d_comm_destroy(s3d_ctx *ctx)
 {
+	if (ctx->p2p.peer_lo) cudaIpcCloseMemHandle(ctx->p2p.peer_lo);
+	if (ctx->p2p.peer_hi) cudaIpcCloseMemHandle(ctx->p2p.peer_hi);
+	if (ctx->p2p.win) cudaFree(ctx->p2p.win);
+	if (ctx->p2p.ticket) cudaFree(ctx->p2p.ticket);
+	ctx->p2p = s3d_ctx::P2P();
 	if (ctx->comm) { S3D_NCCL(ctx, g_nccl.CommDestroy(ctx->comm)); ctx->comm = nullptr; }
 	ctx->rank = 0; ctx->nranks = 1;
 	return S3D_OK;
@@ -500,12 +505,155 @@ int s3d_comm_destroy(s3d_ctx *ctx)
 
 // One contiguous z-plane (vplane doubles: ghost rows and padding included, all zero there) per direction.
 // Plane nz (top real) goes up into the neighbour's ghost plane 0; plane 1 goes down into its ghost plane nz+1.
+// ---- halo exchange over peer memory.
+// The reference has no counterpart (its native path is one process, cartmesh.cpp:107-109).  One process per GPU here, so the planes
+// travel between processes: every rank owns a WINDOW (four plane slots + four flags) that its two z-neighbours map through CUDA IPC.
+// An exchange is two small kernels on the compute stream, no NCCL call:
+//   push: copy my first / last real plane straight into the lower / upper neighbour's window over NVLink, fence at system scope,
+//         and the last block to finish stores the epoch into the neighbour's flag;
+//   pull: wait until my own flags show the epoch (the neighbours' planes have landed), copy the slots into my ghost planes.
+// Slots alternate with the parity of the epoch: slot p is rewritten by the neighbour's push of epoch e+2, which it can only issue after
+// its pull of e+1, which needs my push of e+1, which follows my pull of e in stream order -- so no acknowledgement is needed.
+// Measured against grouped ncclSend/ncclRecv: profiles/r1_p2p_halo.md.
+namespace {
+
+constexpr int P2P_HEADER = 32;   // doubles reserved for the flags
+
+__global__ void __launch_bounds__(256)
+halo_push_kernel(const double *lo_plane, const double *hi_plane, double *dst_lo, double *dst_hi, long long n, int *flag_lo, int *flag_hi,
+                 unsigned *ticket, int epoch)
+{
+	const long long n2 = n >> 1;
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+		if (dst_lo) reinterpret_cast<double2 *>(dst_lo)[i] = reinterpret_cast<const double2 *>(lo_plane)[i];
+		if (dst_hi) reinterpret_cast<double2 *>(dst_hi)[i] = reinterpret_cast<const double2 *>(hi_plane)[i];
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const unsigned t = atomicAdd(ticket, 1u);
+		if (t == gridDim.x - 1) {
+			*ticket = 0;
+			__threadfence_system();
+			if (flag_lo) *(volatile int *)flag_lo = epoch;
+			if (flag_hi) *(volatile int *)flag_hi = epoch;
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256)
+halo_pull_kernel(double *ghost_lo, double *ghost_hi, const double *src_lo, const double *src_hi, long long n, const int *flag_lo,
+                 const int *flag_hi, int epoch)
+{
+	if (threadIdx.x == 0) {
+		const long long t0 = clock64();
+		while ((flag_lo && *(const volatile int *)flag_lo != epoch) || (flag_hi && *(const volatile int *)flag_hi != epoch))
+			if (clock64() - t0 > (20ll << 30)) __trap();   // ~10 s: a neighbour died; fail loudly instead of hanging the GPU
+		__threadfence_system();
+	}
+	__syncthreads();
+	const long long n2 = n >> 1;
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+		if (src_lo) reinterpret_cast<double2 *>(ghost_lo)[i] = __ldcg(reinterpret_cast<const double2 *>(src_lo) + i);
+		if (src_hi) reinterpret_cast<double2 *>(ghost_hi)[i] = __ldcg(reinterpret_cast<const double2 *>(src_hi) + i);
+	}
+}
+
+// (Re)creates the window for planes of n doubles and maps the neighbours' windows.  Collective: every rank gets here at the same
+// exchange with the same n.  Any failure on any rank leaves p2p.ok false on all of them (NCCL carries the exchange then).
+int p2p_ensure(s3d_ctx *ctx, const s3d_grid *g)
+{
+	s3d_ctx::P2P &w = ctx->p2p;
+	const size_t n = (size_t)g->vplane;
+	if (w.win && w.plane_cap >= n) return S3D_OK;
+	const int up = g->rank + 1, dn = g->rank - 1;
+	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	double *sync = nullptr;   // a small allreduce is the barrier before old windows go away and the vote after the new ones are mapped
+	S3D_CUDA(ctx, cudaMalloc(&sync, 2 * sizeof(double)));
+	auto vote = [&](double mine, double &sum) -> int {
+		S3D_CUDA(ctx, cudaMemcpy(sync, &mine, sizeof(double), cudaMemcpyHostToDevice));
+		S3D_NCCL(ctx, g_nccl.AllReduce(sync, sync + 1, 1, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+		S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		S3D_CUDA(ctx, cudaMemcpy(&sum, sync + 1, sizeof(double), cudaMemcpyDeviceToHost));
+		return S3D_OK;
+	};
+	double sum = 0;
+	int rc = vote(0.0, sum);
+	if (rc != S3D_OK) { cudaFree(sync); return rc; }
+	if (w.peer_lo) cudaIpcCloseMemHandle(w.peer_lo);
+	if (w.peer_hi) cudaIpcCloseMemHandle(w.peer_hi);
+	if (w.win) cudaFree(w.win);
+	w.peer_lo = w.peer_hi = w.win = nullptr; w.ok = false; w.plane_cap = 0; w.epoch = 0;
+	bool good = true;
+	const size_t cap = (n + 15) / 16 * 16;
+	cudaIpcMemHandle_t mine, from_lo, from_hi;
+	memset(&mine, 0, sizeof mine);
+	good = good && cudaMalloc(&w.win, (P2P_HEADER + 4 * cap) * sizeof(double)) == cudaSuccess;
+	good = good && cudaMemset(w.win, 0, (P2P_HEADER + 4 * cap) * sizeof(double)) == cudaSuccess;
+	if (!w.ticket) good = good && cudaMalloc(&w.ticket, sizeof(unsigned)) == cudaSuccess && cudaMemset(w.ticket, 0, sizeof(unsigned)) == cudaSuccess;
+	good = good && cudaIpcGetMemHandle(&mine, w.win) == cudaSuccess;
+	cudaGetLastError();
+	// the handles travel through NCCL (device staging buffers): [0] mine, [1] from below, [2] from above
+	char *hb = nullptr;
+	S3D_CUDA(ctx, cudaMalloc(&hb, 3 * sizeof(cudaIpcMemHandle_t)));
+	S3D_CUDA(ctx, cudaMemcpy(hb, &mine, sizeof mine, cudaMemcpyHostToDevice));
+	S3D_NCCL(ctx, g_nccl.GroupStart());
+	if (up < g->nranks) {
+		S3D_NCCL(ctx, g_nccl.Send(hb, sizeof mine, ncclChar, up, ctx->comm, ctx->stream));
+		S3D_NCCL(ctx, g_nccl.Recv(hb + 2 * sizeof mine, sizeof mine, ncclChar, up, ctx->comm, ctx->stream));
+	}
+	if (dn >= 0) {
+		S3D_NCCL(ctx, g_nccl.Send(hb, sizeof mine, ncclChar, dn, ctx->comm, ctx->stream));
+		S3D_NCCL(ctx, g_nccl.Recv(hb + sizeof mine, sizeof mine, ncclChar, dn, ctx->comm, ctx->stream));
+	}
+	S3D_NCCL(ctx, g_nccl.GroupEnd());
+	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	S3D_CUDA(ctx, cudaMemcpy(&from_lo, hb + sizeof mine, sizeof mine, cudaMemcpyDeviceToHost));
+	S3D_CUDA(ctx, cudaMemcpy(&from_hi, hb + 2 * sizeof mine, sizeof mine, cudaMemcpyDeviceToHost));
+	cudaFree(hb);
+	if (good && dn >= 0) good = cudaIpcOpenMemHandle((void **)&w.peer_lo, from_lo, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+	if (good && up < g->nranks) good = cudaIpcOpenMemHandle((void **)&w.peer_hi, from_hi, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+	cudaGetLastError();
+	rc = vote(good ? 0.0 : 1.0, sum);
+	cudaFree(sync);
+	if (rc != S3D_OK) return rc;
+	w.plane_cap = cap;
+	w.ok = (sum == 0.0);
+	if (!w.ok && ctx->rank == 0) fprintf(stderr, "[struct3d_b200] peer-memory halo windows unavailable (CUDA IPC); using NCCL send/recv\n");
+	return S3D_OK;
+}
+
+}  // namespace
+
 int s3d_halo_exchange(s3d_ctx *ctx, const s3d_grid *g, double *d_x)
 {
 	if (g->nranks == 1) return S3D_OK;
 	if (!ctx->comm) return s3d_fail(ctx, S3D_ERR_STATE, "halo exchange needs s3d_comm_init");
 	const size_t n = (size_t)g->vplane;
 	const int up = g->rank + 1, dn = g->rank - 1;
+	if (ctx->p2p.mode == 1) {
+		const int rc = p2p_ensure(ctx, g);
+		if (rc != S3D_OK) return rc;
+	}
+	if (ctx->p2p.mode == 1 && ctx->p2p.ok) {
+		s3d_ctx::P2P &w = ctx->p2p;
+		const int epoch = ++w.epoch, par = epoch & 1;
+		const size_t cap = w.plane_cap;
+		// slot (side, parity): side 0 = written by the rank below, side 1 = written by the rank above
+		auto slot = [&](double *win, int side) { return win + P2P_HEADER + (size_t)(side * 2 + par) * cap; };
+		auto flag = [&](double *win, int side) { return reinterpret_cast<int *>(win) + side * 2 + par; };
+		const bool has_lo = dn >= 0, has_hi = up < g->nranks;
+		const unsigned nb = (unsigned)std::min<size_t>((n / 2 + 255) / 256, (size_t)ctx->sm_count * 2);
+		halo_push_kernel<<<nb, 256, 0, ctx->stream>>>(d_x + n, d_x + n * g->nz, has_lo ? slot(w.peer_lo, 1) : nullptr, has_hi ? slot(w.peer_hi, 0) : nullptr,
+		                                               (long long)n, has_lo ? flag(w.peer_lo, 1) : nullptr, has_hi ? flag(w.peer_hi, 0) : nullptr, w.ticket, epoch);
+		S3D_LAUNCHED(ctx);
+		halo_pull_kernel<<<nb, 256, 0, ctx->stream>>>(d_x, d_x + n * (g->nz + 1), has_lo ? slot(w.win, 0) : nullptr, has_hi ? slot(w.win, 1) : nullptr,
+		                                               (long long)n, has_lo ? flag(w.win, 0) : nullptr, has_hi ? flag(w.win, 1) : nullptr, epoch);
+		S3D_LAUNCHED(ctx);
+		return S3D_OK;
+	}
 	S3D_NCCL(ctx, g_nccl.GroupStart());
 	if (up < g->nranks) {
 		S3D_NCCL(ctx, g_nccl.Send(d_x + n * g->nz, n, ncclDouble, up, ctx->comm, ctx->stream));

@@ -359,6 +359,7 @@ int s3d_tune_set(s3d_ctx *ctx, const char *key, int value)
 		}
 	}
 	else if (!strcmp(key, "halo_overlap")) ctx->no_overlap = (value == 0);
+	else if (!strcmp(key, "halo_p2p")) ctx->p2p.mode = value ? 1 : 0;
 	else if (!strcmp(key, "spmv_variant")) {
 		S3D_REQUIRE(ctx, value >= S3D_SPMV_MARCH && value <= S3D_SPMV_PAIR, "unknown SpMV variant");
 		g_tune.variant = value;
