@@ -489,7 +489,7 @@ def run_ours(a):
         line = {"metric": "spmv_7pt_fp64_hbm_gbs", "value": value, "unit": "GB/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"poisson3d_uniform_{n}^3_fp64_7pt_spmv", "grid_per_gpu": f"{nx}x{ny}x{nzl}", "grid_total": f"{nx}x{ny}x{nzg}",
-                           "decomposition": f"z-slabs x{world}, one-plane halo by NCCL send/recv" if world > 1 else "single GPU",
+                           "decomposition": (f"z-slabs x{world}, one-plane halo " + ("pushed into the neighbours' peer-memory windows (CUDA IPC over NVLink) and read by the SpMV itself" if a.halo_p2p else "by NCCL send/recv")) if world > 1 else "single GPU",
                            "l2": f"inputs exceed L2: {BYTES_SPMV * N_local / 1e9:.2f} GB streamed per step vs 126 MB L2 (no flush needed)",
                            "step": "halo exchange (N>1) + SMat::apply (y = A x)", "bytes_per_point": BYTES_SPMV},
                 "value_frac_of_measured_peak": value / (peak * world), "value_frac_of_nominal_8TBs": value / (8000.0 * world),

@@ -9,6 +9,13 @@
 
 #include "s3d_cuda.h"
 
+// what a z-slab SpMV reads instead of x's two ghost planes: the slots of this rank's peer-memory window (context.cu)
+struct s3d_halo_view {
+	const double *lo = nullptr, *hi = nullptr;         // plane-shaped slots (null at the ends of the global grid)
+	const int *flag_lo = nullptr, *flag_hi = nullptr;  // hold `epoch` once the neighbour's plane has landed
+	int epoch = 0;
+};
+
 struct s3d_ctx {
 	int device = 0;
 	int sm_count = 148;

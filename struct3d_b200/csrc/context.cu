@@ -627,30 +627,49 @@ int p2p_ensure(s3d_ctx *ctx, const s3d_grid *g)
 
 }  // namespace
 
+// The sending half of a peer-memory exchange: push the two boundary planes of x into the neighbours' windows.  On success `hv`
+// describes where the planes this rank RECEIVES will land (its own window slots and flags, for epoch hv->epoch); hv->epoch == 0
+// means peer memory is not in use and the caller must run the NCCL exchange.
+int s3d_internal_halo_push(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, s3d_halo_view *hv)
+{
+	*hv = s3d_halo_view();
+	if (ctx->p2p.mode != 1) return S3D_OK;
+	const int rc = p2p_ensure(ctx, g);
+	if (rc != S3D_OK) return rc;
+	if (!ctx->p2p.ok) return S3D_OK;
+	s3d_ctx::P2P &w = ctx->p2p;
+	const size_t n = (size_t)g->vplane;
+	const int up = g->rank + 1, dn = g->rank - 1;
+	const int epoch = ++w.epoch, par = epoch & 1;
+	const size_t cap = w.plane_cap;
+	// slot (side, parity): side 0 = written by the rank below, side 1 = written by the rank above
+	auto slot = [&](double *win, int side) { return win + P2P_HEADER + (size_t)(side * 2 + par) * cap; };
+	auto flag = [&](double *win, int side) { return reinterpret_cast<int *>(win) + side * 2 + par; };
+	const bool has_lo = dn >= 0, has_hi = up < g->nranks;
+	const unsigned nb = (unsigned)std::min<size_t>((n / 2 + 255) / 256, (size_t)ctx->sm_count * 2);
+	halo_push_kernel<<<nb, 256, 0, ctx->stream>>>(d_x + n, d_x + n * g->nz, has_lo ? slot(w.peer_lo, 1) : nullptr, has_hi ? slot(w.peer_hi, 0) : nullptr,
+	                                               (long long)n, has_lo ? flag(w.peer_lo, 1) : nullptr, has_hi ? flag(w.peer_hi, 0) : nullptr, w.ticket, epoch);
+	S3D_LAUNCHED(ctx);
+	hv->lo = has_lo ? slot(w.win, 0) : nullptr;
+	hv->hi = has_hi ? slot(w.win, 1) : nullptr;
+	hv->flag_lo = has_lo ? flag(w.win, 0) : nullptr;
+	hv->flag_hi = has_hi ? flag(w.win, 1) : nullptr;
+	hv->epoch = epoch;
+	return S3D_OK;
+}
+
 int s3d_halo_exchange(s3d_ctx *ctx, const s3d_grid *g, double *d_x)
 {
 	if (g->nranks == 1) return S3D_OK;
 	if (!ctx->comm) return s3d_fail(ctx, S3D_ERR_STATE, "halo exchange needs s3d_comm_init");
 	const size_t n = (size_t)g->vplane;
 	const int up = g->rank + 1, dn = g->rank - 1;
-	if (ctx->p2p.mode == 1) {
-		const int rc = p2p_ensure(ctx, g);
-		if (rc != S3D_OK) return rc;
-	}
-	if (ctx->p2p.mode == 1 && ctx->p2p.ok) {
-		s3d_ctx::P2P &w = ctx->p2p;
-		const int epoch = ++w.epoch, par = epoch & 1;
-		const size_t cap = w.plane_cap;
-		// slot (side, parity): side 0 = written by the rank below, side 1 = written by the rank above
-		auto slot = [&](double *win, int side) { return win + P2P_HEADER + (size_t)(side * 2 + par) * cap; };
-		auto flag = [&](double *win, int side) { return reinterpret_cast<int *>(win) + side * 2 + par; };
-		const bool has_lo = dn >= 0, has_hi = up < g->nranks;
+	s3d_halo_view hv;
+	const int rcp = s3d_internal_halo_push(ctx, g, d_x, &hv);
+	if (rcp != S3D_OK) return rcp;
+	if (hv.epoch) {
 		const unsigned nb = (unsigned)std::min<size_t>((n / 2 + 255) / 256, (size_t)ctx->sm_count * 2);
-		halo_push_kernel<<<nb, 256, 0, ctx->stream>>>(d_x + n, d_x + n * g->nz, has_lo ? slot(w.peer_lo, 1) : nullptr, has_hi ? slot(w.peer_hi, 0) : nullptr,
-		                                               (long long)n, has_lo ? flag(w.peer_lo, 1) : nullptr, has_hi ? flag(w.peer_hi, 0) : nullptr, w.ticket, epoch);
-		S3D_LAUNCHED(ctx);
-		halo_pull_kernel<<<nb, 256, 0, ctx->stream>>>(d_x, d_x + n * (g->nz + 1), has_lo ? slot(w.win, 0) : nullptr, has_hi ? slot(w.win, 1) : nullptr,
-		                                               (long long)n, has_lo ? flag(w.win, 0) : nullptr, has_hi ? flag(w.win, 1) : nullptr, epoch);
+		halo_pull_kernel<<<nb, 256, 0, ctx->stream>>>(d_x, d_x + n * (g->nz + 1), hv.lo, hv.hi, (long long)n, hv.flag_lo, hv.flag_hi, hv.epoch);
 		S3D_LAUNCHED(ctx);
 		return S3D_OK;
 	}

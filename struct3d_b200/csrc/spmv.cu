@@ -39,18 +39,39 @@ __device__ __forceinline__ double stencil7(double a0, double a1, double a2, doub
 // grid: (ceil(nx/64), ceil(ny/BY), ceil(nz/kchunk)); block: (32, BY)
 // The fused reductions only do stage 1 (per-block partials) in this kernel; the fixed-order sum over blocks
 // is the separate s3d_final_reduce launch.  Inlining stage 2 here cost 102 registers (2 blocks/SM).
-template <int BY, int MINB, bool RES, bool DOTW, bool DOTYY>
+// HALO = true (z-slab runs, see s3d_spmv_exchange): the planes below k = 0 and above k = nz-1 are not x's ghost planes but the
+// slots of this rank's peer-memory window, which the neighbours' push kernels fill while this kernel already runs.  The two
+// k-chunks that touch them are dispatched LAST (block order remapped) and only their blocks wait for the window flags, so the
+// exchange overlaps the interior planes tile by tile and needs no launch of its own on the receiving side.
+template <int BY, int MINB, bool RES, bool DOTW, bool DOTYY, bool HALO = false>
 __global__ void __launch_bounds__(32 * BY, MINB)
 spmv_march_kernel(const GridDev g, const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ y,
                   const double *__restrict__ b, const double *__restrict__ w, const RedOut ro, const int *stop,
-                  const int kchunk)
+                  const int kchunk, const s3d_halo_view hv = s3d_halo_view())
 {
 	if (s3d_stopped(stop)) return;
 	const int lane = threadIdx.x;
 	const int i0 = (blockIdx.x * 32 + lane) * 2;
 	const int j = blockIdx.y * BY + threadIdx.y;
-	const int kbeg = blockIdx.z * kchunk;
+	int kz = blockIdx.z;
+	if (HALO && gridDim.z >= 3) {   // chunk 0 and the last chunk go to the end of the dispatch order
+		const int nz_ = (int)gridDim.z;
+		kz = (kz < nz_ - 2) ? kz + 1 : (kz == nz_ - 2 ? 0 : nz_ - 1);
+	}
+	const int kbeg = kz * kchunk;
 	const int kend = min(g.nz, kbeg + kchunk);
+	if (HALO) {
+		const bool need_lo = hv.lo && kbeg == 0, need_hi = hv.hi && kend == g.nz;
+		if (need_lo || need_hi) {
+			if (threadIdx.x == 0 && threadIdx.y == 0) {
+				const long long t0 = clock64();
+				while ((need_lo && *(const volatile int *)hv.flag_lo != hv.epoch) || (need_hi && *(const volatile int *)hv.flag_hi != hv.epoch))
+					if (clock64() - t0 > (20ll << 30)) __trap();   // ~10 s: a neighbour died; fail loudly instead of hanging
+				__threadfence_system();
+			}
+			__syncthreads();
+		}
+	}
 	const bool active = (i0 < g.nx) && (j < g.ny);
 	const unsigned mask = __ballot_sync(0xffffffffu, active);
 	double acc[2] = {0.0, 0.0};
@@ -67,9 +88,10 @@ spmv_march_kernel(const GridDev g, const double *__restrict__ A, const double *_
 		const double *ap = A + (long long)kbeg * g.cplane + (long long)j * g.cpitch + i0;
 		const long long cs = g.cstride;
 
-		double2 xm = ld2(xp - g.vplane);
+		const long long inplane = (g.voff - g.vplane) + (long long)j * g.vpitch + i0;   // the same point inside a window slot
+		double2 xm = (HALO && hv.lo && kbeg == 0) ? __ldcg(reinterpret_cast<const double2 *>(hv.lo + inplane)) : ld2(xp - g.vplane);
 		double2 xc = ld2(xp);
-		auto plane = [&]() {
+		auto plane = [&](const int k) {
 			// the seven coefficient streams: read once, evict-first
 			const double2 a0 = ld_stream2(ap);
 			const double2 a1 = ld_stream2(ap + cs);
@@ -79,7 +101,7 @@ spmv_march_kernel(const GridDev g, const double *__restrict__ A, const double *_
 			const double2 a5 = ld_stream2(ap + 5 * cs);
 			const double2 a6 = ld_stream2(ap + 6 * cs);
 			// x: the next plane (first touch of these values), and the two j-neighbour rows of this plane
-			const double2 xn = ld2(xp + g.vplane);
+			const double2 xn = (HALO && hv.hi && k == g.nz - 1) ? __ldcg(reinterpret_cast<const double2 *>(hv.hi + inplane)) : ld2(xp + g.vplane);
 			const double2 xjm = ld2(xp - g.vpitch);
 			const double2 xjp = ld2(xp + g.vpitch);
 			double2 bv = make_double2(0.0, 0.0);
@@ -111,9 +133,9 @@ spmv_march_kernel(const GridDev g, const double *__restrict__ A, const double *_
 		};
 		if constexpr (DOTW || DOTYY) {
 #pragma unroll 1   // unrolled, the fused-reduction forms take >100 registers
-			for (int k = kbeg; k < kend; ++k) plane();
+			for (int k = kbeg; k < kend; ++k) plane(k);
 		} else {
-			for (int k = kbeg; k < kend; ++k) plane();
+			for (int k = kbeg; k < kend; ++k) plane(k);
 		}
 	}
 	if (DOTW || DOTYY) grid_reduce<2, true>(acc, ro);
@@ -212,7 +234,7 @@ spmv_naive_kernel(const GridDev g, const double *__restrict__ A, const double *_
 
 template <int BY, int MINB>
 int launch_march(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *x, double *y, const double *b,
-                 const double *w, bool yy, double *d_red, const int *stop, int kchunk)
+                 const double *w, bool yy, double *d_red, const int *stop, int kchunk, const s3d_halo_view *hv = nullptr)
 {
 	const GridDev gd = to_dev(g);
 	dim3 block(32, BY);
@@ -225,7 +247,11 @@ int launch_march(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double 
 		if (rc != S3D_OK) return rc;
 	}
 	RedOut ro{ctx->partials + first * 2, nullptr, d_red};
-#define GO(RES, DW, DY) spmv_march_kernel<BY, MINB, RES, DW, DY><<<grid, block, 0, ctx->stream>>>(gd, A, x, y, b, w, ro, stop, kchunk)
+#define GO(RES, DW, DY)                                                                                                        \
+	do {                                                                                                                       \
+		if (MINB == 3 && hv) spmv_march_kernel<BY, 3, RES, DW, DY, true><<<grid, block, 0, ctx->stream>>>(gd, A, x, y, b, w, ro, stop, kchunk, *hv); \
+		else spmv_march_kernel<BY, MINB, RES, DW, DY><<<grid, block, 0, ctx->stream>>>(gd, A, x, y, b, w, ro, stop, kchunk);      \
+	} while (0)
 	const int sel = (b ? 4 : 0) | (w ? 2 : 0) | (yy ? 1 : 0);
 	switch (sel) {
 	case 0: GO(false, false, false); break;
@@ -325,6 +351,7 @@ int s3d_spmv_tma(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double 
                  const double *w, bool yy, double *d_red, const int *stop);
 
 extern "C" void s3d_internal_set_ew_unroll(int u);
+extern "C" int s3d_internal_halo_push(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, s3d_halo_view *hv);
 
 extern "C" {
 
@@ -408,6 +435,21 @@ int s3d_spmv_exchange(s3d_ctx *ctx, const s3d_grid *g, const double *A, double *
 {
 	S3D_REQUIRE(ctx, g && A && d_x && d_y, "null argument");
 	if (g->nranks == 1) return s3d_spmv(ctx, g, A, d_x, d_y, d_b, d_w, want_yy, d_red, d_stop, S3D_SPMV_AUTO);
+	if (ctx->no_overlap && g_tune.variant == S3D_SPMV_MARCH && (g_tune.minb == 0 || g_tune.minb == 3) && ctx->comm) {
+		// peer-memory exchange fused into the multiply: push my planes, then a SpMV that reads the neighbours' planes from the
+		// window and whose two boundary chunks (dispatched last) are the only blocks that wait for them
+		s3d_halo_view hv;
+		const int rc = s3d_internal_halo_push(ctx, g, d_x, &hv);
+		if (rc != S3D_OK) return rc;
+		if (hv.epoch) {
+			S3D_REQUIRE(ctx, d_x != d_y, "x and y must not alias");
+			const bool yy = want_yy != 0;
+			S3D_REQUIRE(ctx, !(d_w || yy) || d_red, "fused reductions need d_red");
+			const int kc = pick_kchunk(ctx, g, d_w != nullptr || yy);
+			return launch_march<8, 3>(ctx, g, A, d_x, d_y, d_b, d_w, yy, d_red, d_stop ? d_stop : ctx->gate, kc, &hv);
+		}
+		// no peer memory: the exchange below
+	}
 	if (g->nz < 3 || g_tune.variant != S3D_SPMV_MARCH || ctx->no_overlap) {
 		const int rc = s3d_halo_exchange(ctx, g, d_x);
 		if (rc != S3D_OK) return rc;
