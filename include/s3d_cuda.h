@@ -99,7 +99,10 @@ int  s3d_timer_stop_ms(s3d_ctx *ctx, double *ms);
 
 /* kernel tuning knobs for sweeps: "spmv_kchunk" (planes per march, 0 = automatic), "spmv_minb" (resident blocks per
  * SM the march kernel is compiled for: 0 auto, 3, 4, 6), "spmv_hints" (evict-first hints on/off for the PAIR/NAIVE
- * variants), "spmv_variant" (what S3D_SPMV_AUTO resolves to), "halo_overlap" (0 = exchange first, then multiply) */
+ * variants), "spmv_variant" (what S3D_SPMV_AUTO resolves to), "halo_overlap" (0 = exchange first, then multiply), "halo_p2p" (1 = halo
+ * planes through peer-memory windows, 0 = NCCL), "ew_unroll" (items a thread of the element-wise kernels keeps in flight: 0 = each
+ * kernel's own choice, 2/4/8, -1 = grid-stride order), "sgs_variant" (0 = warp-per-tile dataflow sweep, 1 = block-per-tile),
+ * "sgs_tile_i" (16/32), "sgs_pencils" (1/2/0 = by grid size), "sgs_warps_per_sm", "sgs_profile" (timing experiments). */
 int  s3d_tune_set(s3d_ctx *ctx, const char *key, int value);
 
 /* Replaces the size arithmetic of SVec::SVec / SMat::SMat (matvec.cpp:8-57).  nz is the local slab. */
@@ -293,8 +296,11 @@ int  s3d_assemble_rhs_separable(s3d_ctx *ctx, const s3d_grid *g, int nterms, con
 int  s3d_comm_unique_id(void *id_out /* S3D_COMM_ID_BYTES */);       /* rank 0 creates, caller broadcasts */
 int  s3d_comm_init(s3d_ctx *ctx, int rank, int nranks, const void *id);
 int  s3d_comm_destroy(s3d_ctx *ctx);
-/* fills ghost planes k=-1 and k=nz of x with the neighbours' boundary planes (NCCL send/recv over NVLink);
- * the global ends keep their Dirichlet zeros.  No-op for one rank. */
+/* fills ghost planes k=-1 and k=nz of x with the neighbours' boundary planes; the global ends keep their Dirichlet zeros.
+ * No-op for one rank.  The planes go through peer memory: each rank's window is mapped by its two neighbours (CUDA IPC, set up at
+ * the first exchange of a plane size -- a collective step), a push kernel stores my planes into their windows over NVLink and raises
+ * their flags, a pull kernel waits for mine and fills the ghost planes.  s3d_tune_set("halo_p2p", 0), or a failed IPC setup on any
+ * rank, selects grouped ncclSend/ncclRecv instead.  s3d_spmv_exchange goes one step further: its SpMV reads the window itself. */
 int  s3d_halo_exchange(s3d_ctx *ctx, const s3d_grid *g, double *d_x);
 
 #ifdef __cplusplus
