@@ -383,7 +383,7 @@ def run_ours(a):
     def e2e_step():
         if world == 1:
             # SMat::apply for host vectors: upload of x, multiply and download of y pipelined in z-chunks (s3d_spmv_host)
-            ctx.spmv_host(g, dA, hx_p, hy_p, dx, dy, nchunks=16)
+            ctx.spmv_host(g, dA, hx_p, hy_p, dx, dy, nchunks=a.e2e_chunks)
         else:
             ctx.call("s3d_vec_upload", C.byref(g), capi._ptr(dx), capi._ptr(hx_p))
             H.apply(A, x, y)
@@ -401,7 +401,7 @@ def run_ours(a):
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
     e2e = {"value": BYTES_SPMV * N_total / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(nbytes),
            "ms_per_step": e2e_ms, "steps": e2e_steps, "check_max_abs_y": float(np.abs(hy).max()),
-           "note": "per step: x from pinned host memory -> y = A x -> y into pinned host memory; single GPU: pipelined in 16 z-chunks over three streams (s3d_spmv_host), multi-GPU: upload, halo exchange + SMat::apply, download"}
+           "note": "per step: x from pinned host memory -> y = A x -> y into pinned host memory; single GPU: pipelined in z-chunks over three streams (s3d_spmv_host), multi-GPU: upload, halo exchange + SMat::apply, download"}
     ctx.host_free(hx_p); ctx.host_free(hy_p)
 
     # ---- extras: the solvers through the reference's call sequence (not part of the timed steps)
@@ -514,6 +514,7 @@ def main():
     ap.add_argument("--strong-iters", type=int, default=40)
     ap.add_argument("--halo-overlap", type=int, default=0, help="0: exchange halos first, then multiply (A/B switch)")
     ap.add_argument("--halo-p2p", type=int, default=1, help="1: halo planes through peer-memory windows (CUDA IPC), 0: NCCL send/recv (A/B switch)")
+    ap.add_argument("--e2e-chunks", type=int, default=32, help="z-chunks of the pipelined host-buffer SpMV (e2e)")
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--solves", action="store_true", help="whole solves: the reference on the host cores beside this library (SURVEY 8d)")
