@@ -88,6 +88,9 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+// cp.async groups are tracked per WARP (one scoreboard): commit and wait must be warp-uniform
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 struct SgsFlow {
 	int *flags;        // one per tile: epoch of the last sweep that completed it
@@ -552,6 +555,249 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 	}
 }
 
+// ---------------------------------------------------------------- warp-per-LINE dataflow
+//
+// The warp-per-tile kernel pays the skew of its pencils (tj + tk - 2 steps) once per tile: 26 steps for 16 columns.  Here a warp
+// owns a whole LINE of the grid -- the 4 x 8 (j,k) pencils of a (cj, ck) cell over ALL nx columns -- and marches through it once:
+// the skew is paid once per line, every step computes 32 points, the i-neighbour stays in a register, and there are no flags,
+// mailboxes or pipeline drains along i.  The inputs stream through a ring of 32 columns in shared memory:
+//   - columns come in groups of 8 (physical, 16-byte aligned); at every step h = 4 (mod 8) the group all lanes have left
+//     (logical columns [h-20, h-12)) is copied out to `out` as 64-byte row pieces and the group [h+12, h+20) is staged into the
+//     same ring slots with cp.async -- 12 steps before its first use;
+//   - dependencies are per (line, block of 16 columns): a line needs the last-j rows of line (cj-1, ck) and the last-k rows of line
+//     (cj, ck-1); their flags are polled 8 steps before the block is entered and the halo rows then stream into two small rings;
+//   - a block's flag is published 36 steps after its first column was entered (its stores have drained by then, the fence is cheap).
+// Same arithmetic, same roundings, same lane mapping and bank map as the tile kernel; lines are dispatched in (cj + ck) order.
+constexpr int SGL_W = 32;                  // ring width in columns
+constexpr int SGL_R = SGL_W + 2;           // row stride in doubles (== 2 mod 16, see sgw_row)
+constexpr size_t sgl_smem(int na, int p) { return (size_t)(na * 32 * p + 8 + 4 * p) * SGL_R * sizeof(double); }
+
+template <int MODE, int P>
+__global__ void __launch_bounds__(32)
+sgs_lineflow_kernel(const GridDev g, const double *__restrict__ in0, const double *__restrict__ c0,
+                    const double *__restrict__ c1, const double *__restrict__ c2, const double *__restrict__ dinv,
+                    double *out, const SgsFlow f, const int *stop)
+{
+	constexpr bool FWD = (MODE != 1);
+	constexpr bool ILU = (MODE == 2);
+	constexpr int NA = ILU ? 4 : 5;
+	constexpr int DIR = FWD ? 1 : -1;
+	constexpr int TJ = 4 * P, TK = SGW_TK, NROWS = TJ * TK;
+	constexpr int R = SGL_R, ASZ = NROWS * R;
+	constexpr int S = TJ + TK - 2 + (P - 1);                 // steps the last pencil of the warp lags the first
+	static_assert(S <= 12 && P == 1, "the copy-out / staging schedule below assumes a skew of at most 12 steps and one pencil per lane");
+	constexpr unsigned FULL = 0xffffffffu;
+	if (s3d_stopped(stop)) return;
+	const int epoch = __ldcg(f.epoch_p);
+	extern __shared__ __align__(16) double smem[];
+	double *s_a = smem;                                       // [stream][row rho][R], column i lives in slot i & 31
+	double *s_hj = s_a + NA * ASZ;                            // [c][R]  rows j0-1 / j0+tj of the neighbouring line
+	double *s_hk = s_hj + 8 * R;                              // [b][R]  rows of plane k0-1 / k0+tk
+
+	const int lane = threadIdx.x;
+	const int m = lane >> 3, cc = lane & 7;
+	const int b0 = m;
+	const int s0 = b0 + cc;
+	const int rho0 = sgw_row<P, FWD>(b0, cc);
+	const int nlines = f.nty * f.ntz;
+	const int nwarps = gridDim.x;
+	// logical columns c = 0 .. ncol-1 in sweep order; backward sweeps start at the top of the last 8-column group, so that
+	// logical groups [8n, 8n+8) are physical, 16-byte aligned groups in either direction
+	const int gmax = (g.nx - 1) >> 3, itop = 8 * gmax + 7;
+	const int ncol = FWD ? g.nx : itop + 1;
+	const int ngroups = gmax + 1, nblocks = (ncol + 15) >> 4;
+	const int fstride = f.ntx;                                // flags per line (>= nblocks of either direction)
+	const int nsteps = ncol + S;
+
+	int ticket = blockIdx.x;
+	int line = (ticket < nlines) ? f.order[FWD ? ticket : nlines - 1 - ticket] : -1;
+	while (line >= 0) {
+		const int cj = line % f.nty, ck = line / f.nty;
+		const int j0 = cj * TJ, k0 = ck * TK;
+		const int tj = min(TJ, g.ny - j0), tk = min(TK, g.nz - k0);
+		const long long vline = g.voff + (long long)k0 * g.vplane + (long long)j0 * g.vpitch;
+		const long long cline = (long long)k0 * g.cplane + (long long)j0 * g.cpitch;
+		const bool act0 = (b0 < tj) && (cc < tk);
+		const int pj = FWD ? (cj > 0 ? line - 1 : -1) : (cj < f.nty - 1 ? line + 1 : -1);
+		const int pk = FWD ? (ck > 0 ? line - f.nty : -1) : (ck < f.ntz - 1 ? line + f.nty : -1);
+
+		// what this lane moves in a burst: NROWS / 8 (row, 16-byte chunk) items; everything that does not depend on the group
+		// is computed once per line
+		constexpr int NU = NROWS / 8;
+		long long it_cv[NU], it_vv[NU];       // global offsets of the item's row in the coefficient / vector layout, + 2*chunk
+		int it_s[NU];                         // shared-memory offset of the item's row (doubles), or -1 when the row is outside the grid
+#pragma unroll
+		for (int u = 0; u < NU; u++) {
+			const int q = lane + 32 * u, ch = q & 3, row = q >> 2, rb = row >> 3, rc = row & 7;
+			const int jp = FWD ? rb : tj - 1 - rb, kp = FWD ? rc : tk - 1 - rc;
+			it_cv[u] = cline + (long long)kp * g.cplane + (long long)jp * g.cpitch + 2 * ch;
+			it_vv[u] = vline + (long long)kp * g.vplane + (long long)jp * g.vpitch + 2 * ch;
+			it_s[u] = (rb < tj && rc < tk) ? sgw_row<P, FWD>(rb, rc) * R + 2 * ch : -1;
+		}
+		auto stage_group = [&](int n) {                         // logical group n of every row, all streams
+			const int i8 = 8 * (FWD ? n : gmax - n), sl = i8 & (SGL_W - 1);
+#pragma unroll
+			for (int u = 0; u < NU; u++)
+				if (it_s[u] >= 0) {
+					double *dst = s_a + it_s[u] + sl;
+					const long long cv = it_cv[u] + i8;
+					cp_async16(dst, in0 + (ILU ? cv : it_vv[u] + i8));
+					cp_async16(dst + ASZ, c0 + cv);
+					cp_async16(dst + 2 * ASZ, c1 + cv);
+					cp_async16(dst + 3 * ASZ, c2 + cv);
+					if (!ILU) cp_async16(dst + 4 * ASZ, dinv + cv);
+				}
+		};
+		auto copy_group = [&](int n) {                          // results of logical group n: whole 64-byte row pieces
+			const int i8 = 8 * (FWD ? n : gmax - n), sl = i8 & (SGL_W - 1);
+#pragma unroll
+			for (int u = 0; u < NU; u++) {
+				const int i = i8 + 2 * ((lane + 32 * u) & 3);
+				if (it_s[u] >= 0 && i < g.nx) {
+					const double2 v = *reinterpret_cast<const double2 *>(s_a + it_s[u] + sl);
+					double *dst = out + it_vv[u] + i8;
+					if (i + 1 < g.nx) *reinterpret_cast<double2 *>(dst) = v;
+					else *dst = v.x;
+				}
+			}
+		};
+		auto stage_halo = [&](int bl) {                         // logical block bl (16 columns) of the 8 + TJ halo rows
+			const int i16 = FWD ? 16 * bl : itop - 16 * bl - 15;
+#pragma unroll
+			for (int u = 0; u < (8 + TJ) * 8 / 32; u++) {
+				const int q = lane + 32 * u, ch = q & 7, row = q >> 3;
+				const int i = i16 + 2 * ch;
+				if (i >= 0 && i < g.nx) {
+					if (row < 8) {
+						if (row < tk)
+							cp_async16(s_hj + row * R + (i & (SGL_W - 1)),
+							           out + vline + (long long)(FWD ? row : tk - 1 - row) * g.vplane + (long long)(FWD ? -1 : tj) * g.vpitch + i);
+					} else {
+						const int r = row - 8;
+						if (r < tj)
+							cp_async16(s_hk + r * R + (i & (SGL_W - 1)),
+							           out + vline + (long long)(FWD ? -1 : tk) * g.vplane + (long long)(FWD ? r : tj - 1 - r) * g.vpitch + i);
+					}
+				}
+			}
+		};
+		// flags of the two predecessor lines: lane 0 watches (cj-1, ck), lane 1 (cj, ck-1).  The load is issued early (flag_peek) and
+		// looked at 8 steps later (flag_wait, a warp-uniform vote -- a partial-warp poll loop leaves the warp split)
+		const int mypred = (lane == 0) ? pj : (lane == 1) ? pk : -1;
+		int peeked = 0;
+		auto flag_peek = [&](int bl) { if (mypred >= 0) peeked = ld_acquire(f.flags + (long long)mypred * fstride + bl); };
+		auto flag_wait = [&](int bl) {
+			bool done = (mypred < 0) || (peeked == epoch);
+			for (;;) {
+				if (__all_sync(FULL, done)) break;
+				if (!done) done = (ld_acquire(f.flags + (long long)mypred * fstride + bl) == epoch);
+			}
+		};
+
+		// ---- prologue: two groups of inputs, the first block of halo rows, the ghost column
+		__syncwarp();
+		flag_peek(0);
+		stage_group(0); cp_async_commit();
+		if (ngroups > 1) stage_group(1);
+		cp_async_commit();
+		const int jp0 = FWD ? b0 : tj - 1 - b0, kp0 = FWD ? cc : tk - 1 - cc;
+		const long long vrow0 = vline + (long long)kp0 * g.vplane + (long long)jp0 * g.vpitch;
+		double last0 = act0 ? __ldcg(out + vrow0 + (FWD ? -1 : g.nx)) : 0.0;   // the ghost column
+		int nticket = 0, nline = -1;
+		if (lane == 0) nticket = (int)atomicAdd(f.ticket, 1u) + nwarps;
+		flag_wait(0);
+		stage_halo(0); cp_async_commit();
+		cp_async_wait_all();
+		__syncwarp();
+
+		// ---- the march.  Lane at logical column u0 = h - s0, physical column FWD ? u0 : itop - u0.
+		double *pa_base = s_a + rho0 * R;
+		const double *phj_base = s_hj + cc * R, *phk_base = s_hk + b0 * R;
+		const bool jhalo = (m == 0), khalo = (cc == 0);
+		int icol = FWD ? -s0 : itop + s0;                       // physical column of this lane at step h
+		int slot = icol & (SGL_W - 1);
+		double a_in = pa_base[slot], a_c0 = pa_base[slot + ASZ], a_c1 = pa_base[slot + 2 * ASZ], a_c2 = pa_base[slot + 3 * ASZ];
+		double a_dv = ILU ? 0.0 : pa_base[slot + (NA - 1) * ASZ];
+		double hj0 = jhalo ? phj_base[slot] : 0.0, hk0 = khalo ? phk_base[slot] : 0.0;
+		int next_copy = 0, next_pub = 0;
+		long long tq0 = 0, tq_wait = 0, tq_flag = 0, tq_trig = 0, tq = 0;
+		if (f.prof) tq0 = clock64();
+		// steps come in octets so that the housekeeping sits at compile-time positions of a fully unrolled inner loop
+#pragma unroll 1
+		for (int h8 = 0; h8 < nsteps; h8 += 8) {
+			const bool odd = (h8 & 8) != 0;
+#pragma unroll
+			for (int q = 0; q < 8; q++) {
+				const int h = h8 + q;
+				if (q == 0 && !odd) flag_peek(min((h + 16) >> 4, nblocks - 1));            // looked at 8 steps from now
+				if (q == 0 && odd) {                                                          // h = 8 (mod 16): halo rows of the next block
+					const int bl = (h + 8) >> 4;
+					if (f.prof) tq = clock64();
+					if (bl < nblocks) { flag_wait(bl); stage_halo(bl); }
+					cp_async_commit();
+					if (f.prof) tq_flag += clock64() - tq;
+				}
+				if (q == 4) {                                                                 // h = 4 (mod 8)
+					if (f.prof) tq = clock64();
+					if (!odd && h >= 36 && next_pub < nblocks) {                                // h = 4 (mod 16): the stores of block next_pub left 8+ steps ago
+						asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+						__syncwarp();
+						if (lane == 0) *(volatile int *)(f.flags + (long long)line * fstride + next_pub) = epoch;
+						next_pub++;
+					}
+					__syncwarp();
+					if (h >= 20 && next_copy < ngroups) copy_group(next_copy++);
+					__syncwarp();
+					const int nin = (h + 12) >> 3;
+					if (nin < ngroups) stage_group(nin);
+					cp_async_commit();
+					if (f.prof) tq_trig += clock64() - tq;
+				}
+				if (q == 7) {                                                                 // the group (and halo block) entered at step h+1 has landed
+					if (f.prof) tq = clock64();
+					cp_async_wait_group<1>(); __syncwarp();
+					if (f.prof) tq_wait += clock64() - tq;
+				}
+				const double shj = __shfl_up_sync(FULL, last0, 8);
+				const double shk0 = __shfl_up_sync(FULL, last0, 1);
+				const int islot = slot;                              // where this step's result goes
+				const bool in0 = act0 && (unsigned)icol < (unsigned)g.nx;
+				icol += DIR;
+				slot = icol & (SGL_W - 1);
+				const double n_a_in = pa_base[slot], n_a_c0 = pa_base[slot + ASZ], n_a_c1 = pa_base[slot + 2 * ASZ], n_a_c2 = pa_base[slot + 3 * ASZ];
+				const double n_a_dv = ILU ? 0.0 : pa_base[slot + (NA - 1) * ASZ];
+				const double n_hj0 = jhalo ? phj_base[slot] : 0.0, n_hk0 = khalo ? phk_base[slot] : 0.0;
+				const double wj0 = jhalo ? hj0 : shj, wk0 = khalo ? hk0 : shk0;
+				double v0;
+				if (ILU) v0 = __dsub_rn(__dsub_rn(__dsub_rn(a_in, __ddiv_rn(a_c0, last0)), __ddiv_rn(a_c1, wj0)), __ddiv_rn(a_c2, wk0));
+				else if (FWD) v0 = __dmul_rn(__dsub_rn(__dsub_rn(__dsub_rn(a_in, __dmul_rn(a_c0, last0)), __dmul_rn(a_c1, wj0)), __dmul_rn(a_c2, wk0)), a_dv);
+				else v0 = __dsub_rn(a_in, __dmul_rn(a_dv, __dadd_rn(__dadd_rn(__dmul_rn(a_c0, last0), __dmul_rn(a_c1, wj0)), __dmul_rn(a_c2, wk0))));
+				if (in0) { last0 = v0; pa_base[islot] = v0; }          // results replace the staged input
+				a_in = n_a_in; a_c0 = n_a_c0; a_c1 = n_a_c1; a_c2 = n_a_c2; a_dv = n_a_dv; hj0 = n_hj0; hk0 = n_hk0;
+			}
+			if (h8 == 16 && lane == 0) nline = (nticket < nlines) ? f.order[FWD ? nticket : nlines - 1 - nticket] : -1;
+		}
+		if (f.prof && lane == 0) {
+			atomicAdd((unsigned long long *)f.prof + 0, (unsigned long long)tq_flag);              // flag waits + halo issue
+			atomicAdd((unsigned long long *)f.prof + 1, (unsigned long long)tq_wait);              // cp.async waits
+			atomicAdd((unsigned long long *)f.prof + 2, (unsigned long long)(clock64() - tq0));    // whole march
+			atomicAdd((unsigned long long *)f.prof + 3, (unsigned long long)tq_trig);              // copy-out + staging + publish
+			atomicAdd((unsigned long long *)f.prof + 4, 1ull);
+			atomicAdd((unsigned long long *)f.prof + 5, (unsigned long long)nsteps);
+		}
+		// ---- epilogue: the groups still in the ring, then the remaining flags
+		cp_async_wait_all();
+		__syncwarp();
+		while (next_copy < ngroups) copy_group(next_copy++);
+		asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+		__syncwarp();
+		if (lane == 0)
+			for (int bl = next_pub; bl < nblocks; bl++) *(volatile int *)(f.flags + (long long)line * fstride + bl) = epoch;
+		if (nsteps <= 16 && lane == 0) nline = (nticket < nlines) ? f.order[FWD ? nticket : nlines - 1 - nticket] : -1;   // short lines never reach the look-up above
+		line = __shfl_sync(FULL, nline, 0);
+	}
+}
+
 // ---------------------------------------------------------------- red-black
 
 // phase 0: y_R = r_R dinv                       (red:   (i+j+k) even in the reference's 1-based indices = odd+... see parity())
@@ -735,9 +981,12 @@ __global__ void sgs_begin_kernel(int *ctl, const int *stop)
 // flags / dispatch table / occupancy for the dataflow kernels; returns the number of persistent blocks
 int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblocks)
 {
-	const int tile_i = (ctx->sgs_variant == 0) ? sgw_tile_i(ctx) : SGS_TI;
-	const int tile_j = (ctx->sgs_variant == 0) ? 4 * sgw_pencils(ctx, g) : SGS_TJ;
-	f.ntx = (g->nx + tile_i - 1) / tile_i; f.nty = (g->ny + tile_j - 1) / tile_j; f.ntz = (g->nz + SGS_TK - 1) / SGS_TK;
+	const bool lines = (ctx->sgs_variant == 3);
+	const int tile_i = lines ? 16 : (ctx->sgs_variant == 0) ? sgw_tile_i(ctx) : SGS_TI;
+	const int tile_j = lines ? 4 : (ctx->sgs_variant == 0) ? 4 * sgw_pencils(ctx, g) : SGS_TJ;
+	// lines: "ntx" is the number of 16-column flag blocks of a line (backward sweeps start at the top of the last 8-column group)
+	f.ntx = lines ? (((g->nx + 7) / 8) * 8 + 15) / 16 : (g->nx + tile_i - 1) / tile_i;
+	f.nty = (g->ny + tile_j - 1) / tile_j; f.ntz = (g->nz + SGS_TK - 1) / SGS_TK;
 	const size_t ntiles = (size_t)f.ntx * f.nty * f.ntz;
 	if (!ctx->sgs_ctl) {
 		S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_ctl, 2 * sizeof(int)));
@@ -762,23 +1011,25 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 		if (blocks_per_sm < 1) blocks_per_sm = 1;
 		configured = true;
 	}
-	if (ctx->sgs_order_dims[0] != f.ntx || ctx->sgs_order_dims[1] != f.nty || ctx->sgs_order_dims[2] != f.ntz) {
-		// counting sort of the tiles by hyperplane
-		const int nd = f.ntx + f.nty + f.ntz - 2;
-		std::vector<int> start(nd + 1, 0), order(ntiles);
+	const int okey = lines ? -f.ntx : f.ntx;   // lines and tiles never share a dispatch table
+	if (ctx->sgs_order_dims[0] != okey || ctx->sgs_order_dims[1] != f.nty || ctx->sgs_order_dims[2] != f.ntz) {
+		// counting sort of the tiles (or lines) by hyperplane
+		const int ox = lines ? 1 : f.ntx;
+		const int nd = ox + f.nty + f.ntz - 2;
+		std::vector<int> start(nd + 1, 0), order((size_t)ox * f.nty * f.ntz);
 		for (int ck = 0; ck < f.ntz; ck++)
 			for (int cj = 0; cj < f.nty; cj++)
-				for (int ci = 0; ci < f.ntx; ci++) start[ci + cj + ck + 1]++;
+				for (int ci = 0; ci < ox; ci++) start[ci + cj + ck + 1]++;
 		for (int d = 0; d < nd; d++) start[d + 1] += start[d];
 		for (int ck = 0; ck < f.ntz; ck++)
 			for (int cj = 0; cj < f.nty; cj++)
-				for (int ci = 0; ci < f.ntx; ci++) order[start[ci + cj + ck]++] = (ck * f.nty + cj) * f.ntx + ci;
+				for (int ci = 0; ci < ox; ci++) order[start[ci + cj + ck]++] = (ck * f.nty + cj) * ox + ci;
 		S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 		if (ctx->sgs_order) S3D_CUDA(ctx, cudaFree(ctx->sgs_order));
 		ctx->sgs_order = nullptr;
-		S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_order, ntiles * sizeof(int)));
-		S3D_CUDA(ctx, cudaMemcpy(ctx->sgs_order, order.data(), ntiles * sizeof(int), cudaMemcpyHostToDevice));
-		ctx->sgs_order_dims[0] = f.ntx; ctx->sgs_order_dims[1] = f.nty; ctx->sgs_order_dims[2] = f.ntz;
+		S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_order, order.size() * sizeof(int)));
+		S3D_CUDA(ctx, cudaMemcpy(ctx->sgs_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+		ctx->sgs_order_dims[0] = okey; ctx->sgs_order_dims[1] = f.nty; ctx->sgs_order_dims[2] = f.ntz;
 		// another tiling: start the epochs over
 		S3D_CUDA(ctx, cudaMemsetAsync(ctx->sgs_flags, 0, ctx->sgs_flags_cap * sizeof(int), ctx->stream));
 		S3D_CUDA(ctx, cudaMemsetAsync(ctx->sgs_ctl, 0, 2 * sizeof(int), ctx->stream));
@@ -791,6 +1042,24 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 	f.prof = ctx->sgs_prof;
 	f.ticket = reinterpret_cast<unsigned *>(ctx->sgs_ctl);
 	f.epoch_p = ctx->sgs_ctl + 1;
+	if (lines) {
+		static bool lconfigured = false;
+		static int lines_per_sm = 1;
+		if (!lconfigured) {
+			S3D_CUDA(ctx, cudaFuncSetAttribute(sgs_lineflow_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sgl_smem(5, 1)));
+			S3D_CUDA(ctx, cudaFuncSetAttribute(sgs_lineflow_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sgl_smem(5, 1)));
+			S3D_CUDA(ctx, cudaFuncSetAttribute(sgs_lineflow_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sgl_smem(4, 1)));
+			int a = 1, b = 1;
+			S3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sgs_lineflow_kernel<0, 1>, 32, sgl_smem(5, 1)));
+			S3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sgs_lineflow_kernel<1, 1>, 32, sgl_smem(5, 1)));
+			lines_per_sm = std::max(1, std::min(a, b));
+			lconfigured = true;
+		}
+		int wps = lines_per_sm;
+		if (ctx->sgs_warps_per_sm > 0) wps = std::min(wps, ctx->sgs_warps_per_sm);
+		nblocks = (unsigned)std::min<size_t>((size_t)f.nty * f.ntz, (size_t)ctx->sm_count * wps);
+		return S3D_OK;
+	}
 	if (ctx->sgs_variant == 0) {
 		if (ctx->sgs_iface_cap < ntiles * 64) {
 			S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -894,14 +1163,18 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		const long long cs = g->cstride;
 		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
 		S3D_LAUNCHED(ctx);
-		if (ctx->sgs_variant == 0)
+		if (ctx->sgs_variant == 3)
+			sgs_lineflow_kernel<0, 1><<<nblocks, 32, sgl_smem(5, 1), ctx->stream>>>(gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, ctx->gate);
+		else if (ctx->sgs_variant == 0)
 			sgw_launch<0>(ctx, g, nblocks, gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, (const int *)ctx->gate);
 		else
 			sgs_dataflow_kernel<0><<<nblocks, block, SGS_SMEM, ctx->stream>>>(gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, ctx->gate);
 		S3D_LAUNCHED(ctx);
 		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
 		S3D_LAUNCHED(ctx);
-		if (ctx->sgs_variant == 0)
+		if (ctx->sgs_variant == 3)
+			sgs_lineflow_kernel<1, 1><<<nblocks, 32, sgl_smem(5, 1), ctx->stream>>>(gd, d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f, ctx->gate);
+		else if (ctx->sgs_variant == 0)
 			sgw_launch<1>(ctx, g, nblocks, gd, (const double *)d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f, (const int *)ctx->gate);
 		else
 			sgs_dataflow_kernel<1><<<nblocks, block, SGS_SMEM, ctx->stream>>>(gd, d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f, ctx->gate);
@@ -951,7 +1224,10 @@ int s3d_strilu_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuil
 		ctx->launches++;
 		e = cudaGetLastError();
 		if (e == cudaSuccess) {
-			if (ctx->sgs_variant == 0)
+			if (ctx->sgs_variant == 3)
+				sgs_lineflow_kernel<2, 1><<<nblocks, 32, sgl_smem(4, 1), ctx->stream>>>(gd, A + 3 * (size_t)g->cstride, P, P + g->cstride, P + 2 * (size_t)g->cstride,
+				                                                                         nullptr, D, f, nullptr);
+			else if (ctx->sgs_variant == 0)
 				sgw_launch<2>(ctx, g, nblocks, gd, A + 3 * (size_t)g->cstride, (const double *)P, (const double *)(P + g->cstride),
 				              (const double *)(P + 2 * (size_t)g->cstride), (const double *)nullptr, D, f, (const int *)nullptr);
 			else

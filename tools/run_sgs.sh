@@ -1,8 +1,7 @@
 #!/bin/bash
 # SGS kernel check + timing on one GPU (bounded by timeouts: the dataflow kernels spin on flags)
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k "sgs or ilu or jacobi or fixtures" > gpurun_out/sgs_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/sgs_tests.log
+timeout 300 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k "sgs_dataflow_variants" > gpurun_out/sgs_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/sgs_tests.log
 tail -5 gpurun_out/sgs_tests.log
 timeout 300 python tools/sgs_probe.py 64 128 256 512 > gpurun_out/sgs_probe.log 2>&1; echo "probe rc=$?" >> gpurun_out/sgs_probe.log
 cat gpurun_out/sgs_probe.log
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/lat_probe tools/lat_probe.cu && timeout 60 /tmp/lat_probe > gpurun_out/lat_probe.log 2>&1; cat gpurun_out/lat_probe.log
