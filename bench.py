@@ -481,6 +481,22 @@ def run_ours(a):
                 solve[key] = {"seconds": dt2, "iters": i2["iters"], "converged": i2["converged"], "precapply_seconds": i2["precapplywtime"]}
                 del s2
             del A2, b2, u2
+            if n >= 512:
+                # the metric's own size (BASELINE.json: "CG/BiCGSTAB solve s at 512^3"): BiCGSTAB + exact lexicographic SGS
+                m3, _ = H._capture_stdout(lambda: H.Mesh((514, 514, 514)))
+                A3, b3, u3 = p2.lhs(m3), p2.vector(m3, "manufactured_rhs"), H.Vec(m3)
+                H.set_options({"-s3d_ksp_type": "bcgs", "-s3d_pc_type": "sgs", "-ksp_rtol": 1e-6, "-ksp_max_it": 5000, "-s3d_pc_apply_sweeps": 1,
+                               "-s3d_thread_chunk_size": 1024, "-s3d_pc_use_threaded_apply": "false", "-s3d_sgs_ordering": "lexicographic"})
+                (s3, _) = H._capture_stdout(lambda: H.Solver(A3))
+                s3.update()
+                H.sync()
+                t0 = time.perf_counter()
+                i3, _ = H._capture_stdout(lambda: s3.apply(b3, u3))
+                H.sync()
+                dt3 = time.perf_counter() - t0
+                solve["bicgstab_sgs_lexicographic_convdiff512"] = {"seconds": dt3, "iters": i3["iters"], "converged": i3["converged"],
+                                                                   "precapply_seconds": i3["precapplywtime"], "ms_per_iter": dt3 * 1e3 / max(1, i3["iters"])}
+                del s3, A3, b3, u3
 
     cb = None
     if rank == 0 and world == 1 and not a.no_cpu:
