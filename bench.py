@@ -410,7 +410,7 @@ def run_ours(a):
         b = H.Vec(mesh)
         b.set(xh)
         u = H.Vec(mesh)
-        opts = {"-s3d_ksp_type": "cg", "-s3d_pc_type": "jacobi", "-ksp_rtol": 1e-6, "-ksp_max_it": 20000}
+        opts = {"-s3d_ksp_type": "cg", "-s3d_pc_type": "jacobi", "-ksp_rtol": 1e-6, "-ksp_max_it": a.cg_max_it}
         H.set_options(opts)
         (s, _) = H._capture_stdout(lambda: H.Solver(A))
         s.update()
@@ -532,6 +532,7 @@ def main():
     ap.add_argument("--halo-p2p", type=int, default=1, help="1: halo planes through peer-memory windows (CUDA IPC), 0: NCCL send/recv (A/B switch)")
     ap.add_argument("--e2e-chunks", type=int, default=32, help="z-chunks of the pipelined host-buffer SpMV (e2e)")
     ap.add_argument("--no-solve", action="store_true")
+    ap.add_argument("--cg-max-it", type=int, default=20000, help="iteration cap of the CG solve of the solve block (A/B runs shorten it)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--solves", action="store_true", help="whole solves: the reference on the host cores beside this library (SURVEY 8d)")
     ap.add_argument("--solves-large", type=int, default=256, help="grid size of the two benchmark cases in --solves (0 = skip them)")

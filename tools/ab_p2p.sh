@@ -2,11 +2,9 @@
 # Correctness (tools/mgpu_check.py, default = peer-memory halo) and A/B of the halo exchange on N GPUs: peer-memory windows vs NCCL send/recv.
 N=${1:-2}
 mkdir -p gpurun_out
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 tools/mgpu_check.py > gpurun_out/mgpu_check_p2p.log 2>&1; echo "mgpu_check rc=$?"
-grep -v "^\[W\|^W0\|warn" gpurun_out/mgpu_check_p2p.log | tail -12
 for p2p in 1 0 1 0; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2953$p2p \
-      bench.py --gpus $N --steps 30 --warmup 3 --strong 1024 --strong-iters 40 --halo-p2p $p2p 2>gpurun_out/ab_p2p_$p2p.err > /tmp/ab_$p2p.json || tail -5 gpurun_out/ab_p2p_$p2p.err
+      bench.py --gpus $N --steps 30 --warmup 3 --strong 1024 --strong-iters 40 --cg-max-it ${CGMAX:-20000} --halo-p2p $p2p 2>gpurun_out/ab_p2p_$p2p.err > /tmp/ab_$p2p.json || tail -5 gpurun_out/ab_p2p_$p2p.err
   python - "$p2p" <<'PY'
 import json, sys
 v = sys.argv[1]
