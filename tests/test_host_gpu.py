@@ -294,6 +294,7 @@ def test_zero_rhs_and_nosolver(H):
     ["gridconv", os.path.join(INPUT, "cdcirc_conv.control"), "-options_file", os.path.join(INPUT, "richardson_strilu.perc")],
     ["runcase", os.path.join(INPUT, "convdiff64.control"), "-options_file", os.path.join(INPUT, "richardson_sgs.perc")],
     ["runcase", os.path.join(INPUT, "poisson16_cheb.control"), "-options_file", os.path.join(INPUT, "gcr_jacobi.perc")],
+    ["scaling", os.path.join(INPUT, "convdiff48.control"), "-options_file", os.path.join(INPUT, "scaling_gpus.perc")],
 ])
 def test_cpp_drivers(args):
     """The C++ drivers (counterparts of the reference's testmatvec / gridconv / runcase) run as processes."""
@@ -306,5 +307,15 @@ def test_cpp_drivers(args):
         # NB: runcase uses test_rhs like the reference's driver, the goldens for these two cases use other RHS;
         # so only check convergence and the report format here
         assert "Avg solver iters:" in text and "Time taken by native linear solver" in text
+    elif args[0] == "scaling":
+        # the reference's scaling-output.txt layout (scaling_openmp.cpp:185-211): header of the reference run, column titles,
+        # the reference line, then one line per (build sweeps, apply sweeps) pair for this GPU count
+        rep = open("/tmp/s3d_scaling-output.txt").read().splitlines()
+        assert rep[0].startswith("Reference run: Threads 1, build sweeps 1, apply sweeps 4")
+        assert rep[4].split() == ["b.swps.", "a.swps.", "threads", "iters", "dev.iters", "b.spdp", "a.spdp", "spdp", "dev.b.time", "dev.a.time", "dev.resnorm"]
+        lines = [ln.split() for ln in rep[6:] if ln.strip()]
+        assert [ln[:3] for ln in lines] == [["1", "4", "1"], ["1", "3", "1"], ["1", "6", "1"]]
+        assert all(len(ln) == 11 and int(ln[3]) > 0 for ln in lines)
+        assert int(lines[2][3]) <= int(lines[0][3]) <= int(lines[1][3])      # more sweeps per factor: never more iterations
     else:
         assert "PASSED" in text
