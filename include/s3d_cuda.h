@@ -202,6 +202,13 @@ int  s3d_strilu_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbui
 #define S3D_SGS_REDBLACK      1
 #define S3D_SGS_JACOBI_SWEEPS 3  /* nsweeps synchronous Jacobi sweeps per triangular factor: the deterministic counterpart of the
                                   * reference's asynchronous threaded sweeps (threadedapply = true); exact for nsweeps >= nx+ny+nz-2 */  /* two-colour ordering: four fully parallel half-sweeps (changes the iteration) */
+/* Exact (lexicographic) SGS on a z-slab decomposition: the sweep runs THROUGH the slabs -- the last plane of tiles of rank p pushes its
+ * k-face rows into rank p+1's peer-memory window (backward: p-1) and raises per-tile flags there, so results and iteration counts are
+ * those of the single-process reference (s3d_sgspreconditioners.cpp:14-115) at any GPU count; the ranks work as a pipeline.
+ * *yes = 1 when that is possible for this grid (one rank: always; several: the CUDA-IPC windows could be mapped on every rank).
+ * Collective over the ranks of the communicator. */
+int  s3d_sgs_slab_sweeps_available(s3d_ctx *ctx, const s3d_grid *g, int *yes);
+
 /* SGS_like_preconditioner::apply (s3d_sgspreconditioners.cpp:14-115): z = (D+U)^-1 D (D+L)^-1 r.
  * d_y: scratch vector (vlen doubles); it is re-zeroed by the call like the reference's temporary. */
 int  s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_dinv,

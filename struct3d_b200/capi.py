@@ -59,7 +59,7 @@ _SIGS = {
     "s3d_dot_host": [_P, _G, _vp, _vp, _dp], "s3d_nrm2_host": [_P, _G, _vp, _dp],
     "s3d_allreduce_sum": [_P, _vp, _vp, _I],
     "s3d_jacobi_apply": [_P, _G, _vp, _vp, _vp], "s3d_sgs_setup": [_P, _G, _vp, _vp], "s3d_strilu_setup": [_P, _G, _vp, _I, _vp],
-    "s3d_sgs_apply": [_P, _G, _vp, _vp, _vp, _vp, _vp, _I, _I],
+    "s3d_sgs_apply": [_P, _G, _vp, _vp, _vp, _vp, _vp, _I, _I], "s3d_sgs_slab_sweeps_available": [_P, _G, C.POINTER(C.c_int)],
     "s3d_cg_update": [_P, _G, Scalar, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "s3d_cg_direction_jacobi": [_P, _G, Scalar, _vp, _vp, _vp, _vp],
     "s3d_bicg_direction": [_P, _G, Scalar, Scalar, _vp, _vp, _vp, _vp],

@@ -16,6 +16,16 @@ struct s3d_halo_view {
 	int epoch = 0;
 };
 
+// cross-rank (z-slab) extension of the exact SGS sweeps: where a slab's first plane of tiles finds the k-face rows of the rank before
+// it in sweep order, and where its last plane of tiles puts its own (context.cu: s3d_internal_sgs_window)
+struct s3d_sgs_window {
+	int ok = 0;
+	const double *fwd_in_plane = nullptr, *bwd_in_plane = nullptr;
+	const int *fwd_in_flags = nullptr, *bwd_in_flags = nullptr;
+	double *fwd_out_plane = nullptr, *bwd_out_plane = nullptr;
+	int *fwd_out_flags = nullptr, *bwd_out_flags = nullptr;
+};
+
 struct s3d_ctx {
 	int device = 0;
 	int sm_count = 148;
@@ -82,6 +92,12 @@ struct s3d_ctx {
 		unsigned *ticket = nullptr;   // last-block election of the push kernel
 		int epoch = 0;
 	} p2p;
+	struct SgsWin {
+		bool tried = false, ok = false;
+		double *win = nullptr, *peer_lo = nullptr, *peer_hi = nullptr;
+		int ntx = 0, nty = 0;
+		size_t plane = 0;
+	} sgswin;
 	int rank = 0, nranks = 1;
 	char err[512] = "";
 };

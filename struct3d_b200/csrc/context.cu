@@ -498,6 +498,10 @@ int s3d_comm_destroy(s3d_ctx *ctx)
 	if (ctx->p2p.win) cudaFree(ctx->p2p.win);
 	if (ctx->p2p.ticket) cudaFree(ctx->p2p.ticket);
 	ctx->p2p = s3d_ctx::P2P();
+	if (ctx->sgswin.peer_lo) cudaIpcCloseMemHandle(ctx->sgswin.peer_lo);
+	if (ctx->sgswin.peer_hi) cudaIpcCloseMemHandle(ctx->sgswin.peer_hi);
+	if (ctx->sgswin.win) cudaFree(ctx->sgswin.win);
+	ctx->sgswin = s3d_ctx::SgsWin();
 	if (ctx->comm) { S3D_NCCL(ctx, g_nccl.CommDestroy(ctx->comm)); ctx->comm = nullptr; }
 	ctx->rank = 0; ctx->nranks = 1;
 	return S3D_OK;
@@ -561,16 +565,16 @@ halo_pull_kernel(double *ghost_lo, double *ghost_hi, const double *src_lo, const
 	}
 }
 
-// (Re)creates the window for planes of n doubles and maps the neighbours' windows.  Collective: every rank gets here at the same
-// exchange with the same n.  Any failure on any rank leaves p2p.ok false on all of them (NCCL carries the exchange then).
-int p2p_ensure(s3d_ctx *ctx, const s3d_grid *g)
+// Allocates a zeroed window of `bytes` on this rank and maps the windows of the two z-neighbours (CUDA IPC; the handles travel through
+// NCCL).  Collective: every rank calls it at the same point with the same size.  An allreduce is the barrier before the caller's old
+// window goes away (`release_old` runs after it) and the vote after the mapping: *ok is true only when it worked on EVERY rank.
+extern "C++" template <class F>
+int peer_window_create(s3d_ctx *ctx, const s3d_grid *g, size_t bytes, F release_old, void **win, void **peer_lo, void **peer_hi, bool *ok)
 {
-	s3d_ctx::P2P &w = ctx->p2p;
-	const size_t n = (size_t)g->vplane;
-	if (w.win && w.plane_cap >= n) return S3D_OK;
 	const int up = g->rank + 1, dn = g->rank - 1;
+	*ok = false;
 	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	double *sync = nullptr;   // a small allreduce is the barrier before old windows go away and the vote after the new ones are mapped
+	double *sync = nullptr;
 	S3D_CUDA(ctx, cudaMalloc(&sync, 2 * sizeof(double)));
 	auto vote = [&](double mine, double &sum) -> int {
 		S3D_CUDA(ctx, cudaMemcpy(sync, &mine, sizeof(double), cudaMemcpyHostToDevice));
@@ -582,21 +586,16 @@ int p2p_ensure(s3d_ctx *ctx, const s3d_grid *g)
 	double sum = 0;
 	int rc = vote(0.0, sum);
 	if (rc != S3D_OK) { cudaFree(sync); return rc; }
-	if (w.peer_lo) cudaIpcCloseMemHandle(w.peer_lo);
-	if (w.peer_hi) cudaIpcCloseMemHandle(w.peer_hi);
-	if (w.win) cudaFree(w.win);
-	w.peer_lo = w.peer_hi = w.win = nullptr; w.ok = false; w.plane_cap = 0; w.epoch = 0;
+	release_old();
+	*win = *peer_lo = *peer_hi = nullptr;
 	bool good = true;
-	const size_t cap = (n + 15) / 16 * 16;
 	cudaIpcMemHandle_t mine, from_lo, from_hi;
 	memset(&mine, 0, sizeof mine);
-	good = good && cudaMalloc(&w.win, (P2P_HEADER + 4 * cap) * sizeof(double)) == cudaSuccess;
-	good = good && cudaMemset(w.win, 0, (P2P_HEADER + 4 * cap) * sizeof(double)) == cudaSuccess;
-	if (!w.ticket) good = good && cudaMalloc(&w.ticket, sizeof(unsigned)) == cudaSuccess && cudaMemset(w.ticket, 0, sizeof(unsigned)) == cudaSuccess;
-	good = good && cudaIpcGetMemHandle(&mine, w.win) == cudaSuccess;
+	good = good && cudaMalloc(win, bytes) == cudaSuccess;
+	good = good && cudaMemset(*win, 0, bytes) == cudaSuccess;
+	good = good && cudaIpcGetMemHandle(&mine, *win) == cudaSuccess;
 	cudaGetLastError();
-	// the handles travel through NCCL (device staging buffers): [0] mine, [1] from below, [2] from above
-	char *hb = nullptr;
+	char *hb = nullptr;   // device staging of the handles: [0] mine, [1] from below, [2] from above
 	S3D_CUDA(ctx, cudaMalloc(&hb, 3 * sizeof(cudaIpcMemHandle_t)));
 	S3D_CUDA(ctx, cudaMemcpy(hb, &mine, sizeof mine, cudaMemcpyHostToDevice));
 	S3D_NCCL(ctx, g_nccl.GroupStart());
@@ -613,14 +612,37 @@ int p2p_ensure(s3d_ctx *ctx, const s3d_grid *g)
 	S3D_CUDA(ctx, cudaMemcpy(&from_lo, hb + sizeof mine, sizeof mine, cudaMemcpyDeviceToHost));
 	S3D_CUDA(ctx, cudaMemcpy(&from_hi, hb + 2 * sizeof mine, sizeof mine, cudaMemcpyDeviceToHost));
 	cudaFree(hb);
-	if (good && dn >= 0) good = cudaIpcOpenMemHandle((void **)&w.peer_lo, from_lo, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
-	if (good && up < g->nranks) good = cudaIpcOpenMemHandle((void **)&w.peer_hi, from_hi, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+	if (good && dn >= 0) good = cudaIpcOpenMemHandle(peer_lo, from_lo, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+	if (good && up < g->nranks) good = cudaIpcOpenMemHandle(peer_hi, from_hi, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
 	cudaGetLastError();
-	rc = vote(good ? 0.0 : 1.0, sum);
+	rc = vote(good ? 0.0 : 1.0, sum);   // also the barrier after which every rank's zeroed window may be written by its neighbours
 	cudaFree(sync);
 	if (rc != S3D_OK) return rc;
+	*ok = (sum == 0.0);
+	return S3D_OK;
+}
+
+// (Re)creates the halo window for planes of n doubles.  Any failure on any rank leaves p2p.ok false on all of them (NCCL carries the
+// exchange then).
+int p2p_ensure(s3d_ctx *ctx, const s3d_grid *g)
+{
+	s3d_ctx::P2P &w = ctx->p2p;
+	const size_t n = (size_t)g->vplane;
+	if (w.win && w.plane_cap >= n) return S3D_OK;
+	const size_t cap = (n + 15) / 16 * 16;
+	if (!w.ticket) {
+		S3D_CUDA(ctx, cudaMalloc(&w.ticket, sizeof(unsigned)));
+		S3D_CUDA(ctx, cudaMemset(w.ticket, 0, sizeof(unsigned)));
+	}
+	auto release = [&]() {
+		if (w.peer_lo) cudaIpcCloseMemHandle(w.peer_lo);
+		if (w.peer_hi) cudaIpcCloseMemHandle(w.peer_hi);
+		if (w.win) cudaFree(w.win);
+		w.peer_lo = w.peer_hi = w.win = nullptr; w.ok = false; w.plane_cap = 0; w.epoch = 0;
+	};
+	const int rc = peer_window_create(ctx, g, (P2P_HEADER + 4 * cap) * sizeof(double), release, (void **)&w.win, (void **)&w.peer_lo, (void **)&w.peer_hi, &w.ok);
+	if (rc != S3D_OK) return rc;
 	w.plane_cap = cap;
-	w.ok = (sum == 0.0);
 	if (!w.ok && ctx->rank == 0) fprintf(stderr, "[struct3d_b200] peer-memory halo windows unavailable (CUDA IPC); using NCCL send/recv\n");
 	return S3D_OK;
 }
@@ -655,6 +677,43 @@ int s3d_internal_halo_push(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, s
 	hv->flag_lo = has_lo ? flag(w.win, 0) : nullptr;
 	hv->flag_hi = has_hi ? flag(w.win, 1) : nullptr;
 	hv->epoch = epoch;
+	return S3D_OK;
+}
+
+// Window of the exact (lexicographic) SGS sweeps across z-slabs: the tiles of a slab's last plane of tiles push their last-k rows into
+// the next rank's window and raise a per-tile flag there; that rank's first plane of tiles waits for it (sgs.cu).  Layout (doubles):
+// [2 * nflags ints of flags, padded to 32 doubles][plane for forward sweeps: rows from the rank below][plane for backward sweeps: rows
+// from the rank above]; a plane has the in-plane layout of a vector plane (vplane doubles).  (Re)created -- zeroed flags, barrier --
+// whenever the tile grid or the plane size changes, which is also when the sweep epochs start over.
+int s3d_internal_sgs_window(s3d_ctx *ctx, const s3d_grid *g, int ntx, int nty, s3d_sgs_window *out)
+{
+	*out = s3d_sgs_window();
+	if (g->nranks == 1 || ctx->p2p.mode != 1 || !ctx->comm) return S3D_OK;
+	s3d_ctx::SgsWin &w = ctx->sgswin;
+	const size_t nflags = (size_t)ntx * nty, plane = ((size_t)g->vplane + 15) / 16 * 16;
+	const size_t header = (2 * nflags * sizeof(int) + 255) / 256 * 32;   // in doubles
+	if (!w.tried || w.ntx != ntx || w.nty != nty || w.plane != plane) {
+		auto release = [&]() {
+			if (w.peer_lo) cudaIpcCloseMemHandle(w.peer_lo);
+			if (w.peer_hi) cudaIpcCloseMemHandle(w.peer_hi);
+			if (w.win) cudaFree(w.win);
+			w.peer_lo = w.peer_hi = w.win = nullptr; w.ok = false;
+		};
+		const int rc = peer_window_create(ctx, g, (header + 2 * plane) * sizeof(double), release, (void **)&w.win, (void **)&w.peer_lo, (void **)&w.peer_hi, &w.ok);
+		if (rc != S3D_OK) return rc;
+		w.tried = true; w.ntx = ntx; w.nty = nty; w.plane = plane;
+	}
+	if (!w.ok) return S3D_OK;
+	const bool has_lo = g->rank > 0, has_hi = g->rank + 1 < g->nranks;
+	auto flags = [&](double *win, int dir) { return reinterpret_cast<int *>(win) + (size_t)dir * nflags; };
+	auto planep = [&](double *win, int dir) { return win + header + (size_t)dir * plane; };
+	out->ok = 1;
+	// forward sweeps: my input comes from below (dir 0 of MY window), my output goes to dir 0 of the window above
+	out->fwd_in_plane = has_lo ? planep(w.win, 0) : nullptr;  out->fwd_in_flags = has_lo ? flags(w.win, 0) : nullptr;
+	out->fwd_out_plane = has_hi ? planep(w.peer_hi, 0) : nullptr; out->fwd_out_flags = has_hi ? flags(w.peer_hi, 0) : nullptr;
+	// backward sweeps: input from above (dir 1 of my window), output to dir 1 of the window below
+	out->bwd_in_plane = has_hi ? planep(w.win, 1) : nullptr;  out->bwd_in_flags = has_hi ? flags(w.win, 1) : nullptr;
+	out->bwd_out_plane = has_lo ? planep(w.peer_lo, 1) : nullptr; out->bwd_out_flags = has_lo ? flags(w.peer_lo, 1) : nullptr;
 	return S3D_OK;
 }
 

@@ -100,6 +100,9 @@ struct SgsFlow {
 	const int *epoch_p; // device word holding the epoch of this sweep (bumped on the device, so a captured graph can be replayed)
 	int ntx, nty, ntz;
 	int sleep_ns;      // 0: busy-spin on the flag
+	// z-slab runs (warp-per-tile kernel): the k-face rows of the rank before this one in sweep order arrive in x_in_plane (a plane of
+	// this rank's peer-memory window, flag per (ci, cj) in x_in_flags); this rank's own go to x_out_plane / x_out_flags of the next rank
+	const double *x_in_plane; const int *x_in_flags; double *x_out_plane; int *x_out_flags;
 	long long *prof;   // optional per-phase cycle accumulators (warp kernel; timing experiments only)
 	int debug;         // timing experiments only (results become wrong): 1 skip wavefront, 2 skip staging, 4 skip fences, 8 skip waits
 };
@@ -302,6 +305,12 @@ __device__ __forceinline__ int ld_acquire(const int *p)
 	asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
 	return v;
 }
+__device__ __forceinline__ int ld_acquire_sys(const int *p)
+{
+	int v;
+	asm volatile("ld.acquire.sys.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
 __device__ __forceinline__ double2 ldcg2(const double *p)
 {
 	double2 v;
@@ -386,6 +395,11 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		const int ti = min(TI, g.nx - i0), tj = min(TJ, g.ny - j0), tk = min(TK, g.nz - k0);
 		const long long vtile = g.voff + (long long)k0 * g.vplane + (long long)j0 * g.vpitch + i0;
 		const bool act0 = (b0 < tj) && (cc < tk), act1 = (P == 2) && (b1 < tj) && (cc < tk);
+		// z-slabs: the first plane of tiles (in sweep order) takes its k-halo from the window, the last one feeds the next rank's
+		const bool xin = f.x_in_plane && (FWD ? ck == 0 : ck == f.ntz - 1);
+		const bool xout = f.x_out_plane && (FWD ? ck == f.ntz - 1 : ck == 0);
+		const int xidx = cj * f.ntx + ci;
+		const long long inpl = (g.voff - g.vplane) + (long long)j0 * g.vpitch + i0;   // the tile's first column inside a plane
 		const int lk = FWD ? cc : tk - 1 - cc;
 		const int lj0 = FWD ? b0 : tj - 1 - b0, lj1 = FWD ? b1 : tj - 1 - b1;
 		const long long vv0 = vtile + (long long)lk * g.vplane + (long long)lj0 * g.vpitch;
@@ -404,7 +418,8 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 					if (row < tk) hp[u] = out + vtile + (long long)(FWD ? row : tk - 1 - row) * g.vplane + (long long)(FWD ? -1 : tj) * g.vpitch + 2 * i2;
 				} else {
 					const int r = row - 8;
-					if (r < tj) hp[u] = out + vtile + (long long)(FWD ? -1 : tk) * g.vplane + (long long)(FWD ? r : tj - 1 - r) * g.vpitch + 2 * i2;
+					if (r < tj)
+						hp[u] = (xin ? f.x_in_plane + inpl : out + vtile + (long long)(FWD ? -1 : tk) * g.vplane) + (long long)(FWD ? r : tj - 1 - r) * g.vpitch + 2 * i2;
 				}
 			}
 		}
@@ -414,20 +429,23 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		const double *wp1 = !act1 ? nullptr : iedge ? out + vv1 + (FWD ? -1 : ti) : box + b1 * 8 + cc;
 		// ---- wait for the three predecessor tiles (warp-uniform vote, see above)
 		{
-			int pred = -1;
+			const int *fp = nullptr;
+			const int sk = f.ntx * f.nty;
 			if (FWD) {
-				if (lane == 0 && ci > 0) pred = tile - 1;
-				if (lane == 1 && cj > 0) pred = tile - f.ntx;
-				if (lane == 2 && ck > 0) pred = tile - f.ntx * f.nty;
+				if (lane == 0 && ci > 0) fp = f.flags + tile - 1;
+				if (lane == 1 && cj > 0) fp = f.flags + tile - f.ntx;
+				if (lane == 2) fp = (ck > 0) ? f.flags + tile - sk : xin ? f.x_in_flags + xidx : nullptr;
 			} else {
-				if (lane == 0 && ci < f.ntx - 1) pred = tile + 1;
-				if (lane == 1 && cj < f.nty - 1) pred = tile + f.ntx;
-				if (lane == 2 && ck < f.ntz - 1) pred = tile + f.ntx * f.nty;
+				if (lane == 0 && ci < f.ntx - 1) fp = f.flags + tile + 1;
+				if (lane == 1 && cj < f.nty - 1) fp = f.flags + tile + f.ntx;
+				if (lane == 2) fp = (ck < f.ntz - 1) ? f.flags + tile + sk : xin ? f.x_in_flags + xidx : nullptr;
 			}
-			bool done = (pred < 0) || (f.debug & 1);
+			bool done = (fp == nullptr) || (f.debug & 1);
+			const long long tw0 = xin ? clock64() : 0;
 			for (;;) {
-				if (!done) done = (ld_acquire(f.flags + pred) == epoch);
+				if (!done) done = ((xin ? ld_acquire_sys(fp) : ld_acquire(fp)) == epoch);
 				if (__all_sync(FULL, done)) break;
+				if (xin && clock64() - tw0 > (40ll << 30)) __trap();   // ~20 s without the neighbouring rank: fail loudly instead of hanging
 			}
 		}
 		__syncwarp();
@@ -530,11 +548,27 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 			const int rb = (fr < 8) ? tj - 1 : fr - 8, rc = (fr < 8) ? fr : tk - 1;
 			if (rc < tk && rb < tj && (fr < 8 || rb < tj - 1) && 2 * i2 < ti) copy_row_chunk(rb, rc, i2);
 		}
-		asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+		if (xout) {
+			// the last-k rows also go to the next rank's window, straight over NVLink
+#pragma unroll
+			for (int u = 0; u < (TJ * CH + 31) / 32; u++) {
+				const int q = lane + 32 * u, i2 = q % CH, rb = q / CH;
+				if (rb < tj && 2 * i2 < ti) {
+					const double2 v = *reinterpret_cast<const double2 *>(s_a + sgw_row<P, FWD>(rb, tk - 1) * R + 2 * i2);
+					double *dst = f.x_out_plane + inpl + (long long)(FWD ? rb : tj - 1 - rb) * g.vpitch + 2 * i2;
+					if (2 * i2 + 1 < ti) *reinterpret_cast<double2 *>(dst) = v;
+					else *dst = v.x;
+				}
+			}
+			__threadfence_system();
+		} else {
+			asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+		}
 		__syncwarp();
 		if (f.prof) tp3 = clock64();
 		if (lane == 0) {
 			*(volatile int *)(f.flags + tile) = epoch;
+			if (xout) *(volatile int *)(f.x_out_flags + xidx) = epoch;
 			if (f.prof) {
 				const long long tp4 = clock64();
 				atomicAdd((unsigned long long *)f.prof + 0, (unsigned long long)(tp1 - tp0));   // flag wait
@@ -945,7 +979,9 @@ inline int sgw_tile_i(const s3d_ctx *ctx) { return ctx->sgs_tile_i == 32 ? 32 : 
 inline int sgw_pencils(const s3d_ctx *ctx, const s3d_grid *g)
 {
 	if (ctx->sgs_pencils == 1 || ctx->sgs_pencils == 2) return ctx->sgs_pencils;
-	return ((long long)g->nx * g->ny * g->nz >= (64ll << 20)) ? 1 : 2;
+	// every rank of a z-slab run must pick the same tile shape (the cross-rank flags are per (ci, cj)): decide on the mean slab
+	const long long nzl = (g->nranks > 1) ? ((long long)g->nz_global + g->nranks - 1) / g->nranks : g->nz;
+	return ((long long)g->nx * g->ny * nzl >= (64ll << 20)) ? 1 : 2;
 }
 
 template <int MODE, typename... Args> void sgw_launch(s3d_ctx *ctx, const s3d_grid *g, unsigned nblocks, Args... args)
@@ -1036,6 +1072,7 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 	}
 	f.flags = ctx->sgs_flags;
 	f.iface = ctx->sgs_iface;
+	f.x_in_plane = nullptr; f.x_in_flags = nullptr; f.x_out_plane = nullptr; f.x_out_flags = nullptr;
 	f.order = ctx->sgs_order;
 	f.sleep_ns = 0;
 	f.debug = ctx->sgs_sleep_ns;   // reuses the tuning slot: debug bit mask
@@ -1089,7 +1126,27 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 
 }  // namespace
 
+extern "C" int s3d_internal_sgs_window(s3d_ctx *ctx, const s3d_grid *g, int ntx, int nty, s3d_sgs_window *out);
+
 extern "C" {
+
+// can the exact sweep run through the z-slabs of this grid?  (collective: creates the peer-memory window)
+int s3d_sgs_slab_sweeps_available(s3d_ctx *ctx, const s3d_grid *g, int *yes)
+{
+	S3D_REQUIRE(ctx, g && yes, "null argument");
+	*yes = 0;
+	if (g->nranks == 1) { *yes = 1; return S3D_OK; }
+	if (ctx->sgs_variant != 0) return S3D_OK;
+	SgsFlow f;
+	unsigned nblocks = 0;
+	int rc = sgs_flow_prepare(ctx, g, f, nblocks);
+	if (rc != S3D_OK) return rc;
+	s3d_sgs_window xw;
+	rc = s3d_internal_sgs_window(ctx, g, f.ntx, f.nty, &xw);
+	if (rc != S3D_OK) return rc;
+	*yes = xw.ok;
+	return S3D_OK;
+}
 
 int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_dinv, const double *d_r,
                   double *d_z, double *d_y, int ordering, int nsweeps)
@@ -1149,8 +1206,8 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 	}
 	if (ordering != S3D_SGS_LEXICOGRAPHIC && ordering != S3D_SGS_LEXICOGRAPHIC_PLANES)
 		return s3d_fail(ctx, S3D_ERR_ARG, "unknown SGS ordering %d", ordering);
-	if (g->nranks > 1)
-		return s3d_fail(ctx, S3D_ERR_ARG, "lexicographic SGS serialises across z-slabs; use S3D_SGS_REDBLACK on a decomposed grid");
+	if (g->nranks > 1 && (ordering != S3D_SGS_LEXICOGRAPHIC || ctx->sgs_variant != 0))
+		return s3d_fail(ctx, S3D_ERR_ARG, "across z-slabs only the warp-per-tile lexicographic sweep (or red-black / sweeps) is available");
 	// the scratch vector's real entries are all overwritten and its ghosts stay zero (they are never
 	// written), so the per-call zero fill of the reference (s3d_sgspreconditioners.cpp:25-28) is implicit.
 	// Sequential sweeps are idempotent, so nsweeps > 1 repeats identical work; do one.
@@ -1161,6 +1218,14 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		if (rcp != S3D_OK) return rcp;
 		dim3 block(SGS_NT);
 		const long long cs = g->cstride;
+		s3d_sgs_window xw;
+		if (g->nranks > 1) {
+			// the sweep runs THROUGH the slabs: rank p's first plane of tiles waits for rank p-1's last one (peer-memory window)
+			const int rcw = s3d_internal_sgs_window(ctx, g, f.ntx, f.nty, &xw);
+			if (rcw != S3D_OK) return rcw;
+			if (!xw.ok) return s3d_fail(ctx, S3D_ERR_STATE, "lexicographic SGS across z-slabs needs the peer-memory windows (CUDA IPC); use S3D_SGS_REDBLACK");
+			f.x_in_plane = xw.fwd_in_plane; f.x_in_flags = xw.fwd_in_flags; f.x_out_plane = xw.fwd_out_plane; f.x_out_flags = xw.fwd_out_flags;
+		}
 		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
 		S3D_LAUNCHED(ctx);
 		if (ctx->sgs_variant == 3)
@@ -1170,6 +1235,7 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		else
 			sgs_dataflow_kernel<0><<<nblocks, block, SGS_SMEM, ctx->stream>>>(gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, ctx->gate);
 		S3D_LAUNCHED(ctx);
+		if (g->nranks > 1) { f.x_in_plane = xw.bwd_in_plane; f.x_in_flags = xw.bwd_in_flags; f.x_out_plane = xw.bwd_out_plane; f.x_out_flags = xw.bwd_out_flags; }
 		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
 		S3D_LAUNCHED(ctx);
 		if (ctx->sgs_variant == 3)

@@ -235,8 +235,14 @@ SGS_like_preconditioner::SGS_like_preconditioner(const SMat &lhs, const PreconPa
 		else throw std::runtime_error("-s3d_sgs_ordering must be lexicographic, redblack or sweeps");
 	}
 	if (d.nranks() > 1 && order == S3D_SGS_LEXICOGRAPHIC) {
-		if (d.rank() == 0) std::printf(" WARNING: SGS: lexicographic sweeps serialise across z-slabs; using the red-black ordering.\n");
-		order = S3D_SGS_REDBLACK;
+		// the exact sweep can run through the slabs as a pipeline over peer memory (same iterations as one GPU); without the
+		// peer-memory windows the red-black ordering takes over
+		int yes = 0;
+		d.check(s3d_sgs_slab_sweeps_available(d.ctx(), &A.grid(), &yes), "s3d_sgs_slab_sweeps_available");
+		if (!yes) {
+			if (d.rank() == 0) std::printf(" WARNING: SGS: no peer-memory windows for lexicographic sweeps across z-slabs; using the red-black ordering.\n");
+			order = S3D_SGS_REDBLACK;
+		}
 	}
 }
 

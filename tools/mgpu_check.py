@@ -93,17 +93,34 @@ for ksp, pc in (("cg", "jacobi"), ("richardson", "jacobi"), ("gcr", "jacobi")):
     if len(info["hist"]) == len(hist) and len(hist) > 1:
         check(np.max(np.abs(info["hist"] - hist) / hist) <= 1e-6, f"{ksp}+{pc} residual history matches the oracle to 1e-6")
 
-# BiCGSTAB + SGS: lexicographic sweeps serialise across slabs, so the factory switches to red-black
+# exact (lexicographic) SGS THROUGH the slabs (peer-memory windows): the preconditioner is bit-identical to the sequential sweep over
+# the whole grid, so BiCGSTAB + SGS needs the oracle's iterations (5 %: BiCGSTAB amplifies the summation order of the dots)
+H.set_options({})
+z = H.Vec(m)
+H.Prec(A, "sgs").apply(b, z)
+zc = cport.sgs_like_apply(cm, Ac, cport.sgs_setup(cm, Ac), bc, 1)
+check(np.array_equal(z.a[1:-1], zc[sl][1:-1]), f"lexicographic SGS through {world} slabs is bit-identical to the sequential sweep over the whole grid")
+H.Prec(A, "sgs").apply(b, z)
+check(np.array_equal(z.a[1:-1], zc[sl][1:-1]), "... and again (epochs and window flags of the first sweep do not satisfy the second)")
 u = H.Vec(m)
 info, _ = H._capture_stdout(lambda: H.solve(A, b, u, {"-s3d_ksp_type": "bcgs", "-s3d_pc_type": "sgs", "-ksp_rtol": 1e-8, "-ksp_max_it": 2000,
                                                      "-s3d_pc_apply_sweeps": 1, "-s3d_thread_chunk_size": 1024}))
 r = H.Vec(m)
 H.apply_res(A, b, u, r)
 rel = H.norm_vector_l2(r) / H.norm_vector_l2(b)
+_, oi, _ = cport.solve(cm, Ac, bc, "bcgs", "sgs", 1e-8, 2000)
+check(info["converged"] and rel <= 2e-8 and abs(info["iters"] - oi["iters"]) <= max(2, oi["iters"] // 20),
+      f"bcgs + lexicographic SGS through {world} slabs: {info['iters']} iterations (oracle on the whole grid {oi['iters']}), true relative residual {rel:.2e}")
+# red-black SGS (explicit option): converges, and the sweep is bit-identical to the oracle's red-black statement on the whole grid
+u = H.Vec(m)
+info, _ = H._capture_stdout(lambda: H.solve(A, b, u, {"-s3d_ksp_type": "bcgs", "-s3d_pc_type": "sgs", "-ksp_rtol": 1e-8, "-ksp_max_it": 2000,
+                                                     "-s3d_pc_apply_sweeps": 1, "-s3d_thread_chunk_size": 1024, "-s3d_sgs_ordering": "redblack"}))
+H.apply_res(A, b, u, r)
+rel = H.norm_vector_l2(r) / H.norm_vector_l2(b)
 check(info["converged"] and rel <= 2e-8, f"bcgs + red-black SGS over {world} slabs: {info['iters']} iterations, true relative residual {rel:.2e}")
-# red-black SGS itself against the oracle's red-black statement on the whole grid
-z = H.Vec(m)
+H.set_options({"-s3d_sgs_ordering": "redblack"})
 H.Prec(A, "sgs").apply(b, z)
+H.set_options({})
 zc = cport.sgs_redblack_apply(cm, Ac, cport.sgs_setup(cm, Ac), bc)
 check(np.array_equal(z.a[1:-1], zc[sl][1:-1]), "red-black SGS across slabs is bit-identical to the oracle's red-black statement")
 say("ALL PASS" if ok else "SOME CHECKS FAILED")
