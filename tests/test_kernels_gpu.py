@@ -20,7 +20,7 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 # reference MatVec sizes (test/matvectest.cpp: 18^3 -> 36^3 -> 72^3), ragged/odd shapes, tiny and thin grids
 SHAPES = [(18, 18, 18), (36, 36, 36), (72, 72, 72), (20, 14, 18), (19, 23, 11), (3, 3, 3), (4, 9, 3), (131, 7, 5), (67, 66, 35)]
-VARIANTS = [capi.SPMV_PAIR, capi.SPMV_MARCH, capi.SPMV_NAIVE]
+VARIANTS = [capi.SPMV_PAIR, capi.SPMV_MARCH, capi.SPMV_NAIVE, capi.SPMV_TMA]
 
 
 def grid_of(m):

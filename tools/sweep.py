@@ -74,6 +74,7 @@ def main():
             rec(n, "spmv auto (march k8)", 72, timeit(ctx, lambda: ctx.spmv(g, dA, x, y), reps), round=rnd)
             rec(n, "spmv naive", 72, timeit(ctx, lambda: ctx.spmv(g, dA, x, y, variant=capi.SPMV_NAIVE), reps), round=rnd)
             rec(n, "spmv pair", 72, timeit(ctx, lambda: ctx.spmv(g, dA, x, y, variant=capi.SPMV_PAIR), reps), round=rnd)
+            rec(n, "spmv tma (x planes staged in shared memory by cp.async.bulk)", 72, timeit(ctx, lambda: ctx.spmv(g, dA, x, y, variant=capi.SPMV_TMA), reps), round=rnd)
             rec(n, "spmv auto res (b-Ax)+yy", 80, timeit(ctx, lambda: ctx.spmv(g, dA, x, y, b=b, want_yy=True, red=red), reps), round=rnd)
             rec(n, "spmv auto +(x,Ax)", 72, timeit(ctx, lambda: ctx.spmv(g, dA, x, y, w=x, red=red), reps), round=rnd)
             if a.full:
