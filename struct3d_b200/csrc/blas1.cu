@@ -481,7 +481,7 @@ int s3d_final_reduce(s3d_ctx *ctx, int nr, unsigned nblocks, double *out)
 
 extern "C" {
 
-void s3d_internal_set_ew_unroll(int u) { g_ew_unroll = u; }
+S3D_HIDDEN void s3d_internal_set_ew_unroll(int u) { g_ew_unroll = u; }
 
 int s3d_vecset(s3d_ctx *ctx, const s3d_grid *g, double a, double *d_x)
 {

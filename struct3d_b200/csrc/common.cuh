@@ -10,6 +10,9 @@
 #include "s3d_cuda.h"
 
 // what a z-slab SpMV reads instead of x's two ghost planes: the slots of this rank's peer-memory window (context.cu)
+// cross-file helpers of the library that are not part of the C-ABI (include/s3d_cuda.h)
+#define S3D_HIDDEN __attribute__((visibility("hidden")))
+
 struct s3d_halo_view {
 	const double *lo = nullptr, *hi = nullptr;         // plane-shaped slots (null at the ends of the global grid)
 	const int *flag_lo = nullptr, *flag_hi = nullptr;  // hold `epoch` once the neighbour's plane has landed

@@ -652,7 +652,7 @@ int p2p_ensure(s3d_ctx *ctx, const s3d_grid *g)
 // The sending half of a peer-memory exchange: push the two boundary planes of x into the neighbours' windows.  On success `hv`
 // describes where the planes this rank RECEIVES will land (its own window slots and flags, for epoch hv->epoch); hv->epoch == 0
 // means peer memory is not in use and the caller must run the NCCL exchange.
-int s3d_internal_halo_push(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, s3d_halo_view *hv)
+S3D_HIDDEN int s3d_internal_halo_push(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, s3d_halo_view *hv)
 {
 	*hv = s3d_halo_view();
 	if (ctx->p2p.mode != 1) return S3D_OK;
@@ -685,7 +685,7 @@ int s3d_internal_halo_push(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, s
 // [2 * nflags ints of flags, padded to 32 doubles][plane for forward sweeps: rows from the rank below][plane for backward sweeps: rows
 // from the rank above]; a plane has the in-plane layout of a vector plane (vplane doubles).  (Re)created -- zeroed flags, barrier --
 // whenever the tile grid or the plane size changes, which is also when the sweep epochs start over.
-int s3d_internal_sgs_window(s3d_ctx *ctx, const s3d_grid *g, int ntx, int nty, s3d_sgs_window *out)
+S3D_HIDDEN int s3d_internal_sgs_window(s3d_ctx *ctx, const s3d_grid *g, int ntx, int nty, s3d_sgs_window *out)
 {
 	*out = s3d_sgs_window();
 	if (g->nranks == 1 || ctx->p2p.mode != 1 || !ctx->comm) return S3D_OK;

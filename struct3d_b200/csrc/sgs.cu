@@ -1126,7 +1126,7 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 
 }  // namespace
 
-extern "C" int s3d_internal_sgs_window(s3d_ctx *ctx, const s3d_grid *g, int ntx, int nty, s3d_sgs_window *out);
+extern "C" S3D_HIDDEN int s3d_internal_sgs_window(s3d_ctx *ctx, const s3d_grid *g, int ntx, int nty, s3d_sgs_window *out);
 
 extern "C" {
 

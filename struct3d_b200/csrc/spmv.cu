@@ -350,8 +350,8 @@ int pick_kchunk(const s3d_ctx *, const s3d_grid *g, bool fused)
 int s3d_spmv_tma(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *x, double *y, const double *b,
                  const double *w, bool yy, double *d_red, const int *stop);
 
-extern "C" void s3d_internal_set_ew_unroll(int u);
-extern "C" int s3d_internal_halo_push(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, s3d_halo_view *hv);
+extern "C" S3D_HIDDEN void s3d_internal_set_ew_unroll(int u);
+extern "C" S3D_HIDDEN int s3d_internal_halo_push(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, s3d_halo_view *hv);
 
 extern "C" {
 
