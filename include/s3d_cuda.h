@@ -144,14 +144,17 @@ int  s3d_host_free(s3d_ctx *ctx, void *h_ptr);
 int  s3d_spmv(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_x, double *d_y,
               const double *d_b, const double *d_w, int want_yy, double *d_red, const int *d_stop, int variant);
 
-/* SMat::apply / apply_res on a z-slab in ONE call: the one-plane halo exchange of x (NCCL, on a second stream) overlapped with
- * the multiply of the interior planes; the two boundary planes follow once the halos have landed; fused reductions as in s3d_spmv.
- * Writes the ghost planes of d_x.  One rank: identical to s3d_spmv. */
+/* SMat::apply / apply_res on a z-slab in ONE call, fused reductions as in s3d_spmv.  With peer-memory windows (the default, see
+ * s3d_halo_exchange) a push kernel stores this rank's two boundary planes of x into the neighbours' windows and the multiply reads the
+ * neighbours' planes from its own window: the two k-chunks that need them are dispatched last and only their blocks wait for the flags,
+ * so the transfer overlaps the interior planes (the ghost planes of d_x are not written in this mode).  Without peer memory: halo
+ * exchange by NCCL, then the multiply; with "halo_overlap" the NCCL exchange runs on a second stream beside the interior planes and the
+ * two boundary planes follow.  One rank: identical to s3d_spmv. */
 int  s3d_spmv_exchange(s3d_ctx *ctx, const s3d_grid *g, const double *A, double *d_x, double *d_y, const double *d_b,
                        const double *d_w, int want_yy, double *d_red, const int *d_stop);
 
 /* SMat::apply / apply_res for HOST vectors (the reference's SVec lives in host memory): y = A x, or b - A x with a device-resident
- * d_b.  Pipelined in nchunks z-chunks (<= 0: 16) over three streams, so the upload of x, the kernel and the download of y overlap and
+ * d_b.  Pipelined in nchunks z-chunks (<= 0: 16; bench.py uses 32) over three streams, so the upload of x, the kernel and the download of y overlap and
  * the call runs at PCIe speed.  h_x / h_y: host SVec layout, pinned (s3d_host_alloc) for full speed; d_x / d_y: device vectors used
  * as staging (d_y as allocated by s3d_vec_alloc: zero ghosts).  Single GPU; blocks until h_y is complete. */
 int  s3d_spmv_host(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *h_x, double *h_y, double *d_x, double *d_y,
@@ -199,9 +202,9 @@ int  s3d_sgs_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, double *d_d
 int  s3d_strilu_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuildsweeps, double *d_dinv);
 #define S3D_SGS_LEXICOGRAPHIC 0  /* the reference's ordering, executed as a tile-level dataflow wavefront: same arithmetic */
 #define S3D_SGS_LEXICOGRAPHIC_PLANES 2  /* same result, one launch per hyperplane i+j+k (slow; kept for cross-checks) */
-#define S3D_SGS_REDBLACK      1
+#define S3D_SGS_REDBLACK      1  /* two-colour ordering: fully parallel half-sweeps (another operator: changes the iteration counts) */
 #define S3D_SGS_JACOBI_SWEEPS 3  /* nsweeps synchronous Jacobi sweeps per triangular factor: the deterministic counterpart of the
-                                  * reference's asynchronous threaded sweeps (threadedapply = true); exact for nsweeps >= nx+ny+nz-2 */  /* two-colour ordering: four fully parallel half-sweeps (changes the iteration) */
+                                  * reference's asynchronous threaded sweeps (threadedapply = true); exact for nsweeps >= nx+ny+nz-2 */
 /* Exact (lexicographic) SGS on a z-slab decomposition: the sweep runs THROUGH the slabs -- the last plane of tiles of rank p pushes its
  * k-face rows into rank p+1's peer-memory window (backward: p-1) and raises per-tile flags there, so results and iteration counts are
  * those of the single-process reference (s3d_sgspreconditioners.cpp:14-115) at any GPU count; the ranks work as a pipeline.
