@@ -101,7 +101,7 @@ int  s3d_timer_stop_ms(s3d_ctx *ctx, double *ms);
  * SM the march kernel is compiled for: 0 auto, 3, 4, 6), "spmv_hints" (evict-first hints on/off for the PAIR/NAIVE
  * variants), "spmv_variant" (what S3D_SPMV_AUTO resolves to), "halo_overlap" (0 = exchange first, then multiply), "halo_p2p" (1 = halo
  * planes through peer-memory windows, 0 = NCCL), "ew_unroll" (items a thread of the element-wise kernels keeps in flight: 0 = each
- * kernel's own choice, 2/4/8, -1 = grid-stride order), "sgs_variant" (0 = warp-per-tile dataflow sweep, 1 = block-per-tile),
+ * kernel's own choice, 2/4/8, -1 = grid-stride order), "sgs_variant" (0 = warp-per-tile dataflow sweep, 1 = block-per-tile, 3 = warp-per-line, experimental),
  * "sgs_tile_i" (16/32), "sgs_pencils" (1/2/0 = by grid size), "sgs_warps_per_sm", "sgs_profile" (timing experiments). */
 int  s3d_tune_set(s3d_ctx *ctx, const char *key, int value);
 

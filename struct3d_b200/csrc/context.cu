@@ -684,7 +684,7 @@ S3D_HIDDEN int s3d_internal_halo_push(s3d_ctx *ctx, const s3d_grid *g, const dou
 // the next rank's window and raise a per-tile flag there; that rank's first plane of tiles waits for it (sgs.cu).  Layout (doubles):
 // [2 * nflags ints of flags, padded to 32 doubles][plane for forward sweeps: rows from the rank below][plane for backward sweeps: rows
 // from the rank above]; a plane has the in-plane layout of a vector plane (vplane doubles).  (Re)created -- zeroed flags, barrier --
-// whenever the tile grid or the plane size changes, which is also when the sweep epochs start over.
+// whenever the tile grid or the plane size changes; the sweep epochs only ever grow, so old flags never satisfy a wait.
 S3D_HIDDEN int s3d_internal_sgs_window(s3d_ctx *ctx, const s3d_grid *g, int ntx, int nty, s3d_sgs_window *out)
 {
 	*out = s3d_sgs_window();

@@ -1035,8 +1035,9 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 		S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_flags, (ntiles + 1) * sizeof(int)));
 		S3D_CUDA(ctx, cudaMemsetAsync(ctx->sgs_flags, 0, (ntiles + 1) * sizeof(int), ctx->stream));
 		ctx->sgs_flags_cap = ntiles + 1;
-		S3D_CUDA(ctx, cudaMemsetAsync(ctx->sgs_ctl, 0, 2 * sizeof(int), ctx->stream));
 	}
+	// The epoch is never rewound: it only grows, so whatever an old sweep (of this or another tiling) left in a flag is smaller than
+	// every later epoch and cannot satisfy a wait.  On z-slabs this also keeps the ranks' epochs equal whatever their local tile counts.
 	static bool configured = false;
 	static int blocks_per_sm = 1;
 	if (!configured) {
@@ -1066,9 +1067,6 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 		S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_order, order.size() * sizeof(int)));
 		S3D_CUDA(ctx, cudaMemcpy(ctx->sgs_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
 		ctx->sgs_order_dims[0] = okey; ctx->sgs_order_dims[1] = f.nty; ctx->sgs_order_dims[2] = f.ntz;
-		// another tiling: start the epochs over
-		S3D_CUDA(ctx, cudaMemsetAsync(ctx->sgs_flags, 0, ctx->sgs_flags_cap * sizeof(int), ctx->stream));
-		S3D_CUDA(ctx, cudaMemsetAsync(ctx->sgs_ctl, 0, 2 * sizeof(int), ctx->stream));
 	}
 	f.flags = ctx->sgs_flags;
 	f.iface = ctx->sgs_iface;
