@@ -123,6 +123,28 @@ def test_redblack_sgs_is_the_same_operator_reordered():
     assert np.linalg.norm(M @ z[1:-1, 1:-1, 1:-1].ravel() - r[1:-1, 1:-1, 1:-1].ravel()) <= 1e-12 * np.linalg.norm(rr)
 
 
+def test_jacobi_sweeps_statement_converges_to_the_exact_sweep():
+    """orc_sgs_jacobi_sweeps_apply is not in the reference (it is the deterministic counterpart of its asynchronous threaded
+    sweeps), so pin it by its defining properties: n synchronous Jacobi sweeps on a triangular system with
+    dependency depth d = nx+ny+nz-2 are exact from n = d on (bit-identical to the sequential sweep), monotonically closer before,
+    and one sweep from zero is the Jacobi-scaled right-hand side."""
+    m = cport.Mesh((9, 7, 8), grid="chebyshev")
+    A = cport.lhs(m, "convdiff", V1, 0.1)
+    di = cport.sgs_setup(m, A)
+    rng = np.random.default_rng(3)
+    r = m.zeros(); r[1:-1, 1:-1, 1:-1] = rng.uniform(-1, 1, tuple(reversed(m.n)))
+    exact = cport.sgs_like_apply(m, A, di, r, 1)
+    depth = sum(m.n) - 2
+    assert np.array_equal(cport.sgs_jacobi_sweeps_apply(m, A, di, r, depth), exact)
+    assert np.array_equal(cport.sgs_jacobi_sweeps_apply(m, A, di, r, depth + 3), exact)
+    errs = [np.abs(cport.sgs_jacobi_sweeps_apply(m, A, di, r, n) - exact).max() for n in (1, 2, 4, 8, depth - 1)]
+    assert errs[0] > errs[2] > errs[3] and errs[-1] <= errs[3]
+    assert errs[-1] > 0.0 or depth <= 2        # one sweep short of the depth is not yet exact (generic data)
+    one = cport.sgs_jacobi_sweeps_apply(m, A, di, r, 1)
+    # forward sweep 1 from zero: y = r * dinv; backward sweep 1 from zero: z = y  =>  z = r / diag
+    assert np.array_equal(one[1:-1, 1:-1, 1:-1], (r[1:-1, 1:-1, 1:-1] * di))
+
+
 @pytest.mark.skipif(not refshim.available(), reason="oracle/_ref not built (no /root/reference here)")
 def test_oracle_convdiff_circular_matches_live_reference():
     """the rotational-velocity operator, reproduced as the reference has it."""
