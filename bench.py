@@ -15,8 +15,14 @@ y = A x through SMat::apply, the reference-facing call (SMat::apply, reference s
   roofline   the SpMV kernel against the measured HBM copy peak (MEASURED_PEAKS.json);
   cpu_baseline / --impl reference: the reference's own CPU SMat::apply (oracle/_ref, built from the
              unmodified reference sources; falls back to the C port) on the box's host cores;
-  solve      extra, not part of the timed steps: CG+Jacobi on the same grid and BiCGSTAB+SGS on
-             convection-diffusion 256^3 through createSolver()/apply(), the reference's call sequence.
+  solve      extra, not part of the timed steps, through createSolver()/apply(), the reference's call sequence: CG+Jacobi on the
+             same grid; CG+Jacobi on a FIXED 1024^3 grid (strong scaling); one GPU: BiCGSTAB with every SGS ordering on
+             convection-diffusion 256^3 and the exact SGS at 512^3; several GPUs: BiCGSTAB + the exact SGS through the z-slabs.
+             A failure in this block is reported as solve.error; the line is printed regardless.
+
+Two more modes (single GPU, not used by the driver; both may time oracle/_ref as the CPU baseline):
+  --sweep    SpMV / axpy / dot bandwidth 32^3 .. 1024^3 against the roofline, reference CPU kernels beside it (BASELINE configs[4]);
+  --solves   whole solves of the reference's as-is cases and the 256^3 cases: the reference on the host cores beside this library.
 """
 import argparse
 import json
