@@ -481,6 +481,7 @@ def run_ours(a):
                 dtx = max_over_ranks(time.perf_counter() - t0)
                 solve["bicgstab_sgs_lexicographic_slabs_convdiff256perGPU"] = {"grid": f"256x256x{256 * world}", "seconds": dtx, "iters": ix["iters"],
                                                                                "converged": ix["converged"], "ms_per_iter": dtx * 1e3 / max(1, ix["iters"]),
+                                                                               "ordering": "lexicographic through the slabs" if a.halo_p2p else "red-black (peer memory switched off)",
                                                                                "precapply_seconds": ix["precapplywtime"]}
                 del sx, Ax, bx, ux
             if world == 1 and n >= 256:
