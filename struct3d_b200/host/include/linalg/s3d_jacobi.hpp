@@ -1,15 +1,3 @@
-// Jacobi preconditioner z = r / diag(A)  (reference: src/linalg/s3d_jacobi.hpp).
-#ifndef STRUCT3D_B200_JACOBI_HPP
-#define STRUCT3D_B200_JACOBI_HPP
-
-#include "s3d_solverbase.hpp"
-
-class JacobiPreconditioner : public SolverBase
-{
-public:
-	JacobiPreconditioner(const SMat &lhs);
-	void updateOperator();
-	SolveInfo apply(const SVec &r, SVec &z) const;
-};
-
-#endif
+// JacobiPreconditioner (reference: src/linalg/s3d_jacobi.hpp): declared in s3d_linalg_solvers.hpp; this header keeps the reference's include path working.
+#pragma once
+#include "linalg/s3d_linalg_solvers.hpp"

@@ -285,14 +285,20 @@ def test_zero_rhs_and_nosolver(H):
     assert info["iters"] == oi["iters"] and np.abs(x.a - xo).max() <= 1e-12 * np.abs(xo).max()
 
 
+# option sets given on the command line (the drivers take "-key value" like PetscInitialize does): Richardson + StrILU as in the
+# reference's discretization-verification runs (sequential build and apply, 1 build sweep, 2 apply sweeps), and Richardson + SGS
+STRILU_SEQ = ["-s3d_ksp_type", "richardson", "-ksp_rtol", "1e-6", "-ksp_max_it", "1000", "-s3d_pc_type", "strilu", "-s3d_pc_use_threaded_build", "false", "-s3d_pc_use_threaded_apply", "false", "-s3d_pc_build_sweeps", "1", "-s3d_pc_apply_sweeps", "2", "-s3d_thread_chunk_size", "1024"]
+SGS_SEQ = ["-s3d_ksp_type", "richardson", "-ksp_rtol", "1e-6", "-ksp_max_it", "1000", "-s3d_pc_type", "sgs", "-s3d_pc_use_threaded_apply", "false", "-s3d_pc_build_sweeps", "1", "-s3d_pc_apply_sweeps", "1", "-s3d_thread_chunk_size", "1024"]
+
+
 @pytest.mark.parametrize("args", [
     ["testmatvec", os.path.join(INPUT, "poisson_conv.control")],
     ["gridconv", os.path.join(INPUT, "poisson_conv.control"), "-options_file", os.path.join(INPUT, "cg_jacobi.perc")],
     ["gridconv", os.path.join(INPUT, "convdiff_conv.control"), "-options_file", os.path.join(INPUT, "bcgs_sgs.perc"), "-ksp_rtol", "1e-8"],
-    ["gridconv", os.path.join(INPUT, "poisson_conv.control"), "-options_file", os.path.join(INPUT, "richardson_strilu.perc")],
-    ["gridconv", os.path.join(INPUT, "convdiff_conv.control"), "-options_file", os.path.join(INPUT, "richardson_strilu.perc")],
-    ["gridconv", os.path.join(INPUT, "cdcirc_conv.control"), "-options_file", os.path.join(INPUT, "richardson_strilu.perc")],
-    ["runcase", os.path.join(INPUT, "convdiff64.control"), "-options_file", os.path.join(INPUT, "richardson_sgs.perc")],
+    ["gridconv", os.path.join(INPUT, "poisson_conv.control")] + STRILU_SEQ,
+    ["gridconv", os.path.join(INPUT, "convdiff_conv.control")] + STRILU_SEQ,
+    ["gridconv", os.path.join(INPUT, "cdcirc_conv.control")] + STRILU_SEQ,
+    ["runcase", os.path.join(INPUT, "convdiff64.control")] + SGS_SEQ,
     ["runcase", os.path.join(INPUT, "poisson16_cheb.control"), "-options_file", os.path.join(INPUT, "gcr_jacobi.perc")],
     ["scaling", os.path.join(INPUT, "convdiff48.control"), "-options_file", os.path.join(INPUT, "scaling_gpus.perc")],
 ])
