@@ -132,9 +132,20 @@ def main():
                    "solves": solves, "known": known}, f, indent=1)
 
     # full fields on three small grids
-    for name, npdim, grid, pde, vel, mu in (("poisson16_cheb", (16, 16, 16), "chebyshev", "poisson", (0, 0, 0), 0.0),
-                                            ("convdiff_20x14x18", (20, 14, 18), "uniform", "convdiff", V1, 0.1),
-                                            ("convdiff_18x22x12_cheb", (18, 22, 12), "chebyshev", "convdiff", V2, 0.05)):
+    write_fields((("fields_poisson16_cheb", (16, 16, 16), "chebyshev", "poisson", (0, 0, 0), 0.0),
+                  ("fields_convdiff_20x14x18", (20, 14, 18), "uniform", "convdiff", V1, 0.1),
+                  ("fields_convdiff_18x22x12_cheb", (18, 22, 12), "chebyshev", "convdiff", V2, 0.05)))
+    write_circ()
+
+
+def write_circ():
+    """The third PDE of src/pde (convdiff_circular) on a ragged Chebyshev grid.  Its own file-name prefix: the
+    fixture tests that loop over fields_*.npz assemble with the Poisson / convection-diffusion kernels."""
+    write_fields((("circ_17x21x13_cheb", (17, 21, 13), "chebyshev", "convdiff_circular", (1.3, 0, 0), 0.07),))
+
+
+def write_fields(specs):
+    for name, npdim, grid, pde, vel, mu in specs:
         m = R.Mesh(npdim, grid=grid)
         P = R.Pde(pde, vel, mu)
         A = P.lhs(m)
@@ -150,7 +161,7 @@ def main():
         ax.a[...] = b.a
         R.vecaxpy(0.37, x, ax)
         trhs, msol = P.vector(m, "test_rhs"), P.vector(m, "manufactured_solution")   # keep the owners alive: .a is a view
-        np.savez_compressed(os.path.join(OUT, f"fields_{name}.npz"),
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"),
                             npdim=np.array(npdim), grid=grid, pde=pde, vel=np.array(vel), mu=mu,
                             cx=m.coords(0), cy=m.coords(1), cz=m.coords(2), A=A.stacked(), x=x.a,
                             test_rhs=trhs.a.copy(), manufactured_rhs=b.a.copy(),
@@ -162,4 +173,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--circ-only" in sys.argv:
+        write_circ()
+    else:
+        main()

@@ -19,7 +19,7 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 SOLVES = json.load(open(os.path.join(GOLD, "solves.json")))
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "fields_*.npz"))))
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "fields_*.npz")) + glob.glob(os.path.join(GOLD, "circ_*.npz"))))
 def test_oracle_fields_match_reference_fixtures(path):
     G = np.load(path)
     npdim = tuple(int(v) for v in G["npdim"])

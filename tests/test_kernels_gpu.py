@@ -347,7 +347,7 @@ def test_fused_cg_and_bicg_steps(ctx):
     assert abs(got[1] - cport.inner_vector_l2(m, rh, rref)) <= 1e-13 * np.linalg.norm(rh) * np.linalg.norm(rref)
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "fields_*.npz"))))
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "fields_*.npz")) + glob.glob(os.path.join(GOLD, "circ_*.npz"))))
 def test_against_reference_fixtures(ctx, path):
     """Golden vectors produced by the REAL reference (oracle/make_golden.py): coefficients, y = Ax,
     b - Ax, Jacobi, sequential SGS, axpy, norms."""
@@ -358,6 +358,8 @@ def test_against_reference_fixtures(ctx, path):
     dA = ctx.mat_alloc(g)
     if str(G["pde"]) == "poisson":
         ctx.assemble_poisson(g, coords, dA)
+    elif str(G["pde"]) == "convdiff_circular":
+        ctx.assemble_convdiff_circ(g, coords, float(G["mu"]), dA)
     else:
         ctx.assemble_convdiff(g, coords, G["vel"], float(G["mu"]), dA)
     assert np.array_equal(ctx.mat_download(g, dA), G["A"])
