@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """Multi-GPU (z-slab) check, run under torchrun with one rank per GPU:
-  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/mgpu_check.py
+  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/mgpu_check.py
 Every rank holds a z-slab; the results are compared with the CPU oracle run on the WHOLE grid:
 assembly and SpMV bit-exact per slab (this exercises the NCCL halo exchange), dot/norm allreduce to 1e-13,
-CG+Jacobi iteration count equal to the oracle's, BiCGSTAB with red-black SGS converging to the true residual."""
+CG / Richardson / GCR iteration counts equal to the oracle's, the exact SGS sweep THROUGH the slabs bit-identical to the sequential
+sweep over the whole grid (BiCGSTAB + SGS with the oracle's iteration count), red-black SGS bit-identical to its oracle statement.
+Not collected by pytest (needs torchrun and N GPUs): tools/run_mgpu.sh N runs it."""
 import os
 import sys
 

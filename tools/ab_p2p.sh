@@ -1,5 +1,5 @@
 #!/bin/bash
-# Correctness (tools/mgpu_check.py, default = peer-memory halo) and A/B of the halo exchange on N GPUs: peer-memory windows vs NCCL send/recv.
+# Correctness (tests/mgpu_check.py, default = peer-memory halo) and A/B of the halo exchange on N GPUs: peer-memory windows vs NCCL send/recv.
 N=${1:-2}
 mkdir -p gpurun_out
 for p2p in 1 0 1 0; do

@@ -1,9 +1,9 @@
 #!/bin/bash
-# N-GPU check: tools/mgpu_check.py (correctness over N slabs, peer-memory halo), then bench.py with the peer-memory halo and a
+# N-GPU check: tests/mgpu_check.py (correctness over N slabs, peer-memory halo), then bench.py with the peer-memory halo and a
 # short NCCL run beside it
 N=${1:-8}
 mkdir -p gpurun_out
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 tools/mgpu_check.py > gpurun_out/mgpu_check_n$N.log 2>&1; echo "mgpu_check rc=$?"
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 tests/mgpu_check.py > gpurun_out/mgpu_check_n$N.log 2>&1; echo "mgpu_check rc=$?"
 grep "PASS\|FAIL" gpurun_out/mgpu_check_n$N.log | tail -4
 timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29532 \
     bench.py --gpus $N --steps 30 --warmup 3 --halo-p2p 1 2>gpurun_out/bench_n${N}_p2p1.err > gpurun_out/bench_n${N}_p2p1.json; echo "bench p2p rc=$?"
