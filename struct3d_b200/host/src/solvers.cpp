@@ -81,7 +81,14 @@ struct DeviceLoop {
 		if (!use_graph || index == 0) { enqueue(); return; }
 		if (!graph) {
 			d.check(s3d_graph_begin(ctx), "s3d_graph_begin");
-			enqueue();
+			try {
+				enqueue();
+			} catch (...) {
+				// leave the stream usable: close the capture, drop what was recorded, let the caller see the error
+				s3d_graph *dead = nullptr;
+				if (s3d_graph_end(ctx, &dead) == S3D_OK) s3d_graph_destroy(ctx, dead);
+				throw;
+			}
 			d.check(s3d_graph_end(ctx, &graph), "s3d_graph_end");
 		}
 		d.check(s3d_graph_launch(ctx, graph), "s3d_graph_launch");
