@@ -91,6 +91,7 @@ struct s3d_ctx {
 		bool ok = false;              // windows of the neighbours are mapped on every rank
 		double *win = nullptr;        // [32 doubles of header: 4 int flags][4 planes: (from below, from above) x parity]
 		size_t plane_cap = 0;         // doubles per plane slot
+		size_t tried_cap = 0;         // plane size the window set-up was last attempted for (the attempt is collective: never repeat it on one rank only)
 		double *peer_lo = nullptr, *peer_hi = nullptr;   // the windows of rank-1 / rank+1 as mapped here
 		unsigned *ticket = nullptr;   // last-block election of the push kernel
 		int epoch = 0;

@@ -628,7 +628,7 @@ int p2p_ensure(s3d_ctx *ctx, const s3d_grid *g)
 {
 	s3d_ctx::P2P &w = ctx->p2p;
 	const size_t n = (size_t)g->vplane;
-	if (w.win && w.plane_cap >= n) return S3D_OK;
+	if (w.tried_cap >= n) return S3D_OK;                    // decided for this plane size (on every rank alike), whatever the outcome
 	const size_t cap = (n + 15) / 16 * 16;
 	if (!w.ticket) {
 		S3D_CUDA(ctx, cudaMalloc(&w.ticket, sizeof(unsigned)));
@@ -643,6 +643,7 @@ int p2p_ensure(s3d_ctx *ctx, const s3d_grid *g)
 	const int rc = peer_window_create(ctx, g, (P2P_HEADER + 4 * cap) * sizeof(double), release, (void **)&w.win, (void **)&w.peer_lo, (void **)&w.peer_hi, &w.ok);
 	if (rc != S3D_OK) return rc;
 	w.plane_cap = cap;
+	w.tried_cap = cap;
 	if (!w.ok && ctx->rank == 0) fprintf(stderr, "[struct3d_b200] peer-memory halo windows unavailable (CUDA IPC); using NCCL send/recv\n");
 	return S3D_OK;
 }
