@@ -123,6 +123,110 @@ def test_redblack_sgs_is_the_same_operator_reordered():
     assert np.linalg.norm(M @ z[1:-1, 1:-1, 1:-1].ravel() - r[1:-1, 1:-1, 1:-1].ravel()) <= 1e-12 * np.linalg.norm(rr)
 
 
+def _sgw_row(P, fwd, b, c):
+    """Python statement of sgw_row<P, FWD> in struct3d_b200/csrc/sgs.cu (the row a (b, c) pencil's inputs occupy in shared memory)."""
+    if P == 2:
+        lo, hi = 5 * (b >> 1) + 2 * (c >> 1), (b >> 2) * 4 + (c & 1) * 2 + (b & 1)
+    else:
+        lo, hi = ((b + c + 1) >> 1) + (c >> 1) + 4 * (b & 1), 2 * (b & 1) + (c & 1)
+    return 8 * hi + ((lo if fwd else -lo) & 7)
+
+
+@pytest.mark.parametrize("P", [1, 2])
+@pytest.mark.parametrize("fwd", [True, False])
+@pytest.mark.parametrize("TI", [16, 32])
+def test_sgs_shared_memory_row_map_is_conflict_free(P, fwd, TI):
+    """The warp-per-tile SGS kernel addresses a tile's inputs as row(pencil) * (TI + 2) + i, and lane (m, c) reads i = h - s
+    (forward) or ti - 1 - (h - s) (backward) at step h, s = b + c.  The map must (1) be a bijection of the 32 P pencils onto rows,
+    (2) put a lane's second pencil 8 rows after its first (one shared pointer + immediates), (3) give the 16 lanes of every
+    half-warp 16 different 8-byte banks at every step, for both pencils."""
+    R = TI + 2
+    rows = {_sgw_row(P, fwd, b, c) for b in range(4 * P) for c in range(8)}
+    assert rows == set(range(32 * P))
+    for lane in range(32):
+        m, c = lane >> 3, lane & 7
+        if P == 2:
+            assert _sgw_row(2, fwd, 2 * m + 1, c) == _sgw_row(2, fwd, 2 * m, c) + 8
+    for e in range(P):
+        for h in range(TI + 4 * P + 8):
+            for half in (range(0, 16), range(16, 32)):
+                banks = set()
+                for lane in half:
+                    m, c = lane >> 3, lane & 7
+                    b = P * m + e
+                    u = h - (b + c)
+                    i = u if fwd else TI - 1 - u
+                    banks.add((_sgw_row(P, fwd, b, c) * R + i) % 16)
+                assert len(banks) == 16, (P, fwd, TI, e, h)
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 4])
+def test_peer_memory_halo_protocol_needs_no_acknowledgement(nranks):
+    """Model of the peer-memory halo exchange (struct3d_b200/csrc/context.cu): every rank runs, in stream order, push(1), consume(1),
+    push(2), consume(2), ...  push(e) writes this rank's boundary planes into the neighbours' window slots of parity e & 1 and then
+    their flags; consume(e) (the pull kernel, or the boundary blocks of the SpMV) cannot finish before BOTH neighbours' push(e) have.
+    Claim: two slots per direction suffice without acknowledgements -- whenever a rank overwrites a neighbour's slot with epoch e,
+    that neighbour has already consumed epoch e - 2.  Checked over every reachable interleaving of the ranks."""
+    nepochs = 5
+    nops = 2 * nepochs                        # op index 2(e-1) = push(e), 2(e-1)+1 = consume(e)
+    start = tuple([0] * nranks)
+    seen, todo = {start}, [start]
+    while todo:
+        pc = todo.pop()
+        for r in range(nranks):
+            if pc[r] >= nops:
+                continue
+            e, is_consume = pc[r] // 2 + 1, pc[r] % 2 == 1
+            nbrs = [q for q in (r - 1, r + 1) if 0 <= q < nranks]
+            if is_consume:
+                if not all(pc[q] > 2 * (e - 1) for q in nbrs):      # a neighbour has not pushed epoch e yet: the kernel waits
+                    continue
+            else:
+                for q in nbrs:                                       # push(e) overwrites the neighbour's slot of parity e & 1
+                    assert e <= 2 or pc[q] > 2 * (e - 3) + 1, f"rank {r} overwrites epoch {e - 2} in rank {q}'s window before it was consumed"
+            nxt = pc[:r] + (pc[r] + 1,) + pc[r + 1:]
+            if nxt not in seen:
+                seen.add(nxt)
+                todo.append(nxt)
+    assert tuple([nops] * nranks) in seen                            # and the schedule cannot deadlock
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 4])
+def test_sgs_slab_window_is_safe_with_one_buffer_per_direction(nranks):
+    """Model of the exact SGS sweep through z-slabs (sgs.cu / context.cu): every rank runs forward sweep, backward sweep, forward, ...
+    as kernels in stream order.  While rank p runs a forward sweep it WRITES k-face rows into rank p+1's forward window and READS its
+    own forward window (filled by rank p-1); it can only finish after rank p-1 has finished the same sweep (its last plane of tiles
+    comes last).  Backward sweeps mirror that.  Claim: one window plane per direction suffices -- when a rank starts writing sweep n
+    into a neighbour's window, that neighbour has finished reading sweep n-1 of the same direction.  Every interleaving is explored."""
+    napplies = 3
+    nev = 4 * napplies                         # per rank: start F1, end F1, start B1, end B1, start F2, ...
+    start = tuple([0] * nranks)
+    seen, todo = {start}, [start]
+
+    def ended(pc_q, k, backward):              # has rank q finished sweep (k, direction)?
+        return pc_q > 4 * (k - 1) + (3 if backward else 1)
+
+    while todo:
+        pc = todo.pop()
+        for r in range(nranks):
+            if pc[r] >= nev:
+                continue
+            k, phase = pc[r] // 4 + 1, pc[r] % 4          # phase 0 start F, 1 end F, 2 start B, 3 end B
+            backward, is_end = phase >= 2, phase % 2 == 1
+            src = r + 1 if backward else r - 1             # whose rows this rank reads
+            dst = r - 1 if backward else r + 1             # whose window this rank writes
+            if is_end:
+                if 0 <= src < nranks and not ended(pc[src], k, backward):
+                    continue                                # still waiting for the neighbour's last plane of tiles
+            elif 0 <= dst < nranks and k > 1:
+                assert ended(pc[dst], k - 1, backward), f"rank {r} starts sweep {k} into rank {dst}'s window while it still reads sweep {k - 1}"
+            nxt = pc[:r] + (pc[r] + 1,) + pc[r + 1:]
+            if nxt not in seen:
+                seen.add(nxt)
+                todo.append(nxt)
+    assert tuple([nev] * nranks) in seen
+
+
 def test_jacobi_sweeps_statement_converges_to_the_exact_sweep():
     """orc_sgs_jacobi_sweeps_apply is not in the reference (it is the deterministic counterpart of its asynchronous threaded
     sweeps), so pin it by its defining properties: n synchronous Jacobi sweeps on a triangular system with
