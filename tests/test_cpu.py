@@ -227,6 +227,43 @@ def test_sgs_slab_window_is_safe_with_one_buffer_per_direction(nranks):
     assert tuple([nev] * nranks) in seen
 
 
+@pytest.mark.parametrize("dims,nworkers", [((2, 2, 2), 1), ((2, 2, 2), 3), ((3, 2, 2), 2), ((2, 3, 3), 4)])
+def test_sgs_tile_dispatch_cannot_deadlock(dims, nworkers):
+    """Model of the dataflow dispatch of the exact SGS sweep (sgs.cu): tiles are handed out in hyperplane order (ci + cj + ck, then
+    lexicographic); worker w starts with ticket w, and claims its NEXT ticket from a shared counter as soon as the predecessors of
+    its current tile are done (the kernel prefetches the ticket before it sweeps); a tile may be swept only after its three
+    predecessors.  Every reachable interleaving must be able to finish all tiles, with any number of workers."""
+    ntx, nty, ntz = dims
+    tiles = sorted(((ci, cj, ck) for ck in range(ntz) for cj in range(nty) for ci in range(ntx)), key=lambda t: (sum(t), t[2], t[1], t[0]))
+    index = {t: n for n, t in enumerate(tiles)}
+    preds = [[index[p] for p in ((ci - 1, cj, ck), (ci, cj - 1, ck), (ci, cj, ck - 1)) if p in index] for ci, cj, ck in tiles]
+    nt = len(tiles)
+    # state: (frozenset of finished tiles, per worker (current ticket or None, prefetched ticket or None), next counter value)
+    init = (frozenset(), tuple((w if w < nt else None, None) for w in range(nworkers)), nworkers)
+    seen, todo, finished = {init}, [init], False
+    while todo:
+        done, workers, counter = todo.pop()
+        if len(done) == nt:
+            finished = True
+            continue
+        moves = 0
+        for w, (cur, nxt) in enumerate(workers):
+            if cur is None:
+                continue
+            if not all(p in done for p in preds[cur]):
+                continue                                              # spinning on a flag
+            moves += 1
+            if nxt is None and counter < nt + nworkers:               # after the wait: claim the next ticket, then sweep
+                st = (done, workers[:w] + ((cur, counter),) + workers[w + 1:], counter + 1)
+            else:                                                     # sweep, publish, move on to the prefetched ticket
+                st = (done | {cur}, workers[:w] + ((nxt if (nxt is not None and nxt < nt) else None, None),) + workers[w + 1:], counter)
+            if st not in seen:
+                seen.add(st)
+                todo.append(st)
+        assert moves > 0, f"deadlock with finished={sorted(done)} workers={workers}"
+    assert finished
+
+
 def test_jacobi_sweeps_statement_converges_to_the_exact_sweep():
     """orc_sgs_jacobi_sweeps_apply is not in the reference (it is the deterministic counterpart of its asynchronous threaded
     sweeps), so pin it by its defining properties: n synchronous Jacobi sweeps on a triangular system with
