@@ -187,6 +187,18 @@ def sgs_like_apply(mesh, A, diaginv, r, nsweeps=1):
     return z
 
 
+def sgs_forward_inplace(mesh, A, diaginv, r, y):
+    """forward half-sweep into y, reading y's ghost entries as they are"""
+    lib().orc_sgs_forward_inplace(_np(mesh.npdim), _d(A), _d(diaginv), _d(r), _d(y))
+    return y
+
+
+def sgs_backward_inplace(mesh, A, diaginv, y, z):
+    """backward half-sweep into z, reading z's ghost entries as they are"""
+    lib().orc_sgs_backward_inplace(_np(mesh.npdim), _d(A), _d(diaginv), _d(y), _d(z))
+    return z
+
+
 def sgs_jacobi_sweeps_apply(mesh, A, diaginv, r, nsweeps):
     z = mesh.zeros()
     lib().orc_sgs_jacobi_sweeps_apply(_np(mesh.npdim), _d(A), _d(diaginv), int(nsweeps), _d(r), _d(z))

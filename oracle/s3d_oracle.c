@@ -395,6 +395,35 @@ void orc_sgs_like_apply(const int npdim[3], const double *A, const double *diagi
 	free(y);
 }
 
+/* The two half-sweeps of the apply above on their own, reading whatever the GHOST entries of the output hold instead of zeros.
+ * Not a separate function in the reference (s3d_sgspreconditioners.cpp:53-111 runs both inside apply on a zeroed scratch); split out
+ * to state the z-slab pipeline on the CPU: a slab whose bottom ghost plane holds the forward result of the slab below (top ghost plane:
+ * the backward result of the slab above) reproduces the global sweep restricted to the slab. */
+void orc_sgs_forward_inplace(const int npdim[3], const double *A, const double *diaginv, const double *r, double *y)
+{
+	DIMS;
+	FOR_REAL {
+		const i64 q = RI(i - 1, j - 1, k - 1);
+		double t = r[GI(i, j, k)] - A[0 * N + q] * y[GI(i - 1, j, k)] - A[1 * N + q] * y[GI(i, j - 1, k)]
+		         - A[2 * N + q] * y[GI(i, j, k - 1)];
+		t *= diaginv[q];
+		y[GI(i, j, k)] = t;
+	}
+}
+
+void orc_sgs_backward_inplace(const int npdim[3], const double *A, const double *diaginv, const double *y, double *z)
+{
+	DIMS;
+	for (int k = nz; k >= 1; k--)
+		for (int j = ny; j >= 1; j--)
+			for (int i = nx; i >= 1; i--) {
+				const i64 q = RI(i - 1, j - 1, k - 1);
+				z[GI(i, j, k)] = y[GI(i, j, k)]
+				    - diaginv[q] * (A[4 * N + q] * z[GI(i + 1, j, k)] + A[5 * N + q] * z[GI(i, j + 1, k)]
+				                    + A[6 * N + q] * z[GI(i, j, k + 1)]);
+			}
+}
+
 /* Synchronous multi-sweep variant of the same apply: every sweep recomputes ALL points from the previous sweep's values
  * (Jacobi iterations on the two triangular systems, starting from zero):
  *   forward  y <- dinv (r - A0 y[i-1] - A1 y[j-1] - A2 y[k-1]),   backward  z <- y - dinv (A4 z[i+1] + A5 z[j+1] + A6 z[k+1]).

@@ -72,6 +72,10 @@ void   orc_sgs_setup(const int npdim[3], const double *A, double *diaginv);
 void   orc_strilu_setup(const int npdim[3], const double *A, int nbuildsweeps, double *diaginv);
 void   orc_sgs_like_apply(const int npdim[3], const double *A, const double *diaginv, int nsweeps,
                           const double *r, double *z);
+/* the forward / backward half of orc_sgs_like_apply on its own, honouring the ghost entries of the output (the CPU statement of the
+ * sweep THROUGH z-slabs: the ghost plane holds the neighbouring slab's result) */
+void   orc_sgs_forward_inplace(const int npdim[3], const double *A, const double *diaginv, const double *r, double *y);
+void   orc_sgs_backward_inplace(const int npdim[3], const double *A, const double *diaginv, const double *y, double *z);
 /* synchronous Jacobi sweeps on the two triangular systems: NOT in the reference as such; the deterministic counterpart of its
  * asynchronous threaded sweeps, used to pin the GPU's S3D_SGS_JACOBI_SWEEPS ordering. */
 void   orc_sgs_jacobi_sweeps_apply(const int npdim[3], const double *A, const double *diaginv, int nsweeps,

@@ -446,6 +446,25 @@ part = torch.tensor([cport.inner_vector_l2(lm, ly, ly)], dtype=torch.float64)
 dist.all_reduce(part)
 full = cport.inner_vector_l2(m, y_global, y_global)
 assert abs(part.item() - full) <= 1e-13 * full
+# the exact SGS sweep THROUGH the slabs (sgs.cu + the peer-memory window of context.cu, stated on the CPU): forward sweeps run rank 0
+# then rank 1 -- rank 1's bottom ghost plane holds rank 0's top plane of y --, backward sweeps run rank 1 then rank 0; the pieces
+# must be the sequential sweep over the whole grid, bit for bit
+dinv = cport.sgs_setup(m, A)
+rr = golden_vec(m)[::-1].copy(); rr[0] = 0; rr[-1] = 0
+z_global = cport.sgs_like_apply(m, A, dinv, rr, 1)
+ldinv = np.ascontiguousarray(dinv[k0:k0 + nzl])
+lr = np.ascontiguousarray(rr[k0:k0 + nzl + 2]).copy()
+ly2, lz2 = np.zeros_like(lr), np.zeros_like(lr)
+if rank > 0:                                                     # wait for the slab below: its last plane of y
+    t = torch.empty(lr[0].shape, dtype=torch.float64); dist.recv(t, rank - 1); ly2[0] = t.numpy()
+cport.sgs_forward_inplace(lm, lA, ldinv, lr, ly2)
+if rank + 1 < P:
+    dist.send(torch.from_numpy(ly2[nzl].copy()), rank + 1)
+    t = torch.empty(lr[0].shape, dtype=torch.float64); dist.recv(t, rank + 1); lz2[nzl + 1] = t.numpy()   # the slab above: its first plane of z
+cport.sgs_backward_inplace(lm, lA, ldinv, ly2, lz2)
+if rank > 0:
+    dist.send(torch.from_numpy(lz2[1].copy()), rank - 1)
+assert np.array_equal(lz2[1:-1], z_global[k0 + 1:k0 + nzl + 1]), "SGS through the slabs differs from the sequential sweep over the whole grid"
 # NCCL id plumbing used by bench.py: rank 0's bytes reach every rank unchanged
 obj = [bytes(range(128)) if rank == 0 else None]
 dist.broadcast_object_list(obj, src=0)
@@ -458,7 +477,8 @@ print("rank", rank, "ok")
 def test_two_rank_slab_decomposition_gloo(tmp_path):
     """world_size-2 gloo run of the z-slab logic on CPU: the library's slab arithmetic + the halo protocol
     (top plane up, bottom plane down, Dirichlet zeros at the ends) reproduce the global SpMV bit for bit,
-    and slab partial dots allreduce to the global dot."""
+    slab partial dots allreduce to the global dot, and the SGS sweep pipelined through the slabs (forward: rank 0 then 1 with
+    rank 0's top plane as rank 1's ghost; backward: rank 1 then 0) is the sequential sweep over the whole grid."""
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     import socket
