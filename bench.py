@@ -95,13 +95,31 @@ def golden_field(n_real_total, shape):
 
 # ---------------------------------------------------------------------------------------------- reference arm
 
-def cpu_spmv(n, reps, threads=None):
-    """Times the reference's own CPU SMat::apply (or the C port when oracle/_ref is absent) on Poisson n^3."""
+def host_threads():
+    """Threads the reference's OpenMP path may use on this box: the cores this process is allowed on.  torchrun exports
+    OMP_NUM_THREADS=1 to its workers; that must not turn 'the reference on the host cores' into one core."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def bench_config(n, world):
+    """The workload, described the same way by both arms (identical keys and values)."""
+    return {"workload": f"poisson3d_uniform_{n}^3_fp64_7pt_spmv", "grid_per_gpu": f"{n}x{n}x{n}", "grid_total": f"{n}x{n}x{n * world}",
+            "step": "SMat::apply (y = A x) over the whole grid, incl. the one-plane halo exchange where the grid is split into z-slabs",
+            "bytes_per_point": BYTES_SPMV,
+            "l2": f"inputs exceed L2: {BYTES_SPMV * n ** 3 / 1e9:.2f} GB streamed per step and GPU vs 126 MB L2 (no flush needed)"}
+
+
+def cpu_spmv(n, reps, threads=None, perf=True):
+    """Times the reference's own CPU SMat::apply (or the C port when oracle/_ref is absent) on Poisson n^3, on `threads` host threads."""
     from oracle import cport, refshim
     npd = (n + 2,) * 3
+    threads = threads or host_threads()
     if refshim.available():
-        if threads:
-            refshim.set_num_threads(threads)
+        build = refshim.use_perf_build() if perf else "parity build"
+        refshim.set_num_threads(threads)
         cores = refshim.num_threads()
         _, _ = refshim._capture_stdout(lambda: None)
         m, _t = refshim._capture_stdout(lambda: refshim.Mesh(npd))
@@ -114,7 +132,9 @@ def cpu_spmv(n, reps, threads=None):
         kind = "reference"
         chk = float(np.abs(y.a).max())
     else:
-        cores = os.cpu_count()
+        build = "oracle/s3d_oracle.c (C port; oracle/_ref was not built)"
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+        cores = threads
         m = cport.Mesh(npd)
         A = np.empty(m.mshape)
         h2 = (2.0 / (n + 1)) ** 2
@@ -129,8 +149,9 @@ def cpu_spmv(n, reps, threads=None):
         kind = "port"
         chk = float(np.abs(y).max())
     gbs = BYTES_SPMV * n ** 3 / best / 1e9
-    return {"value": gbs, "unit": "GB/s", "cores": cores, "kind": kind, "ms": best * 1e3, "check_max_abs_y": chk,
-            "sample": f"Poisson {n}^3 fp64, SMat::apply (y = A x), best of {reps} after 1 warm-up, OMP threads = {cores}"}
+    return {"value": gbs, "unit": "GB/s", "cores": cores, "kind": kind, "ms": best * 1e3, "check_max_abs_y": chk, "build": build,
+            "sample": f"one {n}^3 slab of the grid (Poisson, fp64), SMat::apply (y = A x), best of {reps} after 1 warm-up, {cores} OpenMP threads "
+                      f"(all cores this process may use); GB/s per point is independent of the slab count; build: {build}"}
 
 
 def run_reference(a):
@@ -142,10 +163,10 @@ def run_reference(a):
     cb = cpu_spmv(n, max(1, a.steps))
     line = {"impl": "reference", "metric": "spmv_7pt_fp64_hbm_gbs", "value": cb["value"], "unit": "GB/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": cb["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": f"poisson3d_uniform_{n}^3_fp64_7pt_spmv", "grid": f"{n}^3 unknowns (npdim {n + 2})",
-                                             "note": "reference CPU path on host cores; the reference is single-process, so every N reports the same single-host number"},
+            "data": "synthetic", "config": bench_config(n, a.gpus),
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference's native path is single-process (src/cartmesh.cpp:107-109 refuses MPI size > 1): one host, all its cores, at every N",
             "gpu_launches": 0, "wall_s": time.time() - t0}
     _emit(json.dumps(line))
 
@@ -288,6 +309,7 @@ def run_solves(a):
 # ---------------------------------------------------------------------------------------------- our arm
 
 def run_ours(a):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     from struct3d_b200 import capi, hostapi
@@ -309,6 +331,7 @@ def run_ours(a):
     H = hostapi
     ctx.tune("halo_overlap", a.halo_overlap)
     ctx.tune("halo_p2p", a.halo_p2p)
+    V = (0.577350269189626, 0.7, 0.3)
 
     def barrier():
         H.sync()
@@ -322,11 +345,13 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def quiet(fn):
+        return H._capture_stdout(fn)[0]
+
     n = a.size
     nzg = n * world                                   # weak scaling: 512 planes per GPU
-    null = open(os.devnull, "w")
-    mesh, _ = H._capture_stdout(lambda: H.Mesh((n + 2, n + 2, nzg + 2)))
-    pde, _ = H._capture_stdout(lambda: H.Pde("poisson"))
+    mesh = quiet(lambda: H.Mesh((n + 2, n + 2, nzg + 2)))
+    pde = quiet(lambda: H.Pde("poisson"))
     t0 = time.perf_counter()
     A = pde.lhs(mesh)
     H.sync()
@@ -335,8 +360,9 @@ def run_ours(a):
     nx, ny, nzl = mesh.local
     N_local = nx * ny * nzl
     N_total = nx * ny * nzg
+    gold = golden_field(N_total, (nzg, ny, nx))
     xh = np.zeros(mesh.vshape)
-    xh[1:-1, 1:-1, 1:-1] = golden_field(N_total, (nzg, ny, nx))[mesh.k0:mesh.k0 + nzl]
+    xh[1:-1, 1:-1, 1:-1] = gold[mesh.k0:mesh.k0 + nzl]
     x.set(xh)
     g = capi.make_grid(nx, ny, nzg, rank, world) if world > 1 else capi.make_grid(nx, ny, nzl)
 
@@ -358,8 +384,30 @@ def run_ours(a):
     ms_step = max_over_ranks(ms_total / a.steps)
     value = BYTES_SPMV * N_total / (ms_step * 1e-3) / 1e9
 
-    # kernel-only duration on this rank (no halo exchange): the roofline numerator
     dA, dx, dy = A.device_ptr(), x.device_ptr(), y.device_ptr()
+    # ---- N > 1 self-check of the exchange: every rank recomputes its slab with the ghost planes filled from the KNOWN global field,
+    #      through the plain single-GPU kernel, and compares bit for bit with what the exchanging path produced
+    halo_check = None
+    if world > 1:
+        xg = xh.copy()
+        if mesh.k0 > 0:
+            xg[0, 1:-1, 1:-1] = gold[mesh.k0 - 1]
+        if mesh.k0 + nzl < nzg:
+            xg[-1, 1:-1, 1:-1] = gold[mesh.k0 + nzl]
+        x2, y2 = H.Vec(mesh), H.Vec(mesh)
+        x2.set(xg)
+        H.apply(A, x, y)
+        g1 = capi.make_grid(nx, ny, nzl)
+        ctx.spmv(g1, dA, x2.device_ptr(), y2.device_ptr())
+        ctx.vecaxpy(g1, -1.0, dy, y2.device_ptr())
+        diff = ctx.nrm2(g1, y2.device_ptr())
+        ynorm = ctx.nrm2(g1, dy)
+        bad = max_over_ranks(0.0 if (diff == 0.0 and ynorm > 0.0) else 1.0)
+        halo_check = "bit-identical" if bad == 0.0 else "MISMATCH"
+        del x2, y2, xg
+    del gold
+
+    # kernel-only duration on this rank (no halo exchange): the roofline numerator
     for _ in range(3):
         ctx.spmv(g, dA, dx, dy)
     H.sync()
@@ -369,35 +417,37 @@ def run_ours(a):
     ms_kernel = ctx.timer_stop_ms() / a.steps
     peak, peak_src = peaks()
     achieved = BYTES_SPMV * N_local / (ms_kernel * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("spmv_march_512", {}).get("dram_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        ent = tj.get("spmv_march_512_default") or tj.get("spmv_march_512", {})
+        traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "spmv_march_kernel<BY=8,MINB=3,plain> (2-plane z-march, 2 points/thread)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": BYTES_SPMV * N_local, "avg_launch_ms": ms_kernel}
 
     # ---- end to end: host vectors in, host vectors out, every step
     nbytes = xh.nbytes
     hx_p, hy_p = ctx.host_alloc(nbytes), ctx.host_alloc(nbytes)
-    import ctypes as C
     hx = np.ctypeslib.as_array(C.cast(hx_p, C.POINTER(C.c_double)), shape=(xh.size,)).reshape(xh.shape)
     hy = np.ctypeslib.as_array(C.cast(hy_p, C.POINTER(C.c_double)), shape=(xh.size,)).reshape(xh.shape)
     hx[...] = xh
 
     def e2e_step():
-        if world == 1:
-            # SMat::apply for host vectors: upload of x, multiply and download of y pipelined in z-chunks (s3d_spmv_host)
-            ctx.spmv_host(g, dA, hx_p, hy_p, dx, dy, nchunks=a.e2e_chunks)
-        else:
-            ctx.call("s3d_vec_upload", C.byref(g), capi._ptr(dx), capi._ptr(hx_p))
-            H.apply(A, x, y)
-            ctx.call("s3d_vec_download", C.byref(g), capi._ptr(dy), capi._ptr(hy_p))
+        # SMat::apply for host vectors: upload of x, (halo planes first on a z-slab), multiply and download of y pipelined in z-chunks
+        ctx.spmv_host(g, dA, hx_p, hy_p, dx, dy, nchunks=a.e2e_chunks)
 
-    x.device_ptr()
     for _ in range(2):
         e2e_step()
+    e2e_same = None
+    if world > 1:
+        H.apply(A, x, y)                                  # device-resident result of the same x
+        ref_y = y.a.copy()
+        e2e_step()
+        e2e_same = bool(np.array_equal(hy[1:-1], ref_y[1:-1]))
+        del ref_y
     barrier()
     e2e_steps = max(2, min(a.steps, 10))
     t0 = time.perf_counter()
@@ -407,36 +457,79 @@ def run_ours(a):
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
     e2e = {"value": BYTES_SPMV * N_total / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(nbytes),
            "ms_per_step": e2e_ms, "steps": e2e_steps, "check_max_abs_y": float(np.abs(hy).max()),
-           "note": "per step: x from pinned host memory -> y = A x -> y into pinned host memory; single GPU: pipelined in z-chunks over three streams (s3d_spmv_host), multi-GPU: upload, halo exchange + SMat::apply, download"}
+           "note": "per step and rank: x from pinned host memory -> y = A x -> y into pinned host memory, pipelined in z-chunks over three streams (s3d_spmv_host); "
+                   "on z-slabs the two boundary planes go up first and travel through the neighbours' peer-memory windows"}
+    if e2e_same is not None:
+        e2e["equals_device_resident_result"] = e2e_same
     ctx.host_free(hx_p); ctx.host_free(hy_p)
+    del hx, hy
 
     # ---- extras: the solvers through the reference's call sequence (not part of the timed steps)
-    solve = {}
-    if not a.no_solve:
-        try:
-            b = H.Vec(mesh)
-            b.set(xh)
-            u = H.Vec(mesh)
-            opts = {"-s3d_ksp_type": "cg", "-s3d_pc_type": "jacobi", "-ksp_rtol": 1e-6, "-ksp_max_it": a.cg_max_it}
-            H.set_options(opts)
-            (s, _) = H._capture_stdout(lambda: H.Solver(A))
-            s.update()
+    solve, summary = {}, {}
+
+    def timed_solve(Am, bv, uv, opts, repeats=1):
+        """createSolver -> updateOperator -> apply; wall time of apply, max over ranks; best of `repeats` (each from a zero guess)."""
+        H.set_options(opts)
+        sv = quiet(lambda: H.Solver(Am))
+        sv.update()
+        best, info = None, None
+        for _ in range(repeats):
+            H.vecset(0.0, uv)
             barrier()
             t0 = time.perf_counter()
-            info, _ = H._capture_stdout(lambda: s.apply(b, u))
+            info = quiet(lambda: sv.apply(bv, uv))
             H.sync()
             dt = max_over_ranks(time.perf_counter() - t0)
+            best = dt if best is None else min(best, dt)
+        del sv
+        return best, info
+
+    SGS = {"-s3d_pc_apply_sweeps": 1, "-s3d_thread_chunk_size": 1024, "-s3d_pc_use_threaded_apply": "false"}
+    if not a.no_solve:
+        try:
+            # (1) weak: CG + Jacobi on the bench grid (512^3 per GPU), to rtol 1e-6
+            b = H.Vec(mesh); b.set(xh)
+            u = H.Vec(mesh)
+            dt, info = timed_solve(A, b, u, {"-s3d_ksp_type": "cg", "-s3d_pc_type": "jacobi", "-ksp_rtol": 1e-6, "-ksp_max_it": a.cg_max_it})
             solve["cg_jacobi_poisson"] = {"grid": f"{nx}x{ny}x{nzg}", "rhs": "golden non-eigenvector field (SURVEY 8d)", "rtol": 1e-6, "seconds": dt,
                                           "iters": info["iters"], "converged": info["converged"], "rel_res": info["resnorm"] / H.norm_vector_l2(b),
                                           "ms_per_iter": dt * 1e3 / max(1, info["iters"]),
                                           "credited_gbs": BYTES_CG_ITER * N_total * info["iters"] / dt / 1e9, "moved_bytes_per_point_iter": 160}
-            del s, u, b
-            # north_star's scaling target: CG+Jacobi Poisson on a FIXED 1024^3 grid (strong scaling over the z-slabs),
-            # a fixed number of iterations so that every N does the same work; the driver/judge derives the efficiency
+            del u, b
+            del y, x, A
+            # (2) BASELINE's metric: solves to rtol 1e-6 on a FIXED 512^3 grid at every GPU count (strong scaling of a whole solve)
+            nf = a.fixed
+            if nf > 0 and nf >= world:
+                mf = quiet(lambda: H.Mesh((nf + 2, nf + 2, nf + 2)))
+                Af = pde.lhs(mf)
+                nzf = mf.local[2]
+                bf, uf = H.Vec(mf), H.Vec(mf)
+                gf = golden_field(nf ** 3, (nf, nf, nf))
+                ch = np.zeros((nzf + 2, nf + 2, nf + 2)); ch[1:-1, 1:-1, 1:-1] = gf[mf.k0:mf.k0 + nzf]
+                bf.set(ch); del ch, gf
+                dt, info = timed_solve(Af, bf, uf, {"-s3d_ksp_type": "cg", "-s3d_pc_type": "jacobi", "-ksp_rtol": 1e-6, "-ksp_max_it": a.cg_max_it})
+                solve["cg_jacobi_poisson_fixed"] = {"grid_total": f"{nf}^3", "grid_per_gpu": f"{nf}x{nf}x{nzf}", "rtol": 1e-6, "seconds": dt, "iters": info["iters"],
+                                                    "converged": info["converged"], "ms_per_iter": dt * 1e3 / max(1, info["iters"])}
+                summary[f"cg_jacobi_{nf}^3_solve_s"] = dt
+                summary[f"cg_jacobi_{nf}^3_iters"] = info["iters"]
+                del Af, bf, uf
+                pcd = quiet(lambda: H.Pde("convdiff", V, 0.1))
+                Ac, bc, uc = pcd.lhs(mf), pcd.vector(mf, "manufactured_rhs"), H.Vec(mf)
+                o = {"-s3d_ksp_type": "bcgs", "-s3d_pc_type": "sgs", "-ksp_rtol": 1e-6, "-ksp_max_it": 5000}
+                o.update(SGS)
+                dt, info = timed_solve(Ac, bc, uc, o)
+                solve["bicgstab_sgs_convdiff_fixed"] = {"grid_total": f"{nf}^3", "grid_per_gpu": f"{nf}x{nf}x{nzf}", "rtol": 1e-6, "seconds": dt, "iters": info["iters"],
+                                                        "converged": info["converged"], "ms_per_iter": dt * 1e3 / max(1, info["iters"]),
+                                                        "precapply_seconds": info["precapplywtime"],
+                                                        "ordering": "lexicographic (the reference's sweep, exact)" if world == 1 else "slab-local (exact sweep inside every slab)"}
+                summary[f"bicgstab_sgs_{nf}^3_solve_s"] = dt
+                summary[f"bicgstab_sgs_{nf}^3_iters"] = info["iters"]
+                del Ac, bc, uc, mf
+            # (3) north_star's scaling target: CG+Jacobi Poisson on a FIXED 1024^3 grid, a fixed number of iterations so that every N does the
+            #     same work: one warm-up solve, then `strong_repeats` timed solves of `strong_iters` iterations; min and median per iteration
             if a.strong > 0 and a.strong >= world:
                 ns = a.strong
-                del y
-                ms_, _ = H._capture_stdout(lambda: H.Mesh((ns + 2, ns + 2, ns + 2)))
+                ms_ = quiet(lambda: H.Mesh((ns + 2, ns + 2, ns + 2)))
                 As = pde.lhs(ms_)
                 bs_, us_ = H.Vec(ms_), H.Vec(ms_)
                 nzs = ms_.local[2]
@@ -444,85 +537,52 @@ def run_ours(a):
                 chunk[1:-1, 1:-1, 1:-1] = golden_field(ns * ns * nzs, (nzs, ns, ns))   # any non-eigenvector field will do for timing
                 bs_.set(chunk)
                 del chunk
-                def timed_solve(its):
-                    H.set_options({"-s3d_ksp_type": "cg", "-s3d_pc_type": "jacobi", "-ksp_rtol": 1e-300, "-ksp_max_it": its})
-                    (ss, _) = H._capture_stdout(lambda: H.Solver(As))
-                    ss.update()
+                so = {"-s3d_ksp_type": "cg", "-s3d_pc_type": "jacobi", "-ksp_rtol": 1e-300, "-ksp_max_it": a.strong_iters}
+                timed_solve(As, bs_, us_, dict(so, **{"-ksp_max_it": 5}))                 # warm-up (kernel loading, work-vector allocation)
+                H.set_options(so)
+                ss = quiet(lambda: H.Solver(As))
+                ss.update()
+                per = []
+                for _ in range(a.strong_repeats):
                     H.vecset(0.0, us_)
                     barrier()
                     t0 = time.perf_counter()
-                    info_, _ = H._capture_stdout(lambda: ss.apply(bs_, us_))
+                    inf = quiet(lambda: ss.apply(bs_, us_))
                     H.sync()
-                    return max_over_ranks(time.perf_counter() - t0), info_["iters"]
-
-                timed_solve(3)                                        # warm-up (kernel loading, work-vector allocation)
-                ta, ia = timed_solve(a.strong_iters // 2)
-                tb, ib = timed_solve(a.strong_iters + a.strong_iters // 2)
-                per_iter = (tb - ta) / max(1, ib - ia)                # set-up and the initial residual cancel in the difference
-                solve["cg_jacobi_poisson_strong"] = {"grid_total": f"{ns}^3", "grid_per_gpu": f"{ns}x{ns}x{nzs}", "scaling": "strong",
-                                                     "ms_per_iter": per_iter * 1e3, "iters": [ia, ib], "seconds": [ta, tb],
-                                                     "credited_gbs": BYTES_CG_ITER * float(ns) ** 3 / per_iter / 1e9,
-                                                     "moved_gbs": 160 * float(ns) ** 3 / per_iter / 1e9,
-                                                     "note": "fixed iteration counts (rtol disabled); ms_per_iter = (t(ib) - t(ia)) / (ib - ia), identical work at every GPU count"}
-                del us_, bs_, As
-            if world > 1 and n >= 256:
-                # BiCGSTAB + exact (lexicographic) SGS THROUGH the z-slabs (peer-memory pipeline): 256 x 256 x 256 N convection-diffusion
-                mx, _ = H._capture_stdout(lambda: H.Mesh((258, 258, 256 * world + 2)))
-                px, _ = H._capture_stdout(lambda: H.Pde("convdiff", (0.577350269189626, 0.7, 0.3), 0.1))
+                    per.append(max_over_ranks(time.perf_counter() - t0) * 1e3 / max(1, inf["iters"]))
+                del ss
+                per.sort()
+                solve["cg_jacobi_poisson_strong"] = {"grid_total": f"{ns}^3", "grid_per_gpu": f"{ns}x{ns}x{nzs}", "scaling": "strong", "iters_per_solve": a.strong_iters,
+                                                     "repeats": a.strong_repeats, "ms_per_iter_min": per[0], "ms_per_iter_median": per[len(per) // 2], "ms_per_iter_all": per,
+                                                     "credited_gbs": BYTES_CG_ITER * float(ns) ** 3 / (per[0] * 1e-3) / 1e9,
+                                                     "moved_gbs": 160 * float(ns) ** 3 / (per[0] * 1e-3) / 1e9,
+                                                     "note": "fixed iteration count (rtol disabled), whole solve / iterations, incl. set-up of the loop and the initial residual; identical work at every GPU count"}
+                summary[f"cg_jacobi_{ns}^3_strong_ms_per_iter_min"] = per[0]
+                summary[f"cg_jacobi_{ns}^3_strong_ms_per_iter_median"] = per[len(per) // 2]
+                del us_, bs_, As, ms_
+            # (4) BiCGSTAB + SGS on convection-diffusion, 256 x 256 x 256 N (weak), every ordering that applies
+            if n >= 256:
+                mx = quiet(lambda: H.Mesh((258, 258, 256 * world + 2)))
+                px = quiet(lambda: H.Pde("convdiff", V, 0.1))
                 Ax, bx, ux = px.lhs(mx), px.vector(mx, "manufactured_rhs"), H.Vec(mx)
-                H.set_options({"-s3d_ksp_type": "bcgs", "-s3d_pc_type": "sgs", "-ksp_rtol": 1e-6, "-ksp_max_it": 5000, "-s3d_pc_apply_sweeps": 1,
-                               "-s3d_thread_chunk_size": 1024, "-s3d_pc_use_threaded_apply": "false"})
-                (sx, _) = H._capture_stdout(lambda: H.Solver(Ax))
-                sx.update()
-                barrier()
-                t0 = time.perf_counter()
-                ix, _ = H._capture_stdout(lambda: sx.apply(bx, ux))
-                H.sync()
-                dtx = max_over_ranks(time.perf_counter() - t0)
-                solve["bicgstab_sgs_lexicographic_slabs_convdiff256perGPU"] = {"grid": f"256x256x{256 * world}", "seconds": dtx, "iters": ix["iters"],
-                                                                               "converged": ix["converged"], "ms_per_iter": dtx * 1e3 / max(1, ix["iters"]),
-                                                                               "ordering": "lexicographic through the slabs" if a.halo_p2p else "red-black (peer memory switched off)",
-                                                                               "precapply_seconds": ix["precapplywtime"]}
-                del sx, Ax, bx, ux
-            if world == 1 and n >= 256:
-                m2, _ = H._capture_stdout(lambda: H.Mesh((258, 258, 258)))
-                p2, _ = H._capture_stdout(lambda: H.Pde("convdiff", (0.577350269189626, 0.7, 0.3), 0.1))
-                A2, b2, u2 = p2.lhs(m2), p2.vector(m2, "manufactured_rhs"), H.Vec(m2)
-                for pc, extra in (("sgs", {"-s3d_sgs_ordering": "lexicographic"}), ("sgs", {"-s3d_sgs_ordering": "redblack"}),
-                                  ("sgs", {"-s3d_sgs_ordering": "sweeps", "-s3d_pc_apply_sweeps": 2}),
-                                  ("sgs", {"-s3d_sgs_ordering": "sweeps", "-s3d_pc_apply_sweeps": 4}), ("jacobi", {})):
-                    o = {"-s3d_ksp_type": "bcgs", "-s3d_pc_type": pc, "-ksp_rtol": 1e-6, "-ksp_max_it": 5000, "-s3d_pc_apply_sweeps": 1,
-                         "-s3d_thread_chunk_size": 1024, "-s3d_pc_use_threaded_apply": "false"}
-                    o.update(extra)
-                    H.set_options(o)
-                    H.vecset(0.0, u2)
-                    (s2, _) = H._capture_stdout(lambda: H.Solver(A2))
-                    s2.update()
-                    H.sync()
-                    t0 = time.perf_counter()
-                    i2, _ = H._capture_stdout(lambda: s2.apply(b2, u2))
-                    H.sync()
-                    dt2 = time.perf_counter() - t0
-                    key = "bicgstab_" + pc + ("_" + extra["-s3d_sgs_ordering"] if extra else "") + (str(extra["-s3d_pc_apply_sweeps"]) if "-s3d_pc_apply_sweeps" in extra else "") + "_convdiff256"
-                    solve[key] = {"seconds": dt2, "iters": i2["iters"], "converged": i2["converged"], "precapply_seconds": i2["precapplywtime"]}
-                    del s2
-                del A2, b2, u2
-                if n >= 512:
-                    # the metric's own size (BASELINE.json: "CG/BiCGSTAB solve s at 512^3"): BiCGSTAB + exact lexicographic SGS
-                    m3, _ = H._capture_stdout(lambda: H.Mesh((514, 514, 514)))
-                    A3, b3, u3 = p2.lhs(m3), p2.vector(m3, "manufactured_rhs"), H.Vec(m3)
-                    H.set_options({"-s3d_ksp_type": "bcgs", "-s3d_pc_type": "sgs", "-ksp_rtol": 1e-6, "-ksp_max_it": 5000, "-s3d_pc_apply_sweeps": 1,
-                                   "-s3d_thread_chunk_size": 1024, "-s3d_pc_use_threaded_apply": "false", "-s3d_sgs_ordering": "lexicographic"})
-                    (s3, _) = H._capture_stdout(lambda: H.Solver(A3))
-                    s3.update()
-                    H.sync()
-                    t0 = time.perf_counter()
-                    i3, _ = H._capture_stdout(lambda: s3.apply(b3, u3))
-                    H.sync()
-                    dt3 = time.perf_counter() - t0
-                    solve["bicgstab_sgs_lexicographic_convdiff512"] = {"seconds": dt3, "iters": i3["iters"], "converged": i3["converged"],
-                                                                       "precapply_seconds": i3["precapplywtime"], "ms_per_iter": dt3 * 1e3 / max(1, i3["iters"])}
-                    del s3, A3, b3, u3
+                if world == 1:
+                    cases = [("sgs", {"-s3d_sgs_ordering": "lexicographic"}), ("sgs", {"-s3d_sgs_ordering": "redblack"}),
+                             ("sgs", {"-s3d_sgs_ordering": "sweeps", "-s3d_pc_apply_sweeps": 2}), ("jacobi", {})]
+                else:
+                    cases = [("sgs", {"-s3d_sgs_ordering": "slablocal"}), ("sgs", {"-s3d_sgs_ordering": "lexicographic"}), ("sgs", {"-s3d_sgs_ordering": "redblack"})]
+                for pc, extra in cases:
+                    o = {"-s3d_ksp_type": "bcgs", "-s3d_pc_type": pc, "-ksp_rtol": 1e-6, "-ksp_max_it": 5000}
+                    o.update(SGS); o.update(extra)
+                    dt2, i2 = timed_solve(Ax, bx, ux, o)
+                    key = "bicgstab_" + pc + ("_" + extra["-s3d_sgs_ordering"] if extra else "") + (str(extra["-s3d_pc_apply_sweeps"]) if "-s3d_pc_apply_sweeps" in extra else "") + "_convdiff256perGPU"
+                    solve[key] = {"grid": f"256x256x{256 * world}", "seconds": dt2, "iters": i2["iters"], "converged": i2["converged"],
+                                  "ms_per_iter": dt2 * 1e3 / max(1, i2["iters"]), "precapply_seconds": i2["precapplywtime"],
+                                  "precapply_ms_per_apply": i2["precapplywtime"] * 1e3 / max(1, 2 * i2["iters"])}
+                k0_ = "bicgstab_sgs_" + ("lexicographic" if world == 1 else "slablocal") + "_convdiff256perGPU"
+                summary["bicgstab_sgs_256perGPU_ms_per_iter"] = solve[k0_]["ms_per_iter"]
+                summary["bicgstab_sgs_256perGPU_iters"] = solve[k0_]["iters"]
+                summary["sgs_apply_256perGPU_ms"] = solve[k0_]["precapply_ms_per_apply"]
+                del Ax, bx, ux, mx
         except Exception as e:  # the headline numbers above are measured already: report the failure instead of losing the line
             solve["error"] = f"{type(e).__name__}: {e}"[:400]
 
@@ -530,15 +590,16 @@ def run_ours(a):
     if rank == 0 and world == 1 and not a.no_cpu:
         cb = cpu_spmv(n, 5)
     if rank == 0:
+        e2e["solves"] = summary      # whole solves through createSolver()/apply(): the figures BASELINE.json's metric names beside the SpMV rate
         line = {"metric": "spmv_7pt_fp64_hbm_gbs", "value": value, "unit": "GB/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"poisson3d_uniform_{n}^3_fp64_7pt_spmv", "grid_per_gpu": f"{nx}x{ny}x{nzl}", "grid_total": f"{nx}x{ny}x{nzg}",
-                           "decomposition": (f"z-slabs x{world}, one-plane halo " + ("pushed into the neighbours' peer-memory windows (CUDA IPC over NVLink) and read by the SpMV itself" if a.halo_p2p else "by NCCL send/recv")) if world > 1 else "single GPU",
-                           "l2": f"inputs exceed L2: {BYTES_SPMV * N_local / 1e9:.2f} GB streamed per step vs 126 MB L2 (no flush needed)",
-                           "step": "halo exchange (N>1) + SMat::apply (y = A x)", "bytes_per_point": BYTES_SPMV},
+                "config": bench_config(n, world),
+                "decomposition": (f"z-slabs x{world}, one-plane halo " + ("pushed into the neighbours' peer-memory windows (CUDA IPC over NVLink) and read by the SpMV itself" if a.halo_p2p else "by NCCL send/recv")) if world > 1 else "single GPU",
                 "value_frac_of_measured_peak": value / (peak * world), "value_frac_of_nominal_8TBs": value / (8000.0 * world),
                 "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "assembly_seconds": t_assemble, "solve": solve}
+        if halo_check is not None:
+            line["halo_check"] = halo_check
         if cb is not None:
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         _emit(json.dumps(line))
@@ -555,7 +616,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=512, help="unknowns per axis (per GPU along z)")
     ap.add_argument("--strong", type=int, default=1024, help="grid size of the strong-scaling CG block (0 disables)")
-    ap.add_argument("--strong-iters", type=int, default=40)
+    ap.add_argument("--strong-iters", type=int, default=200, help="iterations of each timed strong-scaling solve")
+    ap.add_argument("--strong-repeats", type=int, default=3)
+    ap.add_argument("--fixed", type=int, default=512, help="grid size of the fixed-grid solves to rtol at every GPU count (BASELINE's 'solve s at 512^3'; 0 disables)")
     ap.add_argument("--halo-overlap", type=int, default=0, help="0: exchange halos first, then multiply (A/B switch)")
     ap.add_argument("--halo-p2p", type=int, default=1, help="1: halo planes through peer-memory windows (CUDA IPC), 0: NCCL send/recv (A/B switch)")
     ap.add_argument("--e2e-chunks", type=int, default=32, help="z-chunks of the pipelined host-buffer SpMV (e2e)")

@@ -203,6 +203,8 @@ int  s3d_strilu_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbui
 #define S3D_SGS_LEXICOGRAPHIC 0  /* the reference's ordering, executed as a tile-level dataflow wavefront: same arithmetic */
 #define S3D_SGS_LEXICOGRAPHIC_PLANES 2  /* same result, one launch per hyperplane i+j+k (slow; kept for cross-checks) */
 #define S3D_SGS_REDBLACK      1  /* two-colour ordering: fully parallel half-sweeps (another operator: changes the iteration counts) */
+#define S3D_SGS_SLABLOCAL     4  /* the exact lexicographic sweep INSIDE every z-slab, nothing taken from the neighbouring slabs (block Jacobi across
+                                  * the slab faces): no exchange and no cross-rank wait, so it scales; one rank: identical to LEXICOGRAPHIC */
 #define S3D_SGS_JACOBI_SWEEPS 3  /* nsweeps synchronous Jacobi sweeps per triangular factor: the deterministic counterpart of the
                                   * reference's asynchronous threaded sweeps (threadedapply = true); exact for nsweeps >= nx+ny+nz-2 */
 /* Exact (lexicographic) SGS on a z-slab decomposition: the sweep runs THROUGH the slabs -- the last plane of tiles of rank p pushes its

@@ -30,6 +30,31 @@ def available():
     return os.path.exists(_PATH)
 
 
+def use_perf_build():
+    """bench.py's timing legs only: switch to the performance build of the same sources (oracle/Makefile PERFFLAGS: -O3, FMA
+    contraction, forced SIMD; x86-64-v4 where the host has AVX-512, else v3).  Must be called before the library is first used.
+    Returns a description of the build that will be timed."""
+    global _PATH
+    if _LIB is not None:
+        raise RuntimeError("use_perf_build() must come before the first use of the reference library")
+    flags = ""
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("flags"):
+                    flags = line
+                    break
+    except OSError:
+        pass
+    level = "v4" if all(f" {w}" in flags for w in ("avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl")) else "v3"
+    for lv in (level, "v3"):
+        p = os.path.join(_HERE, "_ref", f"libs3dref_perf_{lv}.so")
+        if os.path.exists(p):
+            _PATH = p
+            return f"-O3 -march=x86-64-{lv} -fopenmp (reference's performance flags; built where the sources are)"
+    return "-O3 -march=x86-64-v3 -ffp-contract=off -DNOFORCESIMD (parity build: no performance build found)"
+
+
 def lib():
     global _LIB
     if _LIB is None:

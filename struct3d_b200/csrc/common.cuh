@@ -55,7 +55,10 @@ struct s3d_ctx {
 	bool capturing = false;       // between s3d_graph_begin and s3d_graph_end
 	int64_t capture_launches0 = 0;
 	int sgs_sleep_ns = 0;
-	int sgs_variant = 0;        // 0: warp-per-tile dataflow kernel, 1: block-per-tile kernel (r1's first version)
+	int sgs_variant = 4;        // 4: warp-per-line streaming kernel (TMA rings + sentinel mailboxes, the default), 0: warp-per-tile dataflow
+	                            // kernel (also what the exact sweep THROUGH z-slabs uses), 1: block-per-tile kernel, 3: r1's warp-per-line experiment
+	unsigned long long *sgs_mail = nullptr;   // streaming kernel: face mailboxes (sentinel-filled outside a sweep)
+	size_t sgs_mail_cap = 0;
 	int sgs_warps_per_sm = 0;   // 0: as many as fit
 	long long *sgs_prof = nullptr;   // timing experiments: per-phase cycle sums of the warp kernel (tuning key sgs_profile)
 	int sgs_tile_i = 0;         // warp kernel: tile length along i, 16 (default) or 32
@@ -76,6 +79,8 @@ struct s3d_ctx {
 	cudaEvent_t comm_ev[2] = {};
 	double *stage = nullptr;       // device staging for contiguous host uploads (repacked into the padded layout on the device)
 	size_t stage_cap = 0;
+	double *stage_y = nullptr;     // device staging for contiguous host downloads (results packed into the host layout on the device)
+	size_t stage_y_cap = 0;
 	int *h_slots = nullptr;        // 8 pinned slots of 8 ints for pipelined flag polling
 	cudaEvent_t slot_ev[8] = {};
 	cudaEvent_t *chunk_ev = nullptr;

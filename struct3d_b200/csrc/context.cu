@@ -143,7 +143,7 @@ int s3d_ctx_destroy(s3d_ctx *ctx)
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
 	cudaFree(ctx->partials); cudaFree(ctx->ticket); cudaFree(ctx->tab); cudaFree(ctx->red_tmp);
-	cudaFree(ctx->sgs_flags); cudaFree(ctx->sgs_ctl); cudaFree(ctx->sgs_iface); cudaFree(ctx->sgs_order); cudaFree(ctx->sweep_buf); cudaFree(ctx->stage);
+	cudaFree(ctx->sgs_flags); cudaFree(ctx->sgs_ctl); cudaFree(ctx->sgs_iface); cudaFree(ctx->sgs_order); cudaFree(ctx->sgs_mail); cudaFree(ctx->sweep_buf); cudaFree(ctx->stage); cudaFree(ctx->stage_y);
 	cudaFreeHost(ctx->h_pinned);
 	if (ctx->h_slots) { cudaFreeHost(ctx->h_slots); for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->slot_ev[i]); }
 	cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);

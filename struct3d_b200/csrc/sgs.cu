@@ -1015,12 +1015,20 @@ __global__ void sgs_begin_kernel(int *ctl, const int *stop)
 	ctl[1] += 1;
 }
 
-// flags / dispatch table / occupancy for the dataflow kernels; returns the number of persistent blocks
-int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblocks)
+// which build of the exact sweep runs: the streaming kernel (4) works inside one slab; a sweep that has to run THROUGH the z-slabs
+// (exact lexicographic ordering on a decomposed grid) is the warp-per-tile kernel's (0)
+inline int sgs_effective_variant(const s3d_ctx *ctx, const s3d_grid *g, bool through_slabs)
 {
-	const bool lines = (ctx->sgs_variant == 3);
-	const int tile_i = lines ? 16 : (ctx->sgs_variant == 0) ? sgw_tile_i(ctx) : SGS_TI;
-	const int tile_j = lines ? 4 : (ctx->sgs_variant == 0) ? 4 * sgw_pencils(ctx, g) : SGS_TJ;
+	if (ctx->sgs_variant == 4 && through_slabs && g->nranks > 1) return 0;
+	return ctx->sgs_variant;
+}
+
+// flags / dispatch table / occupancy for the dataflow kernels; returns the number of persistent blocks
+int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblocks, int variant)
+{
+	const bool lines = (variant == 3 || variant == 4);
+	const int tile_i = lines ? 16 : (variant == 0) ? sgw_tile_i(ctx) : SGS_TI;
+	const int tile_j = lines ? 4 : (variant == 0) ? 4 * sgw_pencils(ctx, g) : SGS_TJ;
 	// lines: "ntx" is the number of 16-column flag blocks of a line (backward sweeps start at the top of the last 8-column group)
 	f.ntx = lines ? (((g->nx + 7) / 8) * 8 + 15) / 16 : (g->nx + tile_i - 1) / tile_i;
 	f.nty = (g->ny + tile_j - 1) / tile_j; f.ntz = (g->nz + SGS_TK - 1) / SGS_TK;
@@ -1078,6 +1086,7 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 	f.prof = ctx->sgs_prof;
 	f.ticket = reinterpret_cast<unsigned *>(ctx->sgs_ctl);
 	f.epoch_p = ctx->sgs_ctl + 1;
+	if (variant == 4) { nblocks = 0; return S3D_OK; }   // the streaming kernel sizes its own launch (sgs_stream.cu)
 	if (lines) {
 		static bool lconfigured = false;
 		static int lines_per_sm = 1;
@@ -1096,7 +1105,7 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 		nblocks = (unsigned)std::min<size_t>((size_t)f.nty * f.ntz, (size_t)ctx->sm_count * wps);
 		return S3D_OK;
 	}
-	if (ctx->sgs_variant == 0) {
+	if (variant == 0) {
 		if (ctx->sgs_iface_cap < ntiles * 64) {
 			S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 			if (ctx->sgs_iface) S3D_CUDA(ctx, cudaFree(ctx->sgs_iface));
@@ -1126,6 +1135,10 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 }  // namespace
 
 extern "C" S3D_HIDDEN int s3d_internal_sgs_window(s3d_ctx *ctx, const s3d_grid *g, int ntx, int nty, s3d_sgs_window *out);
+extern "C" S3D_HIDDEN int s3d_internal_sgs_stream(s3d_ctx *ctx, const s3d_grid *g, int mode, const double *in0, const double *c0,
+                                                  const double *c1, const double *c2, const double *dinv, double *out,
+                                                  const int *order, int nty, int ntz, unsigned *ticket, int klo_zero, int khi_zero,
+                                                  const int *stop);
 
 extern "C" {
 
@@ -1135,10 +1148,10 @@ int s3d_sgs_slab_sweeps_available(s3d_ctx *ctx, const s3d_grid *g, int *yes)
 	S3D_REQUIRE(ctx, g && yes, "null argument");
 	*yes = 0;
 	if (g->nranks == 1) { *yes = 1; return S3D_OK; }
-	if (ctx->sgs_variant != 0) return S3D_OK;
+	if (sgs_effective_variant(ctx, g, true) != 0) return S3D_OK;
 	SgsFlow f;
 	unsigned nblocks = 0;
-	int rc = sgs_flow_prepare(ctx, g, f, nblocks);
+	int rc = sgs_flow_prepare(ctx, g, f, nblocks, 0);
 	if (rc != S3D_OK) return rc;
 	s3d_sgs_window xw;
 	rc = s3d_internal_sgs_window(ctx, g, f.ntx, f.nty, &xw);
@@ -1203,20 +1216,37 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		}
 		return S3D_OK;
 	}
-	if (ordering != S3D_SGS_LEXICOGRAPHIC && ordering != S3D_SGS_LEXICOGRAPHIC_PLANES)
+	if (ordering != S3D_SGS_LEXICOGRAPHIC && ordering != S3D_SGS_LEXICOGRAPHIC_PLANES && ordering != S3D_SGS_SLABLOCAL)
 		return s3d_fail(ctx, S3D_ERR_ARG, "unknown SGS ordering %d", ordering);
-	if (g->nranks > 1 && (ordering != S3D_SGS_LEXICOGRAPHIC || ctx->sgs_variant != 0))
-		return s3d_fail(ctx, S3D_ERR_ARG, "across z-slabs only the warp-per-tile lexicographic sweep (or red-black / sweeps) is available");
+	// slab-local: the exact lexicographic sweep inside every z-slab, nothing taken from the neighbouring slabs (block Jacobi across the
+	// slab faces): no exchange, no cross-rank wait.  On one rank it IS the lexicographic sweep.
+	const bool slablocal = (ordering == S3D_SGS_SLABLOCAL);
+	if (slablocal) ordering = S3D_SGS_LEXICOGRAPHIC;
+	const int variant = sgs_effective_variant(ctx, g, !slablocal);
+	if (g->nranks > 1 && !slablocal && (ordering != S3D_SGS_LEXICOGRAPHIC || variant != 0))
+		return s3d_fail(ctx, S3D_ERR_ARG, "across z-slabs only the warp-per-tile lexicographic sweep (or slab-local / red-black / sweeps) is available");
+	if (g->nranks > 1 && slablocal && variant != 4)
+		return s3d_fail(ctx, S3D_ERR_ARG, "the slab-local ordering runs on the streaming kernel (sgs_variant 4)");
 	// the scratch vector's real entries are all overwritten and its ghosts stay zero (they are never
 	// written), so the per-call zero fill of the reference (s3d_sgspreconditioners.cpp:25-28) is implicit.
 	// Sequential sweeps are idempotent, so nsweeps > 1 repeats identical work; do one.
 	if (ordering == S3D_SGS_LEXICOGRAPHIC) {
 		SgsFlow f;
 		unsigned nblocks = 0;
-		const int rcp = sgs_flow_prepare(ctx, g, f, nblocks);
+		const int rcp = sgs_flow_prepare(ctx, g, f, nblocks, variant);
 		if (rcp != S3D_OK) return rcp;
 		dim3 block(SGS_NT);
 		const long long cs = g->cstride;
+		if (variant == 4) {
+			const int klo = slablocal && g->rank > 0, khi = slablocal && g->rank < g->nranks - 1;
+			sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
+			S3D_LAUNCHED(ctx);
+			int rcs = s3d_internal_sgs_stream(ctx, g, 0, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f.order, f.nty, f.ntz, f.ticket, klo, khi, ctx->gate);
+			if (rcs != S3D_OK) return rcs;
+			sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
+			S3D_LAUNCHED(ctx);
+			return s3d_internal_sgs_stream(ctx, g, 1, d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f.order, f.nty, f.ntz, f.ticket, klo, khi, ctx->gate);
+		}
 		s3d_sgs_window xw;
 		if (g->nranks > 1) {
 			// the sweep runs THROUGH the slabs: rank p's first plane of tiles waits for rank p-1's last one (peer-memory window)
@@ -1227,9 +1257,9 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		}
 		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
 		S3D_LAUNCHED(ctx);
-		if (ctx->sgs_variant == 3)
+		if (variant == 3)
 			sgs_lineflow_kernel<0, 1><<<nblocks, 32, sgl_smem(5, 1), ctx->stream>>>(gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, ctx->gate);
-		else if (ctx->sgs_variant == 0)
+		else if (variant == 0)
 			sgw_launch<0>(ctx, g, nblocks, gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, (const int *)ctx->gate);
 		else
 			sgs_dataflow_kernel<0><<<nblocks, block, SGS_SMEM, ctx->stream>>>(gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, ctx->gate);
@@ -1237,9 +1267,9 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		if (g->nranks > 1) { f.x_in_plane = xw.bwd_in_plane; f.x_in_flags = xw.bwd_in_flags; f.x_out_plane = xw.bwd_out_plane; f.x_out_flags = xw.bwd_out_flags; }
 		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
 		S3D_LAUNCHED(ctx);
-		if (ctx->sgs_variant == 3)
+		if (variant == 3)
 			sgs_lineflow_kernel<1, 1><<<nblocks, 32, sgl_smem(5, 1), ctx->stream>>>(gd, d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f, ctx->gate);
-		else if (ctx->sgs_variant == 0)
+		else if (variant == 0)
 			sgw_launch<1>(ctx, g, nblocks, gd, (const double *)d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f, (const int *)ctx->gate);
 		else
 			sgs_dataflow_kernel<1><<<nblocks, block, SGS_SMEM, ctx->stream>>>(gd, d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f, ctx->gate);
@@ -1283,16 +1313,21 @@ int s3d_strilu_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuil
 	ctx->launches++;
 	SgsFlow f;
 	unsigned nblocks = 0;
-	int rc = sgs_flow_prepare(ctx, g, f, nblocks);
+	const int variant = ctx->sgs_variant;
+	int rc = sgs_flow_prepare(ctx, g, f, nblocks, variant);
 	if (rc == S3D_OK) {
 		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, nullptr);
 		ctx->launches++;
 		e = cudaGetLastError();
 		if (e == cudaSuccess) {
-			if (ctx->sgs_variant == 3)
+			if (variant == 4) {
+				rc = s3d_internal_sgs_stream(ctx, g, 2, A + 3 * (size_t)g->cstride, P, P + g->cstride, P + 2 * (size_t)g->cstride, nullptr, D,
+				                             f.order, f.nty, f.ntz, f.ticket, 0, 0, nullptr);
+				ctx->launches--;   // counted below
+			} else if (variant == 3)
 				sgs_lineflow_kernel<2, 1><<<nblocks, 32, sgl_smem(4, 1), ctx->stream>>>(gd, A + 3 * (size_t)g->cstride, P, P + g->cstride, P + 2 * (size_t)g->cstride,
 				                                                                         nullptr, D, f, nullptr);
-			else if (ctx->sgs_variant == 0)
+			else if (variant == 0)
 				sgw_launch<2>(ctx, g, nblocks, gd, A + 3 * (size_t)g->cstride, (const double *)P, (const double *)(P + g->cstride),
 				              (const double *)(P + 2 * (size_t)g->cstride), (const double *)nullptr, D, f, (const int *)nullptr);
 			else

@@ -505,27 +505,37 @@ int s3d_spmv_exchange(s3d_ctx *ctx, const s3d_grid *g, const double *A, double *
 // directions run concurrently and the kernel hides behind them.  h_x / h_y: host arrays in the SVec layout (pinned memory for
 // full speed); d_x / d_y: device vectors used as staging (contents are overwritten; d_y's ghost planes must be zero, as
 // after s3d_vec_alloc).  Blocks until h_y is complete.
+// On a z-slab (g->nranks > 1, collective over the ranks) every rank passes its own slab: its first and last real plane of x go up
+// first and are pushed into the neighbours' peer-memory windows, the interior chunks follow as on one GPU, and the two chunks that
+// touch a neighbour's plane are multiplied last, reading it from the window (they are the only blocks that may wait).  The host
+// ghost planes of x at interior cuts are ignored (the neighbour owns those values); without peer memory the planes travel by NCCL.
 int s3d_spmv_host(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *h_x, double *h_y, double *d_x, double *d_y,
                   const double *d_b, int nchunks)
 {
 	S3D_REQUIRE(ctx, g && A && h_x && h_y && d_x && d_y, "null argument");
-	S3D_REQUIRE(ctx, g->nranks == 1, "the host-buffer SpMV is a single-GPU call");
+	const bool slab = g->nranks > 1;
+	S3D_REQUIRE(ctx, !slab || ctx->comm, "a z-slab needs s3d_comm_init");
 	if (nchunks <= 0) nchunks = 16;
 	if (nchunks > g->nz) nchunks = g->nz;
+	if (slab && nchunks < 3 && g->nz >= 3) nchunks = 3;
 	if (!ctx->up_stream) {
 		S3D_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
 		S3D_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
 	}
-	if (ctx->chunk_ev_cap < 2 * nchunks + 1) {
-		cudaEvent_t *ne = (cudaEvent_t *)realloc(ctx->chunk_ev, (2 * nchunks + 1) * sizeof(cudaEvent_t));
+	const int nev = 2 * nchunks + 2;
+	if (ctx->chunk_ev_cap < nev) {
+		cudaEvent_t *ne = (cudaEvent_t *)realloc(ctx->chunk_ev, nev * sizeof(cudaEvent_t));
 		if (!ne) return s3d_fail(ctx, S3D_ERR_ARG, "out of host memory");
-		for (int i = ctx->chunk_ev_cap; i < 2 * nchunks + 1; i++) S3D_CUDA(ctx, cudaEventCreateWithFlags(&ne[i], cudaEventDisableTiming));
-		ctx->chunk_ev = ne; ctx->chunk_ev_cap = 2 * nchunks + 1;
+		ctx->chunk_ev = ne;
+		for (int i = ctx->chunk_ev_cap; i < nev; i++) {
+			S3D_CUDA(ctx, cudaEventCreateWithFlags(&ne[i], cudaEventDisableTiming));
+			ctx->chunk_ev_cap = i + 1;
+		}
 	}
 	const size_t hrow = (size_t)(g->nx + 2) * sizeof(double), drow = (size_t)g->vpitch * sizeof(double);
 	const size_t rows_per_plane = (size_t)(g->ny + 2);
 	const size_t hplane = (size_t)(g->nx + 2) * rows_per_plane;     // doubles per host plane
-	const size_t glen = hplane * (g->nz + 2);
+	const size_t glen = hplane * (g->nz + 2 + (slab ? 2 : 0));
 	if (ctx->stage_cap < glen) {
 		S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 		if (ctx->stage) S3D_CUDA(ctx, cudaFree(ctx->stage));
@@ -533,11 +543,70 @@ int s3d_spmv_host(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		S3D_CUDA(ctx, cudaMalloc(&ctx->stage, glen * sizeof(double)));
 		ctx->stage_cap = glen;
 	}
+	if (ctx->stage_y_cap < glen) {
+		S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		if (ctx->stage_y) S3D_CUDA(ctx, cudaFree(ctx->stage_y));
+		ctx->stage_y = nullptr; ctx->stage_y_cap = 0;
+		S3D_CUDA(ctx, cudaMalloc(&ctx->stage_y, glen * sizeof(double)));
+		ctx->stage_y_cap = glen;
+	}
 	// the copy streams must not start before earlier work on the compute stream (previous users of d_x / d_y) is done
 	cudaEvent_t start = ctx->chunk_ev[2 * nchunks];
 	S3D_CUDA(ctx, cudaEventRecord(start, ctx->stream));
 	S3D_CUDA(ctx, cudaStreamWaitEvent(ctx->up_stream, start, 0));
 	S3D_CUDA(ctx, cudaStreamWaitEvent(ctx->down_stream, start, 0));
+	// repack ghosted planes [from, to) of the staging buffer into the padded device layout (compute stream)
+	auto repack = [&](const double *src, int from, int to) -> cudaError_t {
+		return cudaMemcpy2DAsync(d_x + (size_t)from * g->vplane + g->vlead - 1, drow, src, hrow, hrow, rows_per_plane * (to - from),
+		                         cudaMemcpyDeviceToDevice, ctx->stream);
+	};
+	s3d_halo_view hv;
+	const bool has_lo = slab && g->rank > 0, has_hi = slab && g->rank + 1 < g->nranks;
+	if (slab) {
+		// my two boundary planes first: the neighbours need them before anything else
+		double *bst = ctx->stage + hplane * (g->nz + 2);
+		S3D_CUDA(ctx, cudaMemcpyAsync(bst, h_x + hplane, hplane * sizeof(double), cudaMemcpyHostToDevice, ctx->up_stream));
+		S3D_CUDA(ctx, cudaMemcpyAsync(bst + hplane, h_x + hplane * g->nz, hplane * sizeof(double), cudaMemcpyHostToDevice, ctx->up_stream));
+		cudaEvent_t bev = ctx->chunk_ev[2 * nchunks + 1];
+		S3D_CUDA(ctx, cudaEventRecord(bev, ctx->up_stream));
+		S3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, bev, 0));
+		S3D_CUDA(ctx, repack(bst, 1, 2));
+		S3D_CUDA(ctx, repack(bst + hplane, g->nz, g->nz + 1));
+		int rc = s3d_internal_halo_push(ctx, g, d_x, &hv);
+		if (rc != S3D_OK) return rc;
+		if (!hv.epoch) {
+			rc = s3d_halo_exchange(ctx, g, d_x);      // NCCL: fills the ghost planes of d_x, which the repacks below leave alone
+			if (rc != S3D_OK) return rc;
+		}
+	}
+	auto multiply = [&](int c, int k0, int k1) -> int {
+		s3d_grid sub = *g;
+		sub.nz = k1 - k0;
+		const size_t voff = (size_t)k0 * g->vplane, coff = (size_t)k0 * g->cplane;
+		int rc;
+		if (hv.epoch && ((k0 == 0 && hv.lo) || (k1 == g->nz && hv.hi))) {
+			s3d_halo_view h = hv;
+			if (k0 != 0) { h.lo = nullptr; h.flag_lo = nullptr; }
+			if (k1 != g->nz) { h.hi = nullptr; h.flag_hi = nullptr; }
+			rc = launch_march<8, 3>(ctx, &sub, A + coff, d_x + voff, d_y + voff, d_b ? d_b + voff : nullptr, nullptr, false, nullptr, ctx->gate,
+			                        pick_kchunk(ctx, &sub, false), &h);
+		} else {
+			rc = s3d_spmv(ctx, &sub, A + coff, d_x + voff, d_y + voff, d_b ? d_b + voff : nullptr, nullptr, 0, nullptr, nullptr, S3D_SPMV_AUTO);
+		}
+		if (rc != S3D_OK) return rc;
+		// y: the chunk's real planes, plus the bottom / top ghost plane with the first / last chunk (ghosted planes [lo, hi)):
+		// packed into the host layout on the device, then ONE contiguous D2H copy (pitched copies run slower while the other PCIe
+		// direction is busy)
+		const int lo = (c == 0) ? 0 : k0 + 1, hi = (c == nchunks - 1) ? g->nz + 2 : k1 + 1;
+		S3D_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_y + (size_t)lo * hplane, hrow, d_y + (size_t)lo * g->vplane + g->vlead - 1, drow, hrow,
+		                                rows_per_plane * (hi - lo), cudaMemcpyDeviceToDevice, ctx->stream));
+		S3D_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[2 * c + 1], ctx->stream));
+		S3D_CUDA(ctx, cudaStreamWaitEvent(ctx->down_stream, ctx->chunk_ev[2 * c + 1], 0));
+		S3D_CUDA(ctx, cudaMemcpyAsync(h_y + (size_t)lo * hplane, ctx->stage_y + (size_t)lo * hplane, (size_t)(hi - lo) * hplane * sizeof(double),
+		                              cudaMemcpyDeviceToHost, ctx->down_stream));
+		return S3D_OK;
+	};
+	const bool defer_first = hv.epoch && has_lo && nchunks > 1, defer_last = hv.epoch && has_hi && nchunks > 1;
 	int up_to = 0;   // ghosted planes [0, up_to) of x are enqueued for upload
 	for (int c = 0; c < nchunks; c++) {
 		const int k0 = (int)((long long)c * g->nz / nchunks), k1 = (int)((long long)(c + 1) * g->nz / nchunks);   // real planes [k0, k1)
@@ -552,21 +621,22 @@ int s3d_spmv_host(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		}
 		S3D_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[2 * c], ctx->up_stream));
 		S3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[2 * c], 0));
-		// ... then repacked into the padded row layout on the device, at HBM speed
-		if (up_to > from)
-			S3D_CUDA(ctx, cudaMemcpy2DAsync(d_x + (size_t)from * g->vplane + g->vlead - 1, drow, ctx->stage + (size_t)from * hplane, hrow, hrow,
-			                                rows_per_plane * (up_to - from), cudaMemcpyDeviceToDevice, ctx->stream));
-		s3d_grid sub = *g;
-		sub.nz = k1 - k0;
-		const size_t voff = (size_t)k0 * g->vplane, coff = (size_t)k0 * g->cplane;
-		const int rc = s3d_spmv(ctx, &sub, A + coff, d_x + voff, d_y + voff, d_b ? d_b + voff : nullptr, nullptr, 0, nullptr, nullptr, S3D_SPMV_AUTO);
+		// ... then repacked into the padded row layout on the device, at HBM speed (ghost planes at interior cuts stay as they are)
+		if (up_to > from) {
+			const int rf = (has_lo && from == 0) ? 1 : from, rt = (has_hi && up_to == g->nz + 2) ? g->nz + 1 : up_to;
+			if (rt > rf) S3D_CUDA(ctx, repack(ctx->stage + (size_t)rf * hplane, rf, rt));
+		}
+		if ((c == 0 && defer_first) || (c == nchunks - 1 && defer_last)) continue;
+		const int rc = multiply(c, k0, k1);
 		if (rc != S3D_OK) return rc;
-		S3D_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[2 * c + 1], ctx->stream));
-		S3D_CUDA(ctx, cudaStreamWaitEvent(ctx->down_stream, ctx->chunk_ev[2 * c + 1], 0));
-		// y: the chunk's real planes, plus the bottom / top ghost plane with the first / last chunk (ghosted planes [lo, hi))
-		const int lo = (c == 0) ? 0 : k0 + 1, hi = (c == nchunks - 1) ? g->nz + 2 : k1 + 1;
-		S3D_CUDA(ctx, cudaMemcpy2DAsync(h_y + (size_t)lo * hplane, hrow, d_y + (size_t)lo * g->vplane + g->vlead - 1, drow, hrow,
-		                                rows_per_plane * (hi - lo), cudaMemcpyDeviceToHost, ctx->down_stream));
+	}
+	if (defer_first) {
+		const int rc = multiply(0, 0, (int)((long long)g->nz / nchunks));
+		if (rc != S3D_OK) return rc;
+	}
+	if (defer_last) {
+		const int rc = multiply(nchunks - 1, (int)((long long)(nchunks - 1) * g->nz / nchunks), g->nz);
+		if (rc != S3D_OK) return rc;
 	}
 	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->down_stream));
 	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -1,8 +1,12 @@
 // Process-wide GPU context and the coherent host mirror (see s3d_device.hpp).
 #include <chrono>
 #include <cstdlib>
-#include <fstream>
+#include <cstring>
+#include <string>
 #include <thread>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include "s3d_device.hpp"
 
 namespace s3d {
@@ -47,24 +51,40 @@ void Device::initialize_from_env()
 	if (world <= 1) { get(); return; }
 	const int rank = env_int("RANK", 0);
 	const int local = env_int("LOCAL_RANK", rank);
-	const std::string path = std::string("/tmp/s3d_nccl_id_") + (std::getenv("MASTER_PORT") ? std::getenv("MASTER_PORT") : "0")
-	                         + "_" + (std::getenv("TORCHELASTIC_RUN_ID") ? std::getenv("TORCHELASTIC_RUN_ID") : "run");
+	// The NCCL id travels from rank 0 to the other ranks of THIS launch through a small file.  Its name carries the launcher's pid
+	// (all ranks are children of one torchrun agent), so a file left by an earlier launch on the same port can never be picked up;
+	// it is created exclusively with mode 0600 (no following of planted links) and removed once every rank has joined.
+	const char *tmpdir = std::getenv("TMPDIR");
+	const std::string path = std::string(tmpdir && *tmpdir ? tmpdir : "/tmp") + "/s3d_nccl_id_" + std::to_string((long)getuid()) + "_"
+	                         + (std::getenv("MASTER_PORT") ? std::getenv("MASTER_PORT") : "0") + "_" + std::to_string((long)getppid());
+	struct Record { char magic[8]; long ppid; char id[S3D_COMM_ID_BYTES]; } rec;
 	char id[S3D_COMM_ID_BYTES];
 	if (rank == 0) {
 		if (s3d_comm_unique_id(id) != S3D_OK) throw std::runtime_error("s3d_comm_unique_id failed");
-		std::ofstream f(path + ".tmp", std::ios::binary);
-		f.write(id, sizeof id);
-		f.close();
-		std::rename((path + ".tmp").c_str(), path.c_str());
+		std::memcpy(rec.magic, "S3DNCCL", 8); rec.ppid = (long)getppid(); std::memcpy(rec.id, id, sizeof id);
+		const std::string tmp = path + ".tmp";
+		::unlink(tmp.c_str());
+		::unlink(path.c_str());                     // same launcher pid, same port: can only be a leftover of a crashed attempt of ours
+		const int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW, 0600);
+		if (fd < 0 || ::write(fd, &rec, sizeof rec) != (ssize_t)sizeof rec) { if (fd >= 0) ::close(fd); throw std::runtime_error("cannot write the NCCL id file " + tmp); }
+		::close(fd);
+		if (std::rename(tmp.c_str(), path.c_str()) != 0) throw std::runtime_error("cannot publish the NCCL id file " + path);
 	} else {
 		for (int tries = 0;; tries++) {
-			std::ifstream f(path, std::ios::binary);
-			if (f && f.read(id, sizeof id)) break;
-			if (tries > 3000) throw std::runtime_error("timed out waiting for the NCCL id file " + path);
+			const int fd = ::open(path.c_str(), O_RDONLY | O_NOFOLLOW);
+			if (fd >= 0) {
+				struct stat st;
+				const bool mine = ::fstat(fd, &st) == 0 && st.st_uid == getuid() && (st.st_mode & 077) == 0;
+				const bool got = mine && ::read(fd, &rec, sizeof rec) == (ssize_t)sizeof rec && !std::memcmp(rec.magic, "S3DNCCL", 8) && rec.ppid == (long)getppid();
+				::close(fd);
+				if (got) { std::memcpy(id, rec.id, sizeof id); break; }
+			}
+			if (tries > 6000) throw std::runtime_error("timed out waiting for the NCCL id file " + path);
 			std::this_thread::sleep_for(std::chrono::milliseconds(10));
 		}
 	}
-	initialize(local, rank, world, id);
+	initialize(local, rank, world, id);            // ncclCommInitRank is collective: every rank has read the id when it returns
+	if (rank == 0) ::unlink(path.c_str());
 }
 
 void Device::shutdown()

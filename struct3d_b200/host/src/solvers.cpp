@@ -234,12 +234,17 @@ SGS_like_preconditioner::SGS_like_preconditioner(const SMat &lhs, const PreconPa
 {
 	const Device &d = Device::get();
 	diaginv = d.scalars((int)std::min<long long>(A.grid().cstride, INT_MAX));
+	// On z-slabs the default is the slab-local ordering: the reference's lexicographic sweep inside every slab, no coupling across
+	// the slab faces (it needs no exchange and no cross-rank wait, so it scales with the GPU count; measured iteration counts in
+	// profiles/r2_sgs_slablocal.md).  `-s3d_sgs_ordering lexicographic` asks for the exact sweep THROUGH the slabs (a pipeline).
+	if (d.nranks() > 1) order = S3D_SGS_SLABLOCAL;
 	if (s3d::options_has("-s3d_sgs_ordering")) {
 		const std::string o = petscoptions_get_string("-s3d_sgs_ordering", 40);
 		if (o == "redblack" || o == "multicolour" || o == "multicolor") order = S3D_SGS_REDBLACK;
 		else if (o == "lexicographic") order = S3D_SGS_LEXICOGRAPHIC;
+		else if (o == "slablocal") order = S3D_SGS_SLABLOCAL;
 		else if (o == "sweeps" || o == "jacobi_sweeps" || o == "async") order = S3D_SGS_JACOBI_SWEEPS;
-		else throw std::runtime_error("-s3d_sgs_ordering must be lexicographic, redblack or sweeps");
+		else throw std::runtime_error("-s3d_sgs_ordering must be lexicographic, slablocal, redblack or sweeps");
 	}
 	if (d.nranks() > 1 && order == S3D_SGS_LEXICOGRAPHIC) {
 		// the exact sweep can run through the slabs as a pipeline over peer memory (same iterations as one GPU); without the

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Times the exact-lexicographic SGS apply: warp-per-tile (variant 0) against block-per-tile (variant 1), and warps per SM."""
+"""Times the exact-lexicographic SGS apply: streaming warp-per-line kernel (variant 4, the default) against warp-per-tile (variant 0)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -17,7 +17,7 @@ for n in sizes:
     ctx.tune("sgs_variant", 0)
     ctx.sgs_apply(g, A, dinv, r, zr, y, capi.SGS_LEXICOGRAPHIC, 1)
     ref = ctx.vec_download(g, zr)
-    for variant, wps, depth, dbgv in ((0, 0, 16, 2), (0, 0, 16, 1), (0, 0, 0, 0)):
+    for variant, wps, depth, dbgv in ((0, 0, 0, 0), (4, 0, 0, 0), (4, 3, 0, 0), (4, 2, 0, 0)):
         ctx.tune("sgs_variant", variant); ctx.tune("sgs_warps_per_sm", wps); ctx.tune("sgs_tile_i", depth)
         ctx.tune("sgs_pencils", dbgv)
         for _ in range(2): ctx.sgs_apply(g, A, dinv, r, z, y, capi.SGS_LEXICOGRAPHIC, 1)
@@ -26,7 +26,12 @@ for n in sizes:
         for _ in range(5): ctx.sgs_apply(g, A, dinv, r, z, y, capi.SGS_LEXICOGRAPHIC, 1)
         ms = ctx.timer_stop_ms() / 5
         print(f"{n:4d}^3 variant={variant} warps/SM={wps} tile_i={depth} pencils={dbgv}  {ms:9.4f} ms   {96*n**3/ms/1e6:8.1f} GB/s(96B/pt)  bitwise_same={same}", flush=True)
-    ctx.tune("sgs_variant", 0); ctx.tune("sgs_warps_per_sm", 0); ctx.tune("sgs_tile_i", 0); ctx.tune("sgs_pencils", 0)
+        if variant == 4 and wps == 0 and os.environ.get("SGS_PROF"):
+            import ctypes
+            ctx.tune("sgs_profile", 1)
+            ctx.sgs_apply(g, A, dinv, r, z, y, capi.SGS_LEXICOGRAPHIC, 1)
+            ctx.tune("sgs_profile", 0)
+    ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT); ctx.tune("sgs_warps_per_sm", 0); ctx.tune("sgs_tile_i", 0); ctx.tune("sgs_pencils", 0)
     for dbg in ():
         ctx.tune("sgs_sleep_ns", dbg)
         ctx.tune("sgs_profile", 1)
