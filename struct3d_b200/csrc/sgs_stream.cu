@@ -42,7 +42,10 @@ struct StreamArgs {
 	unsigned *ticket;
 	unsigned long long *mail_j;    // [line][8 k-rows][nxp]   last-j pencils of the line
 	unsigned long long *mail_k;    // [line][TJ j-rows][nxp]  last-k pencils of the line
-	const double *out;             // the output vector, for its ghost column / rows / planes only
+	double *out;                   // the output vector: its ghost column / rows / planes are read; the last column of an odd nx is
+	                               // stored directly (the TMA store's inner bound is 16-byte granular: measured on B200, a box over
+	                               // an odd-length row also writes the element after it -- the ghost column)
+	int nx_tma;                    // nx & ~1: columns the out tensor map covers
 	int klo_zero, khi_zero;        // slab-local sweeps: what lies below k = 0 / above k = nz-1 is taken as zero
 	long long *prof;
 };
@@ -74,16 +77,16 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ ulonglong2 ld_mail2(const unsigned long long *p)
 {
 	ulonglong2 v;
-	asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];\n" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+	asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];\n" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
 	return v;
 }
 __device__ __forceinline__ void st_mail2(unsigned long long *p, unsigned long long a, unsigned long long b)
 {
-	asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};\n" ::"l"(p), "l"(a), "l"(b) : "memory");
+	asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};\n" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 __device__ __forceinline__ void st_mail_if(unsigned long long *p, double v, bool on)
 {
-	asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.relaxed.gpu.global.f64 [%0], %1;\n}\n" ::"l"(p), "d"(v), "r"((unsigned)on) : "memory");
+	asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.global.cg.f64 [%0], %1;\n}\n" ::"l"(p), "d"(v), "r"((unsigned)on) : "memory");
 }
 
 // MODE 0: forward sweep  y = (r - A0 y[i-1] - A1 y[j-1] - A2 y[k-1]) dinv
@@ -152,6 +155,7 @@ sgs_stream_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_const
 		const int pkl = FWD ? (ck > 0 ? line - a.nty : -1) : (ck < a.ntz - 1 ? line + a.nty : -1);
 		const bool jsucc = FWD ? (cj < a.nty - 1) : (cj > 0), ksucc = FWD ? (ck < a.ntz - 1) : (ck > 0);
 		const bool jprod = act && jsucc && (m == tj - 1), kprod = act && ksucc && (cc == tk - 1);
+		double *odd_dst = a.out + a.voff + (long long)(k0 + pk) * a.vplane + (long long)(j0 + pj) * a.vpitch;   // used for column nx-1 of an odd nx only
 		unsigned long long *mj_dst = a.mail_j + ((size_t)line * 8 + pk) * a.nxp;
 		unsigned long long *mk_dst = a.mail_k + ((size_t)line * TJ + pj) * a.nxp;
 		// face items of this lane: (row, 16-byte chunk) of an 8-column group
@@ -252,7 +256,7 @@ sgs_stream_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_const
 						__syncwarp();
 						if (lane == 0) {
 							const int pg = FWD ? nt : gmax - nt;
-							tma_store3(&tm_out, 8 * pg, j0, k0, s_u32(s_out + (pg & (NO - 1)) * GD));
+							if (8 * pg < a.nx_tma) tma_store3(&tm_out, 8 * pg, j0, k0, s_u32(s_out + (pg & (NO - 1)) * GD));
 							bulk_commit();
 							if (nt + NG < ngroups) stage(nt + NG);
 						}
@@ -290,6 +294,7 @@ sgs_stream_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_const
 				const bool inr = act && (unsigned)ic < (unsigned)a.nx;
 				last0 = inr ? v0 : last0;
 				s_out[inr ? outoff(ic) : trash] = v0;
+				st_mail_if(reinterpret_cast<unsigned long long *>(odd_dst + ic), v0, inr && ic >= a.nx_tma);
 				st_mail_if(mj_dst + ic, v0, inr && jprod);
 				st_mail_if(mk_dst + ic, v0, inr && kprod);
 				a_in = n_a_in; a_c0 = n_a_c0; a_c1 = n_a_c1; a_c2 = n_a_c2; a_dv = n_a_dv; hj0 = n_hj0; hk0 = n_hk0;
@@ -302,7 +307,7 @@ sgs_stream_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_const
 		if (lane == 0) {
 			for (int nt = next_store; nt < ngroups; nt++) {
 				const int pg = FWD ? nt : gmax - nt;
-				tma_store3(&tm_out, 8 * pg, j0, k0, s_u32(s_out + (pg & (NO - 1)) * GD));
+				if (8 * pg < a.nx_tma) tma_store3(&tm_out, 8 * pg, j0, k0, s_u32(s_out + (pg & (NO - 1)) * GD));
 			}
 			bulk_commit();
 			bulk_wait_read<0>();
@@ -391,7 +396,7 @@ extern "C" S3D_HIDDEN int s3d_internal_sgs_stream(s3d_ctx *ctx, const s3d_grid *
 	a.nx = g->nx; a.ny = g->ny; a.nz = g->nz; a.vpitch = g->vpitch; a.vplane = g->vplane; a.voff = g->voff;
 	a.nty = nty; a.ntz = ntz; a.nxp = nxp; a.order = order; a.ticket = ticket;
 	a.mail_j = ctx->sgs_mail; a.mail_k = ctx->sgs_mail + nlines * 8 * (size_t)nxp;
-	a.out = out; a.klo_zero = klo_zero; a.khi_zero = khi_zero; a.prof = ctx->sgs_prof;
+	a.out = out; a.nx_tma = g->nx & ~1; a.klo_zero = klo_zero; a.khi_zero = khi_zero; a.prof = ctx->sgs_prof;
 	CUtensorMap tm[6];
 	int rc;
 	if (mode == 2) rc = make_map(ctx, &tm[0], in0, g->nx, g->ny, g->nz, g->cpitch, g->cplane);
@@ -402,7 +407,7 @@ extern "C" S3D_HIDDEN int s3d_internal_sgs_stream(s3d_ctx *ctx, const s3d_grid *
 		rc = make_map(ctx, &tm[1 + s], cs[s], g->nx, g->ny, g->nz, g->cpitch, g->cplane);
 		if (rc != S3D_OK) return rc;
 	}
-	rc = make_map(ctx, &tm[5], out + g->voff, g->nx, g->ny, g->nz, g->vpitch, g->vplane);
+	rc = make_map(ctx, &tm[5], out + g->voff, std::max(2, g->nx & ~1), g->ny, g->nz, g->vpitch, g->vplane);   // nx == 1: never used
 	if (rc != S3D_OK) return rc;
 	int wps = warps_per_sm;
 	if (ctx->sgs_warps_per_sm > 0) wps = std::min(wps, ctx->sgs_warps_per_sm);
