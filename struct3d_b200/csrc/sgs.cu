@@ -1019,8 +1019,11 @@ __global__ void sgs_begin_kernel(int *ctl, const int *stop)
 // (exact lexicographic ordering on a decomposed grid) is the warp-per-tile kernel's (0)
 inline int sgs_effective_variant(const s3d_ctx *ctx, const s3d_grid *g, bool through_slabs)
 {
-	if (ctx->sgs_variant == 4 && through_slabs && g->nranks > 1) return 0;
-	return ctx->sgs_variant;
+	int v = ctx->sgs_variant;
+	if ((v == 4 || v == 5) && through_slabs && g->nranks > 1) return 0;
+	// 4 = by grid size (measured crossover, profiles/r2_sgs_stream.md), 5 = the streaming kernel whatever the size
+	if (v == 4 && g->nranks == 1 && (long long)g->nx * g->ny * g->nz > ctx->sgs_stream_max_points) return 0;
+	return v == 5 ? 4 : v;
 }
 
 // flags / dispatch table / occupancy for the dataflow kernels; returns the number of persistent blocks
@@ -1313,7 +1316,7 @@ int s3d_strilu_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuil
 	ctx->launches++;
 	SgsFlow f;
 	unsigned nblocks = 0;
-	const int variant = ctx->sgs_variant;
+	const int variant = sgs_effective_variant(ctx, g, false);
 	int rc = sgs_flow_prepare(ctx, g, f, nblocks, variant);
 	if (rc == S3D_OK) {
 		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, nullptr);

@@ -5,31 +5,40 @@
 // Why another kernel (measured in round 1, profiles/r1_sgs_phases.md): the tile-level dataflow hands work from tile to tile through
 // global memory -- store rows, fence, flag, poll, fetch halo -- and a tile only starts when its three predecessors are COMPLETE, so the
 // dependency chain of a sweep is (#tile hops) x (a whole tile + ~3500 cycles of hand-off): 78 x 7600 cycles at 256^3 against a
-// fundamental chain of nx+ny+nz steps.  Here the hand-off is per COLUMN and needs neither fence nor flag:
+// fundamental chain of nx+ny+nz steps.  Here the hand-off is per column pair and needs neither fence nor flag:
 //
-//   * one warp owns a LINE: the 4 x 8 (j,k) pencils of a (cj, ck) cell over ALL nx columns.  Lane (m, c) marches along i one column
-//     per step, skewed by m + c steps, its i-neighbour in a register, its j/k-neighbours from lanes -8 / -1 by shuffle.  No
-//     i-direction hand-off exists at all;
-//   * the five input streams of the line arrive through TMA: per group of 8 columns ONE elected lane issues five
-//     cp.async.bulk.tensor.3d loads (box 8 x 4 x 8 doubles, mbarrier complete_tx) into a ring of NG groups; the results leave the
-//     same way (cp.async.bulk.tensor store from a small output ring).  No per-lane address arithmetic, no cp.async bursts, and the
-//     box lands [k][j][i]-ordered, which is bank-conflict-free for the skewed lanes;
+//   * a block of three warps owns a LINE at a time: the 4 x 8 (j,k) pencils of a (cj, ck) cell over ALL nx columns.
+//     The COMPUTE warp: lane (m, c) marches along i one column per step, TWO steps behind lanes (m-1, c) and (m, c-1): its i-neighbour
+//     is its own last value, its j/k-neighbours are the values those lanes computed two steps ago (warp shuffle of the value before
+//     last, so the shuffle latency is off the recurrence).  No i-direction hand-off exists at all.
+//     The LOADER warp stages the inputs and stores the results, the FACE warp polls the neighbouring lines' mailboxes.  (Doing this
+//     in the computing warp cost 120 of 265 cycles per step, and one helper warp for both could not keep up: a lone warp issues ~1
+//     dependent instruction per 5 cycles; profiles/r2_sgs_stream.md.)
+//   * the skew lives in the shared-memory layout: the loader puts element (i, pj, pk) of a stream at SHEARED column u = i + 2 pj + 2 pk
+//     of row (pj, pk), so column h of every row holds exactly the element that row's lane needs at step h.  All lanes read the same
+//     column at the same step: the inner loop addresses shared memory with immediates only.  Groups of 8 columns (64-byte row pieces)
+//     travel through a ring of NG slots as 16-byte cp.async copies, completion counted on an mbarrier; the 16-byte chunks of a row
+//     are XOR-swizzled with the row number so that the 16-byte loads of the 32 rows are bank-conflict-free.  (The first working
+//     version made the TMA unit do the shear -- tensor maps with row stride = pitch - 2 elements, SWIZZLE_64B -- which was correct but
+//     slow: every TMA op on a box of 64-byte rows holds the SM's TMA unit for ~130 cycles.)
+//   * results replace the staged input in shared memory (one 16-byte st.shared per lane every other step, same immediate address)
+//     and the loader warp stores them with coalesced 16-byte stores, predicated at the ends of the rows;
 //   * the faces a neighbouring line needs (last-j pencils -> line cj+1, last-k pencils -> line ck+1) go through MAILBOXES in global
-//     memory whose empty state is a sentinel bit pattern (a signalling NaN no arithmetic produces): the producer lane stores each
-//     value the moment it is computed (8-byte store, no fence), the consumer polls THE DATA ITSELF with L2 loads issued a few steps
-//     ahead, and writes the sentinel back once it has the value, so the mailbox is clean again for the next sweep.  The lag between
-//     adjacent lines is the lane skew + one group + one L2 round trip instead of a whole tile + fence + flag + fetch;
+//     memory whose empty state is a sentinel bit pattern (a signalling NaN no arithmetic produces): the producing lane stores each
+//     pair the moment it is complete (no fence), the consuming line's helper polls THE DATA ITSELF with L2 loads, hands the values to
+//     its compute warp through shared memory, and writes the sentinel back, so the mailbox is clean again for the next sweep.  The
+//     lag between adjacent lines is the lane skew + one group + one L2 round trip instead of a whole tile + fence + flag + fetch;
 //   * lines are drawn from a ticket counter in (cj + ck) order, so a line only waits on lines with smaller tickets, which are
 //     running or done: no co-residency assumption, no deadlock (same argument as the tile kernel).
-#include <cuda.h>
-#include <cudaTypedefs.h>
 #include <algorithm>
 #include "common.cuh"
 
 namespace {
 
-constexpr int SG_COLS = 8;                                  // columns per group (64-byte row pieces)
-constexpr int SG_TK = 8;                                    // k planes of a line (lane & 7)
+constexpr int SG_COLS = 8;                                  // box columns (= steps) per group
+constexpr int SG_TJ = 4, SG_TK = 8;                         // pencils of a line: lane = m * 8 + c, m < 4 (j), c < 8 (k)
+constexpr int SG_LQ = 8;                                    // entries of the line queue between the two warps
+constexpr int SG_HW = 64, SG_HP = SG_HW + 2;                // face ring: 8 groups wide; row pitch shifts consecutive rows by 16 bytes in the banks
 constexpr unsigned long long SG_SENT = 0xFFF4A5C3D2E1B497ull;   // "not written yet": a signalling-NaN pattern arithmetic never returns
 
 struct StreamArgs {
@@ -37,43 +46,40 @@ struct StreamArgs {
 	int vpitch;
 	long long vplane, voff;
 	int nty, ntz;                  // lines per plane direction
-	int nxp;                       // mailbox row length (columns rounded up to groups)
+	int nxp;                       // mailbox row length (columns rounded up to even)
 	const int *order;              // lines sorted by cj + ck
 	unsigned *ticket;
 	unsigned long long *mail_j;    // [line][8 k-rows][nxp]   last-j pencils of the line
-	unsigned long long *mail_k;    // [line][TJ j-rows][nxp]  last-k pencils of the line
-	double *out;                   // the output vector: its ghost column / rows / planes are read; the last column of an odd nx is
-	                               // stored directly (the TMA store's inner bound is 16-byte granular: measured on B200, a box over
-	                               // an odd-length row also writes the element after it -- the ghost column)
-	int nx_tma;                    // nx & ~1: columns the out tensor map covers
+	unsigned long long *mail_k;    // [line][4 j-rows][nxp]   last-k pencils of the line
+	const double *in0, *c0, *c1, *c2, *dv;   // input streams: in0 in the vector layout (coefficient layout for the StrILU recurrence)
+	int cpitch;
+	long long cplane;
+	double *out;                   // the output vector (its ghost column / rows / planes are read, never written)
 	int klo_zero, khi_zero;        // slab-local sweeps: what lies below k = 0 / above k = nz-1 is taken as zero
 	long long *prof;
+	int debug;                     // timing experiments only (results become wrong): 1 = no hand-off between lines (no mailbox traffic at all)
 };
 
 __device__ __forceinline__ unsigned s_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sg_mbar_init(unsigned a, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory"); }
 __device__ __forceinline__ void sg_mbar_expect_tx(unsigned a, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void sg_mbar_arrive(unsigned a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(a) : "memory"); }
 __device__ __forceinline__ bool sg_mbar_try_wait(unsigned a, unsigned parity)
 {
 	unsigned ok;
 	asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
 	return ok != 0;
 }
-__device__ __forceinline__ void tma_load3(unsigned dst, const CUtensorMap *tm, int c0, int c1, int c2, unsigned mbar)
+__device__ __forceinline__ bool sg_mbar_test(unsigned a, unsigned parity)
 {
-	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
-	             ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(mbar) : "memory");
+	unsigned ok;
+	asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+	return ok != 0;
 }
-__device__ __forceinline__ void tma_store3(const CUtensorMap *tm, int c0, int c1, int c2, unsigned src)
+__device__ __forceinline__ void cp_async16_if(unsigned dst, const double *src, bool on)
 {
-	asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];\n"
-	             ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(src) : "memory");
+	asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p cp.async.cg.shared.global [%0], [%1], 16;\n}\n" ::"r"(dst), "l"(src), "r"((unsigned)on) : "memory");
 }
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
 __device__ __forceinline__ ulonglong2 ld_mail2(const unsigned long long *p)
 {
 	ulonglong2 v;
@@ -84,269 +90,409 @@ __device__ __forceinline__ void st_mail2(unsigned long long *p, unsigned long lo
 {
 	asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};\n" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
-__device__ __forceinline__ void st_mail_if(unsigned long long *p, double v, bool on)
+// predicated stores of a result pair / of its even-column half (no "memory" clobber: they must not fence the shared-memory loads
+// of the following steps; nothing in this kernel reads these locations back through ordinary loads)
+__device__ __forceinline__ void st_pair_if(double *p, double lo, double hi, bool both, bool lo_only)
 {
-	asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.global.cg.f64 [%0], %1;\n}\n" ::"l"(p), "d"(v), "r"((unsigned)on) : "memory");
+	asm volatile("{\n.reg .pred p, q;\nsetp.ne.u32 p, %3, 0;\nsetp.ne.u32 q, %4, 0;\n@p st.global.cg.v2.f64 [%0], {%1, %2};\n@q st.global.cg.f64 [%0], %1;\n}\n"
+	             ::"l"(p), "d"(lo), "d"(hi), "r"((unsigned)both), "r"((unsigned)lo_only));
 }
+__device__ __forceinline__ void st_pair_on(double *p, double lo, double hi, bool on)
+{
+	asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %3, 0;\n@p st.global.cg.v2.f64 [%0], {%1, %2};\n}\n" ::"l"(p), "d"(lo), "d"(hi), "r"((unsigned)on));
+}
+
+// What both warps derive from a line number.
+//   sheared column  u = i + 2 pj + 2 pk,  0 <= u < W = nx + 2 (tj-1) + 2 (tk-1), in ngroups groups of 8
+//   forward sweeps walk the groups upwards, backward sweeps downwards; the lane of logical pencil (m, c) holds the physical pencil
+//   (m, c) forward and (tj-1-m, tk-1-c) backward, so the lanes it depends on, (m-1, c) and (m, c-1), are two steps ahead of it.
+template <bool FWD> struct LineGeo {
+	int line, cj, ck, j0, k0, tj, tk, ngroups, shmax;
+	bool act;
+	int pj, pk, sh2, row;
+	__device__ __forceinline__ void set(const StreamArgs &a, int ln, int lane)
+	{
+		line = ln;
+		cj = ln % a.nty; ck = ln / a.nty;
+		j0 = cj * SG_TJ; k0 = ck * SG_TK;
+		tj = min(SG_TJ, a.ny - j0); tk = min(SG_TK, a.nz - k0);
+		shmax = 2 * (tj - 1) + 2 * (tk - 1);
+		ngroups = (a.nx + shmax + SG_COLS - 1) / SG_COLS;
+		const int m = lane >> 3, c = lane & 7;
+		act = (m < tj) && (c < tk);
+		pj = act ? (FWD ? m : tj - 1 - m) : 0;
+		pk = act ? (FWD ? c : tk - 1 - c) : 0;
+		sh2 = 2 * pj + 2 * pk;
+		row = act ? pj * SG_TK + pk : lane;   // idle lanes keep a row of their own: it lies outside the grid, nobody reads or stores it
+	}
+	// first sheared column of logical group n
+	__device__ __forceinline__ int u0(int n) const { return SG_COLS * (FWD ? n : ngroups - 1 - n); }
+	__device__ __forceinline__ int chunk(int q) const { return row * SG_COLS + 2 * (q ^ ((row >> 1) & 3)); }
+	__device__ __forceinline__ double *orow(const StreamArgs &a) const { return a.out + a.voff + (long long)(k0 + pk) * a.vplane + (long long)(j0 + pj) * a.vpitch; }
+};
 
 // MODE 0: forward sweep  y = (r - A0 y[i-1] - A1 y[j-1] - A2 y[k-1]) dinv
 // MODE 1: backward sweep z = y - dinv (A4 z[i+1] + A5 z[j+1] + A6 z[k+1])
 // MODE 2: StrILU diagonal d = ((A3 - P0/d[i-1]) - P1/d[j-1]) - P2/d[k-1]   (forward order; in0 = A3 in the coefficient layout)
 template <int MODE, int NG>
-__global__ void __launch_bounds__(32)
-sgs_stream_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_c0,
-                  const __grid_constant__ CUtensorMap tm_c1, const __grid_constant__ CUtensorMap tm_c2,
-                  const __grid_constant__ CUtensorMap tm_dv, const __grid_constant__ CUtensorMap tm_out,
-                  const StreamArgs a, const int *stop)
+__global__ void __launch_bounds__(96)
+sgs_stream_kernel(const StreamArgs a, const int *stop)
 {
 	constexpr bool FWD = (MODE != 1);
 	constexpr bool ILU = (MODE == 2);
 	constexpr int NA = ILU ? 4 : 5;
-	constexpr int DIR = FWD ? 1 : -1;
-	constexpr int TJ = 4, TK = SG_TK, ROWS = TJ * TK;
+	constexpr int TJ = SG_TJ, TK = SG_TK, ROWS = TJ * TK;
 	constexpr int GD = ROWS * SG_COLS;                       // doubles of one stream of one group (2 KB)
 	constexpr int GS = NA * GD;                              // doubles of one group, all streams
-	constexpr int NO = 4;                                    // output ring, groups
-	constexpr int HW = NG * SG_COLS;                         // halo ring width, columns
-	constexpr int S = TJ + TK - 2;                           // steps the last lane lags the first
-	constexpr int QS = (S + 8) & 7, DS = (S + 8) >> 3;       // the last lane leaves group n at step 8 (n + DS) + QS
-	static_assert((NG & (NG - 1)) == 0 && NG >= 4, "ring sizes are powers of two");
+	constexpr int HP = SG_HP;
 	constexpr unsigned FULL = 0xffffffffu;
 	if (s3d_stopped(stop)) return;
 
 	extern __shared__ __align__(1024) double sg_smem[];      // the only shared memory of the kernel: starts at the CTA's window, 1 KB aligned
-	double *s_in = sg_smem;                                  // [NG][NA][GD]
-	double *s_out = s_in + NG * GS;                          // [NO][GD]
-	double *s_hj = s_out + NO * GD;                          // [8][HW]   j-neighbour rows (physical k) of the line before in j
-	double *s_hk = s_hj + 8 * HW;                            // [TJ][HW]  k-neighbour rows (physical j) of the line before in k
-	double *s_trash = s_hk + TJ * HW;                        // [32] where out-of-range steps put their (discarded) result
-	unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_trash + 32);   // [NG]
+	double *s_in = sg_smem;                                  // [NG][NA][j 4][k 8][8], 16-byte chunks swizzled by TMA (SWIZZLE_64B)
+	double *s_hj = s_in + NG * GS;                           // [8 k-rows][HP]  j-neighbour values of group G at columns (G % 8) * 8 ...
+	double *s_hk = s_hj + 8 * HP;                            // [4 j-rows][HP]  k-neighbour values
+	double *s_ghost = s_hk + TJ * HP;                        // [SG_LQ][32]     the ghost column of a line, per lane
+	unsigned long long *s_full = reinterpret_cast<unsigned long long *>(s_ghost + SG_LQ * 32);   // [NG]   inputs + faces of a group are there
+	unsigned long long *s_done = s_full + NG;                // [NG]   the compute warp is done with a group
+	unsigned long long *s_lbar = s_done + NG;                // [SG_LQ] a line-queue entry is valid
+	int *s_lineq = reinterpret_cast<int *>(s_lbar + SG_LQ);  // [SG_LQ] line numbers, -1 = no more lines
 
-	const int lane = threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
 	const int m = lane >> 3, cc = lane & 7;
-	const int s0 = m + cc;
 	const int nlines = a.nty * a.ntz;
-	const int nwarps = gridDim.x;
-	const int gmax = (a.nx - 1) >> 3, itop = 8 * gmax + 7;
-	const int ncol = FWD ? a.nx : itop + 1;
-	const int ngroups = gmax + 1;
-	const int nsteps = ncol + S;
 
-	if (lane == 0) {
+	if (threadIdx.x == 0) {
 #pragma unroll
-		for (int s = 0; s < NG; s++) sg_mbar_init(s_u32(s_bar + s), 1);
+		for (int s = 0; s < NG; s++) { sg_mbar_init(s_u32(s_full + s), 33); sg_mbar_init(s_u32(s_done + s), 1); }
+#pragma unroll
+		for (int s = 0; s < SG_LQ; s++) sg_mbar_init(s_u32(s_lbar + s), 1);
 		asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 	}
-	fence_async_smem();
-	__syncwarp();
-	unsigned phases = 0;                                     // bit s: parity the next wait on ring slot s uses
+	__syncthreads();
 
-	int ticket = blockIdx.x;
-	int line = (ticket < nlines) ? a.order[FWD ? ticket : nlines - 1 - ticket] : -1;
-	while (line >= 0) {
-		const int cj = line % a.nty, ck = line / a.nty;
-		const int j0 = cj * TJ, k0 = ck * TK;
-		const int tj = min(TJ, a.ny - j0), tk = min(TK, a.nz - k0);
-		const bool act = (m < tj) && (cc < tk);
-		const int pj = act ? (FWD ? m : tj - 1 - m) : 0, pk = act ? (FWD ? cc : tk - 1 - cc) : 0;   // physical pencil inside the line
-		const int rowoff = (pk * TJ + pj) * SG_COLS;
-		// the lines this one depends on / feeds (sweep order)
-		const int pjl = FWD ? (cj > 0 ? line - 1 : -1) : (cj < a.nty - 1 ? line + 1 : -1);
-		const int pkl = FWD ? (ck > 0 ? line - a.nty : -1) : (ck < a.ntz - 1 ? line + a.nty : -1);
-		const bool jsucc = FWD ? (cj < a.nty - 1) : (cj > 0), ksucc = FWD ? (ck < a.ntz - 1) : (ck > 0);
-		const bool jprod = act && jsucc && (m == tj - 1), kprod = act && ksucc && (cc == tk - 1);
-		double *odd_dst = a.out + a.voff + (long long)(k0 + pk) * a.vplane + (long long)(j0 + pj) * a.vpitch;   // used for column nx-1 of an odd nx only
-		unsigned long long *mj_dst = a.mail_j + ((size_t)line * 8 + pk) * a.nxp;
-		unsigned long long *mk_dst = a.mail_k + ((size_t)line * TJ + pj) * a.nxp;
-		// face items of this lane: (row, 16-byte chunk) of an 8-column group
-		const int frow = lane >> 2, fch = 2 * (lane & 3);
-		const bool jitem = frow < tk, kitem = (lane < 4 * TJ) && (frow < tj);
-		const bool jpoll = pjl >= 0, kpoll = pkl >= 0;
-		const bool kzero = !kpoll && (FWD ? a.klo_zero : a.khi_zero);
-		const unsigned long long *jsrc = jpoll
-			? a.mail_j + ((size_t)pjl * 8 + frow) * a.nxp + fch
-			: reinterpret_cast<const unsigned long long *>(a.out + a.voff + (long long)(k0 + frow) * a.vplane + (long long)(FWD ? -1 : a.ny) * a.vpitch + fch);
-		const unsigned long long *ksrc = kpoll
-			? a.mail_k + ((size_t)pkl * TJ + frow) * a.nxp + fch
-			: reinterpret_cast<const unsigned long long *>(a.out + a.voff + (long long)(FWD ? -1 : a.nz) * a.vplane + (long long)(j0 + frow) * a.vpitch + fch);
-
-		auto stage = [&](int n) {                               // logical group n -> its ring slot (elected lane only)
-			const int pg = FWD ? n : gmax - n, slot = pg & (NG - 1);
-			const unsigned bar = s_u32(s_bar + slot), dst = s_u32(s_in + slot * GS);
-			sg_mbar_expect_tx(bar, (unsigned)(GS * sizeof(double)));
-			tma_load3(dst, &tm_in0, 8 * pg, j0, k0, bar);
-			tma_load3(dst + GD * 8, &tm_c0, 8 * pg, j0, k0, bar);
-			tma_load3(dst + 2 * GD * 8, &tm_c1, 8 * pg, j0, k0, bar);
-			tma_load3(dst + 3 * GD * 8, &tm_c2, 8 * pg, j0, k0, bar);
-			if (!ILU) tma_load3(dst + 4 * GD * 8, &tm_dv, 8 * pg, j0, k0, bar);
-		};
-		ulonglong2 fj = make_ulonglong2(0, 0), fk = make_ulonglong2(0, 0);
-		auto face_issue = [&](int n) {
-			const int i8 = 8 * (FWD ? n : gmax - n);
-			if (jitem) fj = ld_mail2(jsrc + i8);
-			if (kitem && !kzero) fk = ld_mail2(ksrc + i8);
-		};
-		auto face_take = [&](int n) {                           // poll until the group's faces are there, move them to shared memory
-			const int i8 = 8 * (FWD ? n : gmax - n);
-			const int col = i8 + fch;
-			const bool wj = jitem && jpoll, wk = kitem && kpoll;
-			const long long t0 = clock64();
-			for (;;) {
-				const bool okj = !wj || ((col >= a.nx || fj.x != SG_SENT) && (col + 1 >= a.nx || fj.y != SG_SENT));
-				const bool okk = !wk || ((col >= a.nx || fk.x != SG_SENT) && (col + 1 >= a.nx || fk.y != SG_SENT));
-				if (__all_sync(FULL, okj && okk)) break;
-				if (!okj) fj = ld_mail2(jsrc + i8);
-				if (!okk) fk = ld_mail2(ksrc + i8);
-				if (clock64() - t0 > (40ll << 30)) __trap();       // ~20 s without the producing line: fail loudly instead of hanging
-			}
-			const int hs = i8 & (HW - 1);
-			if (jitem) {
-				*reinterpret_cast<ulonglong2 *>(s_hj + frow * HW + hs + fch) = fj;
-				if (jpoll) st_mail2(const_cast<unsigned long long *>(jsrc) + i8, SG_SENT, SG_SENT);   // clean for the next sweep
-			}
-			if (kitem) {
-				*reinterpret_cast<ulonglong2 *>(s_hk + frow * HW + hs + fch) = fk;
-				if (kpoll) st_mail2(const_cast<unsigned long long *>(ksrc) + i8, SG_SENT, SG_SENT);
-			}
-		};
-
-		// ---- prologue: the first NG groups, the faces of group 0, the ghost column
-		__syncwarp();
-		if (lane == 0)
-			for (int n = 0; n < NG && n < ngroups; n++) stage(n);
-		face_issue(0);
-		double last0 = 0.0;
-		if (act) last0 = __ldcg(a.out + a.voff + (long long)(k0 + pk) * a.vplane + (long long)(j0 + pj) * a.vpitch + (FWD ? -1 : a.nx));
-		int nticket = 0, nline = -1;
-		if (lane == 0) nticket = (int)atomicAdd(a.ticket, 1u) + nwarps;
-		face_take(0);
-		{
-			const int slot = (FWD ? 0 : gmax) & (NG - 1);
-			while (!__all_sync(FULL, sg_mbar_try_wait(s_u32(s_bar + slot), (phases >> slot) & 1u))) { }
-			phases ^= 1u << slot;
-		}
-		__syncwarp();
-
-		// ---- the march.  At step h this lane is at logical column h - s0, physical column icol.
-		const bool jhalo = (m == 0), khalo = (cc == 0);
-		const double *phj = s_hj + pk * HW, *phk = s_hk + pj * HW;
-		int icol = FWD ? -s0 : itop + s0;
-		auto inoff = [&](int ic) { return ((ic >> 3) & (NG - 1)) * GS + (ic & 7) + rowoff; };
-		auto outoff = [&](int ic) { return ((ic >> 3) & (NO - 1)) * GD + (ic & 7) + rowoff; };
-		const int trash = (int)(s_trash - s_out) + lane;
-		int io = inoff(icol);
-		double a_in = s_in[io], a_c0 = s_in[io + GD], a_c1 = s_in[io + 2 * GD], a_c2 = s_in[io + 3 * GD];
-		double a_dv = ILU ? 0.0 : s_in[io + (NA - 1) * GD];
-		double hj0 = jhalo ? phj[icol & (HW - 1)] : 0.0, hk0 = khalo ? phk[icol & (HW - 1)] : 0.0;
-		int next_store = 0;
-		long long tq_face = 0, tq_bar = 0, tq_io = 0, tq0 = 0, tq = 0;
+	if (warp == 0) {
+		// ======================================================================= the COMPUTE warp
+		LineGeo<FWD> L;
+		int G = 0;                                               // groups processed so far (all lines): ring slot G % NG, face ring (G % 8) * 8
+		long long tq_wait = 0, tq0 = 0, nst = 0;
 		if (a.prof) tq0 = clock64();
-#pragma unroll 1
-		for (int h8 = 0; h8 < nsteps; h8 += 8) {
-			const int n1 = (h8 >> 3) + 1;                        // the group the first lane enters after this octet
+		for (int seq = 0;; seq++) {
+			{
+				const unsigned bar = s_u32(s_lbar + (seq % SG_LQ));
+				while (!__all_sync(FULL, sg_mbar_try_wait(bar, (seq / SG_LQ) & 1))) { }
+			}
+			const int line = s_lineq[seq % SG_LQ];
+			if (line < 0) break;
+			L.set(a, line, lane);
+			const bool jsucc = FWD ? (L.cj < a.nty - 1) : (L.cj > 0), ksucc = FWD ? (L.ck < a.ntz - 1) : (L.ck > 0);
+			const bool jprod = L.act && jsucc && (m == L.tj - 1) && !(a.debug & 1), kprod = L.act && ksucc && (cc == L.tk - 1) && !(a.debug & 1);
+			double *mj_dst = reinterpret_cast<double *>(a.mail_j + ((size_t)line * 8 + L.pk) * a.nxp);
+			double *mk_dst = reinterpret_cast<double *>(a.mail_k + ((size_t)line * TJ + L.pj) * a.nxp);
+			int chunk_off[4];
 #pragma unroll
-			for (int q = 0; q < 8; q++) {
-				if (q == 0 && n1 < ngroups) face_issue(n1);
-				if (q == QS) {
-					// every lane has left logical group nt: its results go out, its ring slot takes group nt + NG
-					const int nt = (h8 >> 3) - DS;
-					if (nt >= 0 && nt < ngroups) {
-						if (a.prof) tq = clock64();
-						fence_async_smem();
-						__syncwarp();
-						if (lane == 0) {
-							const int pg = FWD ? nt : gmax - nt;
-							if (8 * pg < a.nx_tma) tma_store3(&tm_out, 8 * pg, j0, k0, s_u32(s_out + (pg & (NO - 1)) * GD));
-							bulk_commit();
-							if (nt + NG < ngroups) stage(nt + NG);
+			for (int q = 0; q < 4; q++) chunk_off[q] = L.chunk(q);
+			const bool jhalo = (m == 0), khalo = (cc == 0);
+			const double *phj = s_hj + L.pk * HP, *phk = s_hk + L.pj * HP;
+			double cur = 0.0, prv = 0.0;                             // the lane's last value (its i-neighbour) and the one before
+#pragma unroll 1
+			for (int n = 0; n < L.ngroups; n++, G++) {
+				const int slot = G % NG;
+				{
+					long long t = 0;
+					if (a.prof) t = clock64();
+					const unsigned bar = s_u32(s_full + slot);
+					while (!__all_sync(FULL, sg_mbar_try_wait(bar, (G / NG) & 1))) { }
+					if (a.prof) tq_wait += clock64() - t;
+				}
+				if (n == 0) cur = s_ghost[(seq % SG_LQ) * 32 + lane];
+				double *g_in = s_in + slot * GS;                        // results overwrite the first stream of the slot
+				const int u0 = L.u0(n);
+				const int hb = (G & 7) * SG_COLS;
+				const int icb = u0 - L.sh2;                             // real column of box column 0
+				double2 o_in, o_c0, o_c1, o_c2, o_dv, o_hj, o_hk;
+				o_dv = make_double2(0.0, 0.0); o_hj = make_double2(0.0, 0.0); o_hk = make_double2(0.0, 0.0);
+				const bool interior = (u0 >= L.shmax) && (u0 + SG_COLS <= a.nx);
+				// one column: the reference's expression, the reference's order of roundings
+				auto column = [&](int el) -> double {
+					const double shj = __shfl_up_sync(FULL, prv, 8);
+					const double shk = __shfl_up_sync(FULL, prv, 1);
+					const double x_in = el ? o_in.y : o_in.x, x_c0 = el ? o_c0.y : o_c0.x, x_c1 = el ? o_c1.y : o_c1.x, x_c2 = el ? o_c2.y : o_c2.x;
+					const double x_dv = el ? o_dv.y : o_dv.x;
+					const double wj = jhalo ? (el ? o_hj.y : o_hj.x) : shj, wk = khalo ? (el ? o_hk.y : o_hk.x) : shk;
+					if (ILU) return __dsub_rn(__dsub_rn(__dsub_rn(x_in, __ddiv_rn(x_c0, cur)), __ddiv_rn(x_c1, wj)), __ddiv_rn(x_c2, wk));
+					if (FWD) return __dmul_rn(__dsub_rn(__dsub_rn(__dsub_rn(x_in, __dmul_rn(x_c0, cur)), __dmul_rn(x_c1, wj)), __dmul_rn(x_c2, wk)), x_dv);
+					return __dsub_rn(x_in, __dmul_rn(x_dv, __dadd_rn(__dadd_rn(__dmul_rn(x_c0, cur), __dmul_rn(x_c1, wj)), __dmul_rn(x_c2, wk))));
+				};
+				auto fetch = [&](int q) {
+					o_in = *reinterpret_cast<const double2 *>(g_in + chunk_off[q]);
+					o_c0 = *reinterpret_cast<const double2 *>(g_in + GD + chunk_off[q]);
+					o_c1 = *reinterpret_cast<const double2 *>(g_in + 2 * GD + chunk_off[q]);
+					o_c2 = *reinterpret_cast<const double2 *>(g_in + 3 * GD + chunk_off[q]);
+					if (!ILU) o_dv = *reinterpret_cast<const double2 *>(g_in + 4 * GD + chunk_off[q]);
+					if (jhalo) o_hj = *reinterpret_cast<const double2 *>(phj + hb + 2 * q);
+					if (khalo) o_hk = *reinterpret_cast<const double2 *>(phk + hb + 2 * q);
+				};
+				if (interior) {
+					// every lane's eight columns lie inside the grid: no range checks, nothing to select
+#pragma unroll
+					for (int p = 0; p < 4; p++) {
+						const int q = FWD ? p : 3 - p;                  // chunk of the box this pair lives in
+						fetch(q);
+						double v[2];
+#pragma unroll
+						for (int e = 0; e < 2; e++) {
+							const int el = FWD ? e : 1 - e;             // forward sweeps take the even column first
+							const double r = column(el);
+							prv = cur; cur = r; v[el] = r;
 						}
-						__syncwarp();
-						next_store = nt + 1;
-						if (a.prof) tq_io += clock64() - tq;
+						*reinterpret_cast<double2 *>(g_in + chunk_off[q]) = make_double2(v[0], v[1]);
+						const int iclo = icb + 2 * q;
+						st_pair_on(mj_dst + iclo, v[0], v[1], jprod);
+						st_pair_on(mk_dst + iclo, v[0], v[1], kprod);
+					}
+				} else {
+#pragma unroll
+					for (int p = 0; p < 4; p++) {
+						const int q = FWD ? p : 3 - p;
+						fetch(q);
+						double v[2];
+						bool in[2];
+#pragma unroll
+						for (int e = 0; e < 2; e++) {
+							const int el = FWD ? e : 1 - e;
+							const int ic = icb + 2 * q + el;
+							const double r = column(el);
+							const bool inr = L.act && (unsigned)ic < (unsigned)a.nx;
+							prv = cur; cur = inr ? r : cur; v[el] = r; in[el] = inr;
+						}
+						*reinterpret_cast<double2 *>(g_in + chunk_off[q]) = make_double2(v[0], v[1]);
+						const int iclo = icb + 2 * q;
+						st_pair_if(mj_dst + iclo, v[0], v[1], jprod && in[0] && in[1], jprod && in[0] && !in[1]);
+						st_pair_if(mk_dst + iclo, v[0], v[1], kprod && in[0] && in[1], kprod && in[0] && !in[1]);
 					}
 				}
-				if (q == 7 && n1 < ngroups) {
-					// the first lane is about to read group n1: its inputs, its faces, and a free slot of the output ring
-					if (a.prof) tq = clock64();
-					if (lane == 0) bulk_wait_read<1>();
-					face_take(n1);
-					if (a.prof) { const long long t = clock64(); tq_face += t - tq; tq = t; }
-					const int slot = (FWD ? n1 : gmax - n1) & (NG - 1);
-					while (!__all_sync(FULL, sg_mbar_try_wait(s_u32(s_bar + slot), (phases >> slot) & 1u))) { }
-					phases ^= 1u << slot;
-					__syncwarp();
-					if (a.prof) tq_bar += clock64() - tq;
-				}
-				const double shj = __shfl_up_sync(FULL, last0, 8);
-				const double shk = __shfl_up_sync(FULL, last0, 1);
-				const int ic = icol;
-				icol += DIR;
-				io = inoff(icol);
-				const double n_a_in = s_in[io], n_a_c0 = s_in[io + GD], n_a_c1 = s_in[io + 2 * GD], n_a_c2 = s_in[io + 3 * GD];
-				const double n_a_dv = ILU ? 0.0 : s_in[io + (NA - 1) * GD];
-				const double n_hj0 = jhalo ? phj[icol & (HW - 1)] : 0.0, n_hk0 = khalo ? phk[icol & (HW - 1)] : 0.0;
-				const double wj = jhalo ? hj0 : shj, wk = khalo ? hk0 : shk;
-				double v0;
-				if (ILU) v0 = __dsub_rn(__dsub_rn(__dsub_rn(a_in, __ddiv_rn(a_c0, last0)), __ddiv_rn(a_c1, wj)), __ddiv_rn(a_c2, wk));
-				else if (FWD) v0 = __dmul_rn(__dsub_rn(__dsub_rn(__dsub_rn(a_in, __dmul_rn(a_c0, last0)), __dmul_rn(a_c1, wj)), __dmul_rn(a_c2, wk)), a_dv);
-				else v0 = __dsub_rn(a_in, __dmul_rn(a_dv, __dadd_rn(__dadd_rn(__dmul_rn(a_c0, last0), __dmul_rn(a_c1, wj)), __dmul_rn(a_c2, wk))));
-				// branch-free commit: out-of-range steps keep the old value and write to the trash slot
-				const bool inr = act && (unsigned)ic < (unsigned)a.nx;
-				last0 = inr ? v0 : last0;
-				s_out[inr ? outoff(ic) : trash] = v0;
-				st_mail_if(reinterpret_cast<unsigned long long *>(odd_dst + ic), v0, inr && ic >= a.nx_tma);
-				st_mail_if(mj_dst + ic, v0, inr && jprod);
-				st_mail_if(mk_dst + ic, v0, inr && kprod);
-				a_in = n_a_in; a_c0 = n_a_c0; a_c1 = n_a_c1; a_c2 = n_a_c2; a_dv = n_a_dv; hj0 = n_hj0; hk0 = n_hk0;
+				// the group's results are in shared memory: over to the loader warp, which stores them
+				__syncwarp();
+				if (lane == 0) sg_mbar_arrive(s_u32(s_done + slot));
 			}
-			if (h8 == 16 && lane == 0) nline = (nticket < nlines) ? a.order[FWD ? nticket : nlines - 1 - nticket] : -1;
+			if (a.prof && lane == 0) nst += (long long)L.ngroups * SG_COLS;
 		}
-		// ---- epilogue: the groups still in the output ring
-		fence_async_smem();
-		__syncwarp();
-		if (lane == 0) {
-			for (int nt = next_store; nt < ngroups; nt++) {
-				const int pg = FWD ? nt : gmax - nt;
-				if (8 * pg < a.nx_tma) tma_store3(&tm_out, 8 * pg, j0, k0, s_u32(s_out + (pg & (NO - 1)) * GD));
-			}
-			bulk_commit();
-			bulk_wait_read<0>();
-			if (nsteps <= 16) nline = (nticket < nlines) ? a.order[FWD ? nticket : nlines - 1 - nticket] : -1;   // short lines never reach the look-up above
-			if (a.prof) {
-				atomicAdd((unsigned long long *)a.prof + 0, (unsigned long long)tq_face);
-				atomicAdd((unsigned long long *)a.prof + 1, (unsigned long long)tq_bar);
-				atomicAdd((unsigned long long *)a.prof + 2, (unsigned long long)(clock64() - tq0));
-				atomicAdd((unsigned long long *)a.prof + 3, (unsigned long long)tq_io);
-				atomicAdd((unsigned long long *)a.prof + 4, 1ull);
-				atomicAdd((unsigned long long *)a.prof + 5, (unsigned long long)nsteps);
-			}
+		if (a.prof && lane == 0) {
+			atomicAdd((unsigned long long *)a.prof + 0, (unsigned long long)tq_wait);
+			atomicAdd((unsigned long long *)a.prof + 2, (unsigned long long)(clock64() - tq0));
+			atomicAdd((unsigned long long *)a.prof + 4, 1ull);
+			atomicAdd((unsigned long long *)a.prof + 5, (unsigned long long)nst);
 		}
-		__syncwarp();
-		line = __shfl_sync(FULL, nline, 0);
+		return;
 	}
-	if (lane == 0) bulk_wait_all();                          // the stores have landed before the warp retires
+
+	if (warp == 1) {
+		// ======================================================================= the LOADER warp
+		// LOAD: the five input streams of a group into a free ring slot -- 16-byte cp.async, each lane four row pieces per stream,
+		// written where the sheared, swizzled layout wants them; completion counted on the slot's `full` barrier.  RETIRE: the
+		// results of the groups the compute warp has finished, shared memory -> global, coalesced 16-byte stores, predicated at the
+		// ends of the rows.  It also draws the lines.  (A first version used TMA tensor copies for all of this: every op on a box of
+		// 64-byte rows held the SM's TMA unit for ~130 cycles, 6 ops per group and 4 lines per SM: 390 cycles per step.)
+		LineGeo<FWD> Ll, Lr;
+		int Gl = 0, Gr = 0, nl = 0, nr = 0, seql = 0, seqr = 0;
+		bool have_l = false, have_r = false, end_l = false;
+		int ticket = blockIdx.x;
+		const int nblocks = gridDim.x;
+		// this lane's pieces: physical pencil (pj = t, pk = lane >> 2), t = 0..3, 16-byte chunk lane & 3 of the pencil's 8 columns
+		const int ppk = lane >> 2, pch = lane & 3;
+		const int soff = ppk * SG_COLS + 2 * (pch ^ ((ppk >> 1) & 3));   // + t * 64 doubles: rows t * 8 + ppk share the swizzle
+		long long hp_load = 0, hp_ret = 0, hp_t = 0;
+		for (;;) {
+			if (a.prof) hp_t = clock64();
+			for (;;) {
+				if (!have_l && !end_l) {
+					// next line of this block: the first comes with the block number, later ones from the ticket counter.  A line-queue
+					// entry is only reused once RETIRE is past its old line: seql - seqr < SG_LQ holds because every line has at least
+					// one group and LOAD is at most NG <= SG_LQ - 2 groups ahead of RETIRE
+					int line = -1;
+					if (lane == 0) {
+						if (seql > 0) ticket = (int)atomicAdd(a.ticket, 1u) + nblocks;
+						line = (ticket < nlines) ? a.order[FWD ? ticket : nlines - 1 - ticket] : -1;
+						s_lineq[seql % SG_LQ] = line;
+						sg_mbar_arrive(s_u32(s_lbar + (seql % SG_LQ)));
+					}
+					line = __shfl_sync(FULL, line, 0);
+					if (line < 0) end_l = true;
+					else { Ll.set(a, line, lane); have_l = true; nl = 0; }
+				}
+				if (!have_l || Gl >= Gr + NG) break;
+				{
+					const int slot = Gl % NG;
+					const unsigned bar = s_u32(s_full + slot), dst = s_u32(s_in + slot * GS + soff);
+					const int c0_ = Ll.u0(nl) + 2 * pch - 2 * ppk;                     // real column of the piece for t = 0; t takes 2 t off
+					const long long cb = (long long)(Ll.k0 + ppk) * a.cplane + (long long)Ll.j0 * a.cpitch;
+					const long long vb = a.voff + (long long)(Ll.k0 + ppk) * a.vplane + (long long)Ll.j0 * a.vpitch;
+#pragma unroll
+					for (int t = 0; t < TJ; t++) {
+						const int c = c0_ - 2 * t;
+						const bool on = (t < Ll.tj) && (ppk < Ll.tk) && c >= 0 && c < a.nx;
+						const long long co = cb + (long long)t * a.cpitch + c;
+						const unsigned d = dst + t * 64 * 8;
+						cp_async16_if(d, ILU ? a.in0 + co : a.in0 + vb + (long long)t * a.vpitch + c, on);
+						cp_async16_if(d + GD * 8, a.c0 + co, on);
+						cp_async16_if(d + 2 * GD * 8, a.c1 + co, on);
+						cp_async16_if(d + 3 * GD * 8, a.c2 + co, on);
+						if (!ILU) cp_async16_if(d + 4 * GD * 8, a.dv + co, on);
+					}
+					asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
+				}
+				Gl++; nl++;
+				if (nl == Ll.ngroups) { have_l = false; seql++; }
+			}
+			if (a.prof) { const long long t = clock64(); hp_load += t - hp_t; hp_t = t; }
+			if (Gr == Gl) break;                                     // nothing loaded that is not retired: the line sequence has ended
+			if (!have_r) { Lr.set(a, s_lineq[seqr % SG_LQ], lane); have_r = true; nr = 0; }
+			{
+				const int slot = Gr % NG;
+				const unsigned bar = s_u32(s_done + slot);
+				while (!__all_sync(FULL, sg_mbar_try_wait(bar, (Gr / NG) & 1))) { }
+				const double *g_out = s_in + slot * GS + soff;
+				const int c0_ = Lr.u0(nr) + 2 * pch - 2 * ppk;
+				double *ob = a.out + a.voff + (long long)(Lr.k0 + ppk) * a.vplane + (long long)Lr.j0 * a.vpitch;
+#pragma unroll
+				for (int t = 0; t < TJ; t++) {
+					const double2 v = *reinterpret_cast<const double2 *>(g_out + t * 64);
+					const int c = c0_ - 2 * t;
+					const bool row_on = (t < Lr.tj) && (ppk < Lr.tk);
+					const bool inlo = row_on && c >= 0 && c < a.nx, inhi = inlo && (c + 1 < a.nx);
+					st_pair_if(ob + (long long)t * a.vpitch + c, v.x, v.y, inhi, inlo && !inhi);
+				}
+				__syncwarp();
+				Gr++; nr++;
+				if (nr == Lr.ngroups) { have_r = false; seqr++; }
+			}
+			if (a.prof) hp_ret += clock64() - hp_t;
+		}
+		if (a.prof && lane == 0) {
+			atomicAdd((unsigned long long *)a.prof + 1, (unsigned long long)hp_load);
+			atomicAdd((unsigned long long *)a.prof + 6, (unsigned long long)hp_ret);
+		}
+		return;
+	}
+
+	// =========================================================================== the FACE warp
+	// Polls the mailboxes of the two lines this one depends on and hands the values -- and the line's ghost column -- to the compute
+	// warp through shared memory; puts the sentinel back.  The polls of three consecutive groups are in flight (an L2 round trip
+	// each); every set of poll registers is written by its own load instruction, never moved, so nothing waits on a poll it does
+	// not need yet.
+	{
+		LineGeo<FWD> Lf;
+		int Gf = 0;
+		const int frow = lane >> 2, fch = 2 * (lane & 3);
+		long long hp_face = 0, hp_t = 0;
+		for (int seq = 0;; seq++) {
+			{
+				const unsigned bar = s_u32(s_lbar + (seq % SG_LQ));
+				while (!__all_sync(FULL, sg_mbar_try_wait(bar, (seq / SG_LQ) & 1))) { }
+			}
+			const int line = s_lineq[seq % SG_LQ];
+			if (line < 0) break;
+			if (a.prof) hp_t = clock64();
+			Lf.set(a, line, lane);
+			const int pjl = FWD ? (Lf.cj > 0 ? line - 1 : -1) : (Lf.cj < a.nty - 1 ? line + 1 : -1);
+			const int pkl = FWD ? (Lf.ck > 0 ? line - a.nty : -1) : (Lf.ck < a.ntz - 1 ? line + a.nty : -1);
+			// face items of this lane: (row, 16-byte chunk) of a group.  Row frow of the j-faces is physical k-row frow of the pencils
+			// with logical m = 0 (physical pj = fpj); row frow of the k-faces is physical j-row frow of the pencils with logical c = 0
+			const int fpj = FWD ? 0 : Lf.tj - 1, fpk = FWD ? 0 : Lf.tk - 1;
+			const bool jitem = frow < Lf.tk, kitem = (lane < 4 * TJ) && (frow < Lf.tj);
+			const bool jpoll = pjl >= 0 && !(a.debug & 1), kpoll = pkl >= 0 && !(a.debug & 1);
+			const bool kzero = !kpoll && (FWD ? a.klo_zero : a.khi_zero);
+			const unsigned long long *jsrc = jpoll
+				? a.mail_j + ((size_t)pjl * 8 + frow) * a.nxp
+				: reinterpret_cast<const unsigned long long *>(a.out + a.voff + (long long)(Lf.k0 + frow) * a.vplane + (long long)(FWD ? -1 : a.ny) * a.vpitch);
+			const unsigned long long *ksrc = kpoll
+				? a.mail_k + ((size_t)pkl * TJ + frow) * a.nxp
+				: reinterpret_cast<const unsigned long long *>(a.out + a.voff + (long long)(FWD ? -1 : a.nz) * a.vplane + (long long)(Lf.j0 + frow) * a.vpitch);
+			const int jsh = 2 * fpj + 2 * frow - fch, ksh = 2 * frow + 2 * fpk - fch;   // real column of the item = u0 - shift
+			double ghostv = 0.0;
+			if (Lf.act) ghostv = __ldcg(Lf.orow(a) + (FWD ? -1 : a.nx));
+			ulonglong2 fj0 = make_ulonglong2(0, 0), fk0 = fj0, fj1 = fj0, fk1 = fj0, fj2 = fj0, fk2 = fj0;
+			auto ask = [&](int n, ulonglong2 &fj, ulonglong2 &fk) {  // the polls of group n of the line
+				if (n >= Lf.ngroups) return;
+				const int u0 = Lf.u0(n);
+				const int cj_ = u0 - jsh, ck_ = u0 - ksh;
+				if (jitem && cj_ >= 0 && cj_ < a.nx) fj = ld_mail2(jsrc + cj_);
+				if (kitem && !kzero && ck_ >= 0 && ck_ < a.nx) fk = ld_mail2(ksrc + ck_);
+			};
+			auto take = [&](int n, ulonglong2 &fj, ulonglong2 &fk) { // wait for group n's faces, hand them over
+				const int u0 = Lf.u0(n);
+				const int cj_ = u0 - jsh, ck_ = u0 - ksh;
+				const bool inj = jitem && cj_ >= 0 && cj_ < a.nx, ink = kitem && !kzero && ck_ >= 0 && ck_ < a.nx;
+				const bool wj = inj && jpoll, wk = ink && kpoll;
+				// the compute warp must be through with the group that had this ring slot before (its `full` phase is then over)
+				if (Gf >= NG) {
+					const unsigned bar = s_u32(s_done + (Gf % NG));
+					while (!__all_sync(FULL, sg_mbar_try_wait(bar, ((Gf - NG) / NG) & 1))) { }
+				}
+				auto there = [&](const ulonglong2 &pj_, const ulonglong2 &pk_) {
+					const bool okj = !wj || (pj_.x != SG_SENT && (cj_ + 1 >= a.nx || pj_.y != SG_SENT));
+					const bool okk = !wk || (pk_.x != SG_SENT && (ck_ + 1 >= a.nx || pk_.y != SG_SENT));
+					return __all_sync(FULL, okj && okk) != 0;
+				};
+				if (!there(fj, fk)) {
+					// not there yet: keep TWO polls in flight, so that the values are seen within half an L2 round trip of landing
+					const long long t0 = clock64();
+					ulonglong2 gj = fj, gk = fk;
+					if (wj) gj = ld_mail2(jsrc + cj_);
+					if (wk) gk = ld_mail2(ksrc + ck_);
+					for (;;) {
+						if (wj) fj = ld_mail2(jsrc + cj_);
+						if (wk) fk = ld_mail2(ksrc + ck_);
+						if (there(gj, gk)) { fj = gj; fk = gk; break; }
+						if (wj) gj = ld_mail2(jsrc + cj_);
+						if (wk) gk = ld_mail2(ksrc + ck_);
+						if (there(fj, fk)) break;
+						if (clock64() - t0 > (40ll << 30)) __trap(); // ~20 s without the producing line: fail loudly instead of hanging
+					}
+				}
+				const int hs = (Gf & 7) * SG_COLS + fch;
+				if (jitem) {
+					*reinterpret_cast<ulonglong2 *>(s_hj + frow * HP + hs) = inj ? fj : make_ulonglong2(0, 0);
+					if (wj) st_mail2(const_cast<unsigned long long *>(jsrc) + cj_, SG_SENT, SG_SENT);   // clean for the next sweep
+				}
+				if (kitem) {
+					*reinterpret_cast<ulonglong2 *>(s_hk + frow * HP + hs) = ink ? fk : make_ulonglong2(0, 0);
+					if (wk) st_mail2(const_cast<unsigned long long *>(ksrc) + ck_, SG_SENT, SG_SENT);
+				}
+				if (n == 0) s_ghost[(seq % SG_LQ) * 32 + lane] = Lf.act ? ghostv : 0.0;
+				__syncwarp();
+				if (lane == 0) sg_mbar_arrive(s_u32(s_full + (Gf % NG)));
+				Gf++;
+			};
+			ask(0, fj0, fk0);
+			ask(1, fj1, fk1);
+#pragma unroll 1
+			for (int n = 0; n < Lf.ngroups; n += 3) {
+				ask(n + 2, fj2, fk2);
+				take(n, fj0, fk0);
+				if (n + 1 >= Lf.ngroups) break;
+				ask(n + 3, fj0, fk0);
+				take(n + 1, fj1, fk1);
+				if (n + 2 >= Lf.ngroups) break;
+				ask(n + 4, fj1, fk1);
+				take(n + 2, fj2, fk2);
+			}
+			if (a.prof) hp_face += clock64() - hp_t;
+		}
+		if (a.prof && lane == 0) atomicAdd((unsigned long long *)a.prof + 3, (unsigned long long)hp_face);
+	}
 }
 
-template <int NG> constexpr size_t sg_smem(int na) { return (size_t)(NG * na * 256 + 4 * 256 + 12 * NG * 8 + 32) * sizeof(double) + NG * 8; }
+template <int NG> constexpr size_t sg_smem(int na)
+{
+	return (size_t)(NG * na * 256 + 12 * SG_HP + SG_LQ * 32) * sizeof(double) + (2 * NG + SG_LQ) * 8 + SG_LQ * 4;
+}
 
 __global__ void __launch_bounds__(256) fill_u64_kernel(unsigned long long *p, size_t n, unsigned long long v)
 {
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
-}
-
-PFN_cuTensorMapEncodeTiled g_encode = nullptr;
-
-int make_map(s3d_ctx *ctx, CUtensorMap *tm, const double *base, int nx, int ny, int nz, long long pitch, long long plane)
-{
-	const cuuint64_t dims[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz};
-	const cuuint64_t strides[2] = {(cuuint64_t)pitch * 8, (cuuint64_t)plane * 8};
-	const cuuint32_t box[3] = {SG_COLS, 4, SG_TK};
-	const cuuint32_t es[3] = {1, 1, 1};
-	const CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(base), dims, strides, box, es,
-	                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-	                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-	if (r != CUDA_SUCCESS) return s3d_fail(ctx, S3D_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %d x %d x %d grid", (int)r, nx, ny, nz);
-	return S3D_OK;
 }
 
 }  // namespace
@@ -360,27 +506,21 @@ extern "C" S3D_HIDDEN int s3d_internal_sgs_stream(s3d_ctx *ctx, const s3d_grid *
                                                   const int *stop)
 {
 	constexpr int NG = 4;
-	if (!g_encode) {
-		void *fn = nullptr;
-		cudaDriverEntryPointQueryResult qres;
-		S3D_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-		if (!fn || qres != cudaDriverEntryPointSuccess) return s3d_fail(ctx, S3D_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-		g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
-	}
+	static_assert(NG <= SG_LQ - 2, "the line queue must outlast the ring");
 	static bool configured = false;
-	static int warps_per_sm = 1;
+	static int blocks_per_sm = 1;
 	if (!configured) {
 		S3D_CUDA(ctx, cudaFuncSetAttribute(sgs_stream_kernel<0, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem<NG>(5)));
 		S3D_CUDA(ctx, cudaFuncSetAttribute(sgs_stream_kernel<1, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem<NG>(5)));
 		S3D_CUDA(ctx, cudaFuncSetAttribute(sgs_stream_kernel<2, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem<NG>(4)));
 		int a = 1, b = 1;
-		S3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sgs_stream_kernel<0, NG>, 32, sg_smem<NG>(5)));
-		S3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sgs_stream_kernel<1, NG>, 32, sg_smem<NG>(5)));
-		warps_per_sm = std::max(1, std::min(a, b));
+		S3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sgs_stream_kernel<0, NG>, 96, sg_smem<NG>(5)));
+		S3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sgs_stream_kernel<1, NG>, 96, sg_smem<NG>(5)));
+		blocks_per_sm = std::max(1, std::min(a, b));
 		configured = true;
 	}
 	// mailboxes: 8 + 4 rows of nxp columns per line, all sentinel outside a sweep (the consumer of a value puts the sentinel back)
-	const int nxp = ((g->nx + 7) / 8) * 8;
+	const int nxp = ((g->nx + 1) / 2) * 2;
 	const size_t nlines = (size_t)nty * ntz;
 	const size_t need = nlines * 12 * (size_t)nxp;
 	if (ctx->sgs_mail_cap < need) {
@@ -396,25 +536,15 @@ extern "C" S3D_HIDDEN int s3d_internal_sgs_stream(s3d_ctx *ctx, const s3d_grid *
 	a.nx = g->nx; a.ny = g->ny; a.nz = g->nz; a.vpitch = g->vpitch; a.vplane = g->vplane; a.voff = g->voff;
 	a.nty = nty; a.ntz = ntz; a.nxp = nxp; a.order = order; a.ticket = ticket;
 	a.mail_j = ctx->sgs_mail; a.mail_k = ctx->sgs_mail + nlines * 8 * (size_t)nxp;
-	a.out = out; a.nx_tma = g->nx & ~1; a.klo_zero = klo_zero; a.khi_zero = khi_zero; a.prof = ctx->sgs_prof;
-	CUtensorMap tm[6];
-	int rc;
-	if (mode == 2) rc = make_map(ctx, &tm[0], in0, g->nx, g->ny, g->nz, g->cpitch, g->cplane);
-	else rc = make_map(ctx, &tm[0], in0 + g->voff, g->nx, g->ny, g->nz, g->vpitch, g->vplane);
-	if (rc != S3D_OK) return rc;
-	const double *cs[4] = {c0, c1, c2, mode == 2 ? c0 : dinv};
-	for (int s = 0; s < 4; s++) {
-		rc = make_map(ctx, &tm[1 + s], cs[s], g->nx, g->ny, g->nz, g->cpitch, g->cplane);
-		if (rc != S3D_OK) return rc;
-	}
-	rc = make_map(ctx, &tm[5], out + g->voff, std::max(2, g->nx & ~1), g->ny, g->nz, g->vpitch, g->vplane);   // nx == 1: never used
-	if (rc != S3D_OK) return rc;
-	int wps = warps_per_sm;
-	if (ctx->sgs_warps_per_sm > 0) wps = std::min(wps, ctx->sgs_warps_per_sm);
-	const unsigned nblocks = (unsigned)std::min<size_t>(nlines, (size_t)ctx->sm_count * wps);
-	if (mode == 0) sgs_stream_kernel<0, NG><<<nblocks, 32, sg_smem<NG>(5), ctx->stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], a, stop);
-	else if (mode == 1) sgs_stream_kernel<1, NG><<<nblocks, 32, sg_smem<NG>(5), ctx->stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], a, stop);
-	else sgs_stream_kernel<2, NG><<<nblocks, 32, sg_smem<NG>(4), ctx->stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], a, stop);
+	a.out = out; a.klo_zero = klo_zero; a.khi_zero = khi_zero; a.prof = ctx->sgs_prof; a.debug = ctx->sgs_sleep_ns;
+	a.in0 = in0; a.c0 = c0; a.c1 = c1; a.c2 = c2; a.dv = (mode == 2) ? c0 : dinv;
+	a.cpitch = g->cpitch; a.cplane = g->cplane;
+	int bps = blocks_per_sm;
+	if (ctx->sgs_warps_per_sm > 0) bps = std::min(bps, ctx->sgs_warps_per_sm);
+	const unsigned nblocks = (unsigned)std::min<size_t>(nlines, (size_t)ctx->sm_count * bps);
+	if (mode == 0) sgs_stream_kernel<0, NG><<<nblocks, 96, sg_smem<NG>(5), ctx->stream>>>(a, stop);
+	else if (mode == 1) sgs_stream_kernel<1, NG><<<nblocks, 96, sg_smem<NG>(5), ctx->stream>>>(a, stop);
+	else sgs_stream_kernel<2, NG><<<nblocks, 96, sg_smem<NG>(4), ctx->stream>>>(a, stop);
 	S3D_LAUNCHED(ctx);
 	return S3D_OK;
 }

@@ -367,6 +367,7 @@ int s3d_tune_set(s3d_ctx *ctx, const char *key, int value)
 	else if (!strcmp(key, "sgs_variant")) ctx->sgs_variant = value;
 	else if (!strcmp(key, "sgs_warps_per_sm")) ctx->sgs_warps_per_sm = value;
 	else if (!strcmp(key, "ew_unroll")) s3d_internal_set_ew_unroll(value);
+	else if (!strcmp(key, "sgs_stream_max_points")) ctx->sgs_stream_max_points = (long long)value;
 	else if (!strcmp(key, "sgs_tile_i")) ctx->sgs_tile_i = value;
 	else if (!strcmp(key, "sgs_pencils")) ctx->sgs_pencils = value;
 	else if (!strcmp(key, "sgs_profile")) {
@@ -379,8 +380,8 @@ int s3d_tune_set(s3d_ctx *ctx, const char *key, int value)
 			S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 			S3D_CUDA(ctx, cudaMemcpy(h, ctx->sgs_prof, sizeof h, cudaMemcpyDeviceToHost));
 			const double t = h[4] ? (double)h[4] : 1.0;
-			fprintf(stderr, "[sgs_profile] tiles %lld  cycles/tile: wait %.0f  halo %.0f  loop %.0f (%.1f per step)  publish %.0f\n", h[4], h[0] / t, h[1] / t,
-			        h[2] / t, h[5] ? (double)h[2] / h[5] : 0.0, h[3] / t);
+			fprintf(stderr, "[sgs_profile] workers %lld  cycles/worker: wait %.0f  total %.0f (%.1f per step, %.1f without the waits)  helper: load %.0f face %.0f retire %.0f passes %.0f\n", h[4], h[0] / t,
+			        h[2] / t, h[5] ? (double)h[2] / h[5] : 0.0, h[5] ? (double)(h[2] - h[0]) / h[5] : 0.0, h[1] / t, h[3] / t, h[6] / t, h[7] / t);
 			S3D_CUDA(ctx, cudaFree(ctx->sgs_prof));
 			ctx->sgs_prof = nullptr;
 		}

@@ -224,7 +224,7 @@ def test_jacobi_and_sgs(ctx, npdim, pde):
 # every build of the exact dataflow sweep: block-per-tile (variant 1), warp-per-tile (variant 0) with 16- or 32-long tiles and one
 # or two pencils per lane; full, ragged and sub-tile grids; forward/backward sweep and the StrILU recurrence
 @pytest.mark.parametrize("npdim", [(18, 18, 18), (35, 11, 20), (3, 3, 3), (50, 23, 14), (131, 9, 6), (21, 38, 27)])
-@pytest.mark.parametrize("variant,tile_i,pencils", [(4, 0, 0), (1, 0, 0), (0, 16, 1), (0, 16, 2), (0, 32, 1), (0, 32, 2), (3, 0, 0)])
+@pytest.mark.parametrize("variant,tile_i,pencils", [(5, 0, 0), (1, 0, 0), (0, 16, 1), (0, 16, 2), (0, 32, 1), (0, 32, 2), (3, 0, 0)])
 def test_sgs_dataflow_variants(ctx, npdim, variant, tile_i, pencils):
     m, A = problem(npdim, "chebyshev", "convdiff", V1, 0.1)
     g = grid_of(m)

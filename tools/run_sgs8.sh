@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k "sgs" > gpurun_out/sgs_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/sgs_tests.log
+tail -3 gpurun_out/sgs_tests.log
+timeout 300 python tools/sgs_lines.py 2048,4,8 2048,8,8 2048,4,16 2048,16,32 > gpurun_out/sgs_lines.log 2>&1; echo "rc=$?" >> gpurun_out/sgs_lines.log
+cat gpurun_out/sgs_lines.log
+SGS_PROF=1 timeout 300 python tools/sgs_probe.py 64 256 512 > gpurun_out/sgs_probe.log 2>&1; echo "probe rc=$?" >> gpurun_out/sgs_probe.log
+grep -v "warps/SM=[23]" gpurun_out/sgs_probe.log

@@ -21,7 +21,7 @@ for npdim in [(3, 3, 3), (4, 3, 3), (3, 4, 3), (3, 3, 4), (10, 3, 3), (11, 3, 3)
         ctx.sgs_setup(g, dA, dinv)
         di = cport.sgs_setup(m, A)
         ref = cport.sgs_like_apply(m, A, di, r, 1)
-        for variant in (0, 4):
+        for variant in (0, 5):
             ctx.tune("sgs_variant", variant)
             ctx.vecset(g, 7.0, dz)
             ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_LEXICOGRAPHIC, 1)

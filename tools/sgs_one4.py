@@ -7,6 +7,7 @@ import numpy as np
 from struct3d_b200 import capi
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 ctx = capi.Context(0)
+ctx.tune("sgs_variant", 5)
 g = capi.make_grid(n, n, n)
 c = [-1.0 + 2.0 * np.arange(n + 2) / (n + 1)] * 3
 A = ctx.mat_alloc(g); ctx.assemble_convdiff(g, c, (0.577, 0.7, 0.3), 0.1, A)

@@ -17,7 +17,9 @@ for n in sizes:
     ctx.tune("sgs_variant", 0)
     ctx.sgs_apply(g, A, dinv, r, zr, y, capi.SGS_LEXICOGRAPHIC, 1)
     ref = ctx.vec_download(g, zr)
-    for variant, wps, depth, dbgv in ((0, 0, 0, 0), (4, 0, 0, 0), (4, 3, 0, 0), (4, 2, 0, 0)):
+    for variant, wps, depth, dbgv in ((0, 0, 0, 0), (5, 0, 0, 0), (5, 2, 0, 0), (5, 0, -1, 0)):
+        ctx.tune("sgs_sleep_ns", 1 if depth == -1 else 0)   # -1: timing experiment without any hand-off between lines (wrong results)
+        if depth == -1: depth = 0
         ctx.tune("sgs_variant", variant); ctx.tune("sgs_warps_per_sm", wps); ctx.tune("sgs_tile_i", depth)
         ctx.tune("sgs_pencils", dbgv)
         for _ in range(2): ctx.sgs_apply(g, A, dinv, r, z, y, capi.SGS_LEXICOGRAPHIC, 1)
@@ -26,11 +28,12 @@ for n in sizes:
         for _ in range(5): ctx.sgs_apply(g, A, dinv, r, z, y, capi.SGS_LEXICOGRAPHIC, 1)
         ms = ctx.timer_stop_ms() / 5
         print(f"{n:4d}^3 variant={variant} warps/SM={wps} tile_i={depth} pencils={dbgv}  {ms:9.4f} ms   {96*n**3/ms/1e6:8.1f} GB/s(96B/pt)  bitwise_same={same}", flush=True)
-        if variant == 4 and wps == 0 and os.environ.get("SGS_PROF"):
+        if variant == 5 and wps in (0,) and os.environ.get("SGS_PROF"):
             import ctypes
             ctx.tune("sgs_profile", 1)
             ctx.sgs_apply(g, A, dinv, r, z, y, capi.SGS_LEXICOGRAPHIC, 1)
             ctx.tune("sgs_profile", 0)
+    ctx.tune("sgs_sleep_ns", 0)
     ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT); ctx.tune("sgs_warps_per_sm", 0); ctx.tune("sgs_tile_i", 0); ctx.tune("sgs_pencils", 0)
     for dbg in ():
         ctx.tune("sgs_sleep_ns", dbg)
