@@ -57,7 +57,7 @@ struct s3d_ctx {
 	int sgs_sleep_ns = 0;
 	int sgs_variant = 4;        // 4: warp-per-line streaming kernel (TMA rings + sentinel mailboxes, the default), 0: warp-per-tile dataflow
 	                            // kernel (also what the exact sweep THROUGH z-slabs uses), 1: block-per-tile kernel, 3: r1's warp-per-line experiment
-	long long sgs_stream_max_points = 3ll << 20;   // variant 4 uses the streaming kernel up to this many points per rank, the tile kernel above
+	long long sgs_stream_max_points = 3ll << 19;   // variant 4 uses the streaming kernel up to this many points per rank, the tile kernel above
 	unsigned long long *sgs_mail = nullptr;   // streaming kernel: face mailboxes (sentinel-filled outside a sweep)
 	size_t sgs_mail_cap = 0;
 	int sgs_warps_per_sm = 0;   // 0: as many as fit

@@ -103,6 +103,7 @@ struct SgsFlow {
 	// z-slab runs (warp-per-tile kernel): the k-face rows of the rank before this one in sweep order arrive in x_in_plane (a plane of
 	// this rank's peer-memory window, flag per (ci, cj) in x_in_flags); this rank's own go to x_out_plane / x_out_flags of the next rank
 	const double *x_in_plane; const int *x_in_flags; double *x_out_plane; int *x_out_flags;
+	int kzero_lo, kzero_hi;   // slab-local sweeps (warp kernel): what lies below k = 0 / above k = nz-1 is taken as zero, not read
 	long long *prof;   // optional per-phase cycle accumulators (warp kernel; timing experiments only)
 	int debug;         // timing experiments only (results become wrong): 1 skip wavefront, 2 skip staging, 4 skip fences, 8 skip waits
 };
@@ -418,7 +419,8 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 					if (row < tk) hp[u] = out + vtile + (long long)(FWD ? row : tk - 1 - row) * g.vplane + (long long)(FWD ? -1 : tj) * g.vpitch + 2 * i2;
 				} else {
 					const int r = row - 8;
-					if (r < tj)
+					const bool kz = FWD ? (f.kzero_lo && ck == 0) : (f.kzero_hi && ck == f.ntz - 1);
+					if (r < tj && !kz)
 						hp[u] = (xin ? f.x_in_plane + inpl : out + vtile + (long long)(FWD ? -1 : tk) * g.vplane) + (long long)(FWD ? r : tj - 1 - r) * g.vpitch + 2 * i2;
 				}
 			}
@@ -1022,7 +1024,7 @@ inline int sgs_effective_variant(const s3d_ctx *ctx, const s3d_grid *g, bool thr
 	int v = ctx->sgs_variant;
 	if ((v == 4 || v == 5) && through_slabs && g->nranks > 1) return 0;
 	// 4 = by grid size (measured crossover, profiles/r2_sgs_stream.md), 5 = the streaming kernel whatever the size
-	if (v == 4 && g->nranks == 1 && (long long)g->nx * g->ny * g->nz > ctx->sgs_stream_max_points) return 0;
+	if (v == 4 && (long long)g->nx * g->ny * g->nz > ctx->sgs_stream_max_points) return 0;
 	return v == 5 ? 4 : v;
 }
 
@@ -1083,6 +1085,7 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 	f.flags = ctx->sgs_flags;
 	f.iface = ctx->sgs_iface;
 	f.x_in_plane = nullptr; f.x_in_flags = nullptr; f.x_out_plane = nullptr; f.x_out_flags = nullptr;
+	f.kzero_lo = 0; f.kzero_hi = 0;
 	f.order = ctx->sgs_order;
 	f.sleep_ns = 0;
 	f.debug = ctx->sgs_sleep_ns;   // reuses the tuning slot: debug bit mask
@@ -1228,8 +1231,8 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 	const int variant = sgs_effective_variant(ctx, g, !slablocal);
 	if (g->nranks > 1 && !slablocal && (ordering != S3D_SGS_LEXICOGRAPHIC || variant != 0))
 		return s3d_fail(ctx, S3D_ERR_ARG, "across z-slabs only the warp-per-tile lexicographic sweep (or slab-local / red-black / sweeps) is available");
-	if (g->nranks > 1 && slablocal && variant != 4)
-		return s3d_fail(ctx, S3D_ERR_ARG, "the slab-local ordering runs on the streaming kernel (sgs_variant 4)");
+	if (g->nranks > 1 && slablocal && variant != 4 && variant != 0)
+		return s3d_fail(ctx, S3D_ERR_ARG, "the slab-local ordering runs on the streaming or the warp-per-tile kernel");
 	// the scratch vector's real entries are all overwritten and its ghosts stay zero (they are never
 	// written), so the per-call zero fill of the reference (s3d_sgspreconditioners.cpp:25-28) is implicit.
 	// Sequential sweeps are idempotent, so nsweeps > 1 repeats identical work; do one.
@@ -1250,8 +1253,9 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 			S3D_LAUNCHED(ctx);
 			return s3d_internal_sgs_stream(ctx, g, 1, d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f.order, f.nty, f.ntz, f.ticket, klo, khi, ctx->gate);
 		}
+		if (slablocal) { f.kzero_lo = g->rank > 0; f.kzero_hi = g->rank < g->nranks - 1; }
 		s3d_sgs_window xw;
-		if (g->nranks > 1) {
+		if (g->nranks > 1 && !slablocal) {
 			// the sweep runs THROUGH the slabs: rank p's first plane of tiles waits for rank p-1's last one (peer-memory window)
 			const int rcw = s3d_internal_sgs_window(ctx, g, f.ntx, f.nty, &xw);
 			if (rcw != S3D_OK) return rcw;
@@ -1267,7 +1271,7 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		else
 			sgs_dataflow_kernel<0><<<nblocks, block, SGS_SMEM, ctx->stream>>>(gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, ctx->gate);
 		S3D_LAUNCHED(ctx);
-		if (g->nranks > 1) { f.x_in_plane = xw.bwd_in_plane; f.x_in_flags = xw.bwd_in_flags; f.x_out_plane = xw.bwd_out_plane; f.x_out_flags = xw.bwd_out_flags; }
+		if (g->nranks > 1 && !slablocal) { f.x_in_plane = xw.bwd_in_plane; f.x_in_flags = xw.bwd_in_flags; f.x_out_plane = xw.bwd_out_plane; f.x_out_flags = xw.bwd_out_flags; }
 		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
 		S3D_LAUNCHED(ctx);
 		if (variant == 3)

@@ -16,7 +16,8 @@
 //     dependent instruction per 5 cycles; profiles/r2_sgs_stream.md.)
 //   * the skew lives in the shared-memory layout: the loader puts element (i, pj, pk) of a stream at SHEARED column u = i + 2 pj + 2 pk
 //     of row (pj, pk), so column h of every row holds exactly the element that row's lane needs at step h.  All lanes read the same
-//     column at the same step: the inner loop addresses shared memory with immediates only.  Groups of 8 columns (64-byte row pieces)
+//     column at the same step: the inner loop addresses shared memory with immediates only.  Data groups of 16 columns (128-byte row
+//     pieces: whole lines for the memory system -- with 64-byte pieces the SM's outstanding requests capped a sweep at 3.8 TB/s)
 //     travel through a ring of NG slots as 16-byte cp.async copies, completion counted on an mbarrier; the 16-byte chunks of a row
 //     are XOR-swizzled with the row number so that the 16-byte loads of the 32 rows are bank-conflict-free.  (The first working
 //     version made the TMA unit do the shear -- tensor maps with row stride = pitch - 2 elements, SWIZZLE_64B -- which was correct but
@@ -25,9 +26,10 @@
 //     and the loader warp stores them with coalesced 16-byte stores, predicated at the ends of the rows;
 //   * the faces a neighbouring line needs (last-j pencils -> line cj+1, last-k pencils -> line ck+1) go through MAILBOXES in global
 //     memory whose empty state is a sentinel bit pattern (a signalling NaN no arithmetic produces): the producing lane stores each
-//     pair the moment it is complete (no fence), the consuming line's helper polls THE DATA ITSELF with L2 loads, hands the values to
-//     its compute warp through shared memory, and writes the sentinel back, so the mailbox is clean again for the next sweep.  The
-//     lag between adjacent lines is the lane skew + one group + one L2 round trip instead of a whole tile + fence + flag + fetch;
+//     pair the moment it is complete (no fence), the consuming line's FACE warp polls THE DATA ITSELF with L2 loads, hands the values
+//     to its compute warp through shared memory in half-groups of 8 columns, and writes the sentinel back, so the mailbox is clean
+//     again for the next sweep.  The lag between adjacent lines is the lane skew + 8 columns + one L2 round trip instead of a whole
+//     tile + fence + flag + fetch;
 //   * lines are drawn from a ticket counter in (cj + ck) order, so a line only waits on lines with smaller tickets, which are
 //     running or done: no co-residency assumption, no deadlock (same argument as the tile kernel).
 #include <algorithm>
@@ -35,10 +37,11 @@
 
 namespace {
 
-constexpr int SG_COLS = 8;                                  // box columns (= steps) per group
+constexpr int SG_COLS = 8;                                  // columns of a half-group: the granularity of the face hand-off
+constexpr int SG_DG = 16;                                   // columns of a data group: 128-byte row pieces
 constexpr int SG_TJ = 4, SG_TK = 8;                         // pencils of a line: lane = m * 8 + c, m < 4 (j), c < 8 (k)
-constexpr int SG_LQ = 8;                                    // entries of the line queue between the two warps
-constexpr int SG_HW = 64, SG_HP = SG_HW + 2;                // face ring: 8 groups wide; row pitch shifts consecutive rows by 16 bytes in the banks
+constexpr int SG_LQ = 8;                                    // entries of the line queue between the warps
+constexpr int SG_HW = 64, SG_HP = SG_HW + 2;                // face ring: 8 half-groups wide; row pitch shifts consecutive rows by 16 bytes in the banks
 constexpr unsigned long long SG_SENT = 0xFFF4A5C3D2E1B497ull;   // "not written yet": a signalling-NaN pattern arithmetic never returns
 
 struct StreamArgs {
@@ -62,18 +65,11 @@ struct StreamArgs {
 
 __device__ __forceinline__ unsigned s_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sg_mbar_init(unsigned a, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory"); }
-__device__ __forceinline__ void sg_mbar_expect_tx(unsigned a, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void sg_mbar_arrive(unsigned a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(a) : "memory"); }
 __device__ __forceinline__ bool sg_mbar_try_wait(unsigned a, unsigned parity)
 {
 	unsigned ok;
 	asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-	return ok != 0;
-}
-__device__ __forceinline__ bool sg_mbar_test(unsigned a, unsigned parity)
-{
-	unsigned ok;
-	asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
 	return ok != 0;
 }
 __device__ __forceinline__ void cp_async16_if(unsigned dst, const double *src, bool on)
@@ -101,13 +97,20 @@ __device__ __forceinline__ void st_pair_on(double *p, double lo, double hi, bool
 {
 	asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %3, 0;\n@p st.global.cg.v2.f64 [%0], {%1, %2};\n}\n" ::"l"(p), "d"(lo), "d"(hi), "r"((unsigned)on));
 }
+__device__ __forceinline__ int ld_volatile_s32(const int *p)
+{
+	int v;
+	asm volatile("ld.volatile.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(s_u32(p)) : "memory");
+	return v;
+}
 
-// What both warps derive from a line number.
-//   sheared column  u = i + 2 pj + 2 pk,  0 <= u < W = nx + 2 (tj-1) + 2 (tk-1), in ngroups groups of 8
-//   forward sweeps walk the groups upwards, backward sweeps downwards; the lane of logical pencil (m, c) holds the physical pencil
+// What the warps derive from a line number.
+//   sheared column  u = i + 2 pj + 2 pk,  0 <= u < W = nx + 2 (tj-1) + 2 (tk-1): nh half-groups of 8 columns, nd data groups of 16
+//   forward sweeps walk the columns upwards, backward sweeps downwards; the lane of logical pencil (m, c) holds the physical pencil
 //   (m, c) forward and (tj-1-m, tk-1-c) backward, so the lanes it depends on, (m-1, c) and (m, c-1), are two steps ahead of it.
+//   Logical data group d holds the logical half-groups 2 d and 2 d + 1; its 16-column window starts at sheared column ud0(d).
 template <bool FWD> struct LineGeo {
-	int line, cj, ck, j0, k0, tj, tk, ngroups, shmax;
+	int line, cj, ck, j0, k0, tj, tk, nh, nd, shmax;
 	bool act;
 	int pj, pk, sh2, row;
 	__device__ __forceinline__ void set(const StreamArgs &a, int ln, int lane)
@@ -117,7 +120,8 @@ template <bool FWD> struct LineGeo {
 		j0 = cj * SG_TJ; k0 = ck * SG_TK;
 		tj = min(SG_TJ, a.ny - j0); tk = min(SG_TK, a.nz - k0);
 		shmax = 2 * (tj - 1) + 2 * (tk - 1);
-		ngroups = (a.nx + shmax + SG_COLS - 1) / SG_COLS;
+		nh = (a.nx + shmax + SG_COLS - 1) / SG_COLS;
+		nd = (nh + 1) / 2;
 		const int m = lane >> 3, c = lane & 7;
 		act = (m < tj) && (c < tk);
 		pj = act ? (FWD ? m : tj - 1 - m) : 0;
@@ -125,9 +129,8 @@ template <bool FWD> struct LineGeo {
 		sh2 = 2 * pj + 2 * pk;
 		row = act ? pj * SG_TK + pk : lane;   // idle lanes keep a row of their own: it lies outside the grid, nobody reads or stores it
 	}
-	// first sheared column of logical group n
-	__device__ __forceinline__ int u0(int n) const { return SG_COLS * (FWD ? n : ngroups - 1 - n); }
-	__device__ __forceinline__ int chunk(int q) const { return row * SG_COLS + 2 * (q ^ ((row >> 1) & 3)); }
+	__device__ __forceinline__ int u0h(int h) const { return SG_COLS * (FWD ? h : nh - 1 - h); }      // first column of logical half-group h
+	__device__ __forceinline__ int ud0(int d) const { return FWD ? SG_DG * d : SG_COLS * (nh - 2 - 2 * d); }   // first column of data group d's window
 	__device__ __forceinline__ double *orow(const StreamArgs &a) const { return a.out + a.voff + (long long)(k0 + pk) * a.vplane + (long long)(j0 + pj) * a.vpitch; }
 };
 
@@ -142,21 +145,23 @@ sgs_stream_kernel(const StreamArgs a, const int *stop)
 	constexpr bool ILU = (MODE == 2);
 	constexpr int NA = ILU ? 4 : 5;
 	constexpr int TJ = SG_TJ, TK = SG_TK, ROWS = TJ * TK;
-	constexpr int GD = ROWS * SG_COLS;                       // doubles of one stream of one group (2 KB)
-	constexpr int GS = NA * GD;                              // doubles of one group, all streams
+	constexpr int GD = ROWS * SG_DG;                         // doubles of one stream of one data group (4 KB)
+	constexpr int GS = NA * GD;                              // doubles of one data group, all streams
 	constexpr int HP = SG_HP;
 	constexpr unsigned FULL = 0xffffffffu;
 	if (s3d_stopped(stop)) return;
 
 	extern __shared__ __align__(1024) double sg_smem[];      // the only shared memory of the kernel: starts at the CTA's window, 1 KB aligned
-	double *s_in = sg_smem;                                  // [NG][NA][j 4][k 8][8], 16-byte chunks swizzled by TMA (SWIZZLE_64B)
-	double *s_hj = s_in + NG * GS;                           // [8 k-rows][HP]  j-neighbour values of group G at columns (G % 8) * 8 ...
+	double *s_in = sg_smem;                                  // [NG][NA][j 4][k 8][16]: 16-byte chunk q of row r sits at chunk q ^ (r & 7)
+	double *s_hj = s_in + NG * GS;                           // [8 k-rows][HP]  j-neighbour values of half-group H at columns (H % 8) * 8 ...
 	double *s_hk = s_hj + 8 * HP;                            // [4 j-rows][HP]  k-neighbour values
 	double *s_ghost = s_hk + TJ * HP;                        // [SG_LQ][32]     the ghost column of a line, per lane
-	unsigned long long *s_full = reinterpret_cast<unsigned long long *>(s_ghost + SG_LQ * 32);   // [NG]   inputs + faces of a group are there
-	unsigned long long *s_done = s_full + NG;                // [NG]   the compute warp is done with a group
-	unsigned long long *s_lbar = s_done + NG;                // [SG_LQ] a line-queue entry is valid
+	unsigned long long *s_full = reinterpret_cast<unsigned long long *>(s_ghost + SG_LQ * 32);   // [NG]   the inputs of a data group have landed
+	unsigned long long *s_done = s_full + NG;                // [NG]   the compute warp is done with a data group
+	unsigned long long *s_face = s_done + NG;                // [8]    the faces of a half-group are in the face ring
+	unsigned long long *s_lbar = s_face + 8;                 // [SG_LQ] a line-queue entry is valid
 	int *s_lineq = reinterpret_cast<int *>(s_lbar + SG_LQ);  // [SG_LQ] line numbers, -1 = no more lines
+	int *s_prog = s_lineq + SG_LQ;                           // half-groups the compute warp has finished (all lines)
 
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
@@ -165,9 +170,12 @@ sgs_stream_kernel(const StreamArgs a, const int *stop)
 
 	if (threadIdx.x == 0) {
 #pragma unroll
-		for (int s = 0; s < NG; s++) { sg_mbar_init(s_u32(s_full + s), 33); sg_mbar_init(s_u32(s_done + s), 1); }
+		for (int s = 0; s < NG; s++) { sg_mbar_init(s_u32(s_full + s), 32); sg_mbar_init(s_u32(s_done + s), 1); }
+#pragma unroll
+		for (int s = 0; s < 8; s++) sg_mbar_init(s_u32(s_face + s), 1);
 #pragma unroll
 		for (int s = 0; s < SG_LQ; s++) sg_mbar_init(s_u32(s_lbar + s), 1);
+		*s_prog = 0;
 		asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 	}
 	__syncthreads();
@@ -175,8 +183,8 @@ sgs_stream_kernel(const StreamArgs a, const int *stop)
 	if (warp == 0) {
 		// ======================================================================= the COMPUTE warp
 		LineGeo<FWD> L;
-		int G = 0;                                               // groups processed so far (all lines): ring slot G % NG, face ring (G % 8) * 8
-		long long tq_wait = 0, tq0 = 0, nst = 0;
+		int G = 0, H = 0;                                        // data groups / half-groups processed so far (all lines)
+		long long tq_wait = 0, tq_fwait = 0, tq0 = 0, nst = 0;
 		if (a.prof) tq0 = clock64();
 		for (int seq = 0;; seq++) {
 			{
@@ -190,14 +198,15 @@ sgs_stream_kernel(const StreamArgs a, const int *stop)
 			const bool jprod = L.act && jsucc && (m == L.tj - 1) && !(a.debug & 1), kprod = L.act && ksucc && (cc == L.tk - 1) && !(a.debug & 1);
 			double *mj_dst = reinterpret_cast<double *>(a.mail_j + ((size_t)line * 8 + L.pk) * a.nxp);
 			double *mk_dst = reinterpret_cast<double *>(a.mail_k + ((size_t)line * TJ + L.pj) * a.nxp);
-			int chunk_off[4];
+			int chunk_off[8];
 #pragma unroll
-			for (int q = 0; q < 4; q++) chunk_off[q] = L.chunk(q);
+			for (int q = 0; q < 8; q++) chunk_off[q] = L.row * SG_DG + 2 * (q ^ (L.row & 7));
 			const bool jhalo = (m == 0), khalo = (cc == 0);
 			const double *phj = s_hj + L.pk * HP, *phk = s_hk + L.pj * HP;
 			double cur = 0.0, prv = 0.0;                             // the lane's last value (its i-neighbour) and the one before
+			long long t_first = 0;
 #pragma unroll 1
-			for (int n = 0; n < L.ngroups; n++, G++) {
+			for (int d = 0; d < L.nd; d++, G++) {
 				const int slot = G % NG;
 				{
 					long long t = 0;
@@ -206,81 +215,110 @@ sgs_stream_kernel(const StreamArgs a, const int *stop)
 					while (!__all_sync(FULL, sg_mbar_try_wait(bar, (G / NG) & 1))) { }
 					if (a.prof) tq_wait += clock64() - t;
 				}
-				if (n == 0) cur = s_ghost[(seq % SG_LQ) * 32 + lane];
 				double *g_in = s_in + slot * GS;                        // results overwrite the first stream of the slot
-				const int u0 = L.u0(n);
-				const int hb = (G & 7) * SG_COLS;
-				const int icb = u0 - L.sh2;                             // real column of box column 0
-				double2 o_in, o_c0, o_c1, o_c2, o_dv, o_hj, o_hk;
-				o_dv = make_double2(0.0, 0.0); o_hj = make_double2(0.0, 0.0); o_hk = make_double2(0.0, 0.0);
-				const bool interior = (u0 >= L.shmax) && (u0 + SG_COLS <= a.nx);
-				// one column: the reference's expression, the reference's order of roundings
-				auto column = [&](int el) -> double {
-					const double shj = __shfl_up_sync(FULL, prv, 8);
-					const double shk = __shfl_up_sync(FULL, prv, 1);
-					const double x_in = el ? o_in.y : o_in.x, x_c0 = el ? o_c0.y : o_c0.x, x_c1 = el ? o_c1.y : o_c1.x, x_c2 = el ? o_c2.y : o_c2.x;
-					const double x_dv = el ? o_dv.y : o_dv.x;
-					const double wj = jhalo ? (el ? o_hj.y : o_hj.x) : shj, wk = khalo ? (el ? o_hk.y : o_hk.x) : shk;
-					if (ILU) return __dsub_rn(__dsub_rn(__dsub_rn(x_in, __ddiv_rn(x_c0, cur)), __ddiv_rn(x_c1, wj)), __ddiv_rn(x_c2, wk));
-					if (FWD) return __dmul_rn(__dsub_rn(__dsub_rn(__dsub_rn(x_in, __dmul_rn(x_c0, cur)), __dmul_rn(x_c1, wj)), __dmul_rn(x_c2, wk)), x_dv);
-					return __dsub_rn(x_in, __dmul_rn(x_dv, __dadd_rn(__dadd_rn(__dmul_rn(x_c0, cur), __dmul_rn(x_c1, wj)), __dmul_rn(x_c2, wk))));
-				};
-				auto fetch = [&](int q) {
-					o_in = *reinterpret_cast<const double2 *>(g_in + chunk_off[q]);
-					o_c0 = *reinterpret_cast<const double2 *>(g_in + GD + chunk_off[q]);
-					o_c1 = *reinterpret_cast<const double2 *>(g_in + 2 * GD + chunk_off[q]);
-					o_c2 = *reinterpret_cast<const double2 *>(g_in + 3 * GD + chunk_off[q]);
-					if (!ILU) o_dv = *reinterpret_cast<const double2 *>(g_in + 4 * GD + chunk_off[q]);
-					if (jhalo) o_hj = *reinterpret_cast<const double2 *>(phj + hb + 2 * q);
-					if (khalo) o_hk = *reinterpret_cast<const double2 *>(phk + hb + 2 * q);
-				};
-				if (interior) {
-					// every lane's eight columns lie inside the grid: no range checks, nothing to select
+				const int ud0 = L.ud0(d);
 #pragma unroll
-					for (int p = 0; p < 4; p++) {
-						const int q = FWD ? p : 3 - p;                  // chunk of the box this pair lives in
-						fetch(q);
-						double v[2];
-#pragma unroll
-						for (int e = 0; e < 2; e++) {
-							const int el = FWD ? e : 1 - e;             // forward sweeps take the even column first
-							const double r = column(el);
-							prv = cur; cur = r; v[el] = r;
-						}
-						*reinterpret_cast<double2 *>(g_in + chunk_off[q]) = make_double2(v[0], v[1]);
-						const int iclo = icb + 2 * q;
-						st_pair_on(mj_dst + iclo, v[0], v[1], jprod);
-						st_pair_on(mk_dst + iclo, v[0], v[1], kprod);
+				for (int hh = 0; hh < 2; hh++) {
+					if (2 * d + hh >= L.nh) break;
+					{
+						long long t = 0;
+						if (a.prof) t = clock64();
+						const unsigned bar = s_u32(s_face + (H & 7));
+						while (!__all_sync(FULL, sg_mbar_try_wait(bar, (H >> 3) & 1))) { }
+						if (a.prof) tq_fwait += clock64() - t;
 					}
-				} else {
-#pragma unroll
-					for (int p = 0; p < 4; p++) {
-						const int q = FWD ? p : 3 - p;
-						fetch(q);
-						double v[2];
-						bool in[2];
-#pragma unroll
-						for (int e = 0; e < 2; e++) {
-							const int el = FWD ? e : 1 - e;
-							const int ic = icb + 2 * q + el;
-							const double r = column(el);
-							const bool inr = L.act && (unsigned)ic < (unsigned)a.nx;
-							prv = cur; cur = inr ? r : cur; v[el] = r; in[el] = inr;
-						}
-						*reinterpret_cast<double2 *>(g_in + chunk_off[q]) = make_double2(v[0], v[1]);
-						const int iclo = icb + 2 * q;
-						st_pair_if(mj_dst + iclo, v[0], v[1], jprod && in[0] && in[1], jprod && in[0] && !in[1]);
-						st_pair_if(mk_dst + iclo, v[0], v[1], kprod && in[0] && in[1], kprod && in[0] && !in[1]);
+					if (d == 0 && hh == 0) {
+						cur = s_ghost[(seq % SG_LQ) * 32 + lane];
+						if (a.prof && FWD) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t_first));
 					}
+					const int pb = FWD ? SG_COLS * hh : SG_COLS * (1 - hh);   // position of the half-group inside the data group's window
+					const int u0 = ud0 + pb;
+					const int hb = (H & 7) * SG_COLS;
+					const int icb = u0 - L.sh2;                         // real column of the half-group's first column
+					double2 o_in, o_c0, o_c1, o_c2, o_dv, o_hj, o_hk;
+					o_dv = make_double2(0.0, 0.0); o_hj = make_double2(0.0, 0.0); o_hk = make_double2(0.0, 0.0);
+					const bool interior = (u0 >= L.shmax) && (u0 + SG_COLS <= a.nx);
+					// one column: the reference's expression, the reference's order of roundings
+					auto column = [&](int el) -> double {
+						const double shj = __shfl_up_sync(FULL, prv, 8);
+						const double shk = __shfl_up_sync(FULL, prv, 1);
+						const double x_in = el ? o_in.y : o_in.x, x_c0 = el ? o_c0.y : o_c0.x, x_c1 = el ? o_c1.y : o_c1.x, x_c2 = el ? o_c2.y : o_c2.x;
+						const double x_dv = el ? o_dv.y : o_dv.x;
+						const double wj = jhalo ? (el ? o_hj.y : o_hj.x) : shj, wk = khalo ? (el ? o_hk.y : o_hk.x) : shk;
+						if (ILU) return __dsub_rn(__dsub_rn(__dsub_rn(x_in, __ddiv_rn(x_c0, cur)), __ddiv_rn(x_c1, wj)), __ddiv_rn(x_c2, wk));
+						if (FWD) return __dmul_rn(__dsub_rn(__dsub_rn(__dsub_rn(x_in, __dmul_rn(x_c0, cur)), __dmul_rn(x_c1, wj)), __dmul_rn(x_c2, wk)), x_dv);
+						return __dsub_rn(x_in, __dmul_rn(x_dv, __dadd_rn(__dadd_rn(__dmul_rn(x_c0, cur), __dmul_rn(x_c1, wj)), __dmul_rn(x_c2, wk))));
+					};
+					auto fetch = [&](int cq, int q) {                   // chunk cq of the window = pair q of the half-group
+						o_in = *reinterpret_cast<const double2 *>(g_in + chunk_off[cq]);
+						o_c0 = *reinterpret_cast<const double2 *>(g_in + GD + chunk_off[cq]);
+						o_c1 = *reinterpret_cast<const double2 *>(g_in + 2 * GD + chunk_off[cq]);
+						o_c2 = *reinterpret_cast<const double2 *>(g_in + 3 * GD + chunk_off[cq]);
+						if (!ILU) o_dv = *reinterpret_cast<const double2 *>(g_in + 4 * GD + chunk_off[cq]);
+						if (jhalo) o_hj = *reinterpret_cast<const double2 *>(phj + hb + 2 * q);
+						if (khalo) o_hk = *reinterpret_cast<const double2 *>(phk + hb + 2 * q);
+					};
+					if (interior) {
+						// every lane's eight columns lie inside the grid: no range checks, nothing to select
+#pragma unroll
+						for (int p = 0; p < 4; p++) {
+							const int q = FWD ? p : 3 - p;              // pair of the half-group
+							const int cq = (FWD ? 4 * hh : 4 * (1 - hh)) + q;
+							fetch(cq, q);
+							double v[2];
+#pragma unroll
+							for (int e = 0; e < 2; e++) {
+								const int el = FWD ? e : 1 - e;         // forward sweeps take the even column first
+								const double r = column(el);
+								prv = cur; cur = r; v[el] = r;
+							}
+							*reinterpret_cast<double2 *>(g_in + chunk_off[cq]) = make_double2(v[0], v[1]);
+							const int iclo = icb + 2 * q;
+							st_pair_on(mj_dst + iclo, v[0], v[1], jprod);
+							st_pair_on(mk_dst + iclo, v[0], v[1], kprod);
+						}
+					} else {
+#pragma unroll
+						for (int p = 0; p < 4; p++) {
+							const int q = FWD ? p : 3 - p;
+							const int cq = (FWD ? 4 * hh : 4 * (1 - hh)) + q;
+							fetch(cq, q);
+							double v[2];
+							bool in[2];
+#pragma unroll
+							for (int e = 0; e < 2; e++) {
+								const int el = FWD ? e : 1 - e;
+								const int ic = icb + 2 * q + el;
+								const double r = column(el);
+								const bool inr = L.act && (unsigned)ic < (unsigned)a.nx;
+								prv = cur; cur = inr ? r : cur; v[el] = r; in[el] = inr;
+							}
+							*reinterpret_cast<double2 *>(g_in + chunk_off[cq]) = make_double2(v[0], v[1]);
+							const int iclo = icb + 2 * q;
+							st_pair_if(mj_dst + iclo, v[0], v[1], jprod && in[0] && in[1], jprod && in[0] && !in[1]);
+							st_pair_if(mk_dst + iclo, v[0], v[1], kprod && in[0] && in[1], kprod && in[0] && !in[1]);
+						}
+					}
+					H++;
+					__syncwarp();
+					if (lane == 0) *reinterpret_cast<volatile int *>(s_prog) = H;   // the face ring entry of this half-group is free again
 				}
 				// the group's results are in shared memory: over to the loader warp, which stores them
 				__syncwarp();
 				if (lane == 0) sg_mbar_arrive(s_u32(s_done + slot));
 			}
-			if (a.prof && lane == 0) nst += (long long)L.ngroups * SG_COLS;
+			if (a.prof && lane == 0) {
+				nst += (long long)L.nh * SG_COLS;
+				if (FWD && line < 2048) {                            // timing experiments: when each line's compute started and ended
+					long long t_end;
+					asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t_end));
+					a.prof[8 + 2 * line] = t_first; a.prof[9 + 2 * line] = t_end;
+				}
+			}
 		}
 		if (a.prof && lane == 0) {
-			atomicAdd((unsigned long long *)a.prof + 0, (unsigned long long)tq_wait);
+			atomicAdd((unsigned long long *)a.prof + 0, (unsigned long long)(tq_wait + tq_fwait));
+			atomicAdd((unsigned long long *)a.prof + 7, (unsigned long long)tq_fwait);
 			atomicAdd((unsigned long long *)a.prof + 2, (unsigned long long)(clock64() - tq0));
 			atomicAdd((unsigned long long *)a.prof + 4, 1ull);
 			atomicAdd((unsigned long long *)a.prof + 5, (unsigned long long)nst);
@@ -290,19 +328,17 @@ sgs_stream_kernel(const StreamArgs a, const int *stop)
 
 	if (warp == 1) {
 		// ======================================================================= the LOADER warp
-		// LOAD: the five input streams of a group into a free ring slot -- 16-byte cp.async, each lane four row pieces per stream,
-		// written where the sheared, swizzled layout wants them; completion counted on the slot's `full` barrier.  RETIRE: the
+		// LOAD: the five input streams of a data group into a free ring slot -- 16-byte cp.async, each lane eight row pieces per
+		// stream, written where the sheared, swizzled layout wants them; completion counted on the slot's `full` barrier.  RETIRE: the
 		// results of the groups the compute warp has finished, shared memory -> global, coalesced 16-byte stores, predicated at the
-		// ends of the rows.  It also draws the lines.  (A first version used TMA tensor copies for all of this: every op on a box of
-		// 64-byte rows held the SM's TMA unit for ~130 cycles, 6 ops per group and 4 lines per SM: 390 cycles per step.)
+		// ends of the rows.  It also draws the lines.
 		LineGeo<FWD> Ll, Lr;
 		int Gl = 0, Gr = 0, nl = 0, nr = 0, seql = 0, seqr = 0;
 		bool have_l = false, have_r = false, end_l = false;
 		int ticket = blockIdx.x;
 		const int nblocks = gridDim.x;
-		// this lane's pieces: physical pencil (pj = t, pk = lane >> 2), t = 0..3, 16-byte chunk lane & 3 of the pencil's 8 columns
-		const int ppk = lane >> 2, pch = lane & 3;
-		const int soff = ppk * SG_COLS + 2 * (pch ^ ((ppk >> 1) & 3));   // + t * 64 doubles: rows t * 8 + ppk share the swizzle
+		// this lane's pieces: 16-byte chunk lane & 7 of rows t * 4 + (lane >> 3), t = 0..7: pencil pj = t >> 1, pk = (t & 1) * 4 + (lane >> 3)
+		const int pch = lane & 7, prl = lane >> 3;
 		long long hp_load = 0, hp_ret = 0, hp_t = 0;
 		for (;;) {
 			if (a.prof) hp_t = clock64();
@@ -325,17 +361,17 @@ sgs_stream_kernel(const StreamArgs a, const int *stop)
 				if (!have_l || Gl >= Gr + NG) break;
 				{
 					const int slot = Gl % NG;
-					const unsigned bar = s_u32(s_full + slot), dst = s_u32(s_in + slot * GS + soff);
-					const int c0_ = Ll.u0(nl) + 2 * pch - 2 * ppk;                     // real column of the piece for t = 0; t takes 2 t off
-					const long long cb = (long long)(Ll.k0 + ppk) * a.cplane + (long long)Ll.j0 * a.cpitch;
-					const long long vb = a.voff + (long long)(Ll.k0 + ppk) * a.vplane + (long long)Ll.j0 * a.vpitch;
+					const unsigned bar = s_u32(s_full + slot), dst = s_u32(s_in + slot * GS);
+					const int ub = Ll.ud0(nl) + 2 * pch;                               // sheared column of this lane's chunk
 #pragma unroll
-					for (int t = 0; t < TJ; t++) {
-						const int c = c0_ - 2 * t;
-						const bool on = (t < Ll.tj) && (ppk < Ll.tk) && c >= 0 && c < a.nx;
-						const long long co = cb + (long long)t * a.cpitch + c;
-						const unsigned d = dst + t * 64 * 8;
-						cp_async16_if(d, ILU ? a.in0 + co : a.in0 + vb + (long long)t * a.vpitch + c, on);
+					for (int t = 0; t < 8; t++) {
+						const int pj = t >> 1, pk = (t & 1) * 4 + prl, row = pj * TK + pk;
+						const int c = ub - 2 * pj - 2 * pk;                            // real column
+						const bool on = (pj < Ll.tj) && (pk < Ll.tk) && c >= 0 && c < a.nx;
+						const long long co = (long long)(Ll.k0 + pk) * a.cplane + (long long)(Ll.j0 + pj) * a.cpitch + c;
+						const long long vo = a.voff + (long long)(Ll.k0 + pk) * a.vplane + (long long)(Ll.j0 + pj) * a.vpitch + c;
+						const unsigned d = dst + (row * SG_DG + 2 * (pch ^ (row & 7))) * 8;
+						cp_async16_if(d, ILU ? a.in0 + co : a.in0 + vo, on);
 						cp_async16_if(d + GD * 8, a.c0 + co, on);
 						cp_async16_if(d + 2 * GD * 8, a.c1 + co, on);
 						cp_async16_if(d + 3 * GD * 8, a.c2 + co, on);
@@ -344,7 +380,7 @@ sgs_stream_kernel(const StreamArgs a, const int *stop)
 					asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
 				}
 				Gl++; nl++;
-				if (nl == Ll.ngroups) { have_l = false; seql++; }
+				if (nl == Ll.nd) { have_l = false; seql++; }
 			}
 			if (a.prof) { const long long t = clock64(); hp_load += t - hp_t; hp_t = t; }
 			if (Gr == Gl) break;                                     // nothing loaded that is not retired: the line sequence has ended
@@ -353,20 +389,19 @@ sgs_stream_kernel(const StreamArgs a, const int *stop)
 				const int slot = Gr % NG;
 				const unsigned bar = s_u32(s_done + slot);
 				while (!__all_sync(FULL, sg_mbar_try_wait(bar, (Gr / NG) & 1))) { }
-				const double *g_out = s_in + slot * GS + soff;
-				const int c0_ = Lr.u0(nr) + 2 * pch - 2 * ppk;
-				double *ob = a.out + a.voff + (long long)(Lr.k0 + ppk) * a.vplane + (long long)Lr.j0 * a.vpitch;
+				const double *g_out = s_in + slot * GS;
+				const int ub = Lr.ud0(nr) + 2 * pch;
 #pragma unroll
-				for (int t = 0; t < TJ; t++) {
-					const double2 v = *reinterpret_cast<const double2 *>(g_out + t * 64);
-					const int c = c0_ - 2 * t;
-					const bool row_on = (t < Lr.tj) && (ppk < Lr.tk);
-					const bool inlo = row_on && c >= 0 && c < a.nx, inhi = inlo && (c + 1 < a.nx);
-					st_pair_if(ob + (long long)t * a.vpitch + c, v.x, v.y, inhi, inlo && !inhi);
+				for (int t = 0; t < 8; t++) {
+					const int pj = t >> 1, pk = (t & 1) * 4 + prl, row = pj * TK + pk;
+					const int c = ub - 2 * pj - 2 * pk;
+					const double2 v = *reinterpret_cast<const double2 *>(g_out + row * SG_DG + 2 * (pch ^ (row & 7)));
+					const bool inlo = (pj < Lr.tj) && (pk < Lr.tk) && c >= 0 && c < a.nx, inhi = inlo && (c + 1 < a.nx);
+					st_pair_if(a.out + a.voff + (long long)(Lr.k0 + pk) * a.vplane + (long long)(Lr.j0 + pj) * a.vpitch + c, v.x, v.y, inhi, inlo && !inhi);
 				}
 				__syncwarp();
 				Gr++; nr++;
-				if (nr == Lr.ngroups) { have_r = false; seqr++; }
+				if (nr == Lr.nd) { have_r = false; seqr++; }
 			}
 			if (a.prof) hp_ret += clock64() - hp_t;
 		}
@@ -379,12 +414,12 @@ sgs_stream_kernel(const StreamArgs a, const int *stop)
 
 	// =========================================================================== the FACE warp
 	// Polls the mailboxes of the two lines this one depends on and hands the values -- and the line's ghost column -- to the compute
-	// warp through shared memory; puts the sentinel back.  The polls of three consecutive groups are in flight (an L2 round trip
-	// each); every set of poll registers is written by its own load instruction, never moved, so nothing waits on a poll it does
-	// not need yet.
+	// warp through shared memory, one half-group of 8 columns at a time; puts the sentinel back.  The polls of three consecutive
+	// half-groups are in flight (an L2 round trip each); every set of poll registers is written by its own load instruction, never
+	// moved, so nothing waits on a poll it does not need yet.
 	{
 		LineGeo<FWD> Lf;
-		int Gf = 0;
+		int Hf = 0;
 		const int frow = lane >> 2, fch = 2 * (lane & 3);
 		long long hp_face = 0, hp_t = 0;
 		for (int seq = 0;; seq++) {
@@ -398,7 +433,7 @@ sgs_stream_kernel(const StreamArgs a, const int *stop)
 			Lf.set(a, line, lane);
 			const int pjl = FWD ? (Lf.cj > 0 ? line - 1 : -1) : (Lf.cj < a.nty - 1 ? line + 1 : -1);
 			const int pkl = FWD ? (Lf.ck > 0 ? line - a.nty : -1) : (Lf.ck < a.ntz - 1 ? line + a.nty : -1);
-			// face items of this lane: (row, 16-byte chunk) of a group.  Row frow of the j-faces is physical k-row frow of the pencils
+			// face items of this lane: (row, 16-byte chunk) of a half-group.  Row frow of the j-faces is physical k-row frow of the pencils
 			// with logical m = 0 (physical pj = fpj); row frow of the k-faces is physical j-row frow of the pencils with logical c = 0
 			const int fpj = FWD ? 0 : Lf.tj - 1, fpk = FWD ? 0 : Lf.tk - 1;
 			const bool jitem = frow < Lf.tk, kitem = (lane < 4 * TJ) && (frow < Lf.tj);
@@ -414,23 +449,21 @@ sgs_stream_kernel(const StreamArgs a, const int *stop)
 			double ghostv = 0.0;
 			if (Lf.act) ghostv = __ldcg(Lf.orow(a) + (FWD ? -1 : a.nx));
 			ulonglong2 fj0 = make_ulonglong2(0, 0), fk0 = fj0, fj1 = fj0, fk1 = fj0, fj2 = fj0, fk2 = fj0;
-			auto ask = [&](int n, ulonglong2 &fj, ulonglong2 &fk) {  // the polls of group n of the line
-				if (n >= Lf.ngroups) return;
-				const int u0 = Lf.u0(n);
+			auto ask = [&](int n, ulonglong2 &fj, ulonglong2 &fk) {  // the polls of half-group n of the line
+				if (n >= Lf.nh) return;
+				if (a.debug & 2) { fj = make_ulonglong2(SG_SENT, SG_SENT); fk = fj; return; }   // experiment: no early polls
+				const int u0 = Lf.u0h(n);
 				const int cj_ = u0 - jsh, ck_ = u0 - ksh;
 				if (jitem && cj_ >= 0 && cj_ < a.nx) fj = ld_mail2(jsrc + cj_);
 				if (kitem && !kzero && ck_ >= 0 && ck_ < a.nx) fk = ld_mail2(ksrc + ck_);
 			};
-			auto take = [&](int n, ulonglong2 &fj, ulonglong2 &fk) { // wait for group n's faces, hand them over
-				const int u0 = Lf.u0(n);
+			auto take = [&](int n, ulonglong2 &fj, ulonglong2 &fk) { // wait for half-group n's faces, hand them over
+				const int u0 = Lf.u0h(n);
 				const int cj_ = u0 - jsh, ck_ = u0 - ksh;
 				const bool inj = jitem && cj_ >= 0 && cj_ < a.nx, ink = kitem && !kzero && ck_ >= 0 && ck_ < a.nx;
 				const bool wj = inj && jpoll, wk = ink && kpoll;
-				// the compute warp must be through with the group that had this ring slot before (its `full` phase is then over)
-				if (Gf >= NG) {
-					const unsigned bar = s_u32(s_done + (Gf % NG));
-					while (!__all_sync(FULL, sg_mbar_try_wait(bar, ((Gf - NG) / NG) & 1))) { }
-				}
+				// the compute warp must be through with the half-group that had this entry of the face ring before
+				while (!__all_sync(FULL, ld_volatile_s32(s_prog) >= Hf - 7)) { }
 				auto there = [&](const ulonglong2 &pj_, const ulonglong2 &pk_) {
 					const bool okj = !wj || (pj_.x != SG_SENT && (cj_ + 1 >= a.nx || pj_.y != SG_SENT));
 					const bool okk = !wk || (pk_.x != SG_SENT && (ck_ + 1 >= a.nx || pk_.y != SG_SENT));
@@ -452,7 +485,7 @@ sgs_stream_kernel(const StreamArgs a, const int *stop)
 						if (clock64() - t0 > (40ll << 30)) __trap(); // ~20 s without the producing line: fail loudly instead of hanging
 					}
 				}
-				const int hs = (Gf & 7) * SG_COLS + fch;
+				const int hs = (Hf & 7) * SG_COLS + fch;
 				if (jitem) {
 					*reinterpret_cast<ulonglong2 *>(s_hj + frow * HP + hs) = inj ? fj : make_ulonglong2(0, 0);
 					if (wj) st_mail2(const_cast<unsigned long long *>(jsrc) + cj_, SG_SENT, SG_SENT);   // clean for the next sweep
@@ -463,21 +496,36 @@ sgs_stream_kernel(const StreamArgs a, const int *stop)
 				}
 				if (n == 0) s_ghost[(seq % SG_LQ) * 32 + lane] = Lf.act ? ghostv : 0.0;
 				__syncwarp();
-				if (lane == 0) sg_mbar_arrive(s_u32(s_full + (Gf % NG)));
-				Gf++;
+				if (lane == 0) sg_mbar_arrive(s_u32(s_face + (Hf & 7)));
+				Hf++;
 			};
-			ask(0, fj0, fk0);
-			ask(1, fj1, fk1);
+			if (a.debug & 4) {
+				// experiment: polls two half-groups ahead
+				ask(0, fj0, fk0);
+				ask(1, fj1, fk1);
 #pragma unroll 1
-			for (int n = 0; n < Lf.ngroups; n += 3) {
-				ask(n + 2, fj2, fk2);
-				take(n, fj0, fk0);
-				if (n + 1 >= Lf.ngroups) break;
-				ask(n + 3, fj0, fk0);
-				take(n + 1, fj1, fk1);
-				if (n + 2 >= Lf.ngroups) break;
-				ask(n + 4, fj1, fk1);
-				take(n + 2, fj2, fk2);
+				for (int n = 0; n < Lf.nh; n += 3) {
+					ask(n + 2, fj2, fk2);
+					take(n, fj0, fk0);
+					if (n + 1 >= Lf.nh) break;
+					ask(n + 3, fj0, fk0);
+					take(n + 1, fj1, fk1);
+					if (n + 2 >= Lf.nh) break;
+					ask(n + 4, fj1, fk1);
+					take(n + 2, fj2, fk2);
+				}
+			} else {
+				// the poll of the next half-group is in flight while this one is handed over: one half-group of lead hides the L2
+				// round trip; more lead only makes the line trail its predecessors by more (measured: the lag settles at the lead)
+				ask(0, fj0, fk0);
+#pragma unroll 1
+				for (int n = 0; n < Lf.nh; n += 2) {
+					ask(n + 1, fj1, fk1);
+					take(n, fj0, fk0);
+					if (n + 1 >= Lf.nh) break;
+					ask(n + 2, fj0, fk0);
+					take(n + 1, fj1, fk1);
+				}
 			}
 			if (a.prof) hp_face += clock64() - hp_t;
 		}
@@ -487,7 +535,7 @@ sgs_stream_kernel(const StreamArgs a, const int *stop)
 
 template <int NG> constexpr size_t sg_smem(int na)
 {
-	return (size_t)(NG * na * 256 + 12 * SG_HP + SG_LQ * 32) * sizeof(double) + (2 * NG + SG_LQ) * 8 + SG_LQ * 4;
+	return (size_t)(NG * na * 512 + 12 * SG_HP + SG_LQ * 32) * sizeof(double) + (2 * NG + 8 + SG_LQ) * 8 + (SG_LQ + 1) * 4;
 }
 
 __global__ void __launch_bounds__(256) fill_u64_kernel(unsigned long long *p, size_t n, unsigned long long v)
@@ -505,7 +553,7 @@ extern "C" S3D_HIDDEN int s3d_internal_sgs_stream(s3d_ctx *ctx, const s3d_grid *
                                                   const int *order, int nty, int ntz, unsigned *ticket, int klo_zero, int khi_zero,
                                                   const int *stop)
 {
-	constexpr int NG = 4;
+	constexpr int NG = 3;
 	static_assert(NG <= SG_LQ - 2, "the line queue must outlast the ring");
 	static bool configured = false;
 	static int blocks_per_sm = 1;

@@ -373,12 +373,17 @@ int s3d_tune_set(s3d_ctx *ctx, const char *key, int value)
 	else if (!strcmp(key, "sgs_profile")) {
 		// 1: start accumulating per-phase cycles in the warp dataflow kernel; 0: print and stop (timing experiments only)
 		if (value && !ctx->sgs_prof) {
-			S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_prof, 8 * sizeof(long long)));
-			S3D_CUDA(ctx, cudaMemset(ctx->sgs_prof, 0, 8 * sizeof(long long)));
+			S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_prof, (8 + 4096) * sizeof(long long)));
+			S3D_CUDA(ctx, cudaMemset(ctx->sgs_prof, 0, (8 + 4096) * sizeof(long long)));
 		} else if (!value && ctx->sgs_prof) {
-			long long h[8];
+			static long long h[8 + 4096];
 			S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 			S3D_CUDA(ctx, cudaMemcpy(h, ctx->sgs_prof, sizeof h, cudaMemcpyDeviceToHost));
+			if (getenv("S3D_SGS_LINELOG")) {
+				long long t0 = 0;
+				for (int l = 0; l < 2048; l++) if (h[8 + 2 * l] && (!t0 || h[8 + 2 * l] < t0)) t0 = h[8 + 2 * l];
+				for (int l = 0; l < 2048; l++) if (h[8 + 2 * l]) fprintf(stderr, "[sgs_line] %d start %.2f us end %.2f us\n", l, (h[8 + 2 * l] - t0) * 1e-3, (h[9 + 2 * l] - t0) * 1e-3);
+			}
 			const double t = h[4] ? (double)h[4] : 1.0;
 			fprintf(stderr, "[sgs_profile] workers %lld  cycles/worker: wait %.0f  total %.0f (%.1f per step, %.1f without the waits)  helper: load %.0f face %.0f retire %.0f passes %.0f\n", h[4], h[0] / t,
 			        h[2] / t, h[5] ? (double)h[2] / h[5] : 0.0, h[5] ? (double)(h[2] - h[0]) / h[5] : 0.0, h[1] / t, h[3] / t, h[6] / t, h[7] / t);

@@ -8,6 +8,8 @@ import numpy as np
 from struct3d_b200 import capi
 ctx = capi.Context(0)
 ctx.tune("sgs_variant", 5)
+dbg = int(os.environ.get("SGS_DEBUG", "0"))
+ctx.tune("sgs_sleep_ns", dbg)
 for spec in sys.argv[1:]:
     nx, ny, nz = (int(v) for v in spec.split(","))
     g = capi.make_grid(nx, ny, nz)
