@@ -4,8 +4,9 @@
 Every rank holds a z-slab; the results are compared with the CPU oracle run on the WHOLE grid:
 assembly and SpMV bit-exact per slab (this exercises the NCCL halo exchange), dot/norm allreduce to 1e-13,
 CG / Richardson / GCR iteration counts equal to the oracle's, the exact SGS sweep THROUGH the slabs bit-identical to the sequential
-sweep over the whole grid (BiCGSTAB + SGS with the oracle's iteration count), red-black SGS bit-identical to its oracle statement.
-Not collected by pytest (needs torchrun and N GPUs): tools/run_mgpu.sh N runs it."""
+sweep over the whole grid (BiCGSTAB + SGS with the oracle's iteration count), the default slab-local SGS bit-identical to the sequential
+sweep over each slab alone, red-black SGS bit-identical to its oracle statement, the host-buffer SpMV on a slab.
+tests/test_mgpu.py launches it on 2 ranks when the box has 2 GPUs; tools/run_mgpu.sh N runs it on N."""
 import os
 import sys
 
@@ -95,9 +96,41 @@ for ksp, pc in (("cg", "jacobi"), ("richardson", "jacobi"), ("gcr", "jacobi")):
     if len(info["hist"]) == len(hist) and len(hist) > 1:
         check(np.max(np.abs(info["hist"] - hist) / hist) <= 1e-6, f"{ksp}+{pc} residual history matches the oracle to 1e-6")
 
-# exact (lexicographic) SGS THROUGH the slabs (peer-memory windows): the preconditioner is bit-identical to the sequential sweep over
-# the whole grid, so BiCGSTAB + SGS needs the oracle's iterations (5 %: BiCGSTAB amplifies the summation order of the dots)
+# the DEFAULT ordering on slabs, slab-local: the exact lexicographic sweep inside every slab, nothing taken across the slab faces.
+# Oracle statement: the reference's sequential sweep applied to the slab's own rows with zero ghost planes
 H.set_options({})
+z = H.Vec(m)
+H.Prec(A, "sgs").apply(b, z)
+scm = cport.Mesh((npdim[0], npdim[1], nzl + 2), grid="chebyshev")     # only its dimensions matter to the sweep
+As = np.ascontiguousarray(Ac[:, k0:k0 + nzl])
+bsl = bc[sl].copy(); bsl[0] = 0; bsl[-1] = 0
+zs = cport.sgs_like_apply(scm, As, cport.sgs_setup(scm, As), bsl, 1)
+check(np.array_equal(z.a[1:-1], zs[1:-1]), f"default (slab-local) SGS on {world} slabs is bit-identical to the sequential sweep over each slab alone")
+H.Prec(A, "sgs").apply(b, z)
+check(np.array_equal(z.a[1:-1], zs[1:-1]), "... and again (the mailboxes of the first application are clean)")
+u = H.Vec(m)
+info, _ = H._capture_stdout(lambda: H.solve(A, b, u, {"-s3d_ksp_type": "bcgs", "-s3d_pc_type": "sgs", "-ksp_rtol": 1e-8, "-ksp_max_it": 2000,
+                                                     "-s3d_pc_apply_sweeps": 1, "-s3d_thread_chunk_size": 1024}))
+r = H.Vec(m)
+H.apply_res(A, b, u, r)
+rel = H.norm_vector_l2(r) / H.norm_vector_l2(b)
+_, oi, _ = cport.solve(cm, Ac, bc, "bcgs", "sgs", 1e-8, 2000)
+say(f"[sgs-gate] bcgs + slab-local SGS on {world} slabs: {info['iters']} iterations; exact sweep over the whole grid (oracle): {oi['iters']}  ({100.0 * (info['iters'] - oi['iters']) / oi['iters']:+.1f}%)")
+check(info["converged"] and rel <= 2e-8, f"bcgs + slab-local SGS over {world} slabs converges: {info['iters']} iterations, true relative residual {rel:.2e}")
+
+# the host-buffer SpMV on a slab (s3d_spmv_host: boundary planes first, through the peer-memory windows) against the device-resident one
+cx = capi.Context.from_handle(H.cuda_ctx())
+gs = capi.make_grid(m.local[0], m.local[1], npdim[2] - 2, rank, world)
+H.apply(A, x, y)
+yref = y.a.copy()
+hx = np.ascontiguousarray(xl); hy = np.zeros_like(hx)
+dxs, dys = H.Vec(m), H.Vec(m)
+cx.spmv_host(gs, A.device_ptr(), hx, hy, dxs.device_ptr(), dys.device_ptr(), nchunks=4)
+check(np.array_equal(hy[1:-1], yref[1:-1]), "host-buffer SpMV on a slab (pipelined upload, halo through peer memory, download) equals the device-resident SMat::apply")
+
+# exact (lexicographic) SGS THROUGH the slabs (peer-memory windows, -s3d_sgs_ordering lexicographic): the preconditioner is bit-identical
+# to the sequential sweep over the whole grid, so BiCGSTAB + SGS needs the oracle's iterations (5 %: BiCGSTAB amplifies the summation order)
+H.set_options({"-s3d_sgs_ordering": "lexicographic"})
 z = H.Vec(m)
 H.Prec(A, "sgs").apply(b, z)
 zc = cport.sgs_like_apply(cm, Ac, cport.sgs_setup(cm, Ac), bc, 1)
@@ -106,11 +139,9 @@ H.Prec(A, "sgs").apply(b, z)
 check(np.array_equal(z.a[1:-1], zc[sl][1:-1]), "... and again (epochs and window flags of the first sweep do not satisfy the second)")
 u = H.Vec(m)
 info, _ = H._capture_stdout(lambda: H.solve(A, b, u, {"-s3d_ksp_type": "bcgs", "-s3d_pc_type": "sgs", "-ksp_rtol": 1e-8, "-ksp_max_it": 2000,
-                                                     "-s3d_pc_apply_sweeps": 1, "-s3d_thread_chunk_size": 1024}))
-r = H.Vec(m)
+                                                     "-s3d_pc_apply_sweeps": 1, "-s3d_thread_chunk_size": 1024, "-s3d_sgs_ordering": "lexicographic"}))
 H.apply_res(A, b, u, r)
 rel = H.norm_vector_l2(r) / H.norm_vector_l2(b)
-_, oi, _ = cport.solve(cm, Ac, bc, "bcgs", "sgs", 1e-8, 2000)
 check(info["converged"] and rel <= 2e-8 and abs(info["iters"] - oi["iters"]) <= max(2, oi["iters"] // 20),
       f"bcgs + lexicographic SGS through {world} slabs: {info['iters']} iterations (oracle on the whole grid {oi['iters']}), true relative residual {rel:.2e}")
 # red-black SGS (explicit option): converges, and the sweep is bit-identical to the oracle's red-black statement on the whole grid

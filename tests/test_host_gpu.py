@@ -116,21 +116,49 @@ def test_cuda_graph_replay_is_identical(H, rec, ordering):
     assert out["on"][0] > 0
 
 
-@pytest.mark.parametrize("case", ["convdiff48", "convdiff64", "poisson26", "poisson64_test_rhs"])
-def test_redblack_sgs_iteration_gate(H, case):
-    """north_star: multicolour SGS must reach the same final residual within 5% more iterations than
-    the reference's (lexicographic) SGS.  Measured for every solver the goldens hold with SGS; the
-    numbers are printed so the judge sees them, and the gate is asserted for the Krylov solvers."""
+def _gate_rows(H, case, ordering):
     rows = []
     for rec in [r for r in SOLVES["solves"] if r["case"] == case and r["pc"] == "sgs"]:
         m, P, A, b = _setup(H, rec)
         x = H.Vec(m)
-        rb = H.solve(A, b, x, _opts(rec, **{"-s3d_sgs_ordering": "redblack"}))
-        rows.append((rec["ksp"], rec["iters"], rb["iters"], rb["converged"], rb["resnorm"] / rec["bnorm"]))
-    for ksp, ref_it, rb_it, conv, rel in rows:
-        print(f"[sgs-gate] {case:20s} {ksp:10s} lexicographic(reference) {ref_it:4d}  red-black {rb_it:4d}  ({100.0 * (rb_it - ref_it) / ref_it:+.1f}%)  rel.res {rel:.3e}")
-        assert conv and rel <= 1e-6
+        extra = {"-s3d_sgs_ordering": ordering} if ordering else {}
+        got = H.solve(A, b, x, _opts(rec, **extra))
+        rows.append((rec["ksp"], rec["iters"], got["iters"], got["converged"], got["resnorm"] / rec["bnorm"]))
     H.set_options({})
+    return rows
+
+
+@pytest.mark.parametrize("case", ["convdiff48", "convdiff64", "poisson26", "poisson64_test_rhs"])
+def test_default_sgs_iteration_gate(H, case):
+    """north_star: the GPU SGS must reach the same final residual within 5% more iterations than the reference's (lexicographic)
+    SGS.  ASSERTED for the ordering the library uses by default on one GPU (the exact lexicographic sweep executed as a dataflow:
+    same operator, so the counts are the reference's own) for every solver the reference goldens hold with SGS."""
+    for ksp, ref_it, it, conv, rel in _gate_rows(H, case, None):
+        print(f"[sgs-gate] {case:20s} {ksp:10s} reference {ref_it:4d}  default ordering {it:4d}  ({100.0 * (it - ref_it) / ref_it:+.1f}%)  rel.res {rel:.3e}")
+        assert conv and rel <= 1e-6
+        assert it <= ref_it * 1.05 + 0.5, f"{ksp}: {it} iterations against the reference's {ref_it}: more than +5%"
+
+
+@pytest.mark.parametrize("case", ["convdiff48", "convdiff64"])
+@pytest.mark.xfail(strict=True, reason="measured: the red-black (two-colour) ordering needs +30..40% iterations on upwinded convection-diffusion "
+                                       "(265 vs 193 at 256^3, driver BENCH r1); it stays selectable but is not the default")
+def test_redblack_sgs_iteration_gate(H, case):
+    """The same gate for the two-colour ordering north_star suggests: it FAILS on the convection-diffusion cases (strict xfail, so
+    that an unexpected pass is noticed); the numbers are printed."""
+    worst = 0.0
+    for ksp, ref_it, it, conv, rel in _gate_rows(H, case, "redblack"):
+        print(f"[sgs-gate] {case:20s} {ksp:10s} reference {ref_it:4d}  red-black {it:4d}  ({100.0 * (it - ref_it) / ref_it:+.1f}%)  rel.res {rel:.3e}")
+        assert conv and rel <= 1e-6
+        if ksp != "richardson":
+            worst = max(worst, (it - ref_it) / ref_it)
+    assert worst <= 0.05
+
+
+@pytest.mark.parametrize("case", ["poisson26", "poisson64_test_rhs"])
+def test_redblack_sgs_converges_on_poisson(H, case):
+    for ksp, ref_it, it, conv, rel in _gate_rows(H, case, "redblack"):
+        print(f"[sgs-gate] {case:20s} {ksp:10s} reference {ref_it:4d}  red-black {it:4d}  ({100.0 * (it - ref_it) / ref_it:+.1f}%)  rel.res {rel:.3e}")
+        assert conv and rel <= 1e-6
 
 
 def test_matvec_suite_like_reference(H):
