@@ -23,4 +23,14 @@ typedef int sint;
 
 enum BCType { S3D_EXTRAPOLATION, S3D_DIRICHLET };
 
+// The reference's struct3d_config.h pulls in <petscsys.h>, and through it MPI: its callers (test/matvectest.cpp,
+// src/perftesting/runcase.cpp, scaling_openmp.cpp) use MPI_Init / MPI_Wtime / PetscInitialize / PetscOptionsSetValue without including
+// anything else.  Where the build offers a petscsys.h (a real PETSc, or the small shim under tests/dropin/ that maps those calls
+// onto this library's option store) it is included here, so those files compile unchanged.
+#if defined(__has_include)
+#if __has_include(<petscsys.h>)
+#include <petscsys.h>
+#endif
+#endif
+
 #endif
