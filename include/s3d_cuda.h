@@ -101,7 +101,8 @@ int  s3d_timer_stop_ms(s3d_ctx *ctx, double *ms);
  * SM the march kernel is compiled for: 0 auto, 3, 4, 6), "spmv_hints" (evict-first hints on/off for the PAIR/NAIVE
  * variants), "spmv_variant" (what S3D_SPMV_AUTO resolves to), "halo_overlap" (0 = exchange first, then multiply), "halo_p2p" (1 = halo
  * planes through peer-memory windows, 0 = NCCL), "ew_unroll" (items a thread of the element-wise kernels keeps in flight: 0 = each
- * kernel's own choice, 2/4/8, -1 = grid-stride order), "sgs_variant" (0 = warp-per-tile dataflow sweep, 1 = block-per-tile, 3 = warp-per-line, experimental),
+ * kernel's own choice, 2/4/8, -1 = grid-stride order), "sgs_variant" (4 = by grid size (default): the streaming warp-per-line kernel up to "sgs_stream_max_points" points per rank, the warp-per-tile dataflow kernel above;
+ * 5 = streaming kernel, 0 = warp-per-tile, 1 = block-per-tile, 3 = r1's warp-per-line experiment),
  * "sgs_tile_i" (16/32), "sgs_pencils" (1/2/0 = by grid size), "sgs_warps_per_sm", "sgs_profile" (timing experiments). */
 int  s3d_tune_set(s3d_ctx *ctx, const char *key, int value);
 
@@ -130,9 +131,9 @@ int  s3d_host_free(s3d_ctx *ctx, void *h_ptr);
 
 #define S3D_SPMV_AUTO      0   /* pick the fastest variant for the grid */
 #define S3D_SPMV_MARCH     1   /* register z-marching, i-neighbours by warp shuffle, j-neighbours via L1 */
-#define S3D_SPMV_TMA       2   /* z-planes of x staged through shared memory by TMA (cp.async.bulk.tensor) */
+#define S3D_SPMV_TMA       2   /* z-planes of x staged through a shared-memory ring by TMA bulk row copies (cp.async.bulk, mbarrier completion) */
 #define S3D_SPMV_NAIVE     3   /* one thread per point, all seven neighbours from global (the first correct version) */
-#define S3D_SPMV_PAIR      4   /* two points per thread, no marching: 128-bit loads, x-reuse through L1/L2 (the default) */
+#define S3D_SPMV_PAIR      4   /* two points per thread, no marching: 128-bit loads, x-reuse through L1/L2 (AUTO resolves to MARCH: measured faster) */
 
 /* y = A x (d_b == NULL) or y = b - A x.  The seven products are formed and summed in stencil order
  * 0..6 with separately rounded multiplies and adds, exactly the reference's expression.
@@ -198,7 +199,8 @@ int  s3d_jacobi_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const do
 /* SGS_preconditioner::updateOperator (s3d_sgspreconditioners.cpp:122-135): dinv = 1/diag, matrix-compact layout (cstride doubles) */
 int  s3d_sgs_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, double *d_dinv);
 /* StrILU_preconditioner::updateOperator, sequential build (s3d_ilu.cpp:17-64): dinv = 1 / (ILU(0) diagonal); use with s3d_sgs_apply.
- * nbuildsweeps > 1 is idempotent for the sequential build and is treated as 1; 0 gives 1/diag.  Single GPU. */
+ * nbuildsweeps > 1 is idempotent for the sequential build and is treated as 1; 0 gives 1/diag.  On a z-slab decomposition the
+ * recurrence runs inside every slab (block ILU(0) by slabs: what the slab-local application, S3D_SGS_SLABLOCAL, goes with). */
 int  s3d_strilu_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuildsweeps, double *d_dinv);
 #define S3D_SGS_LEXICOGRAPHIC 0  /* the reference's ordering, executed as a tile-level dataflow wavefront: same arithmetic */
 #define S3D_SGS_LEXICOGRAPHIC_PLANES 2  /* same result, one launch per hyperplane i+j+k (slow; kept for cross-checks) */

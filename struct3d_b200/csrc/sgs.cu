@@ -1306,7 +1306,8 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 int s3d_strilu_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuildsweeps, double *d_dinv)
 {
 	S3D_REQUIRE(ctx, g && A && d_dinv && nbuildsweeps >= 0, "bad argument");
-	if (g->nranks > 1) return s3d_fail(ctx, S3D_ERR_ARG, "the StrILU recurrence is lexicographic over the whole grid; it is not available on a decomposed grid");
+	// On a z-slab decomposition the recurrence is run inside every slab (nothing taken across the slab faces: the products below are
+	// zero where the k-1 neighbour lives on another rank), the factorisation that goes with the slab-local application.
 	if (nbuildsweeps == 0) return s3d_sgs_setup(ctx, g, A, d_dinv);
 	const GridDev gd = to_dev(g);
 	double *P = nullptr, *D = nullptr;

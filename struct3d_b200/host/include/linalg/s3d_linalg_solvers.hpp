@@ -25,7 +25,7 @@ struct PreconParams {
 	int napplysweeps;
 	int thread_chunk_size;     ///< CPU-thread chunking of the reference; accepted and ignored on the GPU
 	bool threadedbuild;
-	bool threadedapply;        ///< reference: chaotic threaded sweeps.  GPU: true selects the multicolour (red-black) ordering
+	bool threadedapply;        ///< reference: chaotic threaded sweeps.  GPU: the sweep is deterministic whatever this says (a warning is printed when it is asked for)
 };
 
 struct SolveInfo {
@@ -114,12 +114,12 @@ class SGS_like_preconditioner : public SolverBase
 public:
 	SGS_like_preconditioner(const SMat &lhs, const PreconParams parms);
 	~SGS_like_preconditioner();
-	/// z = (D+U)^-1 D (D+L)^-1 r.  Ordering: lexicographic wavefront (bit-identical to the reference's
-	/// sequential sweep) unless params.threadedapply selects the red-black multicolour ordering, or the
-	/// option -s3d_sgs_ordering {lexicographic|redblack|sweeps} says otherwise (sweeps: params.napplysweeps synchronous Jacobi
+	/// z = (D+U)^-1 D (D+L)^-1 r.  Ordering: the reference's lexicographic sweep executed as a dataflow (bit-identical to its
+	/// sequential sweep) on one GPU, the same sweep inside every z-slab on several (slablocal), unless the option
+	/// -s3d_sgs_ordering {lexicographic|slablocal|redblack|sweeps} says otherwise (sweeps: params.napplysweeps synchronous Jacobi
 	/// sweeps per triangular factor, the deterministic counterpart of the reference's asynchronous threaded sweeps).
 	SolveInfo apply(const SVec &r, SVec &z) const;
-	/// S3D_SGS_LEXICOGRAPHIC or S3D_SGS_REDBLACK
+	/// S3D_SGS_LEXICOGRAPHIC, S3D_SGS_SLABLOCAL, S3D_SGS_REDBLACK or S3D_SGS_JACOBI_SWEEPS
 	int ordering() const { return order; }
 
 protected:

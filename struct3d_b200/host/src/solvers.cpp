@@ -246,6 +246,16 @@ SGS_like_preconditioner::SGS_like_preconditioner(const SMat &lhs, const PreconPa
 		else if (o == "sweeps" || o == "jacobi_sweeps" || o == "async") order = S3D_SGS_JACOBI_SWEEPS;
 		else throw std::runtime_error("-s3d_sgs_ordering must be lexicographic, slablocal, redblack or sweeps");
 	}
+	// The reference's threaded apply / build (s3d_sgspreconditioners.cpp:32-53, s3d_ilu.cpp:28-32) runs asynchronous, unordered sweeps
+	// over CPU threads.  Here the sweep is one deterministic dataflow whatever these options say: asked for explicitly, say so once.
+	static bool warned = false;
+	const bool asked = (s3d::options_has("-s3d_pc_use_threaded_apply") && parms.threadedapply) || (s3d::options_has("-s3d_pc_use_threaded_build") && parms.threadedbuild);
+	if (asked && !warned && d.rank() == 0) {
+		std::printf(" WARNING: -s3d_pc_use_threaded_apply / -s3d_pc_use_threaded_build ask for the reference's asynchronous CPU-thread sweeps; "
+		            "the GPU sweeps are deterministic (ordering: %s). Use -s3d_sgs_ordering sweeps with -s3d_pc_apply_sweeps n for n synchronous sweeps.\n",
+		            order == S3D_SGS_LEXICOGRAPHIC ? "lexicographic" : order == S3D_SGS_SLABLOCAL ? "slablocal" : order == S3D_SGS_REDBLACK ? "redblack" : "sweeps");
+		warned = true;
+	}
 	if (d.nranks() > 1 && order == S3D_SGS_LEXICOGRAPHIC) {
 		// the exact sweep can run through the slabs as a pipeline over peer memory (same iterations as one GPU); without the
 		// peer-memory windows the red-black ordering takes over
