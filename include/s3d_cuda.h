@@ -254,6 +254,22 @@ int  s3d_converge_test(s3d_ctx *ctx, const double *d_rr, const double *d_bb, dou
  *   op 3: out[l] = a[l], l < n                       (keep a reduction result for later) */
 int  s3d_scalar_op(s3d_ctx *ctx, int op, double *d_out, const double *a, const double *b, const double *c,
                    const double *d, int n, double scale, int *d_stop);
+/* A whole solve of a SMALL grid in one kernel launch (no counterpart in the reference, whose loops call their kernels one by one,
+ * src/linalg/s3d_solverbase.cpp:45-80): one block runs the complete loop with block barriers between the phases, so an iteration
+ * costs no launch at all.  method: 0 Richardson, 1 CG (GCR: s3d_small_solve_gcr); pc: 0 identity, 1 Jacobi; same expressions and roundings as the stand-alone
+ * kernels, same convergence test as s3d_converge_test.  d_flags[0] = S3D_STOP_* code, d_flags[1] = iterations, d_scal[0] = (r,r) at
+ * exit, d_scal[1] = (b,b), d_hist_or_null[it] = relative residual after iteration it (hist_cap entries).  One rank, at most
+ * S3D_SMALL_MAX_POINTS points. */
+#define S3D_SMALL_MAX_POINTS (1 << 17)
+int  s3d_small_solve(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_b, double *d_x, double *d_w0, double *d_w1,
+                     double *d_w2, int method, int pc, double rtol, int maxiter, int *d_flags, double *d_scal, double *d_hist_or_null,
+                     int hist_cap);
+/* The same for GCR(north) (reference loop: src/linalg/s3d_gcr.cpp:14-86): d_res, d_z work vectors; pq = HOST array of 2*north device
+ * pointers, pq[2i] = p_i, pq[2i+1] = q_i; north <= 32.  The iteration cap is looked at between cycles only and the inner test is the
+ * strict one, as in the reference.  d_scal[0] = 1 when no iteration ran. */
+int  s3d_small_solve_gcr(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_b, double *d_x, double *d_res, double *d_z,
+                         double *const *pq, int north, int pc, double rtol, int maxiter, int *d_flags, double *d_scal,
+                         double *d_hist_or_null, int hist_cap);
 /* Context-wide gate: while set, EVERY kernel this context launches (SpMV, BLAS-1, preconditioners ...) first
  * reads *d_stop and does nothing when it is non-zero, unless the call passes its own d_stop.  A host-driven
  * solver sets the gate to its stop flag for the duration of the loop; pass NULL to clear it. */

@@ -67,6 +67,8 @@ _SIGS = {
     "s3d_bicg_update": [_P, _G, Scalar, _vp, Scalar, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "s3d_converge_test": [_P, _vp, _vp, _D, _I, _I, _vp, _vp, _vp],
     "s3d_scalar_op": [_P, _I, _vp, _vp, _vp, _vp, _vp, _I, _D, _vp],
+    "s3d_small_solve": [_P, _G, _vp, _vp, _vp, _vp, _vp, _vp, _I, _I, _D, _I, _vp, _vp, _vp, _I],
+    "s3d_small_solve_gcr": [_P, _G, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp), _I, _I, _D, _I, _vp, _vp, _vp, _I],
     "s3d_ctx_set_gate": [_P, _vp], "s3d_phase_begin": [_P, _I], "s3d_phase_end": [_P, _I], "s3d_phase_total_ms": [_P, _I, _dp],
     "s3d_graph_begin": [_P], "s3d_graph_end": [_P, C.POINTER(_vp)], "s3d_graph_launch": [_P, _vp], "s3d_graph_destroy": [_P, _vp],
     "s3d_ints_snapshot": [_P, _vp, _I, _I], "s3d_ints_snapshot_wait": [_P, _I, _I, _vp],

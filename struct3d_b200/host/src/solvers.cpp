@@ -54,8 +54,12 @@ struct DeviceLoop {
 	int nbatch = 0;
 
 	DeviceLoop(int cap, int print_every, std::vector<sreal> &out)
-		: d(Device::get()), ctx(d.ctx()), flags(d.ints(2)), hist(d.scalars(cap)), hist_cap(cap), every(print_every), history(out)
+		: d(Device::get()), ctx(d.ctx()), flags(d.ints(2)), hist(nullptr), hist_cap(cap), every(print_every), history(out)
 	{
+		// the device writes one history entry per iteration without a bounds check of its own: an absurd iteration cap (1e9 ...) gets
+		// no history instead of gigabytes of it
+		if (cap < 0 || cap > (1 << 22)) hist_cap = 0;
+		hist = hist_cap ? d.scalars(hist_cap) : nullptr;
 		history.clear();
 		g_time_phases = true;
 	}
@@ -65,7 +69,7 @@ struct DeviceLoop {
 		g_time_phases = true;
 		s3d_ctx_set_gate(ctx, nullptr);
 		s3d_free(ctx, flags);
-		s3d_free(ctx, hist);
+		if (hist) s3d_free(ctx, hist);
 	}
 	void graphs(const s3d_grid &g)
 	{
@@ -184,6 +188,60 @@ struct TimedPrec {   // brackets a preconditioner application with the GPU stopw
 	explicit TimedPrec(const Device &dev) : d(dev) { if (g_time_phases) d.check(s3d_phase_begin(d.ctx(), 0), "s3d_phase_begin"); }
 	~TimedPrec() { if (g_time_phases) s3d_phase_end(d.ctx(), 0); }
 };
+
+// Small grids: the whole solve in ONE kernel launch (s3d_small_solve), for Richardson, CG and GCR with the Jacobi or the identity
+// preconditioner on one GPU.  -s3d_small_solve on|off|auto (auto: up to 32 Ki points, where a host-driven iteration costs 25-35 us of
+// launches against a few microseconds of work; measured in profiles/r2_small_solves.md).
+bool want_small_solve(const Device &d, const s3d_grid &g, const SolverBase *prec)
+{
+	if (d.nranks() > 1) return false;
+	const long long n = (long long)g.nx * g.ny * g.nz;
+	if (n > S3D_SMALL_MAX_POINTS) return false;
+	if (prec && !dynamic_cast<const JacobiPreconditioner *>(prec) && !dynamic_cast<const NoSolver *>(prec)) return false;
+	std::string v = "auto";
+	if (s3d::options_has("-s3d_small_solve")) v = petscoptions_get_string("-s3d_small_solve", 10);
+	if (v == "on" || v == "1" || v == "true") return true;
+	if (v == "off" || v == "0" || v == "false") return false;
+	return n <= (32ll << 10);
+}
+
+SolveInfo small_solve(int method, const SMat &A, const SolverBase *prec, const SVec &b, SVec &x, SVec &w0, SVec *w1, SVec *w2,
+                      const SolveParams &sp, int print_every, std::vector<sreal> &history, double *const *pq = nullptr, int north = 0)
+{
+	const Device &d = Device::get();
+	s3d_ctx *ctx = d.ctx();
+	// result buffers live as long as the process: a cudaMalloc / cudaFree pair per solve would cost more than these solves take
+	constexpr int HCAP = 1 << 16;
+	static int *flags = nullptr;
+	static double *scal = nullptr;
+	if (!flags) { flags = d.ints(2); scal = d.scalars(2 + HCAP); }
+	const int pc = dynamic_cast<const JacobiPreconditioner *>(prec) ? 1 : 0;
+	if (method == 2)
+		d.check(s3d_small_solve_gcr(ctx, &A.grid(), A.dev(), b.dev(), x.dev_rw(), w0.dev_w(), w1->dev_w(), pq, north, pc, sp.rtol, sp.maxiter,
+		                            flags, scal, scal + 2, HCAP), "s3d_small_solve_gcr");
+	else
+		d.check(s3d_small_solve(ctx, &A.grid(), A.dev(), b.dev(), x.dev_rw(), w0.dev_w(), w1 ? w1->dev_w() : nullptr, w2 ? w2->dev_w() : nullptr,
+		                        method, pc, sp.rtol, sp.maxiter, flags, scal, scal + 2, HCAP), "s3d_small_solve");
+	int hf[2];
+	double hs[2];
+	d.check(s3d_ints_download(ctx, flags, 2, hf), "s3d_ints_download");
+	d.check(s3d_scalars_download(ctx, scal, 2, hs), "s3d_scalars_download");
+	const int iterations = hf[1];
+	history.assign(std::min(iterations, HCAP), 0.0);
+	if (!history.empty()) d.check(s3d_scalars_download(ctx, scal + 2, (int)history.size(), history.data()), "s3d_scalars_download");
+	if (d.rank() == 0)
+		for (int i = 0; i < (int)history.size(); i += print_every) {
+			std::printf("      Step %d: Rel res = %g\n", i, history[i]);
+			std::fflush(stdout);
+		}
+	const sreal resnorm = std::sqrt(hs[0]), bnorm = std::sqrt(hs[1]);
+	SolveInfo info;
+	info.converged = (hf[0] != S3D_STOP_BREAKDOWN) && (resnorm / bnorm <= sp.rtol);   // the reference's closing test (s3d_gcr.cpp:80)
+	info.iters = iterations;
+	info.resnorm = resnorm;
+	info.precapplywtime = 0.0;   // the preconditioner is fused into the single launch: there is nothing separate to time
+	return info;
+}
 
 }  // namespace
 
@@ -312,6 +370,7 @@ SolveInfo Richardson::apply(const SVec &b, SVec &x) const
 	s3d_ctx *ctx = d.ctx();
 	const s3d_grid &g = A.grid();
 	SVec &res = work(0), &dx = work(1);
+	if (want_small_solve(d, g, prec)) return small_solve(0, A, prec, b, x, res, nullptr, nullptr, sparams, 10, history);
 	Scalars sc(d, 4);   // [0] (b,b)  [1] unused  [2] (r,r)
 	double *S = sc.S;
 	DeviceLoop loop(sparams.maxiter + 1, 10, history);
@@ -366,6 +425,11 @@ SolveInfo GCR::apply(const SVec &b, SVec &x) const
 	std::vector<SVec *> pp(north), qq(north);
 	for (int i = 0; i < north; i++) { pp[i] = &work(2 + 2 * i); qq[i] = &work(3 + 2 * i); }
 	struct Ref { std::vector<SVec *> &v; SVec &operator[](int i) const { return *v[i]; } } p{pp}, q{qq};
+	if (north <= 32 && want_small_solve(d, g, prec)) {
+		std::vector<double *> pq(2 * north);
+		for (int i = 0; i < north; i++) { pq[2 * i] = pp[i]->dev_w(); pq[2 * i + 1] = qq[i]->dev_w(); }
+		return small_solve(2, A, prec, b, x, res, &z, nullptr, sparams, 5, history, pq.data(), north);
+	}
 
 	// scalars: [0] (b,b)  [1..2] spmv reductions  [3] (res,res)  [4..5] (res,q_k),(q_k,q_k)
 	//          QQ[i] = (q_i,q_i) cached (the reference recomputes the identical value)   DOT[i] = (q_new,q_i)   BETA[i]
@@ -448,6 +512,7 @@ SolveInfo CG::apply(const SVec &b, SVec &x) const
 	const s3d_grid &g = A.grid();
 	const bool jacobi = dynamic_cast<const JacobiPreconditioner *>(prec) != nullptr;
 	SVec &r = work(0), &p = work(1), &q = work(2);
+	if (want_small_solve(d, g, prec)) return small_solve(1, A, prec, b, x, r, &p, &q, sparams, 10, history);
 	SVec &z = jacobi ? work(0) : work(3);   // unused with Jacobi (folded into the kernels)
 	// scalars: [0] (b,b)  [1..2] SpMV reductions: (p,Ap), -  [3,4] and [5,6]: ping-pong pairs {(r,r), (r,z)}
 	Scalars sc(d, 8);
