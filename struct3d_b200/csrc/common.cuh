@@ -55,12 +55,14 @@ struct s3d_ctx {
 	bool capturing = false;       // between s3d_graph_begin and s3d_graph_end
 	int64_t capture_launches0 = 0;
 	int sgs_sleep_ns = 0;
-	int sgs_variant = 4;        // 4: warp-per-line streaming kernel (TMA rings + sentinel mailboxes, the default), 0: warp-per-tile dataflow
+	int sgs_variant = 4;        // 4: by size (streaming kernel below sgs_stream_max_points, warp-per-tile above; the default), 5: streaming, 6: register-streaming
+	                            // (sgs_pencil.cu, opt-in: measured slower, profiles/r2_sgs_pencil.md), 0: warp-per-tile dataflow
 	                            // kernel (also what the exact sweep THROUGH z-slabs uses), 1: block-per-tile kernel, 3: r1's warp-per-line experiment
 	long long sgs_stream_max_points = 3ll << 19;   // variant 4 uses the streaming kernel up to this many points per rank, the tile kernel above
 	unsigned long long *sgs_mail = nullptr;   // streaming kernel: face mailboxes (sentinel-filled outside a sweep)
 	size_t sgs_mail_cap = 0;
 	int sgs_warps_per_sm = 0;   // 0: as many as fit
+	int sgs_pencil_shape = 0;   // register-streaming kernel (variant 6): warps of a block as WJ*10 + WK (+ prefetch depth as a third digit); 0 = default
 	long long *sgs_prof = nullptr;   // timing experiments: per-phase cycle sums of the warp kernel (tuning key sgs_profile)
 	int sgs_tile_i = 0;         // warp kernel: tile length along i, 16 (default) or 32
 	int sgs_pencils = 0;        // warp kernel: (j,k) pencils per lane, 1 (tile TI x 4 x 8) or 2 (tile TI x 8 x 8); 0: by grid size

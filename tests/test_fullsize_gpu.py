@@ -43,7 +43,7 @@ def test_256_fields_bit_exact_against_the_oracle(ctx, pde):
     ctx.sgs_setup(g, dA, dinv)
     ref = cport.sgs_like_apply(m, A, cport.sgs_setup(m, A), x, 1)
     try:
-        for variant in (0, 5):          # warp-per-tile dataflow kernel, streaming kernel
+        for variant in (0, 5, 6):       # warp-per-tile dataflow kernel, streaming kernel, register-streaming kernel
             ctx.tune("sgs_variant", variant)
             ctx.vecset(g, 1.0, dz)
             ctx.sgs_apply(g, dA, dinv, dx, dz, ds, capi.SGS_LEXICOGRAPHIC, 1)

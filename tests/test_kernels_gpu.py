@@ -222,9 +222,10 @@ def test_jacobi_and_sgs(ctx, npdim, pde):
 
 
 # every build of the exact dataflow sweep: block-per-tile (variant 1), warp-per-tile (variant 0) with 16- or 32-long tiles and one
-# or two pencils per lane; full, ragged and sub-tile grids; forward/backward sweep and the StrILU recurrence
+# or two pencils per lane, streaming (5), register-streaming (6, three block shapes); full, ragged and sub-tile grids; forward/backward sweep and the StrILU recurrence
 @pytest.mark.parametrize("npdim", [(18, 18, 18), (35, 11, 20), (3, 3, 3), (50, 23, 14), (131, 9, 6), (21, 38, 27)])
-@pytest.mark.parametrize("variant,tile_i,pencils", [(5, 0, 0), (1, 0, 0), (0, 16, 1), (0, 16, 2), (0, 32, 1), (0, 32, 2), (3, 0, 0)])
+@pytest.mark.parametrize("variant,tile_i,pencils", [(5, 0, 0), (1, 0, 0), (0, 16, 1), (0, 16, 2), (0, 32, 1), (0, 32, 2), (3, 0, 0), (6, 0, 0), (6, 22, 0),
+                                                    (6, 11, 0)])
 def test_sgs_dataflow_variants(ctx, npdim, variant, tile_i, pencils):
     m, A = problem(npdim, "chebyshev", "convdiff", V1, 0.1)
     g = grid_of(m)
@@ -232,7 +233,10 @@ def test_sgs_dataflow_variants(ctx, npdim, variant, tile_i, pencils):
     dA, dr, dz, dy = ctx.mat_from(g, A), ctx.vec_from(g, r), ctx.vec_alloc(g), ctx.vec_alloc(g)
     dinv = ctx.scalars_alloc(int(g.cstride))
     try:
-        ctx.tune("sgs_variant", variant); ctx.tune("sgs_tile_i", tile_i); ctx.tune("sgs_pencils", pencils)
+        if variant == 6:   # the register-streaming kernel: tile_i carries its block shape (warps as WJ*10 + WK, 0 = default 4 x 2)
+            ctx.tune("sgs_variant", 6); ctx.tune("sgs_pencil_shape", tile_i)
+        else:
+            ctx.tune("sgs_variant", variant); ctx.tune("sgs_tile_i", tile_i); ctx.tune("sgs_pencils", pencils)
         ctx.sgs_setup(g, dA, dinv)
         di = cport.sgs_setup(m, A)
         ref = cport.sgs_like_apply(m, A, di, r, 1)
@@ -247,7 +251,7 @@ def test_sgs_dataflow_variants(ctx, npdim, variant, tile_i, pencils):
         ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_LEXICOGRAPHIC, 1)
         assert np.array_equal(ctx.vec_download(g, dz), cport.sgs_like_apply(m, A, want, r, 1)), "StrILU differs"
     finally:
-        ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT); ctx.tune("sgs_tile_i", 0); ctx.tune("sgs_pencils", 0)
+        ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT); ctx.tune("sgs_tile_i", 0); ctx.tune("sgs_pencils", 0); ctx.tune("sgs_pencil_shape", 0)
         for p_ in (dA, dr, dz, dy, dinv):
             ctx.free(p_)
 
