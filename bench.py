@@ -337,6 +337,9 @@ def run_ours(a):
     H = hostapi
     ctx.tune("halo_overlap", a.halo_overlap)
     ctx.tune("halo_p2p", a.halo_p2p)
+    for kv in a.tune:                                   # A/B switches: --tune halo_push_side=0 --tune allreduce_p2p=0 ...
+        k, v = kv.split("=")
+        ctx.tune(k, int(v))
     V = (0.577350269189626, 0.7, 0.3)
 
     def barrier():
@@ -643,6 +646,7 @@ def main():
     ap.add_argument("--fixed", type=int, default=512, help="grid size of the fixed-grid solves to rtol at every GPU count (BASELINE's 'solve s at 512^3'; 0 disables)")
     ap.add_argument("--halo-overlap", type=int, default=0, help="0: exchange halos first, then multiply (A/B switch)")
     ap.add_argument("--halo-p2p", type=int, default=1, help="1: halo planes through peer-memory windows (CUDA IPC), 0: NCCL send/recv (A/B switch)")
+    ap.add_argument("--tune", action="append", default=[], help="library tuning key=value (A/B switches), may be repeated")
     ap.add_argument("--e2e-chunks", type=int, default=32, help="z-chunks of the pipelined host-buffer SpMV (e2e)")
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--cg-max-it", type=int, default=20000, help="iteration cap of the CG solve of the solve block (A/B runs shorten it)")

@@ -79,6 +79,12 @@ struct s3d_ctx {
 	bool red_defer = false;
 	size_t red_blocks = 0;
 	cudaStream_t comm_stream = nullptr;   // NCCL halo traffic, concurrent with the interior SpMV
+	// peer-memory halo: the push of large planes runs on a high-priority side stream, beside the multiply that follows it on the
+	// compute stream (tuning key halo_push_side, default 1); the compute stream re-joins it before anything may touch x again
+	cudaStream_t push_stream = nullptr;
+	cudaEvent_t push_ev[2] = {};
+	bool push_pending = false;
+	int push_side = 1;
 	cudaEvent_t comm_ev[2] = {};
 	double *stage = nullptr;       // device staging for contiguous host uploads (repacked into the padded layout on the device)
 	size_t stage_cap = 0;
@@ -110,6 +116,14 @@ struct s3d_ctx {
 		int ntx = 0, nty = 0;
 		size_t plane = 0;
 	} sgswin;
+	// one-shot all-reduce of a few scalars through peer memory (context.cu): every rank's window is mapped by all the others
+	struct ArWin {
+		int mode = 1;                 // tuning key allreduce_p2p: 1 = peer memory when it can be set up, 0 = ncclAllReduce
+		bool tried = false, ok = false;
+		double *win = nullptr;        // [2 parities][nranks][S3D_AR_STRIDE doubles: 32 values + the epoch]
+		double *peer[16] = {};
+		int epoch = 0;
+	} arwin;
 	int rank = 0, nranks = 1;
 	char err[512] = "";
 };

@@ -352,6 +352,7 @@ int s3d_spmv_tma(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double 
 
 extern "C" S3D_HIDDEN void s3d_internal_set_ew_unroll(int u);
 extern "C" S3D_HIDDEN int s3d_internal_halo_push(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, s3d_halo_view *hv);
+extern "C" S3D_HIDDEN int s3d_internal_halo_join(s3d_ctx *ctx);
 
 extern "C" {
 
@@ -394,6 +395,8 @@ int s3d_tune_set(s3d_ctx *ctx, const char *key, int value)
 	}
 	else if (!strcmp(key, "halo_overlap")) ctx->no_overlap = (value == 0);
 	else if (!strcmp(key, "halo_p2p")) ctx->p2p.mode = value ? 1 : 0;
+	else if (!strcmp(key, "halo_push_side")) ctx->push_side = value ? 1 : 0;
+	else if (!strcmp(key, "allreduce_p2p")) ctx->arwin.mode = value ? 1 : 0;
 	else if (!strcmp(key, "spmv_variant")) {
 		S3D_REQUIRE(ctx, value >= S3D_SPMV_MARCH && value <= S3D_SPMV_PAIR, "unknown SpMV variant");
 		g_tune.variant = value;
@@ -453,7 +456,9 @@ int s3d_spmv_exchange(s3d_ctx *ctx, const s3d_grid *g, const double *A, double *
 			const bool yy = want_yy != 0;
 			S3D_REQUIRE(ctx, !(d_w || yy) || d_red, "fused reductions need d_red");
 			const int kc = pick_kchunk(ctx, g, d_w != nullptr || yy);
-			return launch_march<8, 3>(ctx, g, A, d_x, d_y, d_b, d_w, yy, d_red, d_stop ? d_stop : ctx->gate, kc, &hv);
+			const int rcm = launch_march<8, 3>(ctx, g, A, d_x, d_y, d_b, d_w, yy, d_red, d_stop ? d_stop : ctx->gate, kc, &hv);
+			if (rcm != S3D_OK) return rcm;
+			return s3d_internal_halo_join(ctx);   // the push ran beside the multiply on its own stream
 		}
 		// no peer memory: the exchange below
 	}
@@ -580,6 +585,8 @@ int s3d_spmv_host(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		S3D_CUDA(ctx, repack(bst, 1, 2));
 		S3D_CUDA(ctx, repack(bst + hplane, g->nz, g->nz + 1));
 		int rc = s3d_internal_halo_push(ctx, g, d_x, &hv);
+		if (rc != S3D_OK) return rc;
+		rc = s3d_internal_halo_join(ctx);   // the repacks below rewrite the boundary planes (with the same values): no overlap here
 		if (rc != S3D_OK) return rc;
 		if (!hv.epoch) {
 			rc = s3d_halo_exchange(ctx, g, d_x);      // NCCL: fills the ghost planes of d_x, which the repacks below leave alone
