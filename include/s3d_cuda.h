@@ -209,6 +209,10 @@ int  s3d_strilu_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbui
                                   * the slab faces): no exchange and no cross-rank wait, so it scales; one rank: identical to LEXICOGRAPHIC */
 #define S3D_SGS_JACOBI_SWEEPS 3  /* nsweeps synchronous Jacobi sweeps per triangular factor: the deterministic counterpart of the
                                   * reference's asynchronous threaded sweeps (threadedapply = true); exact for nsweeps >= nx+ny+nz-2 */
+#define S3D_SGS_ASYNC         5  /* nsweeps ASYNCHRONOUS sweeps per triangular factor, the reference's threaded apply itself
+                                  * (s3d_sgspreconditioners.cpp:30-112 with threadedapply = true): chunks of rows dealt to persistent warps that
+                                  * never wait for one another (tuning key sgs_async_chunk = -s3d_thread_chunk_size), exact recurrence along a
+                                  * row.  Timing-dependent like the reference's; across z-slabs it runs slab by slab. */
 /* Exact (lexicographic) SGS on a z-slab decomposition: the sweep runs THROUGH the slabs -- the last plane of tiles of rank p pushes its
  * k-face rows into rank p+1's peer-memory window (backward: p-1) and raises per-tile flags there, so results and iteration counts are
  * those of the single-process reference (s3d_sgspreconditioners.cpp:14-115) at any GPU count; the ranks work as a pipeline.

@@ -1151,6 +1151,9 @@ extern "C" S3D_HIDDEN int s3d_internal_sgs_pencil(s3d_ctx *ctx, const s3d_grid *
                                                   const double *c1, const double *c2, const double *dinv, double *out,
                                                   unsigned *ticket, int klo_zero, int khi_zero, const int *stop);
 
+extern "C" S3D_HIDDEN int s3d_internal_sgs_async(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_dinv, const double *d_r,
+                                                 double *d_z, double *d_y, int nsweeps);
+
 namespace {
 // the ticket counter of the kernels that keep their own dispatch tables (sgs_pencil.cu)
 int sgs_ctl_ensure(s3d_ctx *ctx)
@@ -1239,6 +1242,7 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		}
 		return S3D_OK;
 	}
+	if (ordering == S3D_SGS_ASYNC) return s3d_internal_sgs_async(ctx, g, A, d_dinv, d_r, d_z, d_y, nsweeps);
 	if (ordering != S3D_SGS_LEXICOGRAPHIC && ordering != S3D_SGS_LEXICOGRAPHIC_PLANES && ordering != S3D_SGS_SLABLOCAL)
 		return s3d_fail(ctx, S3D_ERR_ARG, "unknown SGS ordering %d", ordering);
 	// slab-local: the exact lexicographic sweep inside every z-slab, nothing taken from the neighbouring slabs (block Jacobi across the

@@ -23,7 +23,7 @@ struct SolveParams {
 struct PreconParams {
 	int nbuildsweeps;
 	int napplysweeps;
-	int thread_chunk_size;     ///< CPU-thread chunking of the reference; accepted and ignored on the GPU
+	int thread_chunk_size;     ///< rows per chunk of the asynchronous sweeps (-s3d_sgs_ordering async); the deterministic orderings ignore it
 	bool threadedbuild;
 	bool threadedapply;        ///< reference: chaotic threaded sweeps.  GPU: the sweep is deterministic whatever this says (a warning is printed when it is asked for)
 };

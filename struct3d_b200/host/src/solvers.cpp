@@ -301,17 +301,23 @@ SGS_like_preconditioner::SGS_like_preconditioner(const SMat &lhs, const PreconPa
 		if (o == "redblack" || o == "multicolour" || o == "multicolor") order = S3D_SGS_REDBLACK;
 		else if (o == "lexicographic") order = S3D_SGS_LEXICOGRAPHIC;
 		else if (o == "slablocal") order = S3D_SGS_SLABLOCAL;
-		else if (o == "sweeps" || o == "jacobi_sweeps" || o == "async") order = S3D_SGS_JACOBI_SWEEPS;
-		else throw std::runtime_error("-s3d_sgs_ordering must be lexicographic, slablocal, redblack or sweeps");
+		else if (o == "sweeps" || o == "jacobi_sweeps") order = S3D_SGS_JACOBI_SWEEPS;
+		else if (o == "async" || o == "threaded") order = S3D_SGS_ASYNC;
+		else throw std::runtime_error("-s3d_sgs_ordering must be lexicographic, slablocal, redblack, sweeps or async");
 	}
 	// The reference's threaded apply / build (s3d_sgspreconditioners.cpp:32-53, s3d_ilu.cpp:28-32) runs asynchronous, unordered sweeps
-	// over CPU threads.  Here the sweep is one deterministic dataflow whatever these options say: asked for explicitly, say so once.
+	// over CPU threads.  Its GPU counterpart exists (-s3d_sgs_ordering async: S3D_SGS_ASYNC, chunks of -s3d_thread_chunk_size rows dealt
+	// to warps that never wait for one another), but is opt-in: the default stays the deterministic exact sweep, which needs the fewest
+	// iterations and gives the same result on every run.  Asked for through the reference's own switches, say so once.
+	if (order == S3D_SGS_ASYNC) d.check(s3d_tune_set(d.ctx(), "sgs_async_chunk", std::max(1, parms.thread_chunk_size)), "s3d_tune_set");
 	static bool warned = false;
-	const bool asked = (s3d::options_has("-s3d_pc_use_threaded_apply") && parms.threadedapply) || (s3d::options_has("-s3d_pc_use_threaded_build") && parms.threadedbuild);
+	const bool asked = order != S3D_SGS_ASYNC && ((s3d::options_has("-s3d_pc_use_threaded_apply") && parms.threadedapply) || (s3d::options_has("-s3d_pc_use_threaded_build") && parms.threadedbuild));
 	if (asked && !warned && d.rank() == 0) {
 		std::printf(" WARNING: -s3d_pc_use_threaded_apply / -s3d_pc_use_threaded_build ask for the reference's asynchronous CPU-thread sweeps; "
-		            "the GPU sweeps are deterministic (ordering: %s). Use -s3d_sgs_ordering sweeps with -s3d_pc_apply_sweeps n for n synchronous sweeps.\n",
-		            order == S3D_SGS_LEXICOGRAPHIC ? "lexicographic" : order == S3D_SGS_SLABLOCAL ? "slablocal" : order == S3D_SGS_REDBLACK ? "redblack" : "sweeps");
+		            "the GPU sweeps are deterministic unless asked otherwise (ordering: %s). -s3d_sgs_ordering async runs -s3d_pc_apply_sweeps asynchronous "
+		            "sweeps (the threaded apply's GPU counterpart), -s3d_sgs_ordering sweeps as many synchronous ones; the StrILU build is always the exact one.\n",
+		            order == S3D_SGS_LEXICOGRAPHIC ? "lexicographic" : order == S3D_SGS_SLABLOCAL ? "slablocal" : order == S3D_SGS_REDBLACK ? "redblack"
+		            : order == S3D_SGS_ASYNC ? "async" : "sweeps");
 		warned = true;
 	}
 	if (d.nranks() > 1 && order == S3D_SGS_LEXICOGRAPHIC) {

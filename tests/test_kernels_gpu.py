@@ -207,6 +207,27 @@ def test_jacobi_and_sgs(ctx, npdim, pde):
         ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_JACOBI_SWEEPS, n)
         assert np.array_equal(ctx.vec_download(g, dz), cport.sgs_jacobi_sweeps_apply(m, A, di, r, n)), f"{n} Jacobi sweeps differ"
     assert np.array_equal(ctx.vec_download(g, dz), cport.sgs_like_apply(m, A, di, r, 1)), "enough sweeps must reproduce the exact solve"
+    # asynchronous sweeps (the reference's threaded apply, s3d_sgspreconditioners.cpp:30-112): timing-dependent, so no bitwise statement.
+    #  - ONE chunk holds every row: a single warp walks them in order, which IS the sequential sweep up to the rounding of the row scan;
+    #  - small chunks, many warps: every further sweep can only bring the result closer, and after nx+ny+nz sweeps the triangular
+    #    systems are solved whatever the order of the updates was.
+    scale = np.abs(ref).max()
+    try:
+        ctx.tune("sgs_async_chunk", ny * nz)
+        ctx.vecset(g, 5.0, dz)
+        ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_ASYNC, 1)
+        za = ctx.vec_download(g, dz)
+        assert ghosts_untouched(za)
+        assert np.abs(za - ref).max() <= 1e-12 * scale, f"one-chunk asynchronous sweep: {np.abs(za - ref).max() / scale}"
+        ctx.tune("sgs_async_chunk", 2)
+        ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_ASYNC, nx + ny + nz)
+        za = ctx.vec_download(g, dz)
+        assert np.abs(za - ref).max() <= 1e-12 * scale, f"asynchronous sweeps at their fixed point: {np.abs(za - ref).max() / scale}"
+        ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_ASYNC, 1)
+        z1 = ctx.vec_download(g, dz)
+        assert np.all(np.isfinite(z1)) and ghosts_untouched(z1)
+    finally:
+        ctx.tune("sgs_async_chunk", 4)
     # StrILU: the ILU(0) diagonal (same dataflow kernel, divisions) and its application
     dinv2 = ctx.scalars_alloc(int(g.cstride))
     for sweeps in (1, 3, 0):
