@@ -56,7 +56,8 @@ struct s3d_ctx {
 	int64_t capture_launches0 = 0;
 	int sgs_sleep_ns = 0;
 	int sgs_variant = 4;        // 4: by size (streaming kernel below sgs_stream_max_points, warp-per-tile above; the default), 5: streaming, 6: register-streaming
-	                            // (sgs_pencil.cu, opt-in: measured slower, profiles/r2_sgs_pencil.md), 0: warp-per-tile dataflow
+	                            // (sgs_pencil.cu, opt-in: measured slower, profiles/r2_sgs_pencil.md), 7: row-scan wavefront (sgs_rowscan.cu, opt-in: the
+	                            // reference's sweep to rounding, measured slower, profiles/r2_sgs_rowscan.md), 0: warp-per-tile dataflow
 	                            // kernel (also what the exact sweep THROUGH z-slabs uses), 1: block-per-tile kernel, 3: r1's warp-per-line experiment
 	long long sgs_stream_max_points = 3ll << 19;   // variant 4 uses the streaming kernel up to this many points per rank, the tile kernel above
 	unsigned long long *sgs_mail = nullptr;   // streaming kernel: face mailboxes (sentinel-filled outside a sweep)

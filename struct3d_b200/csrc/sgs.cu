@@ -1022,8 +1022,9 @@ __global__ void sgs_begin_kernel(int *ctl, const int *stop)
 inline int sgs_effective_variant(const s3d_ctx *ctx, const s3d_grid *g, bool through_slabs)
 {
 	int v = ctx->sgs_variant;
-	if ((v == 4 || v == 5 || v == 6) && through_slabs && g->nranks > 1) return 0;
+	if ((v == 4 || v == 5 || v == 6 || v == 7) && through_slabs && g->nranks > 1) return 0;
 	if (v == 6) return 6;   // the register-streaming kernel whatever the size
+	if (v == 7) return 7;   // the row-scan kernel whatever the size (the reference's sweep to rounding, not bit for bit)
 	// 4 = by grid size (measured crossover, profiles/r2_sgs_stream.md), 5 = the streaming kernel whatever the size
 	if (v == 4 && (long long)g->nx * g->ny * g->nz > ctx->sgs_stream_max_points) return 0;
 	return v == 5 ? 4 : v;
@@ -1151,6 +1152,9 @@ extern "C" S3D_HIDDEN int s3d_internal_sgs_pencil(s3d_ctx *ctx, const s3d_grid *
                                                   const double *c1, const double *c2, const double *dinv, double *out,
                                                   unsigned *ticket, int klo_zero, int khi_zero, const int *stop);
 
+extern "C" S3D_HIDDEN int s3d_internal_sgs_rowscan(s3d_ctx *ctx, const s3d_grid *g, int mode, const double *in0, const double *c0,
+                                                   const double *c1, const double *c2, const double *dinv, double *out,
+                                                   unsigned *ticket, int klo_zero, int khi_zero, const int *stop);
 extern "C" S3D_HIDDEN int s3d_internal_sgs_async(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_dinv, const double *d_r,
                                                  double *d_z, double *d_y, int nsweeps);
 
@@ -1252,11 +1256,25 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 	const int variant = sgs_effective_variant(ctx, g, !slablocal);
 	if (g->nranks > 1 && !slablocal && (ordering != S3D_SGS_LEXICOGRAPHIC || variant != 0))
 		return s3d_fail(ctx, S3D_ERR_ARG, "across z-slabs only the warp-per-tile lexicographic sweep (or slab-local / red-black / sweeps) is available");
-	if (g->nranks > 1 && slablocal && variant != 4 && variant != 0 && variant != 6)
+	if (g->nranks > 1 && slablocal && variant != 4 && variant != 0 && variant != 6 && variant != 7)
 		return s3d_fail(ctx, S3D_ERR_ARG, "the slab-local ordering runs on the streaming, register-streaming or warp-per-tile kernel");
 	// the scratch vector's real entries are all overwritten and its ghosts stay zero (they are never
 	// written), so the per-call zero fill of the reference (s3d_sgspreconditioners.cpp:25-28) is implicit.
 	// Sequential sweeps are idempotent, so nsweeps > 1 repeats identical work; do one.
+	if (ordering == S3D_SGS_LEXICOGRAPHIC && variant == 7) {
+		const long long cs = g->cstride;
+		const int klo = slablocal && g->rank > 0, khi = slablocal && g->rank < g->nranks - 1;
+		const int rcc = sgs_ctl_ensure(ctx);
+		if (rcc != S3D_OK) return rcc;
+		unsigned *ticket = reinterpret_cast<unsigned *>(ctx->sgs_ctl);
+		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
+		S3D_LAUNCHED(ctx);
+		const int rcs = s3d_internal_sgs_rowscan(ctx, g, 0, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, ticket, klo, khi, ctx->gate);
+		if (rcs != S3D_OK) return rcs;
+		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
+		S3D_LAUNCHED(ctx);
+		return s3d_internal_sgs_rowscan(ctx, g, 1, d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, ticket, klo, khi, ctx->gate);
+	}
 	if (ordering == S3D_SGS_LEXICOGRAPHIC && variant == 6) {
 		const long long cs = g->cstride;
 		const int klo = slablocal && g->rank > 0, khi = slablocal && g->rank < g->nranks - 1;
@@ -1356,7 +1374,8 @@ int s3d_strilu_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuil
 	ctx->launches++;
 	SgsFlow f;
 	unsigned nblocks = 0;
-	const int variant = sgs_effective_variant(ctx, g, false);
+	int variant = sgs_effective_variant(ctx, g, false);
+	if (variant == 7) variant = 0;   // the ILU recurrence is not linear in d[i-1]: no row scan; the bit-exact tile kernel builds it
 	int rc = (variant == 6) ? sgs_ctl_ensure(ctx) : sgs_flow_prepare(ctx, g, f, nblocks, variant);
 	if (rc == S3D_OK) {
 		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, nullptr);

@@ -228,6 +228,19 @@ def test_jacobi_and_sgs(ctx, npdim, pde):
         assert np.all(np.isfinite(z1)) and ghosts_untouched(z1)
     finally:
         ctx.tune("sgs_async_chunk", 4)
+    # the row-scan kernel (sgs_variant 7): the lexicographic sweep with every row solved by an affine warp scan -- the reference's
+    # result to rounding, not bit for bit
+    try:
+        for shape in (0, 101, 204, 404):
+            ctx.tune("sgs_variant", 7); ctx.tune("sgs_pencil_shape", shape)
+            for rep in range(2):
+                ctx.vecset(g, 2.0 + rep, dz)
+                ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_LEXICOGRAPHIC, 1)
+                zr = ctx.vec_download(g, dz)
+                assert ghosts_untouched(zr)
+                assert np.abs(zr - ref).max() <= 1e-13 * scale, f"row-scan sweep (shape {shape}, rep {rep}): {np.abs(zr - ref).max() / scale}"
+    finally:
+        ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT); ctx.tune("sgs_pencil_shape", 0)
     # StrILU: the ILU(0) diagonal (same dataflow kernel, divisions) and its application
     dinv2 = ctx.scalars_alloc(int(g.cstride))
     for sweeps in (1, 3, 0):

@@ -10,6 +10,10 @@ args = sys.argv[1:]
 nolink = "--nolink" in args
 if nolink: args.remove("--nolink")
 shapes = [42, 22, 41, 21]
+variant = 6
+if "--variant" in args:
+    i = args.index("--variant"); variant = int(args[i + 1]); del args[i:i + 2]
+    if variant == 7: shapes = [408, 404, 204]
 if "--shapes" in args:
     i = args.index("--shapes"); shapes = [int(v) for v in args[i + 1].split(",")]; del args[i:i + 2]
 ctx = capi.Context(0)
@@ -33,7 +37,7 @@ for spec in args or ["64", "128", "256"]:
     ref = ctx.vec_download(g, zr)
     npts = nx * ny * nz
     print(f"{spec:>12s} tile kernel            {ms0:9.4f} ms  {96*npts/ms0/1e6:8.1f} GB/s", flush=True)
-    ctx.tune("sgs_variant", 6)
+    ctx.tune("sgs_variant", variant)
     for shape in shapes:
         ctx.tune("sgs_pencil_shape", shape)
         ctx.tune("sgs_sleep_ns", 1 if nolink else 0)
@@ -41,6 +45,7 @@ for spec in args or ["64", "128", "256"]:
         for _ in range(2): ctx.sgs_apply(g, A, dinv, r, z, y, capi.SGS_LEXICOGRAPHIC, 1)
         got = ctx.vec_download(g, z)
         same = np.array_equal(got, ref)
+        rel = float(np.abs(got - ref).max() / np.abs(ref).max())
         ctx.sync(); ctx.timer_start()
         for _ in range(5): ctx.sgs_apply(g, A, dinv, r, z, y, capi.SGS_LEXICOGRAPHIC, 1)
         ms = ctx.timer_stop_ms() / 5
@@ -48,6 +53,6 @@ for spec in args or ["64", "128", "256"]:
         if not same and not nolink:
             bad = np.argwhere(got != ref)
             extra = f" first diff at (k,j,i)={tuple(bad[0])} of {len(bad)}: got {got[tuple(bad[0])]} want {ref[tuple(bad[0])]}"
-        print(f"{spec:>12s} pencil shape {shape:4d}{' nolink' if nolink else ''}  {ms:9.4f} ms  {96*npts/ms/1e6:8.1f} GB/s  bitwise_same={same}{extra}", flush=True)
+        print(f"{spec:>12s} pencil shape {shape:4d}{' nolink' if nolink else ''}  {ms:9.4f} ms  {96*npts/ms/1e6:8.1f} GB/s  bitwise_same={same} max_rel_diff={rel:.2e}{extra if variant == 6 else ''}", flush=True)
     ctx.tune("sgs_sleep_ns", 0); ctx.tune("sgs_pencil_shape", 0); ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT)
     for p in (A, r, z, y, zr, dinv): ctx.free(p)
