@@ -106,7 +106,12 @@ struct SgsFlow {
 	int kzero_lo, kzero_hi;   // slab-local sweeps (warp kernel): what lies below k = 0 / above k = nz-1 is taken as zero, not read
 	long long *prof;   // optional per-phase cycle accumulators (warp kernel; timing experiments only)
 	int debug;         // timing experiments only (results become wrong): 1 skip wavefront, 2 skip staging, 4 skip fences, 8 skip waits
+	// warp kernel, MAILBOX hand-off (one rank or slab-local): per tile the rows of its last j ([8 c][TI]), of its last k ([TJ b][TI]) and
+	// its last i-column ([64]), all holding a sentinel outside a sweep; null: hand-off through `out`, fences and the epoch flags
+	unsigned long long *mail;
+	int mail_stride;   // doubles per tile: 8 TI + TJ TI + 64
 };
+constexpr unsigned long long SGW_SENT = 0xFFF4A5C3D2E1B497ull;   // "not written yet": a signalling-NaN pattern no arithmetic produces
 
 // FWD: in0 = r,  c0,c1,c2 = A0,A1,A2, out = y      y = (r - A0 y[i-1] - A1 y[j-1] - A2 y[k-1]) * dinv
 // BWD: in0 = y,  c0,c1,c2 = A4,A5,A6, out = z      z = y - dinv * (A4 z[i+1] + A5 z[j+1] + A6 z[k+1])
@@ -410,27 +415,39 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		// level c), rows 8..8+TJ-1 the k-halo (plane k0-1 / k0+tk at row b), then the i-neighbours of the lane's pencils
 		constexpr int NH = (8 + TJ) * CH / 32;                  // halo chunks per lane
 		const double *hp[NH];
+		// mailbox hand-off: the faces come from the predecessor tiles' mailboxes (data is its own flag); bit u of hmail: hp[u] is one
+		const bool mailmode = (f.mail != nullptr);
+		unsigned hmail = 0;
+		const bool jpred = FWD ? (cj > 0) : (cj < f.nty - 1), kpred = FWD ? (ck > 0) : (ck < f.ntz - 1);
+		const double *mjp = reinterpret_cast<const double *>(f.mail) + (long long)(FWD ? tile - f.ntx : tile + f.ntx) * f.mail_stride;
+		const double *mkp = reinterpret_cast<const double *>(f.mail) + (long long)(FWD ? tile - f.ntx * f.nty : tile + f.ntx * f.nty) * f.mail_stride + 8 * TI;
 #pragma unroll
 		for (int u = 0; u < NH; u++) {
 			const int q = lane + 32 * u, row = q / CH, i2 = q % CH;
 			hp[u] = nullptr;
 			if (2 * i2 < ti) {
 				if (row < 8) {
-					if (row < tk) hp[u] = out + vtile + (long long)(FWD ? row : tk - 1 - row) * g.vplane + (long long)(FWD ? -1 : tj) * g.vpitch + 2 * i2;
+					if (row < tk) {
+						if (mailmode && jpred) { hp[u] = mjp + row * TI + 2 * i2; hmail |= 1u << u; }
+						else hp[u] = out + vtile + (long long)(FWD ? row : tk - 1 - row) * g.vplane + (long long)(FWD ? -1 : tj) * g.vpitch + 2 * i2;
+					}
 				} else {
 					const int r = row - 8;
 					const bool kz = FWD ? (f.kzero_lo && ck == 0) : (f.kzero_hi && ck == f.ntz - 1);
-					if (r < tj && !kz)
-						hp[u] = (xin ? f.x_in_plane + inpl : out + vtile + (long long)(FWD ? -1 : tk) * g.vplane) + (long long)(FWD ? r : tj - 1 - r) * g.vpitch + 2 * i2;
+					if (r < tj && !kz) {
+						if (mailmode && kpred) { hp[u] = mkp + r * TI + 2 * i2; hmail |= 1u << u; }
+						else hp[u] = (xin ? f.x_in_plane + inpl : out + vtile + (long long)(FWD ? -1 : tk) * g.vplane) + (long long)(FWD ? r : tj - 1 - r) * g.vpitch + 2 * i2;
+					}
 				}
 			}
 		}
 		const bool iedge = FWD ? (ci == 0) : (ci == f.ntx - 1);    // no tile there: the ghost column of `out`
-		const double *box = f.iface + (long long)(FWD ? tile - 1 : tile + 1) * 64;
+		const double *box = mailmode ? reinterpret_cast<const double *>(f.mail) + (long long)(FWD ? tile - 1 : tile + 1) * f.mail_stride + (8 + TJ) * TI
+		                             : f.iface + (long long)(FWD ? tile - 1 : tile + 1) * 64;
 		const double *wp0 = !act0 ? nullptr : iedge ? out + vv0 + (FWD ? -1 : ti) : box + b0 * 8 + cc;
 		const double *wp1 = !act1 ? nullptr : iedge ? out + vv1 + (FWD ? -1 : ti) : box + b1 * 8 + cc;
-		// ---- wait for the three predecessor tiles (warp-uniform vote, see above)
-		{
+		// ---- wait for the three predecessor tiles (warp-uniform vote, see above); with mailboxes the data below is the wait
+		if (!mailmode) {
 			const int *fp = nullptr;
 			const int sk = f.ntx * f.nty;
 			if (FWD) {
@@ -461,7 +478,37 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 			double2 hv[NH];
 #pragma unroll
 			for (int u = 0; u < NH; u++) hv[u] = hp[u] ? ldcg2(hp[u]) : make_double2(0.0, 0.0);
-			const double wi0 = wp0 ? __ldcg(wp0) : 0.0, wi1 = wp1 ? __ldcg(wp1) : 0.0;   // i-neighbours: the adjacent tile's last column / the ghost column
+			double wi0 = wp0 ? __ldcg(wp0) : 0.0, wi1 = wp1 ? __ldcg(wp1) : 0.0;   // i-neighbours: the adjacent tile's last column / the ghost column
+			if (mailmode) {
+				// every value that comes from a mailbox is polled until it is there (the producing warp stores it the moment its sweep is
+				// over: no fence, no flag), then the sentinel goes back so that the box is clean for the next sweep
+				const double sent = __longlong_as_double((long long)SGW_SENT);
+				auto is_sent = [](double v) { return (unsigned long long)__double_as_longlong(v) == SGW_SENT; };
+				const bool mi0 = wp0 && !iedge, mi1 = wp1 && !iedge;
+				const long long tw0 = clock64();
+				for (;;) {
+					bool ok = !(mi0 && is_sent(wi0)) && !(mi1 && is_sent(wi1));
+#pragma unroll
+					for (int u = 0; u < NH; u++) {
+						const int i2 = (lane + 32 * u) % CH;
+						if ((hmail >> u) & 1u) ok = ok && !is_sent(hv[u].x) && (2 * i2 + 1 >= ti || !is_sent(hv[u].y));
+					}
+					if (__all_sync(FULL, ok)) break;
+#pragma unroll
+					for (int u = 0; u < NH; u++) {
+						const int i2 = (lane + 32 * u) % CH;
+						if (((hmail >> u) & 1u) && (is_sent(hv[u].x) || (2 * i2 + 1 < ti && is_sent(hv[u].y)))) hv[u] = ldcg2(hp[u]);
+					}
+					if (mi0 && is_sent(wi0)) wi0 = __ldcg(wp0);
+					if (mi1 && is_sent(wi1)) wi1 = __ldcg(wp1);
+					if (clock64() - tw0 > (8ll << 30)) __trap();   // seconds without the producing tile: fail loudly instead of hanging
+				}
+#pragma unroll
+				for (int u = 0; u < NH; u++)
+					if ((hmail >> u) & 1u) __stcg(reinterpret_cast<double2 *>(const_cast<double *>(hp[u])), make_double2(sent, sent));
+				if (mi0) __stcg(const_cast<double *>(wp0), sent);
+				if (mi1) __stcg(const_cast<double *>(wp1), sent);
+			}
 #pragma unroll
 			for (int u = 0; u < NH; u++) {
 				const int q = lane + 32 * u, row = q / CH, i2 = q % CH;
@@ -534,8 +581,6 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		if (f.prof) tpf = clock64();
 		ntile = __shfl_sync(FULL, ntile, 0);
 		__syncwarp();
-		if (act0) f.iface[(long long)tile * 64 + b0 * 8 + cc] = last0;
-		if (act1) f.iface[(long long)tile * 64 + b1 * 8 + cc] = last1;
 		auto copy_row_chunk = [&](int rb, int rc, int i2) {
 			const int pj = FWD ? rb : tj - 1 - rb, pk = FWD ? rc : tk - 1 - rc;
 			double *dst = out + vtile + (long long)pk * g.vplane + (long long)pj * g.vpitch + 2 * i2;
@@ -543,6 +588,44 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 			if (2 * i2 + 1 < ti) *reinterpret_cast<double2 *>(dst) = v;
 			else *dst = v.x;
 		};
+		if (mailmode) {
+			// MAILBOX hand-off: the faces go into this tile's boxes -- only where a tile of this sweep will read (and re-arm) them --
+			// the moment the sweep is over; no fence, no flag.  Then every row goes to `out`, which only later kernels read.
+			const bool isucc = FWD ? (ci < f.ntx - 1) : (ci > 0), jsucc = FWD ? (cj < f.nty - 1) : (cj > 0), ksucc = FWD ? (ck < f.ntz - 1) : (ck > 0);
+			double *mb = reinterpret_cast<double *>(f.mail) + (long long)tile * f.mail_stride;
+			if (isucc) {
+				if (act0) __stcg(mb + (8 + TJ) * TI + b0 * 8 + cc, last0);
+				if (act1) __stcg(mb + (8 + TJ) * TI + b1 * 8 + cc, last1);
+			}
+#pragma unroll
+			for (int u = 0; u < (8 + TJ) * CH / 32; u++) {
+				const int q = lane + 32 * u, i2 = q % CH, fr = q / CH;
+				const int rb = (fr < 8) ? tj - 1 : fr - 8, rc = (fr < 8) ? fr : tk - 1;
+				if (rc < tk && rb < tj && 2 * i2 < ti && ((fr < 8) ? jsucc : ksucc)) {
+					const double2 v = *reinterpret_cast<const double2 *>(s_a + sgw_row<P, FWD>(rb, rc) * R + 2 * i2);
+					double *dst = mb + fr * TI + 2 * i2;               // rows 0..7: last j at level c = fr; rows 8..: last k at position b = fr - 8
+					if (2 * i2 + 1 < ti) __stcg(reinterpret_cast<double2 *>(dst), v);
+					else __stcg(dst, v.x);
+				}
+			}
+			if (f.prof) tp3 = clock64();
+			if (f.prof && lane == 0) {
+				const long long tp4 = clock64();
+				atomicAdd((unsigned long long *)f.prof + 0, (unsigned long long)(tp1 - tp0));
+				atomicAdd((unsigned long long *)f.prof + 1, (unsigned long long)(tp2 - tp1));   // ticket + polling the boxes + copy completion
+				atomicAdd((unsigned long long *)f.prof + 2, (unsigned long long)(tpf - tp2));   // sweep loop
+				atomicAdd((unsigned long long *)f.prof + 3, (unsigned long long)(tp4 - tpf));   // boxes out
+				atomicAdd((unsigned long long *)f.prof + 4, 1ull);
+				atomicAdd((unsigned long long *)f.prof + 5, (unsigned long long)(ti + tj + tk - 2 + (P - 1)));
+			}
+#pragma unroll
+			for (int u = 0; u < NROWS * CH / 32; u++) {
+				const int q = lane + 32 * u, i2 = q % CH, row = q / CH, rb = row >> 3, rc = row & 7;
+				if (rb < tj && rc < tk && 2 * i2 < ti) copy_row_chunk(rb, rc, i2);
+			}
+		} else {
+		if (act0) f.iface[(long long)tile * 64 + b0 * 8 + cc] = last0;
+		if (act1) f.iface[(long long)tile * 64 + b1 * 8 + cc] = last1;
 		// face rows: 0..7 the last j (b = tj-1) at every c, then the last k (c = tk-1) at every b < tj-1
 #pragma unroll
 		for (int u = 0; u < (8 + TJ) * CH / 32; u++) {
@@ -585,6 +668,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		for (int u = 0; u < NROWS * CH / 32; u++) {
 			const int q = lane + 32 * u, i2 = q % CH, row = q / CH, rb = row >> 3, rc = row & 7;
 			if (rb < tj - 1 && rc < tk - 1 && 2 * i2 < ti) copy_row_chunk(rb, rc, i2);
+		}
 		}
 		if (ntile >= 0) stage(ntile);
 		tile = ntile;
@@ -1008,6 +1092,11 @@ template <int TI, int P> int sgw_configure()
 	return std::max(1, std::min(a, b));
 }
 
+__global__ void __launch_bounds__(256) fill_u64_sgs_kernel(unsigned long long *p, size_t n, unsigned long long v)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
 // start of a dataflow sweep: rewind the ticket counter and move to the next epoch -- on the device, so that a captured CUDA graph
 // of a solver iteration can be replayed (a host-side epoch would be frozen into the graph)
 __global__ void sgs_begin_kernel(int *ctl, const int *stop)
@@ -1086,6 +1175,7 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 	}
 	f.flags = ctx->sgs_flags;
 	f.iface = ctx->sgs_iface;
+	f.mail = nullptr; f.mail_stride = 0;
 	f.x_in_plane = nullptr; f.x_in_flags = nullptr; f.x_out_plane = nullptr; f.x_out_flags = nullptr;
 	f.kzero_lo = 0; f.kzero_hi = 0;
 	f.order = ctx->sgs_order;
@@ -1122,6 +1212,20 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 			ctx->sgs_iface_cap = ntiles * 64;
 		}
 		f.iface = ctx->sgs_iface;
+		if (ctx->sgs_tile_mail) {
+			// mailbox hand-off (the caller drops it again for a sweep that runs THROUGH z-slabs): all sentinel outside a sweep
+			const size_t stride = (size_t)(8 + tile_j) * tile_i + 64, need = ntiles * stride;
+			if (ctx->sgs_mail_cap < need) {
+				S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+				if (ctx->sgs_mail) S3D_CUDA(ctx, cudaFree(ctx->sgs_mail));
+				ctx->sgs_mail = nullptr; ctx->sgs_mail_cap = 0;
+				S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_mail, need * sizeof(unsigned long long)));
+				fill_u64_sgs_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->sgs_mail, need, SGW_SENT);
+				S3D_LAUNCHED(ctx);
+				ctx->sgs_mail_cap = need;
+			}
+			f.mail = ctx->sgs_mail; f.mail_stride = (int)stride;
+		}
 		static bool wconfigured = false;
 		static int warps_per_sm[4] = {1, 1, 1, 1};   // [tile_i == 32][pencils == 2]
 		if (!wconfigured) {
@@ -1309,6 +1413,7 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		if (slablocal) { f.kzero_lo = g->rank > 0; f.kzero_hi = g->rank < g->nranks - 1; }
 		s3d_sgs_window xw;
 		if (g->nranks > 1 && !slablocal) {
+			f.mail = nullptr;   // the cross-rank hand-off is the flag protocol's
 			// the sweep runs THROUGH the slabs: rank p's first plane of tiles waits for rank p-1's last one (peer-memory window)
 			const int rcw = s3d_internal_sgs_window(ctx, g, f.ntx, f.nty, &xw);
 			if (rcw != S3D_OK) return rcw;
