@@ -59,7 +59,8 @@ struct s3d_ctx {
 	                            // (sgs_pencil.cu, opt-in: measured slower, profiles/r2_sgs_pencil.md), 7: row-scan wavefront (sgs_rowscan.cu, opt-in: the
 	                            // reference's sweep to rounding, measured slower, profiles/r2_sgs_rowscan.md), 0: warp-per-tile dataflow
 	                            // kernel (also what the exact sweep THROUGH z-slabs uses), 1: block-per-tile kernel, 3: r1's warp-per-line experiment
-	long long sgs_stream_max_points = 3ll << 19;   // variant 4 uses the streaming kernel up to this many points per rank, the tile kernel above
+	long long sgs_stream_max_points = 0;   // variant 4 uses the streaming kernel up to this many points per rank, the tile kernel above.  0 since the
+	                                       // tile kernel hands its faces over through mailboxes: it is the faster one at every size (profiles/r2_sgs_tile_mail.md)
 	unsigned long long *sgs_mail = nullptr;   // streaming kernel: face mailboxes (sentinel-filled outside a sweep)
 	size_t sgs_mail_cap = 0;
 	int sgs_warps_per_sm = 0;   // 0: as many as fit

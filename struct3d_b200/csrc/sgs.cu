@@ -1061,14 +1061,14 @@ unsigned ew_blocks(const s3d_ctx *ctx, const s3d_grid *g)
 
 inline int sgw_tile_i(const s3d_ctx *ctx) { return ctx->sgs_tile_i == 32 ? 32 : 16; }
 // pencils per lane: 2 (tile TI x 8 x 8) has the shorter dependency chain across the grid, 1 (tile TI x 4 x 8) twice as many tiles in
-// flight per SM.  Measured on B200 (profiles/r1_sgs_phases.md): 256^3 0.79 vs 1.01 ms, 320^3 1.26 vs 1.34, 384^3 1.86 vs 1.73,
-// 448^3 2.73 vs 2.40, 512^3 3.68 vs 3.25 ms: the switch sits at 40 Mi points.
+// flight per SM.  Measured on B200 with the mailbox hand-off (profiles/r2_sgs_tile_mail.md): 256^3 0.770 vs 0.799 ms, 320^3 1.176 vs
+// 1.120, 384^3 1.813 vs 1.521, 512^3 3.859 vs 3.022 ms: the switch sits at 24 Mi points (r1, flags and fences: 40 Mi).
 inline int sgw_pencils(const s3d_ctx *ctx, const s3d_grid *g)
 {
 	if (ctx->sgs_pencils == 1 || ctx->sgs_pencils == 2) return ctx->sgs_pencils;
 	// every rank of a z-slab run must pick the same tile shape (the cross-rank flags are per (ci, cj)): decide on the mean slab
 	const long long nzl = (g->nranks > 1) ? ((long long)g->nz_global + g->nranks - 1) / g->nranks : g->nz;
-	return ((long long)g->nx * g->ny * nzl >= (40ll << 20)) ? 1 : 2;
+	return ((long long)g->nx * g->ny * nzl >= (24ll << 20)) ? 1 : 2;
 }
 
 template <int MODE, typename... Args> void sgw_launch(s3d_ctx *ctx, const s3d_grid *g, unsigned nblocks, Args... args)

@@ -32,7 +32,15 @@ for spec in sys.argv[1:] or ["64", "128", "256", "512"]:
             res[(pencils, mail)] = got
             same = np.array_equal(got, res[(2, 0)])
             print(f"{spec:>12s} pencils/lane={pencils} mailboxes={mail}  {ms:9.4f} ms  {96*nx*ny*nz/ms/1e6:8.1f} GB/s  same_as_flags={same}", flush=True)
-    ctx.tune("sgs_tile_mail", 1); ctx.tune("sgs_pencils", 0); ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT)
+    ctx.tune("sgs_tile_mail", 1); ctx.tune("sgs_pencils", 0)
+    ctx.tune("sgs_variant", 5)                       # the streaming kernel, for the size rule of the default
+    for _ in range(3): ctx.sgs_apply(g, A, dinv, r, z, y, capi.SGS_LEXICOGRAPHIC, 1)
+    same = np.array_equal(ctx.vec_download(g, z), res[(2, 0)])
+    ctx.sync(); ctx.timer_start()
+    for _ in range(10): ctx.sgs_apply(g, A, dinv, r, z, y, capi.SGS_LEXICOGRAPHIC, 1)
+    ms = ctx.timer_stop_ms() / 10
+    print(f"{spec:>12s} streaming kernel             {ms:9.4f} ms  {96*nx*ny*nz/ms/1e6:8.1f} GB/s  same_as_flags={same}", flush=True)
+    ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT)
     for p in (A, r, z, y, dinv): ctx.free(p)
 if os.environ.get("SGS_PROF"):
     # per-tile phase cycles (stderr): wait = flag wait (0 with mailboxes), "load" = ticket + polling / halo fetch, "total" = sweep loop, "face" = publish
