@@ -23,9 +23,14 @@ for _ in range(2):
     ctx.dot_dev(g, x, y, red)
     ctx.jacobi_apply(g, A, x, z)
 dinv = ctx.scalars_alloc(int(g.cstride)); ctx.sgs_setup(g, A, dinv)
-for variant in (0, 5):
-    ctx.tune("sgs_variant", variant)
+# every build of the exact sweep: tile kernel with mailboxes (the default) and with flags + fences (r1), streaming, register-streaming,
+# row-scan; then the asynchronous sweeps
+for variant, mail in ((0, 1), (0, 0), (5, 1), (6, 1), (7, 1)):
+    ctx.tune("sgs_variant", variant); ctx.tune("sgs_tile_mail", mail)
     for _ in range(2):
         ctx.sgs_apply(g, A, dinv, x, z, s, capi.SGS_LEXICOGRAPHIC, 1)
+ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT); ctx.tune("sgs_tile_mail", 1)
+for _ in range(2):
+    ctx.sgs_apply(g, A, dinv, x, z, s, capi.SGS_ASYNC, 2)
 ctx.sync()
 print("done", n)
