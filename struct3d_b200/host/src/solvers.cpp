@@ -71,10 +71,13 @@ struct DeviceLoop {
 		s3d_free(ctx, flags);
 		if (hist) s3d_free(ctx, hist);
 	}
-	void graphs(const s3d_grid &g)
+	int waits = 0, first_batch_iters = 0;   // iterations the first (eager, timed) batch completed: scales its preconditioner time
+	void graphs(const s3d_grid &g) { use_graph = want_graphs(d, g); }
+	// With graphs only the first, eagerly enqueued batch can carry the preconditioner stopwatch (events cannot be timed inside a
+	// replayed capture): SolveInfo::precapplywtime is then that batch's time scaled by the iteration count -- an estimate, and said so.
+	double phase_scale(int iterations) const
 	{
-		use_graph = want_graphs(d, g);
-		g_time_phases = !use_graph;
+		return (use_graph && first_batch_iters > 0 && iterations > first_batch_iters) ? (double)iterations / first_batch_iters : 1.0;
 	}
 	// One batch of iterations.  `enqueue` must issue the same launches every time it is called from the second batch on (an even
 	// number of iterations when the loop ping-pongs its scalars).  The first batch runs eagerly (first-use allocations, the special
@@ -82,7 +85,11 @@ struct DeviceLoop {
 	template <class F> void batch(F &&enqueue)
 	{
 		const int index = nbatch++;
-		if (!use_graph || index == 0) { enqueue(); return; }
+		if (!use_graph || index == 0) {
+			enqueue();
+			if (use_graph) g_time_phases = false;   // from here on the batches are captured / replayed
+			return;
+		}
 		if (!graph) {
 			d.check(s3d_graph_begin(ctx), "s3d_graph_begin");
 			try {
@@ -115,6 +122,7 @@ struct DeviceLoop {
 		int h[2] = {0, 0};
 		d.check(s3d_ints_snapshot_wait(ctx, slot, 2, h), "s3d_ints_snapshot_wait");
 		iterations = h[1];
+		if (waits++ == 1) first_batch_iters = h[1];   // the second snapshot is the state behind the first batch
 		return h[0];
 	}
 	// after the loop: fetch the residual history recorded on the device and print the reference's progress lines
@@ -167,7 +175,7 @@ struct Scalars {
 	}
 };
 
-SolveInfo finish(const Device &d, const double *rr, const double *bb, double rtol, int iterations, int stopcode, int phase_slot)
+SolveInfo finish(const Device &d, const double *rr, const double *bb, double rtol, int iterations, int stopcode, int phase_slot, double phase_scale = 1.0)
 {
 	double h[2];
 	d.check(s3d_scalars_download(d.ctx(), rr, 1, &h[0]), "s3d_scalars_download");
@@ -179,7 +187,10 @@ SolveInfo finish(const Device &d, const double *rr, const double *bb, double rto
 	info.converged = (stopcode != S3D_STOP_BREAKDOWN) && (resnorm / bnorm <= rtol);
 	info.iters = iterations;
 	info.resnorm = resnorm;
-	info.precapplywtime = ms * 1e-3;
+	info.precapplywtime = ms * 1e-3 * phase_scale;
+	if (phase_scale != 1.0 && ms > 0 && d.rank() == 0)
+		std::printf("      (preconditioner time: %.3g s measured over the first batch, scaled by %.3g to all %d iterations: CUDA-graph replay carries no stopwatch)\n",
+		            ms * 1e-3, phase_scale, iterations);
 	return info;
 }
 
@@ -410,7 +421,7 @@ SolveInfo Richardson::apply(const SVec &b, SVec &x) const
 	}
 	d.check(s3d_ctx_set_gate(ctx, nullptr), "s3d_ctx_set_gate");
 	loop.collect(iterations);
-	const SolveInfo info = finish(d, &S[2], &S[0], sparams.rtol, iterations, code, 0);
+	const SolveInfo info = finish(d, &S[2], &S[0], sparams.rtol, iterations, code, 0, loop.phase_scale(iterations));
 	return info;
 }
 
@@ -500,7 +511,7 @@ SolveInfo GCR::apply(const SVec &b, SVec &x) const
 	}
 	d.check(s3d_ctx_set_gate(ctx, nullptr), "s3d_ctx_set_gate");
 	loop.collect(iterations);
-	const SolveInfo info = finish(d, &S[3], &S[0], sparams.rtol, iterations, code, 0);
+	const SolveInfo info = finish(d, &S[3], &S[0], sparams.rtol, iterations, code, 0, loop.phase_scale(iterations));
 	return info;
 }
 
@@ -579,7 +590,7 @@ SolveInfo CG::apply(const SVec &b, SVec &x) const
 	loop.collect(iterations);
 	// the residual norm of the last COUNTED iteration lives in the pair that iteration wrote
 	if (iterations > 0) rr_final = ((iterations - 1) % 2 == 0) ? &S[3] : &S[5];
-	const SolveInfo info = finish(d, rr_final, &S[0], sparams.rtol, iterations, code, 0);
+	const SolveInfo info = finish(d, rr_final, &S[0], sparams.rtol, iterations, code, 0, loop.phase_scale(iterations));
 	return info;
 }
 
@@ -654,7 +665,7 @@ SolveInfo BiCGSTAB::apply(const SVec &b, SVec &x) const
 	loop.collect(iterations);
 	const double *rr_final = &S[7];
 	if (iterations > 0) rr_final = ((iterations - 1) % 2 == 0) ? &S[5] : &S[7];
-	const SolveInfo info = finish(d, rr_final, &S[0], sparams.rtol, iterations, code, 0);
+	const SolveInfo info = finish(d, rr_final, &S[0], sparams.rtol, iterations, code, 0, loop.phase_scale(iterations));
 	return info;
 }
 
