@@ -192,6 +192,84 @@ def test_peer_memory_halo_protocol_needs_no_acknowledgement(nranks):
 
 
 @pytest.mark.parametrize("nranks", [2, 3, 4])
+def test_peer_memory_allreduce_needs_no_acknowledgement(nranks):
+    """Model of the one-shot all-reduce over peer memory (allreduce_peer_kernel, struct3d_b200/csrc/context.cu): the kernels of a rank
+    run in stream order, reduce(1), reduce(2), ...; reduce(e) first WRITES this rank's values and then the epoch into slot [e & 1][rank]
+    of EVERY rank's window, then waits until all slots [e & 1][*] of its OWN window carry epoch e, then READS them.  Modelled as two
+    events per reduction (write, read-done), every interleaving explored.  Claims: (1) when a rank overwrites a slot with epoch e, the
+    owner of that window has finished reading epoch e - 2 from it -- two parities suffice, no acknowledgement; (2) no deadlock; (3) what a
+    rank reads for epoch e is what every rank wrote for epoch e."""
+    nepochs = 5
+    nops = 2 * nepochs                        # op 2(e-1) = write(e) into all windows, op 2(e-1)+1 = read(e) from the own window
+    start = tuple([0] * nranks)
+    seen, todo = {start}, [start]
+    while todo:
+        pc = todo.pop()
+        for r in range(nranks):
+            if pc[r] >= nops:
+                continue
+            e, is_read = pc[r] // 2 + 1, pc[r] % 2 == 1
+            if is_read:
+                if not all(pc[q] > 2 * (e - 1) for q in range(nranks)):   # somebody's epoch e has not landed: the kernel spins
+                    continue
+                # what sits in slot [e & 1][q] of r's window is q's LATEST write of that parity: it must be epoch e, not e + 2
+                for q in range(nranks):
+                    latest = (pc[q] + 1) // 2                              # epochs q has written so far
+                    newest_same_parity = latest if latest % 2 == e % 2 else latest - 1
+                    assert newest_same_parity == e, f"rank {r} reads epoch {e} of rank {q} after it was overwritten by {newest_same_parity}"
+            else:
+                for q in range(nranks):                                    # write(e) overwrites slot [e & 1][r] in q's window
+                    assert e <= 2 or pc[q] > 2 * (e - 3) + 1, f"rank {r} overwrites epoch {e - 2} in rank {q}'s window before it was read"
+            nxt = pc[:r] + (pc[r] + 1,) + pc[r + 1:]
+            if nxt not in seen:
+                seen.add(nxt)
+                todo.append(nxt)
+    assert tuple([nops] * nranks) in seen
+
+
+@pytest.mark.parametrize("dims", [(2, 2, 1), (3, 2, 2), (2, 3, 2)])
+def test_sgs_tile_mailboxes_are_clean_after_every_sweep(dims):
+    """Model of the mailbox hand-off of the warp-per-tile SGS kernel (sgs_warpflow_kernel, struct3d_b200/csrc/sgs.cu): every tile owns
+    three boxes (its last-i column, last-j rows, last-k rows) that hold a sentinel outside a sweep.  A tile polls the boxes of its
+    predecessors (in sweep order) until they are full, re-arms them, sweeps, and fills its own boxes -- but ONLY those a tile of this
+    sweep will read.  Claims, over forward and backward sweeps alternating and EVERY order in which ready tiles can run: a consumer never
+    sees a box written by an earlier sweep (stale faces), a producer never overwrites a full box, and all boxes are empty again when a
+    sweep ends (so the next sweep, whose producers and consumers swap roles, starts clean)."""
+    import itertools
+    nx, ny, nz = dims
+    tiles = list(itertools.product(range(nx), range(ny), range(nz)))
+    boxes = {(t, d): None for t in tiles for d in range(3)}        # (tile, direction) -> sweep number that filled it, None = sentinel
+
+    def neighbour(t, d, step):
+        q = list(t); q[d] += step
+        return tuple(q) if 0 <= q[d] < dims[d] else None
+
+    def run_sweep(n, fwd, order_seed):
+        step = 1 if fwd else -1
+        done = set()
+        rng = np.random.default_rng(order_seed)
+        while len(done) < len(tiles):
+            ready = [t for t in tiles if t not in done and all(neighbour(t, d, -step) is None or boxes[(neighbour(t, d, -step), d)] is not None for d in range(3))]
+            assert ready, "deadlock: no tile can run"
+            t = ready[rng.integers(len(ready))]
+            for d in range(3):
+                p = neighbour(t, d, -step)
+                if p is not None:
+                    assert boxes[(p, d)] == n, f"tile {t} takes a face of sweep {boxes[(p, d)]} in sweep {n}"
+                    boxes[(p, d)] = None                           # re-armed by its reader
+            for d in range(3):
+                if neighbour(t, d, step) is not None:              # only where a tile of this sweep will read it
+                    assert boxes[(t, d)] is None, f"tile {t} overwrites a full box in sweep {n}"
+                    boxes[(t, d)] = n
+            done.add(t)
+        assert all(v is None for v in boxes.values()), f"boxes left full after sweep {n}"
+
+    for seed in range(40):
+        for n in range(4):
+            run_sweep(n, fwd=(n % 2 == 0), order_seed=1000 * seed + n)
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 4])
 def test_sgs_slab_window_is_safe_with_one_buffer_per_direction(nranks):
     """Model of the exact SGS sweep through z-slabs (sgs.cu / context.cu): every rank runs forward sweep, backward sweep, forward, ...
     as kernels in stream order.  While rank p runs a forward sweep it WRITES k-face rows into rank p+1's forward window and READS its
