@@ -816,7 +816,7 @@ allreduce_peer_kernel(const double *local, double *global, int n, ArPeers peers,
 		const double *in = mine + ((size_t)par * nranks + r) * S3D_AR_STRIDE;
 		const long long t0 = clock64();
 		while (*reinterpret_cast<const volatile int *>(in + S3D_AR_MAXN) != epoch)
-			if (clock64() - t0 > (20ll << 30)) __trap();   // ~10 s: a rank died; fail loudly instead of hanging the GPU
+			if (clock64() - t0 > (60ll << 30)) __trap();   // ~30 s: a rank died (ranks may reach a collective seconds apart); fail loudly instead of hanging the GPU
 		__threadfence_system();
 	}
 	__syncthreads();
