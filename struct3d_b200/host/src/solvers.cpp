@@ -225,7 +225,8 @@ SolveInfo small_solve(int method, const SMat &A, const SolverBase *prec, const S
 	constexpr int HCAP = 1 << 16;
 	static int *flags = nullptr;
 	static double *scal = nullptr;
-	if (!flags) { flags = d.ints(2); scal = d.scalars(2 + HCAP); }
+	static s3d_ctx *owner = nullptr;          // the buffers belong to a context: a re-initialised device gets new ones
+	if (owner != ctx) { flags = d.ints(2); scal = d.scalars(2 + HCAP); owner = ctx; }
 	const int pc = dynamic_cast<const JacobiPreconditioner *>(prec) ? 1 : 0;
 	if (method == 2)
 		d.check(s3d_small_solve_gcr(ctx, &A.grid(), A.dev(), b.dev(), x.dev_rw(), w0.dev_w(), w1->dev_w(), pq, north, pc, sp.rtol, sp.maxiter,
