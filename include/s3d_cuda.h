@@ -202,6 +202,9 @@ int  s3d_sgs_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, double *d_d
  * nbuildsweeps > 1 is idempotent for the sequential build and is treated as 1; 0 gives 1/diag.  On a z-slab decomposition the
  * recurrence runs inside every slab (block ILU(0) by slabs: what the slab-local application, S3D_SGS_SLABLOCAL, goes with). */
 int  s3d_strilu_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuildsweeps, double *d_dinv);
+/* The reference's THREADED build (threadedbuild = true, s3d_ilu.cpp:28-32): nbuildsweeps >= 1 ASYNCHRONOUS sweeps from d = diag(A), chunks of rows
+ * (tuning key sgs_async_chunk) dealt to warps that never wait for one another.  Timing-dependent; exact after at most nx+ny+nz sweeps. */
+int  s3d_strilu_setup_async(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuildsweeps, double *d_dinv);
 #define S3D_SGS_LEXICOGRAPHIC 0  /* the reference's ordering, executed as a tile-level dataflow wavefront: same arithmetic */
 #define S3D_SGS_LEXICOGRAPHIC_PLANES 2  /* same result, one launch per hyperplane i+j+k (slow; kept for cross-checks) */
 #define S3D_SGS_REDBLACK      1  /* two-colour ordering: fully parallel half-sweeps (another operator: changes the iteration counts) */

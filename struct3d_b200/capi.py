@@ -59,7 +59,7 @@ _SIGS = {
     "s3d_normL2sq": [_P, _G, _vp, _vp, _vp, _vp, _vp],
     "s3d_dot_host": [_P, _G, _vp, _vp, _dp], "s3d_nrm2_host": [_P, _G, _vp, _dp],
     "s3d_allreduce_sum": [_P, _vp, _vp, _I],
-    "s3d_jacobi_apply": [_P, _G, _vp, _vp, _vp], "s3d_sgs_setup": [_P, _G, _vp, _vp], "s3d_strilu_setup": [_P, _G, _vp, _I, _vp],
+    "s3d_jacobi_apply": [_P, _G, _vp, _vp, _vp], "s3d_sgs_setup": [_P, _G, _vp, _vp], "s3d_strilu_setup": [_P, _G, _vp, _I, _vp], "s3d_strilu_setup_async": [_P, _G, _vp, _I, _vp],
     "s3d_sgs_apply": [_P, _G, _vp, _vp, _vp, _vp, _vp, _I, _I], "s3d_sgs_slab_sweeps_available": [_P, _G, C.POINTER(C.c_int)],
     "s3d_cg_update": [_P, _G, Scalar, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "s3d_cg_direction_jacobi": [_P, _G, Scalar, _vp, _vp, _vp, _vp],
@@ -346,6 +346,9 @@ class Context:
 
     def strilu_setup(self, g, A, nbuildsweeps, dinv):
         self.call("s3d_strilu_setup", C.byref(g), _ptr(A), int(nbuildsweeps), _ptr(dinv))
+
+    def strilu_setup_async(self, g, A, nbuildsweeps, dinv):
+        self.call("s3d_strilu_setup_async", C.byref(g), _ptr(A), int(nbuildsweeps), _ptr(dinv))
 
     def sgs_apply(self, g, A, dinv, r, z, y, ordering=SGS_LEXICOGRAPHIC, nsweeps=1):
         self.call("s3d_sgs_apply", C.byref(g), _ptr(A), _ptr(dinv), _ptr(r), _ptr(z), _ptr(y), ordering, nsweeps)

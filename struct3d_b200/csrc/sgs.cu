@@ -1259,6 +1259,7 @@ extern "C" S3D_HIDDEN int s3d_internal_sgs_pencil(s3d_ctx *ctx, const s3d_grid *
 extern "C" S3D_HIDDEN int s3d_internal_sgs_rowscan(s3d_ctx *ctx, const s3d_grid *g, int mode, const double *in0, const double *c0,
                                                    const double *c1, const double *c2, const double *dinv, double *out,
                                                    unsigned *ticket, int klo_zero, int khi_zero, const int *stop);
+extern "C" S3D_HIDDEN int s3d_internal_strilu_async(s3d_ctx *ctx, const s3d_grid *g, const double *a3, const double *P, double *D, int nsweeps);
 extern "C" S3D_HIDDEN int s3d_internal_sgs_async(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_dinv, const double *d_r,
                                                  double *d_z, double *d_y, int nsweeps);
 
@@ -1461,7 +1462,22 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 // matrix, d_ijk = A3 - A0*A4[i-1]/d[i-1] - A1*A5[j-1]/d[j-1] - A2*A6[k-1]/d[k-1], then dinv = 1/d.  A lexicographic sweep computes
 // the exact fixed point, so further build sweeps reproduce it (they are skipped); 0 sweeps gives dinv = 1/diag like the reference.
 // The result feeds s3d_sgs_apply (same (D+L) D^-1 (D+U) application, SGS_like_preconditioner::apply).
+static int strilu_setup_impl(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuildsweeps, double *d_dinv, bool async);
+
 int s3d_strilu_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuildsweeps, double *d_dinv)
+{
+	return strilu_setup_impl(ctx, g, A, nbuildsweeps, d_dinv, false);
+}
+
+// The reference's THREADED build (threadedbuild = true, s3d_ilu.cpp:28-32): nbuildsweeps asynchronous sweeps from d = diag(A), rows dealt to
+// warps in chunks (tuning key sgs_async_chunk = -s3d_thread_chunk_size) that never wait for one another.  Timing-dependent like the
+// reference's; it reaches the exact diagonal after at most nx + ny + nz sweeps.
+int s3d_strilu_setup_async(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuildsweeps, double *d_dinv)
+{
+	return strilu_setup_impl(ctx, g, A, nbuildsweeps, d_dinv, true);
+}
+
+static int strilu_setup_impl(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuildsweeps, double *d_dinv, bool async)
 {
 	S3D_REQUIRE(ctx, g && A && d_dinv && nbuildsweeps >= 0, "bad argument");
 	// On a z-slab decomposition the recurrence is run inside every slab (nothing taken across the slab faces: the products below are
@@ -1481,6 +1497,19 @@ int s3d_strilu_setup(s3d_ctx *ctx, const s3d_grid *g, const double *A, int nbuil
 	unsigned nblocks = 0;
 	int variant = sgs_effective_variant(ctx, g, false);
 	if (variant == 7) variant = 0;   // the ILU recurrence is not linear in d[i-1]: no row scan; the bit-exact tile kernel builds it
+	if (async) {
+		int rca = s3d_internal_strilu_async(ctx, g, A + 3 * (size_t)g->cstride, P, D, nbuildsweeps);
+		if (rca == S3D_OK) {
+			ilu_invert_kernel<<<nb, 256, 0, ctx->stream>>>(gd, D, d_dinv);
+			ctx->launches++;
+			e = cudaGetLastError();
+			if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+			if (e != cudaSuccess) rca = s3d_fail(ctx, S3D_ERR_CUDA, "s3d_strilu_setup_async: %s", cudaGetErrorString(e));
+		}
+		cudaFree(P);
+		cudaFree(D);
+		return rca;
+	}
 	int rc = (variant == 6) ? sgs_ctl_ensure(ctx) : sgs_flow_prepare(ctx, g, f, nblocks, variant);
 	if (rc == S3D_OK) {
 		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, nullptr);

@@ -86,6 +86,52 @@ sgs_async_kernel(const GridDev g, const double *__restrict__ c0, const double *_
 	}
 }
 
+// ASYNCHRONOUS build of the StrILU diagonal (StrILU_preconditioner::updateOperator with threadedbuild = true, src/linalg/s3d_ilu.cpp:17-64):
+// d starts as the matrix diagonal and every thread of the reference re-evaluates d = A3 - P0 / d[i-1] - P1 / d[j-1] - P2 / d[k-1] over its chunks of
+// rows, `nbuildsweeps` times, without ever waiting for the others (`omp for nowait schedule(dynamic, chunk)`).  Here a LANE walks a row (the
+// recurrence along i is not linear: no scan), the rows of a chunk are dealt to the lanes of the warp the chunk belongs to, warps never wait;
+// neighbour rows are read from and results written to L2.  P_s = A_s A_{s+4}[neighbour] are the exact build's products (zero where the neighbour
+// does not exist), D is a vector-layout array whose ghosts are 1.  Set-up code: uncoalesced and latency-bound, run once per operator.
+__global__ void __launch_bounds__(256)
+strilu_async_kernel(const GridDev g, const double *__restrict__ a3, const double *__restrict__ P, double *D, int nsweeps, int chunk, const int *stop)
+{
+	if (s3d_stopped(stop)) return;
+	const int lane = threadIdx.x & 31;
+	const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+	const int nrows = g.ny * g.nz;
+	const int nchunks = (nrows + chunk - 1) / chunk;
+	const long long cs = g.cstride;
+	for (int swp = 0; swp < nsweeps; swp++)
+		for (int q = warp; q < nchunks; q += nwarps) {
+			const int r0 = q * chunk, r1 = min(nrows, r0 + chunk);
+			for (int row = r0 + lane; row < r1; row += 32) {
+				const int k = row / g.ny, j = row - k * g.ny;
+				const long long vrow = g.voff + (long long)k * g.vplane + (long long)j * g.vpitch;
+				const long long crow = (long long)k * g.cplane + (long long)j * g.cpitch;
+				double prev = 1.0;                                          // the ghost column (P0 is zero there)
+				for (int i = 0; i < g.nx; i++) {
+					const double dj = __ldcg(D + vrow - g.vpitch + i), dk = __ldcg(D + vrow - g.vplane + i);
+					double v = __dsub_rn(a3[crow + i], __ddiv_rn(P[crow + i], prev));
+					v = __dsub_rn(v, __ddiv_rn(P[cs + crow + i], dj));
+					v = __dsub_rn(v, __ddiv_rn(P[2 * cs + crow + i], dk));
+					__stcg(D + vrow + i, v);
+					prev = v;
+				}
+			}
+		}
+}
+
+__global__ void __launch_bounds__(256) strilu_init_kernel(const GridDev g, const double *__restrict__ a3, double *D)
+{
+	const long long total = (long long)g.nx * g.ny * g.nz;
+	for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+		const int i = (int)(t % g.nx);
+		const long long row = t / g.nx;
+		const int j = (int)(row % g.ny), k = (int)(row / g.ny);
+		D[g.voff + (long long)k * g.vplane + (long long)j * g.vpitch + i] = a3[(long long)k * g.cplane + (long long)j * g.cpitch + i];
+	}
+}
+
 __global__ void __launch_bounds__(256) zero_real_kernel(const GridDev g, double *x, const int *stop)
 {
 	if (s3d_stopped(stop)) return;
@@ -99,6 +145,24 @@ __global__ void __launch_bounds__(256) zero_real_kernel(const GridDev g, double 
 }
 
 }  // namespace
+
+// D (vector layout, every entry 1 on entry: ghosts stay 1) <- the diagonal after nsweeps asynchronous sweeps; a3: the matrix diagonal,
+// P: the three product arrays (coefficient layout, stride g->cstride).
+extern "C" S3D_HIDDEN int s3d_internal_strilu_async(s3d_ctx *ctx, const s3d_grid *g, const double *a3, const double *P, double *D, int nsweeps)
+{
+	const GridDev gd = to_dev(g);
+	const int nrows = g->ny * g->nz;
+	int chunk = std::max(1, ctx->sgs_async_chunk);
+	const int want_chunks = ctx->sm_count * 16;
+	if (nrows >= 4 * want_chunks && nrows / chunk < want_chunks) chunk = std::max(1, nrows / want_chunks);
+	const int nchunks = (nrows + chunk - 1) / chunk;
+	const unsigned nb = (unsigned)std::max(1, std::min((nchunks + 7) / 8, ctx->sm_count * 8));
+	strilu_init_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(gd, a3, D);
+	S3D_LAUNCHED(ctx);
+	strilu_async_kernel<<<nb, 256, 0, ctx->stream>>>(gd, a3, P, D, nsweeps, chunk, nullptr);
+	S3D_LAUNCHED(ctx);
+	return S3D_OK;
+}
 
 // d_y: scratch vector (forward result), d_z: output.  Both start from zero, like the reference's y (cpp:25-28).
 extern "C" S3D_HIDDEN int s3d_internal_sgs_async(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_dinv, const double *d_r,

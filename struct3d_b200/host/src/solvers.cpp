@@ -327,7 +327,7 @@ SGS_like_preconditioner::SGS_like_preconditioner(const SMat &lhs, const PreconPa
 	if (asked && !warned && d.rank() == 0) {
 		std::printf(" WARNING: -s3d_pc_use_threaded_apply / -s3d_pc_use_threaded_build ask for the reference's asynchronous CPU-thread sweeps; "
 		            "the GPU sweeps are deterministic unless asked otherwise (ordering: %s). -s3d_sgs_ordering async runs -s3d_pc_apply_sweeps asynchronous "
-		            "sweeps (the threaded apply's GPU counterpart), -s3d_sgs_ordering sweeps as many synchronous ones; the StrILU build is always the exact one.\n",
+		            "sweeps (the threaded apply's GPU counterpart; with it -s3d_pc_use_threaded_build true builds StrILU by asynchronous sweeps as well), -s3d_sgs_ordering sweeps as many synchronous ones.\n",
 		            order == S3D_SGS_LEXICOGRAPHIC ? "lexicographic" : order == S3D_SGS_SLABLOCAL ? "slablocal" : order == S3D_SGS_REDBLACK ? "redblack"
 		            : order == S3D_SGS_ASYNC ? "async" : "sweeps");
 		warned = true;
@@ -371,6 +371,13 @@ StrILU_preconditioner::StrILU_preconditioner(const SMat &lhs, const PreconParams
 void StrILU_preconditioner::updateOperator()
 {
 	const Device &d = Device::get();
+	// -s3d_sgs_ordering async asks for the reference's threaded behaviour as a whole: the factorisation is then built by asynchronous sweeps
+	// too (s3d_ilu.cpp:28-32) unless -s3d_pc_use_threaded_build false keeps the exact build
+	if (order == S3D_SGS_ASYNC && params.threadedbuild && params.nbuildsweeps > 0) {
+		d.check(s3d_tune_set(d.ctx(), "sgs_async_chunk", std::max(1, params.thread_chunk_size)), "s3d_tune_set");
+		d.check(s3d_strilu_setup_async(d.ctx(), &A.grid(), A.dev(), params.nbuildsweeps, diaginv), "s3d_strilu_setup_async");
+		return;
+	}
 	d.check(s3d_strilu_setup(d.ctx(), &A.grid(), A.dev(), params.nbuildsweeps, diaginv), "s3d_strilu_setup");
 }
 

@@ -140,6 +140,24 @@ def test_asynchronous_sgs_sweeps_iteration_bounds(H):
     assert counts[8] <= counts[3] + 3 <= counts[1] + 6, (counts, exact)
 
 
+def test_asynchronous_strilu_build_iteration_bounds(H):
+    """The reference's threaded StrILU build (s3d_ilu.cpp:28-32): asynchronous sweeps from d = diag(A).  GCR + StrILU on the convdiff-large
+    case needs 61 iterations with the exact factorisation (golden); with asynchronously built factors and asynchronous application it
+    converges within 1.5 times that from three sweeps each on, and reproduces the 61 (give or take rounding) with many sweeps."""
+    rec = next(r for r in SOLVES["solves"] if r["case"] == "convdiff64" and r["ksp"] == "gcr" and r["pc"] == "strilu")
+    counts = {}
+    for sweeps in (3, 40):
+        m, P, A, b = _setup(H, rec)
+        x = H.Vec(m)
+        got = H.solve(A, b, x, _opts(rec, **{"-s3d_sgs_ordering": "async", "-s3d_pc_apply_sweeps": sweeps, "-s3d_pc_build_sweeps": sweeps,
+                                             "-s3d_pc_use_threaded_build": "true", "-s3d_thread_chunk_size": 4}))
+        assert got["converged"], (sweeps, got)
+        counts[sweeps] = got["iters"]
+    H.set_options({})
+    print(f"[async-strilu] gcr + asynchronously built and applied StrILU, convdiff 62^3: {counts} iterations (exact: {rec['iters']})")
+    assert counts[3] <= 1.5 * rec["iters"] and abs(counts[40] - rec["iters"]) <= 3, (counts, rec["iters"])
+
+
 def _gate_rows(H, case, ordering):
     rows = []
     for rec in [r for r in SOLVES["solves"] if r["case"] == case and r["pc"] == "sgs"]:

@@ -228,6 +228,23 @@ def test_jacobi_and_sgs(ctx, npdim, pde):
         assert np.all(np.isfinite(z1)) and ghosts_untouched(z1)
     finally:
         ctx.tune("sgs_async_chunk", 4)
+    # asynchronous StrILU build (the reference's threaded build, s3d_ilu.cpp:28-32): from d = diag(A), any order of updates reaches the
+    # exact ILU(0) diagonal after at most nx+ny+nz sweeps; fewer sweeps give something between the diagonal and it
+    dinv3 = ctx.scalars_alloc(int(g.cstride))
+    try:
+        want = cport.strilu_setup(m, A, 1)
+        ctx.tune("sgs_async_chunk", 3)
+        ctx.strilu_setup_async(g, dA, nx + ny + nz, dinv3)
+        ctx.sgs_apply(g, dA, dinv3, dr, dz, dy, capi.SGS_LEXICOGRAPHIC, 1)
+        zs = ctx.vec_download(g, dz)
+        refs = cport.sgs_like_apply(m, A, want, r, 1)
+        assert np.abs(zs - refs).max() <= 1e-12 * np.abs(refs).max(), "asynchronous StrILU build at its fixed point differs from the exact factorisation"
+        ctx.strilu_setup_async(g, dA, 1, dinv3)
+        ctx.sgs_apply(g, dA, dinv3, dr, dz, dy, capi.SGS_LEXICOGRAPHIC, 1)
+        assert np.all(np.isfinite(ctx.vec_download(g, dz)))
+    finally:
+        ctx.tune("sgs_async_chunk", 4)
+        ctx.free(dinv3)
     # the row-scan kernel (sgs_variant 7): the lexicographic sweep with every row solved by an affine warp scan -- the reference's
     # result to rounding, not bit for bit
     try:
