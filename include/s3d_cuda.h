@@ -227,6 +227,14 @@ int  s3d_sgs_slab_sweeps_available(s3d_ctx *ctx, const s3d_grid *g, int *yes);
  * d_y: scratch vector (vlen doubles); it is re-zeroed by the call like the reference's temporary. */
 int  s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_dinv,
                    const double *d_r, double *d_z, double *d_y, int ordering, int nsweeps);
+/* Red-black SGS on COLOUR-PACKED coefficients: a colour occupies every other entry of a row, so the plain red-black kernels use half of every
+ * sector of the coefficient arrays they touch.  s3d_sgs_rb_pack copies A0 A1 A2 A4 A5 A6 and dinv once per operator (after s3d_sgs_setup /
+ * s3d_strilu_setup) into a buffer of s3d_sgs_rb_pack_size doubles in which the entries of one colour are contiguous; s3d_sgs_apply_rb_packed
+ * is s3d_sgs_apply(..., S3D_SGS_REDBLACK, ...) reading from it: same expressions, bit-identical results (no counterpart in the reference). */
+int  s3d_sgs_rb_pack_size(const s3d_grid *g, size_t *ndoubles);
+int  s3d_sgs_rb_pack_alloc(s3d_ctx *ctx, const s3d_grid *g, double **d_out);   /* a buffer of that size; release it with s3d_free */
+int  s3d_sgs_rb_pack(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_dinv, double *d_packed);
+int  s3d_sgs_apply_rb_packed(s3d_ctx *ctx, const s3d_grid *g, const double *d_packed, const double *d_r, double *d_z, double *d_y);
 
 /* ------------------------------------------------------------------ fused solver steps (new: CG / BiCGSTAB) */
 

@@ -60,6 +60,7 @@ _SIGS = {
     "s3d_dot_host": [_P, _G, _vp, _vp, _dp], "s3d_nrm2_host": [_P, _G, _vp, _dp],
     "s3d_allreduce_sum": [_P, _vp, _vp, _I],
     "s3d_jacobi_apply": [_P, _G, _vp, _vp, _vp], "s3d_sgs_setup": [_P, _G, _vp, _vp], "s3d_strilu_setup": [_P, _G, _vp, _I, _vp], "s3d_strilu_setup_async": [_P, _G, _vp, _I, _vp],
+    "s3d_sgs_rb_pack_size": [_G, C.POINTER(C.c_size_t)], "s3d_sgs_rb_pack_alloc": [_P, _G, C.POINTER(_vp)], "s3d_sgs_rb_pack": [_P, _G, _vp, _vp, _vp], "s3d_sgs_apply_rb_packed": [_P, _G, _vp, _vp, _vp, _vp],
     "s3d_sgs_apply": [_P, _G, _vp, _vp, _vp, _vp, _vp, _I, _I], "s3d_sgs_slab_sweeps_available": [_P, _G, C.POINTER(C.c_int)],
     "s3d_cg_update": [_P, _G, Scalar, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "s3d_cg_direction_jacobi": [_P, _G, Scalar, _vp, _vp, _vp, _vp],
@@ -346,6 +347,16 @@ class Context:
 
     def strilu_setup(self, g, A, nbuildsweeps, dinv):
         self.call("s3d_strilu_setup", C.byref(g), _ptr(A), int(nbuildsweeps), _ptr(dinv))
+
+    def sgs_rb_pack(self, g, A, dinv):
+        """colour-packed copy of the coefficients for the red-black SGS; returns the device buffer (free it with ctx.free)"""
+        p = _vp()
+        self.call("s3d_sgs_rb_pack_alloc", C.byref(g), C.byref(p))
+        self.call("s3d_sgs_rb_pack", C.byref(g), _ptr(A), _ptr(dinv), _ptr(p.value))
+        return p.value
+
+    def sgs_apply_rb_packed(self, g, packed, r, z, y):
+        self.call("s3d_sgs_apply_rb_packed", C.byref(g), _ptr(packed), _ptr(r), _ptr(z), _ptr(y))
 
     def strilu_setup_async(self, g, A, nbuildsweeps, dinv):
         self.call("s3d_strilu_setup_async", C.byref(g), _ptr(A), int(nbuildsweeps), _ptr(dinv))

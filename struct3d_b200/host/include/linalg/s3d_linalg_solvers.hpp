@@ -124,6 +124,8 @@ public:
 
 protected:
 	double *diaginv;          ///< device array in the coefficient layout (cstride doubles)
+	double *rbpack = nullptr; ///< red-black ordering: colour-packed copy of the off-diagonal coefficients and diaginv (made by updateOperator)
+	void pack_if_redblack();  ///< to be called at the end of updateOperator()
 	const PreconParams params;
 	int order;
 	mutable SVec scratch;     ///< the reference allocates and zeroes this per call; here once

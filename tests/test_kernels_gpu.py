@@ -270,6 +270,13 @@ def test_jacobi_and_sgs(ctx, npdim, pde):
     ref = cport.sgs_redblack_apply(m, A, di, r)
     assert np.array_equal(z, ref), f"red-black SGS max diff {np.abs(z - ref).max()}"
     assert ghosts_untouched(z)
+    packed = ctx.sgs_rb_pack(g, dA, dinv)                      # the same on colour-packed coefficients
+    ctx.vecset(g, 4.0, dz)
+    ctx.sgs_apply_rb_packed(g, packed, dr, dz, dy)
+    zp = ctx.vec_download(g, dz)
+    ctx.free(packed)
+    assert np.array_equal(zp, ref), f"red-black SGS on packed coefficients: max diff {np.abs(zp - ref).max()}"
+    assert ghosts_untouched(zp)
 
 
 # every build of the exact dataflow sweep: block-per-tile (variant 1), warp-per-tile (variant 0) with 16- or 32-long tiles and one
