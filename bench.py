@@ -201,9 +201,26 @@ def run_sweep(a):
             ctx.sync(); ctx.timer_start()
             for _ in range(reps): fn()
             return ctx.timer_stop_ms() / reps
+        def tg(fn):
+            # the same call replayed from a captured CUDA graph of 20 launches: how the solver loops issue their kernels on grids up to
+            # 4 Mi points (one launch from Python costs ~7 us of host time, more than these kernels run)
+            for _ in range(3): fn()
+            ctx.graph_begin()
+            for _ in range(20): fn()
+            h = ctx.graph_end()
+            ctx.graph_launch(h)
+            ctx.sync(); ctx.timer_start()
+            for _ in range(10): ctx.graph_launch(h)
+            ms = ctx.timer_stop_ms() / 200
+            ctx.graph_destroy(h)
+            return ms
         gpu = {"spmv": BYTES_SPMV * n ** 3 / t(lambda: ctx.spmv(g, dA, dx, dy)) / 1e6,
                "axpy": 24 * n ** 3 / t(lambda: ctx.vecaxpy(g, 1e-9, dx, dy)) / 1e6,
                "dot": 16 * n ** 3 / t(lambda: ctx.dot_dev(g, dx, dy, red)) / 1e6}
+        if n <= 128:
+            gpu["spmv_graph"] = BYTES_SPMV * n ** 3 / tg(lambda: ctx.spmv(g, dA, dx, dy)) / 1e6
+            gpu["axpy_graph"] = 24 * n ** 3 / tg(lambda: ctx.vecaxpy(g, 1e-9, dx, dy)) / 1e6
+            gpu["dot_graph"] = 16 * n ** 3 / tg(lambda: ctx.dot_dev(g, dx, dy, red)) / 1e6
         for p_ in (dA, dx, dy, red): ctx.free(p_)
         cpu = {"spmv": None, "axpy": None, "dot": None}
         cores = None
@@ -222,12 +239,13 @@ def run_sweep(a):
             del A, x, y, m
         rows.append((n, gpu, cpu, cores))
         print(f"[sweep] {n}^3 gpu {gpu} cpu {cpu}", file=sys.stderr, flush=True)
-    out = ["| grid | working set | SpMV GB/s (% of measured peak) | axpy GB/s (%) | dot GB/s (%) | reference CPU SpMV / axpy / dot GB/s (threads) |", "|---|---|---|---|---|---|"]
+    out = ["| grid | working set | SpMV GB/s (% of measured peak) | axpy GB/s (%) | dot GB/s (%) | same three, replayed from a CUDA graph | reference CPU SpMV / axpy / dot GB/s (threads) |", "|---|---|---|---|---|---|---|"]
     for n, gpu, cpu, cores in rows:
         ws = (7 * 8 + 2 * 8) * n ** 3
         note = "L2-resident" if ws < 100e6 else "streams from HBM"
         cp = " / ".join("-" if cpu[k] is None else f"{cpu[k]:.1f}" for k in ("spmv", "axpy", "dot")) + (f" ({cores})" if cores else "")
-        out.append(f"| {n}^3 | {ws / 1e6:.1f} MB, {note} | " + " | ".join(f"{gpu[k]:.0f} ({100 * gpu[k] / peak:.0f} %)" for k in ("spmv", "axpy", "dot")) + f" | {cp} |")
+        gr = " / ".join(f"{gpu[k + '_graph']:.0f}" for k in ("spmv", "axpy", "dot")) if "spmv_graph" in gpu else "-"
+        out.append(f"| {n}^3 | {ws / 1e6:.1f} MB, {note} | " + " | ".join(f"{gpu[k]:.0f} ({100 * gpu[k] / peak:.0f} %)" for k in ("spmv", "axpy", "dot")) + f" | {gr} | {cp} |")
     text = "\n".join(out)
     os.makedirs(os.path.dirname(a.sweep_out), exist_ok=True)
     with open(a.sweep_out, "w") as fh:
