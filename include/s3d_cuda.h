@@ -275,7 +275,7 @@ int  s3d_scalar_op(s3d_ctx *ctx, int op, double *d_out, const double *a, const d
  * kernels, same convergence test as s3d_converge_test.  d_flags[0] = S3D_STOP_* code, d_flags[1] = iterations, d_scal[0] = (r,r) at
  * exit, d_scal[1] = (b,b), d_hist_or_null[it] = relative residual after iteration it (hist_cap entries).  One rank, at most
  * S3D_SMALL_MAX_POINTS points. */
-#define S3D_SMALL_MAX_POINTS (1 << 17)
+#define S3D_SMALL_MAX_POINTS (1 << 22)
 int  s3d_small_solve(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double *d_b, double *d_x, double *d_w0, double *d_w1,
                      double *d_w2, int method, int pc, double rtol, int maxiter, int *d_flags, double *d_scal, double *d_hist_or_null,
                      int hist_cap);

@@ -64,6 +64,7 @@ struct s3d_ctx {
 	unsigned long long *sgs_mail = nullptr;   // streaming kernel: face mailboxes (sentinel-filled outside a sweep)
 	size_t sgs_mail_cap = 0;
 	int sgs_warps_per_sm = 0;   // 0: as many as fit
+	int small_team = 0;         // single-launch solver: 0 = cluster up to 32 Ki points, cooperative grid above; 1 = always the cluster (A/B)
 	int sgs_tile_mail = 1;      // warp-per-tile kernel: hand the faces over through sentinel mailboxes (no fence, no flag) instead of `out` + epoch flags
 	int sgs_async_chunk = 4;    // rows per chunk of the asynchronous sweeps (S3D_SGS_ASYNC); the host passes -s3d_thread_chunk_size
 	int sgs_pencil_shape = 0;   // register-streaming kernel (variant 6): warps of a block as WJ*10 + WK (+ prefetch depth as a third digit); 0 = default

@@ -18,6 +18,7 @@
 //   GCR(north):  the reference's loop, src/linalg/s3d_gcr.cpp:14-86: cycles of `north` directions, each made orthogonal to the earlier
 //                ones of its cycle (up to 8 dot products under one cluster barrier), strict inner test, cap checked between cycles
 // with M = diag(A) (Jacobi, a true division) or the identity, and the device-side convergence test of s3d_converge_test.
+#include <algorithm>
 #include <cooperative_groups.h>
 #include "common.cuh"
 
@@ -38,6 +39,7 @@ struct SmallArgs {
 	double *scal;    // [0] (r,r) at exit, [1] (b,b)
 	double *hist;    // relative residual of every counted iteration (may be null)
 	int hist_cap;
+	double *gpart;   // cooperative-grid team: [4 parities][SM_NV][blocks] partial sums in global memory
 	int north;       // GCR: directions per cycle (the restart length), at most SM_NORTH
 	double *pq[2 * 32];   // GCR: p_0, q_0, p_1, q_1 ...
 };
@@ -91,23 +93,71 @@ __device__ __forceinline__ void cluster_sum_n(double (&v)[NV], double *smn, doub
 	}
 }
 
+// The same two reductions over a whole cooperative GRID (blocks of SM_NT threads): one partial per block in global memory, grid
+// barrier, then every warp adds the partials of all blocks in the same fixed order.  `gp`: this parity's [NV][nblocks] partials.
+__device__ __forceinline__ double grid_sum(double v, double *sm, double *gp, cg::grid_group &gr)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	v = warp_sum(v);
+	__syncthreads();
+	if (lane == 0) sm[warp] = v;
+	__syncthreads();
+	double t = warp_sum(sm[lane]);
+	if (threadIdx.x == 0) __stcg(gp + blockIdx.x, t);
+	gr.sync();
+	double s = 0.0;
+	for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(gp + b);
+	return warp_sum(s);
+}
+template <int NV>
+__device__ __forceinline__ void grid_sum_n(double (&v)[NV], double *smn, double *gp, cg::grid_group &gr)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for (int l = 0; l < NV; l++) v[l] = warp_sum(v[l]);
+	__syncthreads();
+	if (lane == 0) {
+#pragma unroll
+		for (int l = 0; l < NV; l++) smn[l * 32 + warp] = v[l];
+	}
+	__syncthreads();
+	if (warp < NV) {
+		double t = warp_sum(smn[warp * 32 + lane]);
+		if (lane == 0) __stcg(gp + warp * gridDim.x + blockIdx.x, t);
+	}
+	gr.sync();
+#pragma unroll
+	for (int l = 0; l < NV; l++) {
+		double s = 0.0;
+		for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(gp + l * gridDim.x + b);
+		v[l] = warp_sum(s);
+	}
+}
+
 __device__ __forceinline__ double madd2(double a, double x, double y) { return __dadd_rn(y, __dmul_rn(a, x)); }   // y + a x, two roundings
 
-// METHOD 0: Richardson, 1: CG.  JAC: Jacobi preconditioner (else the identity)
-template <int METHOD, bool JAC>
-__global__ void __cluster_dims__(SM_CL, 1, 1) __launch_bounds__(SM_NT, 1) small_solve_kernel(const SmallArgs a)
+// METHOD 0: Richardson, 1: CG, 2: GCR.  JAC: Jacobi preconditioner (else the identity).  GRID: the team is a cooperative grid (one
+// block per SM, grid barrier, partial sums through global memory) instead of one cluster of SM_CL blocks: for grids too large for
+// eight SMs but small enough to live in L2, where an iteration is still bound by its launches.
+template <int METHOD, bool JAC, bool GRID>
+__device__ __forceinline__ void small_solve_body(const SmallArgs &a)
 {
 	__shared__ double sm[32];
 	__shared__ double part[4];          // this block's partial sums, by reduction parity (two reductions may follow one another)
 	__shared__ double smn[METHOD == 2 ? SM_NV * 32 : 1];
 	__shared__ double partn[METHOD == 2 ? 4 * SM_NV : 1];
 	cg::cluster_group cl = cg::this_cluster();
+	cg::grid_group gr = cg::this_grid();
 	const GridDev &g = a.g;
 	const int N = g.nx * g.ny * g.nz;
-	const int tid = cl.block_rank() * SM_NT + threadIdx.x;
-	constexpr int NT = SM_CL * SM_NT;
+	const int tid = GRID ? (int)(blockIdx.x * SM_NT + threadIdx.x) : (int)(cl.block_rank() * SM_NT + threadIdx.x);
+	const int NT = GRID ? (int)(gridDim.x * SM_NT) : SM_CL * SM_NT;
 	int par = 0;
-	auto csum = [&](double v) { par = (par + 1) & 3; return cluster_sum(v, sm, &part[par], cl); };
+	auto tsync = [&]() { if (GRID) gr.sync(); else cl.sync(); };
+	auto csum = [&](double v) {
+		par = (par + 1) & 3;
+		return GRID ? grid_sum(v, sm, a.gpart + (size_t)par * SM_NV * gridDim.x, gr) : cluster_sum(v, sm, &part[par], cl);
+	};
 	const long long cs = g.cstride;
 	auto vaddr = [&](int idx, long long &v, long long &c) {
 		const int i = idx % g.nx, jk = idx / g.nx, j = jk % g.ny, k = jk / g.ny;
@@ -151,7 +201,11 @@ __global__ void __cluster_dims__(SM_CL, 1, 1) __launch_bounds__(SM_NT, 1) small_
 		double *z = a.w1;
 		double qq_kept[SM_NORTH];
 		double rr_g = 1.0;
-		auto csum_n = [&](double (&v)[SM_NV]) { par = (par + 1) & 3; cluster_sum_n<SM_NV>(v, smn, &partn[par * SM_NV], cl); };
+		auto csum_n = [&](double (&v)[SM_NV]) {
+			par = (par + 1) & 3;
+			if (GRID) grid_sum_n<SM_NV>(v, smn, a.gpart + (size_t)par * SM_NV * gridDim.x, gr);
+			else cluster_sum_n<SM_NV>(v, smn, &partn[par * SM_NV], cl);
+		};
 		while (!stop && iters < a.maxiter) {
 			// res = b - A x;  p_0 = M^-1 res
 			double *p0 = a.pq[0], *q0 = a.pq[1];
@@ -161,7 +215,7 @@ __global__ void __cluster_dims__(SM_CL, 1, 1) __launch_bounds__(SM_NT, 1) small_
 				r[v] = rv;
 				p0[v] = JAC ? __ddiv_rn(rv, a.A[3 * cs + c]) : rv;
 			}
-			cl.sync();
+			tsync();
 			// q_0 = A p_0, (res,q_0), (q_0,q_0)
 			double two[SM_NV] = {};
 			for (int idx = tid; idx < N; idx += NT) {
@@ -228,7 +282,7 @@ __global__ void __cluster_dims__(SM_CL, 1, 1) __launch_bounds__(SM_NT, 1) small_
 				rq = nxt[0]; qq = nxt[1];
 			}
 		}
-		cl.sync();
+		tsync();
 		if (tid == 0) {
 			a.flags[0] = stop;
 			a.flags[1] = iters;
@@ -256,7 +310,7 @@ __global__ void __cluster_dims__(SM_CL, 1, 1) __launch_bounds__(SM_NT, 1) small_
 				const double dx = JAC ? __ddiv_rn(r[v], a.A[3 * cs + c]) : r[v];
 				a.x[v] = madd2(1.0, dx, a.x[v]);
 			}
-			cl.sync();
+			tsync();
 			acc = 0.0;
 			for (int idx = tid; idx < N; idx += NT) {
 				long long v, c; vaddr(idx, v, c);
@@ -312,16 +366,49 @@ __global__ void __cluster_dims__(SM_CL, 1, 1) __launch_bounds__(SM_NT, 1) small_
 				const double z = JAC ? __ddiv_rn(r[v], a.A[3 * cs + c]) : r[v];
 				p[v] = madd2(beta, p[v], z);
 			}
-			cl.sync();
+			tsync();
 		}
 	}
-	cl.sync();                          // no block leaves while another may still read its partial sums
+	tsync();                          // no block leaves while another may still read its partial sums
 	if (tid == 0) {
 		a.flags[0] = stop;
 		a.flags[1] = iters;
 		a.scal[0] = rr;
 		a.scal[1] = bb;
 	}
+}
+
+template <int METHOD, bool JAC>
+__global__ void __cluster_dims__(SM_CL, 1, 1) __launch_bounds__(SM_NT, 1) small_solve_kernel(const SmallArgs a)
+{
+	small_solve_body<METHOD, JAC, false>(a);
+}
+
+template <int METHOD, bool JAC>
+__global__ void __launch_bounds__(SM_NT, 1) grid_solve_kernel(const SmallArgs a)
+{
+	small_solve_body<METHOD, JAC, true>(a);
+}
+
+// which team runs a solve: the cluster up to S3D_SMALL_CLUSTER_POINTS points, a cooperative grid of one block per SM above
+constexpr long long S3D_SMALL_CLUSTER_POINTS = 1 << 15;
+
+template <int METHOD, bool JAC>
+int small_launch(s3d_ctx *ctx, SmallArgs &a, long long npoints)
+{
+	if (npoints <= S3D_SMALL_CLUSTER_POINTS || ctx->small_team == 1) {
+		small_solve_kernel<METHOD, JAC><<<SM_CL, SM_NT, 0, ctx->stream>>>(a);
+		S3D_LAUNCHED(ctx);
+		return S3D_OK;
+	}
+	const int nblocks = (int)std::max<long long>(1, std::min<long long>(ctx->sm_count, (npoints + SM_NT - 1) / SM_NT));
+	const int rc = s3d_ensure_partials(ctx, (size_t)4 * SM_NV * nblocks);
+	if (rc != S3D_OK) return rc;
+	a.gpart = ctx->partials;
+	void *params[] = {&a};
+	S3D_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)grid_solve_kernel<METHOD, JAC>, dim3(nblocks), dim3(SM_NT), params, 0, ctx->stream));
+	S3D_LAUNCHED(ctx);
+	return S3D_OK;
 }
 
 }  // namespace
@@ -342,12 +429,12 @@ int s3d_small_solve(s3d_ctx *ctx, const s3d_grid *g, const double *A, const doub
 	a.north = 0;
 	a.g = to_dev(g); a.A = A; a.b = d_b; a.x = d_x; a.w0 = d_w0; a.w1 = d_w1; a.w2 = d_w2;
 	a.rtol = rtol; a.maxiter = maxiter; a.flags = d_flags; a.scal = d_scal; a.hist = d_hist; a.hist_cap = d_hist ? hist_cap : 0;
-	if (method == 0 && pc) small_solve_kernel<0, true><<<SM_CL, SM_NT, 0, ctx->stream>>>(a);
-	else if (method == 0) small_solve_kernel<0, false><<<SM_CL, SM_NT, 0, ctx->stream>>>(a);
-	else if (pc) small_solve_kernel<1, true><<<SM_CL, SM_NT, 0, ctx->stream>>>(a);
-	else small_solve_kernel<1, false><<<SM_CL, SM_NT, 0, ctx->stream>>>(a);
-	S3D_LAUNCHED(ctx);
-	return S3D_OK;
+	a.gpart = nullptr;
+	const long long np = (long long)g->nx * g->ny * g->nz;
+	if (method == 0 && pc) return small_launch<0, true>(ctx, a, np);
+	if (method == 0) return small_launch<0, false>(ctx, a, np);
+	if (pc) return small_launch<1, true>(ctx, a, np);
+	return small_launch<1, false>(ctx, a, np);
 }
 
 // GCR(north) in one launch: d_res, d_z work vectors, d_pq[2 i] = p_i, d_pq[2 i + 1] = q_i (host array of 2 north device pointers).
@@ -364,10 +451,10 @@ int s3d_small_solve_gcr(s3d_ctx *ctx, const s3d_grid *g, const double *A, const 
 	a.rtol = rtol; a.maxiter = maxiter; a.flags = d_flags; a.scal = d_scal; a.hist = d_hist; a.hist_cap = d_hist ? hist_cap : 0;
 	a.north = north;
 	for (int i = 0; i < 2 * SM_NORTH; i++) a.pq[i] = i < 2 * north ? d_pq[i] : nullptr;
-	if (pc) small_solve_kernel<2, true><<<SM_CL, SM_NT, 0, ctx->stream>>>(a);
-	else small_solve_kernel<2, false><<<SM_CL, SM_NT, 0, ctx->stream>>>(a);
-	S3D_LAUNCHED(ctx);
-	return S3D_OK;
+	a.gpart = nullptr;
+	const long long np = (long long)g->nx * g->ny * g->nz;
+	if (pc) return small_launch<2, true>(ctx, a, np);
+	return small_launch<2, false>(ctx, a, np);
 }
 
 }  // extern "C"

@@ -201,9 +201,10 @@ struct TimedPrec {   // brackets a preconditioner application with the GPU stopw
 };
 
 // Small grids: the whole solve in ONE kernel launch (s3d_small_solve), for Richardson, CG and GCR with the Jacobi or the identity
-// preconditioner on one GPU.  -s3d_small_solve on|off|auto (auto: up to 32 Ki points, where a host-driven iteration costs 25-35 us of
-// launches against a few microseconds of work; measured in profiles/r2_small_solves.md).
-bool want_small_solve(const Device &d, const s3d_grid &g, const SolverBase *prec)
+// preconditioner on one GPU.  -s3d_small_solve on|off|auto (auto: up to 32 Ki points -- one cluster of 8 blocks -- where a host-driven
+// iteration costs 25-35 us of launches against a few microseconds of work, and up to 128 Ki points for Richardson and CG -- a cooperative
+// grid of one block per SM; measured in profiles/r2_small_solves.md).
+bool want_small_solve(const Device &d, const s3d_grid &g, const SolverBase *prec, int method)
 {
 	if (d.nranks() > 1) return false;
 	const long long n = (long long)g.nx * g.ny * g.nz;
@@ -213,7 +214,10 @@ bool want_small_solve(const Device &d, const s3d_grid &g, const SolverBase *prec
 	if (s3d::options_has("-s3d_small_solve")) v = petscoptions_get_string("-s3d_small_solve", 10);
 	if (v == "on" || v == "1" || v == "true") return true;
 	if (v == "off" || v == "0" || v == "false") return false;
-	return n <= (32ll << 10);
+	// measured (tools/small_solve_probe.py): the cluster team (up to 32 Ki points) wins for every method; the cooperative-grid team that
+	// takes over above wins up to ~48^3 for Richardson and CG (15.0 vs 21.9 and 37.7 vs 43.2 us per iteration at 48^3, a draw at 64^3)
+	// and loses for GCR, whose Gram-Schmidt step is a grid barrier per group of eight dot products
+	return n <= (32ll << 10) || (method != 2 && n <= (128ll << 10));
 }
 
 SolveInfo small_solve(int method, const SMat &A, const SolverBase *prec, const SVec &b, SVec &x, SVec &w0, SVec *w1, SVec *w2,
@@ -413,7 +417,7 @@ SolveInfo Richardson::apply(const SVec &b, SVec &x) const
 	s3d_ctx *ctx = d.ctx();
 	const s3d_grid &g = A.grid();
 	SVec &res = work(0), &dx = work(1);
-	if (want_small_solve(d, g, prec)) return small_solve(0, A, prec, b, x, res, nullptr, nullptr, sparams, 10, history);
+	if (want_small_solve(d, g, prec, 0)) return small_solve(0, A, prec, b, x, res, nullptr, nullptr, sparams, 10, history);
 	Scalars sc(d, 4);   // [0] (b,b)  [1] unused  [2] (r,r)
 	double *S = sc.S;
 	DeviceLoop loop(sparams.maxiter + 1, 10, history);
@@ -468,7 +472,7 @@ SolveInfo GCR::apply(const SVec &b, SVec &x) const
 	std::vector<SVec *> pp(north), qq(north);
 	for (int i = 0; i < north; i++) { pp[i] = &work(2 + 2 * i); qq[i] = &work(3 + 2 * i); }
 	struct Ref { std::vector<SVec *> &v; SVec &operator[](int i) const { return *v[i]; } } p{pp}, q{qq};
-	if (north <= 32 && want_small_solve(d, g, prec)) {
+	if (north <= 32 && want_small_solve(d, g, prec, 2)) {
 		std::vector<double *> pq(2 * north);
 		for (int i = 0; i < north; i++) { pq[2 * i] = pp[i]->dev_w(); pq[2 * i + 1] = qq[i]->dev_w(); }
 		return small_solve(2, A, prec, b, x, res, &z, nullptr, sparams, 5, history, pq.data(), north);
@@ -555,7 +559,7 @@ SolveInfo CG::apply(const SVec &b, SVec &x) const
 	const s3d_grid &g = A.grid();
 	const bool jacobi = dynamic_cast<const JacobiPreconditioner *>(prec) != nullptr;
 	SVec &r = work(0), &p = work(1), &q = work(2);
-	if (want_small_solve(d, g, prec)) return small_solve(1, A, prec, b, x, r, &p, &q, sparams, 10, history);
+	if (want_small_solve(d, g, prec, 1)) return small_solve(1, A, prec, b, x, r, &p, &q, sparams, 10, history);
 	SVec &z = jacobi ? work(0) : work(3);   // unused with Jacobi (folded into the kernels)
 	// scalars: [0] (b,b)  [1..2] SpMV reductions: (p,Ap), -  [3,4] and [5,6]: ping-pong pairs {(r,r), (r,z)}
 	Scalars sc(d, 8);

@@ -397,7 +397,8 @@ def test_cpp_drivers(args):
         assert "PASSED" in text
 
 
-@pytest.mark.parametrize("npdim,grid", [((16, 16, 16), "chebyshev"), ((26, 26, 26), "uniform"), ((34, 30, 22), "uniform"), ((3, 3, 3), "uniform")])
+@pytest.mark.parametrize("npdim,grid", [((16, 16, 16), "chebyshev"), ((26, 26, 26), "uniform"), ((34, 30, 22), "uniform"), ((3, 3, 3), "uniform"),
+                                        ((50, 40, 34), "uniform"), ((66, 66, 66), "uniform")])   # the last two: the cooperative-grid team
 @pytest.mark.parametrize("ksp,pc", [("richardson", "jacobi"), ("cg", "jacobi"), ("cg", "none"), ("richardson", "none"), ("gcr", "jacobi"),
                                     ("gcr", "none"), ("gcr3", "jacobi")])
 def test_single_launch_solver_equals_the_host_driven_loop(H, npdim, grid, ksp, pc):
