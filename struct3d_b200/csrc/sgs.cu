@@ -1314,6 +1314,7 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 
 }  // namespace
 
+extern "C" S3D_HIDDEN int s3d_internal_dev_alloc(s3d_ctx *ctx, void **d_out, size_t bytes);
 extern "C" S3D_HIDDEN int s3d_internal_sgs_window(s3d_ctx *ctx, const s3d_grid *g, int ntx, int nty, s3d_sgs_window *out);
 extern "C" S3D_HIDDEN int s3d_internal_sgs_stream(s3d_ctx *ctx, const s3d_grid *g, int mode, const double *in0, const double *c0,
                                                   const double *c1, const double *c2, const double *dinv, double *out,
@@ -1380,7 +1381,7 @@ int s3d_sgs_rb_pack_alloc(s3d_ctx *ctx, const s3d_grid *g, double **d_out)
 	S3D_REQUIRE(ctx, g && d_out, "null argument");
 	size_t n = 0;
 	s3d_sgs_rb_pack_size(g, &n);
-	S3D_CUDA(ctx, cudaMalloc(d_out, n * sizeof(double)));
+	{ const int rc = s3d_internal_dev_alloc(ctx, (void **)d_out, n * sizeof(double)); if (rc != S3D_OK) return rc; }   // released with s3d_free
 	S3D_CUDA(ctx, cudaMemsetAsync(*d_out, 0, n * sizeof(double), ctx->stream));   // the padding is read by nobody, but keep it defined
 	return S3D_OK;
 }
