@@ -8,15 +8,18 @@
 //
 //   * NO staging.  A lane owns one (j,k) pencil and walks along i in QUADS of four columns: one 256-bit load per input stream and
 //     quad (LDG.E.256: a whole 32-byte sector per lane, rows are 128-byte aligned), D quads ahead in registers, one 256-bit store
-//     per result quad.  Nothing but 12 KB of mailboxes lives in shared memory, so registers alone bound the pencils per SM.
+//     per result quad.  Nothing but 6 KB of face rings per warp lives in shared memory, so registers alone bound the pencils per SM.
 //   * a lane runs ONE WHOLE QUAD (one loop iteration) behind its j- and k-neighbours, lanes (m-1, c) and (m, c-1) of the 4 x 8
 //     pencils of a warp: the four neighbour values of an iteration are last iteration's results, fetched with eight shuffles at the
 //     top of the iteration, off the recurrence.  The chain of a sweep is ny + nz + nx/4 iterations of four dependent columns.
 //   * a block of WJ x WK warps owns a LINE, the 4 WJ x 8 WK pencils of a (cj, ck) cell over all nx columns.  Between the warps of a
-//     block the faces travel through small shared-memory rings, between blocks through mailboxes in global memory; both use the
-//     sentinel protocol of the streaming kernel (the data is its own flag: an empty slot holds a signalling-NaN pattern no
-//     arithmetic produces; the consumer puts it back).  The global hops of a 256^3 sweep drop from 96 to 32 (16 x 16 pencils per
-//     block), and a hop costs a store, an L2 round trip and a poll -- no fence, no flag.
+//     block the faces travel through small shared-memory rings, between blocks through mailboxes in global memory; in both the data
+//     is its own flag (an empty slot holds a signalling-NaN pattern no arithmetic produces).  A mailbox slot is re-armed by its reader
+//     (clean for the next sweep); a ring slot by its single WRITER, half a ring ahead, which it may do because it never runs half a
+//     ring ahead of the reader's published count.  The global hops of a 256^3 sweep drop from 96 to 32 (16 x 16 pencils per block),
+//     and a hop costs a store, an L2 round trip and a poll -- no fence, no flag.
+//   MEASURED SLOWER than the tile kernel (2.8 vs 0.77 ms at 256^3, 8.8 vs 3.0 ms at 512^3: the quad skew doubles the chain of a sweep
+//   and the uncoalesced 256-bit accesses serialise in the SM's load/store path; profiles/r2_sgs_pencil.md): opt-in, sgs_variant 6.
 //   * every warp walks the block's line sequence on its own (a small line queue in shared memory, filled by the warp that is
 //     first in sweep order): the warps of a block are only coupled through their rings, not through block barriers.
 //   * lines are drawn from a ticket counter in (cj + ck) order, so a line only waits on lines with smaller tickets, which are
