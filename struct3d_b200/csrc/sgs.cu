@@ -396,6 +396,8 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 	while (tile >= 0) {
 		long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0;
 		if (f.prof) tp0 = clock64();
+		long long gt0 = 0, gt1 = 0, gt2 = 0, gt3 = 0, gt4 = 0;   // global-timer stamps of this tile (timing experiments: S3D_SGS_TILELOG)
+		if (f.prof) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(gt0));
 		const int ci = tile % f.ntx, cj = (tile / f.ntx) % f.nty, ck = tile / (f.ntx * f.nty);
 		const int i0 = ci * TI, j0 = cj * TJ, k0 = ck * TK;
 		const int ti = min(TI, g.nx - i0), tj = min(TJ, g.ny - j0), tk = min(TK, g.nz - k0);
@@ -503,6 +505,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 					if (mi1 && is_sent(wi1)) wi1 = __ldcg(wp1);
 					if (clock64() - tw0 > (8ll << 30)) __trap();   // seconds without the producing tile: fail loudly instead of hanging
 				}
+				if (f.prof) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(gt1));
 #pragma unroll
 				for (int u = 0; u < NH; u++)
 					if ((hmail >> u) & 1u) __stcg(reinterpret_cast<double2 *>(const_cast<double *>(hp[u])), make_double2(sent, sent));
@@ -518,7 +521,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 			if (lane == 0) ntile = (nticket < ntiles) ? f.order[FWD ? nticket : ntiles - 1 - nticket] : -1;
 			cp_async_wait_all();
 			__syncwarp();
-			if (f.prof) tp2 = clock64();
+			if (f.prof) { tp2 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(gt2)); }
 
 			// ---- the sweep: pencil 0 is at i-position u0 = h - s0 (li = u0 forward, ti-1-u0 backward), pencil 1 at u0 - 1
 			const int start = FWD ? -s0 : ti - 1 + s0;
@@ -578,7 +581,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		//      the registers) and the rows of the last j and the last k (whole rows of `out`); then the fence and the flag.  The other
 		//      rows follow after the flag -- only later kernels read them.
 		long long tpf = 0;
-		if (f.prof) tpf = clock64();
+		if (f.prof) { tpf = clock64(); asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(gt3)); }
 		ntile = __shfl_sync(FULL, ntile, 0);
 		__syncwarp();
 		auto copy_row_chunk = [&](int rb, int rc, int i2) {
@@ -611,6 +614,11 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 			if (f.prof) tp3 = clock64();
 			if (f.prof && lane == 0) {
 				const long long tp4 = clock64();
+				asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(gt4));
+				if (FWD && tile < 800) {                       // per-tile log of the forward sweep (small grids)
+					long long *tl = f.prof + 8 + 5 * tile;
+					tl[0] = gt0; tl[1] = gt1; tl[2] = gt2; tl[3] = gt3; tl[4] = gt4;
+				}
 				atomicAdd((unsigned long long *)f.prof + 0, (unsigned long long)(tp1 - tp0));
 				atomicAdd((unsigned long long *)f.prof + 1, (unsigned long long)(tp2 - tp1));   // ticket + polling the boxes + copy completion
 				atomicAdd((unsigned long long *)f.prof + 2, (unsigned long long)(tpf - tp2));   // sweep loop

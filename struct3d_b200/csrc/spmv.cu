@@ -384,6 +384,10 @@ int s3d_tune_set(s3d_ctx *ctx, const char *key, int value)
 			static long long h[8 + 4096];
 			S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 			S3D_CUDA(ctx, cudaMemcpy(h, ctx->sgs_prof, sizeof h, cudaMemcpyDeviceToHost));
+			if (getenv("S3D_SGS_TILELOG")) {   // warp-per-tile kernel with mailboxes: begin / data seen / sweep start / sweep end / published, ns
+				for (int t = 0; t < 800; t++)
+					if (h[8 + 5 * t]) fprintf(stderr, "[sgs_tile] %d %lld %lld %lld %lld %lld\n", t, h[8 + 5 * t], h[9 + 5 * t], h[10 + 5 * t], h[11 + 5 * t], h[12 + 5 * t]);
+			}
 			if (getenv("S3D_SGS_LINELOG")) {
 				long long t0 = 0;
 				for (int l = 0; l < 2048; l++) if (h[8 + 2 * l] && (!t0 || h[8 + 2 * l] < t0)) t0 = h[8 + 2 * l];
