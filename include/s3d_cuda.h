@@ -114,8 +114,17 @@ int  s3d_grid_init_slab(s3d_grid *g, int nx, int ny, int nz_global, int rank, in
 /* ------------------------------------------------------------------ storage (SVec / SMat, matvec.hpp:23-89) */
 
 int  s3d_vec_alloc(s3d_ctx *ctx, const s3d_grid *g, double **d_out);          /* zero-filled, ghosts included */
-int  s3d_mat_alloc(s3d_ctx *ctx, const s3d_grid *g, double **d_out);          /* 7*cstride doubles, zero-filled */
+int  s3d_mat_alloc(s3d_ctx *ctx, const s3d_grid *g, double **d_out);          /* 7*cstride doubles, zero-filled (z-slabs: with slack planes, see s3d_coef_alloc) */
 int  s3d_scalars_alloc(s3d_ctx *ctx, int n, double **d_out);                  /* n device doubles, zeroed */
+/* ONE array in the coefficient layout (cstride doubles, zero-filled), e.g. the dinv of the SGS / StrILU preconditioners.  On a z-slab grid
+ * (s3d_grid_init_slab, nranks > 1) it, like every array of s3d_mat_alloc, carries two SLACK planes -- plane -1 and plane nz -- that hold the
+ * neighbouring slabs' boundary planes for S3D_SGS_OVERLAP (cstride covers nz+2 planes there, and the allocation starts one plane before
+ * the pointer handed out; release with s3d_free).  Nothing else reads them. */
+int  s3d_coef_alloc(s3d_ctx *ctx, const s3d_grid *g, double **d_out);
+/* slack planes by hand (another transport than NCCL, tests): host plane in the reference layout (nx*ny doubles) -> plane -1 (side 0) or
+ * plane nz (side 1) of array `stencil` of d_C; s3d_coef_halo_exchange does it between the ranks of the communicator (collective). */
+int  s3d_coef_slack_upload(s3d_ctx *ctx, const s3d_grid *g, double *d_C, int stencil, int side, const double *h_plane);
+int  s3d_coef_halo_exchange(s3d_ctx *ctx, const s3d_grid *g, double *d_C, int narrays);
 int  s3d_free(s3d_ctx *ctx, void *d_ptr);
 int  s3d_vec_upload(s3d_ctx *ctx, const s3d_grid *g, double *d_x, const double *h_x);     /* host ghosted layout -> device */
 int  s3d_vec_download(s3d_ctx *ctx, const s3d_grid *g, const double *d_x, double *h_x);   /* blocks */
@@ -216,6 +225,14 @@ int  s3d_strilu_setup_async(s3d_ctx *ctx, const s3d_grid *g, const double *A, in
                                   * (s3d_sgspreconditioners.cpp:30-112 with threadedapply = true): chunks of rows dealt to persistent warps that
                                   * never wait for one another (tuning key sgs_async_chunk = -s3d_thread_chunk_size), exact recurrence along a
                                   * row.  Timing-dependent like the reference's; across z-slabs it runs slab by slab. */
+#define S3D_SGS_OVERLAP       6  /* z-slabs: the exact lexicographic sweep over every slab EXTENDED by one plane of either neighbour, own planes kept
+                                  * (restricted additive Schwarz, SGS as the subdomain solver): no cross-rank wait like SLABLOCAL, one halo
+                                  * exchange of r per application, and iteration counts within a few per cent of the exact sweep over the whole
+                                  * grid.  Needs the slack planes of s3d_mat_alloc / s3d_coef_alloc and s3d_sgs_overlap_setup; one rank: LEXICOGRAPHIC.
+                                  * The call fills the ghost planes of d_r (halo exchange) and leaves intermediate values in those of d_z / d_y. */
+/* Once per operator, after s3d_sgs_setup / s3d_strilu_setup, for S3D_SGS_OVERLAP: the neighbouring slabs' boundary planes of the seven
+ * coefficient arrays and of dinv go into the slack planes (grouped ncclSend / ncclRecv).  Collective; a no-op on one rank. */
+int  s3d_sgs_overlap_setup(s3d_ctx *ctx, const s3d_grid *g, double *A, double *d_dinv);
 /* Exact (lexicographic) SGS on a z-slab decomposition: the sweep runs THROUGH the slabs -- the last plane of tiles of rank p pushes its
  * k-face rows into rank p+1's peer-memory window (backward: p-1) and raises per-tile flags there, so results and iteration counts are
  * those of the single-process reference (s3d_sgspreconditioners.cpp:14-115) at any GPU count; the ranks work as a pipeline.

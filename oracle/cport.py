@@ -211,6 +211,27 @@ def sgs_redblack_apply(mesh, A, diaginv, r):
     return z
 
 
+def slab_bounds(nz, nslabs):
+    """z-slab decomposition of nz planes (the library's s3d_grid_init_slab): slab p owns planes [p*nz/P, (p+1)*nz/P)"""
+    return [(p * nz // nslabs, (p + 1) * nz // nslabs) for p in range(nslabs)]
+
+
+def sgs_overlap_apply(mesh, A, diaginv, r, nslabs, overlap=1):
+    """The overlapping z-slab ordering (S3D_SGS_OVERLAP; no counterpart in the reference, stated ON TOP of its sequential sweep,
+    s3d_sgspreconditioners.cpp:53-110): the sequential SGS-like application over every slab extended by `overlap` planes of either
+    neighbour (zero inflow beyond them), own planes kept.  overlap = 0 is the slab-local ordering; one slab is the sequential sweep."""
+    nx, ny, nz = mesh.n
+    z = mesh.zeros()
+    for (k0, k1) in slab_bounds(nz, nslabs):
+        e0, e1 = max(0, k0 - overlap), min(nz, k1 + overlap)
+        sm = Mesh((nx + 2, ny + 2, e1 - e0 + 2))            # only its dimensions matter to the sweep
+        rs = sm.zeros()
+        rs[1:-1] = r[1 + e0:1 + e1]
+        zs = sgs_like_apply(sm, np.ascontiguousarray(A[:, e0:e1]), np.ascontiguousarray(diaginv[e0:e1]), rs, 1)
+        z[1 + k0:1 + k1] = zs[1 + (k0 - e0):1 + (k1 - e0)]
+    return z
+
+
 def solve(mesh, A, b, ksp="richardson", pc="jacobi", rtol=1e-6, maxiter=1000, restart=30,
           apply_sweeps=1, build_sweeps=1, x0=None):
     """Returns (x, info dict, hist ndarray of relative residuals per iteration)."""

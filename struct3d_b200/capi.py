@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libs3d_cuda.so")
 
 SPMV_AUTO, SPMV_MARCH, SPMV_TMA, SPMV_NAIVE, SPMV_PAIR = 0, 1, 2, 3, 4
-SGS_LEXICOGRAPHIC, SGS_REDBLACK, SGS_LEXICOGRAPHIC_PLANES, SGS_JACOBI_SWEEPS, SGS_SLABLOCAL, SGS_ASYNC = 0, 1, 2, 3, 4, 5
+SGS_LEXICOGRAPHIC, SGS_REDBLACK, SGS_LEXICOGRAPHIC_PLANES, SGS_JACOBI_SWEEPS, SGS_SLABLOCAL, SGS_ASYNC, SGS_OVERLAP = 0, 1, 2, 3, 4, 5, 6
 SGS_VARIANT_DEFAULT = 4   # warp-per-line streaming kernel (sgs_stream.cu); 0 warp-per-tile, 1 block-per-tile, 3 r1's line experiment
 CONV_STRICT, CONV_INITIAL = 1, 2
 COMM_ID_BYTES = 128
@@ -43,6 +43,8 @@ _SIGS = {
     "s3d_grid_init": [_G, _I, _I, _I], "s3d_grid_init_slab": [_G, _I, _I, _I, _I, _I],
     "s3d_vec_alloc": [_P, _G, C.POINTER(_vp)], "s3d_mat_alloc": [_P, _G, C.POINTER(_vp)],
     "s3d_scalars_alloc": [_P, _I, C.POINTER(_vp)], "s3d_free": [_P, _vp],
+    "s3d_coef_alloc": [_P, _G, C.POINTER(_vp)], "s3d_coef_slack_upload": [_P, _G, _vp, _I, _I, _vp], "s3d_coef_halo_exchange": [_P, _G, _vp, _I],
+    "s3d_sgs_overlap_setup": [_P, _G, _vp, _vp],
     "s3d_vec_upload": [_P, _G, _vp, _vp], "s3d_vec_download": [_P, _G, _vp, _vp],
     "s3d_mat_upload": [_P, _G, _vp, _I, _vp], "s3d_mat_download": [_P, _G, _vp, _I, _vp],
     "s3d_scalars_download": [_P, _vp, _I, _vp], "s3d_scalars_upload": [_P, _vp, _I, _vp],
@@ -186,6 +188,20 @@ class Context:
         p = _vp()
         self.call("s3d_mat_alloc", C.byref(g), C.byref(p))
         return p.value
+
+    def coef_alloc(self, g):
+        """one array in the coefficient layout (z-slab grids: with slack planes)"""
+        p = _vp()
+        self.call("s3d_coef_alloc", C.byref(g), C.byref(p))
+        return p.value
+
+    def coef_slack_upload(self, g, dC, stencil, side, h_plane):
+        h = np.ascontiguousarray(h_plane, dtype=np.float64)
+        assert h.size == g.nx * g.ny
+        self.call("s3d_coef_slack_upload", C.byref(g), _ptr(dC), int(stencil), int(side), h.ctypes.data_as(_vp))
+
+    def sgs_overlap_setup(self, g, A, dinv):
+        self.call("s3d_sgs_overlap_setup", C.byref(g), _ptr(A), _ptr(dinv))
 
     def scalars_alloc(self, n):
         p = _vp()

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <unordered_map>
 #include <nccl.h>
 
 #include "s3d_cuda.h"
@@ -102,6 +103,8 @@ struct s3d_ctx {
 	struct Phase { cudaEvent_t *ev = nullptr; int used = 0, cap = 0; };
 	Phase phase[4];
 	int64_t launches = 0;
+	// coefficient storage handed out with slack planes (z-slab grids, see s3d_mat_alloc): returned pointer -> start of the allocation
+	std::unordered_map<const void *, void *> padded;
 	// z-slab communicator
 	ncclComm_t comm = nullptr;
 	// peer-memory halo window (one process per GPU, neighbours' windows mapped through CUDA IPC); see context.cu

@@ -316,6 +316,10 @@ int s3d_grid_init_slab(s3d_grid *g, int nx, int ny, int nz_global, int rank, int
 	const int rc = s3d_grid_init(g, nx, ny, k1 - k0);
 	if (rc != S3D_OK) return rc;
 	g->nz_global = nz_global; g->k0 = k0; g->rank = rank; g->nranks = nranks;
+	// a slab's coefficient arrays carry two slack planes each: plane nz behind the array, and -- read as plane -1 of the NEXT array --
+	// one more (s3d_mat_alloc puts a leading plane in front of array 0).  They hold the neighbouring slabs' boundary planes for the
+	// overlapping SGS ordering (S3D_SGS_OVERLAP); nothing else reads them.
+	if (nranks > 1) g->cstride = roundup(g->cplane * (g->nz + 2), 32);
 	return S3D_OK;
 }
 
@@ -340,12 +344,43 @@ int s3d_vec_alloc(s3d_ctx *ctx, const s3d_grid *g, double **d_out)
 	return S3D_OK;
 }
 
+// narrays coefficient arrays of cstride doubles.  On a z-slab grid the allocation starts one plane EARLIER than the pointer handed out
+// (the slack plane -1 of array 0; the other slack planes lie inside cstride, see s3d_grid_init_slab); s3d_free knows.
+static int coef_alloc(s3d_ctx *ctx, const s3d_grid *g, int narrays, double **d_out)
+{
+	const size_t lead = (g->nranks > 1 && g->cstride >= g->cplane * (g->nz + 2)) ? (size_t)g->cplane : 0;
+	const size_t bytes = ((size_t)g->cstride * narrays + lead) * sizeof(double);
+	void *base = nullptr;
+	{ const int rc = s3d_internal_dev_alloc(ctx, &base, bytes); if (rc != S3D_OK) return rc; }
+	S3D_CUDA(ctx, cudaMemsetAsync(base, 0, bytes, ctx->stream));
+	*d_out = reinterpret_cast<double *>(base) + lead;
+	if (lead) ctx->padded[*d_out] = base;
+	return S3D_OK;
+}
+
 int s3d_mat_alloc(s3d_ctx *ctx, const s3d_grid *g, double **d_out)
 {
 	S3D_REQUIRE(ctx, g && d_out, "null argument");
-	const size_t bytes = (size_t)g->cstride * S3D_NSTENCIL * sizeof(double);
-	{ const int rc = s3d_internal_dev_alloc(ctx, (void **)d_out, bytes); if (rc != S3D_OK) return rc; }
-	S3D_CUDA(ctx, cudaMemsetAsync(*d_out, 0, bytes, ctx->stream));
+	return coef_alloc(ctx, g, S3D_NSTENCIL, d_out);
+}
+
+int s3d_coef_alloc(s3d_ctx *ctx, const s3d_grid *g, double **d_out)
+{
+	S3D_REQUIRE(ctx, g && d_out, "null argument");
+	return coef_alloc(ctx, g, 1, d_out);
+}
+
+S3D_HIDDEN bool s3d_internal_has_slack(const s3d_ctx *ctx, const void *d_ptr) { return ctx->padded.count(d_ptr) != 0; }
+
+// host plane (reference layout, nx*ny doubles) -> slack plane of coefficient array `s`: side 0 = plane -1, side 1 = plane nz
+int s3d_coef_slack_upload(s3d_ctx *ctx, const s3d_grid *g, double *d_C, int s, int side, const double *h_plane)
+{
+	S3D_REQUIRE(ctx, g && d_C && h_plane && s >= 0 && (side == 0 || side == 1), "bad argument");
+	S3D_REQUIRE(ctx, s3d_internal_has_slack(ctx, d_C), "the array has no slack planes (not from s3d_mat_alloc / s3d_coef_alloc on a z-slab grid)");
+	const size_t w = (size_t)g->nx * sizeof(double);
+	double *dst = d_C + (size_t)s * g->cstride + (side ? (long long)g->nz * g->cplane : -(long long)g->cplane);
+	S3D_CUDA(ctx, cudaMemcpy2DAsync(dst, (size_t)g->cpitch * sizeof(double), h_plane, w, w, (size_t)g->ny, cudaMemcpyHostToDevice, ctx->stream));
+	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // h_plane may be pageable and reused
 	return S3D_OK;
 }
 
@@ -409,6 +444,8 @@ int s3d_ints_snapshot_wait(s3d_ctx *ctx, int slot, int n, int *h_out)
 int s3d_free(s3d_ctx *ctx, void *d_ptr)
 {
 	if (!d_ptr) return S3D_OK;
+	auto it = ctx->padded.find(d_ptr);
+	if (it != ctx->padded.end()) { d_ptr = it->second; ctx->padded.erase(it); }
 	// stream-ordered: the memory is reused only behind everything already enqueued on the context's stream; work on the library's
 	// other streams (copy pipelines, side-stream push) is always joined back into it before a call returns
 	S3D_CUDA(ctx, cudaFreeAsync(d_ptr, ctx->stream));
@@ -801,6 +838,32 @@ int s3d_halo_exchange(s3d_ctx *ctx, const s3d_grid *g, double *d_x)
 	if (dn >= 0) {
 		S3D_NCCL(ctx, g_nccl.Send(d_x + n, n, ncclDouble, dn, ctx->comm, ctx->stream));
 		S3D_NCCL(ctx, g_nccl.Recv(d_x, n, ncclDouble, dn, ctx->comm, ctx->stream));
+	}
+	S3D_NCCL(ctx, g_nccl.GroupEnd());
+	return S3D_OK;
+}
+
+// Boundary planes of `narrays` coefficient arrays into the neighbours' slack planes (collective, once per operator): plane nz-1 of
+// every array goes into plane -1 of rank+1's, plane 0 into plane nz of rank-1's.  Grouped ncclSend / ncclRecv: set-up, not the hot path.
+int s3d_coef_halo_exchange(s3d_ctx *ctx, const s3d_grid *g, double *d_C, int narrays)
+{
+	S3D_REQUIRE(ctx, g && d_C && narrays >= 1, "bad argument");
+	if (g->nranks == 1) return S3D_OK;
+	if (!ctx->comm) return s3d_fail(ctx, S3D_ERR_STATE, "coefficient halo exchange needs s3d_comm_init");
+	S3D_REQUIRE(ctx, s3d_internal_has_slack(ctx, d_C), "the array has no slack planes (not from s3d_mat_alloc / s3d_coef_alloc on a z-slab grid)");
+	const size_t n = (size_t)g->cplane;
+	const int up = g->rank + 1, dn = g->rank - 1;
+	S3D_NCCL(ctx, g_nccl.GroupStart());
+	for (int s = 0; s < narrays; s++) {
+		double *a = d_C + (size_t)s * g->cstride;
+		if (up < g->nranks) {
+			S3D_NCCL(ctx, g_nccl.Send(a + n * (g->nz - 1), n, ncclDouble, up, ctx->comm, ctx->stream));
+			S3D_NCCL(ctx, g_nccl.Recv(a + n * g->nz, n, ncclDouble, up, ctx->comm, ctx->stream));
+		}
+		if (dn >= 0) {
+			S3D_NCCL(ctx, g_nccl.Send(a, n, ncclDouble, dn, ctx->comm, ctx->stream));
+			S3D_NCCL(ctx, g_nccl.Recv(a - n, n, ncclDouble, dn, ctx->comm, ctx->stream));
+		}
 	}
 	S3D_NCCL(ctx, g_nccl.GroupEnd());
 	return S3D_OK;

@@ -1348,6 +1348,7 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 }  // namespace
 
 extern "C" S3D_HIDDEN int s3d_internal_dev_alloc(s3d_ctx *ctx, void **d_out, size_t bytes);
+extern "C" S3D_HIDDEN bool s3d_internal_has_slack(const s3d_ctx *ctx, const void *d_ptr);
 extern "C" S3D_HIDDEN int s3d_internal_sgs_window(s3d_ctx *ctx, const s3d_grid *g, int ntx, int nty, s3d_sgs_window *out);
 extern "C" S3D_HIDDEN int s3d_internal_sgs_stream(s3d_ctx *ctx, const s3d_grid *g, int mode, const double *in0, const double *c0,
                                                   const double *c1, const double *c2, const double *dinv, double *out,
@@ -1395,6 +1396,17 @@ int s3d_sgs_slab_sweeps_available(s3d_ctx *ctx, const s3d_grid *g, int *yes)
 	if (rc != S3D_OK) return rc;
 	*yes = xw.ok;
 	return S3D_OK;
+}
+
+// S3D_SGS_OVERLAP, once per operator (after s3d_sgs_setup / s3d_strilu_setup): the neighbouring slabs' boundary planes of the seven
+// coefficient arrays and of dinv into the slack planes.  Collective.
+int s3d_sgs_overlap_setup(s3d_ctx *ctx, const s3d_grid *g, double *A, double *d_dinv)
+{
+	S3D_REQUIRE(ctx, g && A && d_dinv, "null argument");
+	if (g->nranks == 1) return S3D_OK;
+	int rc = s3d_coef_halo_exchange(ctx, g, A, S3D_NSTENCIL);
+	if (rc != S3D_OK) return rc;
+	return s3d_coef_halo_exchange(ctx, g, d_dinv, 1);
 }
 
 // Red-black SGS on colour-packed coefficients (see rb_pack_kernel): size of the packed buffer in doubles, the packing (once per operator,
@@ -1506,6 +1518,44 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		return S3D_OK;
 	}
 	if (ordering == S3D_SGS_ASYNC) return s3d_internal_sgs_async(ctx, g, A, d_dinv, d_r, d_z, d_y, nsweeps);
+	if (ordering == S3D_SGS_OVERLAP && g->nranks == 1) ordering = S3D_SGS_LEXICOGRAPHIC;
+	if (ordering == S3D_SGS_OVERLAP) {
+		// Overlapping slabs (restricted additive Schwarz with the exact sweep as the subdomain solver): every rank sweeps its own planes
+		// PLUS one plane of either neighbour -- planes -1 .. nz of its ghosted arrays, zero inflow beyond them -- and keeps its own.
+		// The neighbours' planes of r arrive by the ordinary one-plane halo exchange, those of the coefficients and of dinv sit in
+		// the slack planes (s3d_sgs_overlap_setup).  No cross-rank wait inside the sweeps: the cost per application is the slab-local
+		// one plus the exchange of r and 2 / nz more planes, and the iteration count stays within a few per cent of the exact sweep
+		// over the whole grid (slab-local: +5 .. +36 %; tools/sgs_overlap_study.py, profiles/r2_sgs_overlap.md).
+		// The kernel is the warp-per-tile one on a grid descriptor that starts one plane early; it does not know.
+		if (!s3d_internal_has_slack(ctx, A) || !s3d_internal_has_slack(ctx, d_dinv))
+			return s3d_fail(ctx, S3D_ERR_ARG, "S3D_SGS_OVERLAP needs A from s3d_mat_alloc and dinv from s3d_coef_alloc on the z-slab grid (slack planes)");
+		if (ctx->comm) {
+			// (with no communicator the caller has filled the ghost planes of r and the slack planes itself: another transport, tests)
+			const int rch = s3d_halo_exchange(ctx, g, const_cast<double *>(d_r));
+			if (rch != S3D_OK) return rch;
+		}
+		const int lo = g->rank > 0 ? 1 : 0, hi = g->rank < g->nranks - 1 ? 1 : 0;
+		s3d_grid gx = *g;
+		gx.nz = g->nz + lo + hi;
+		gx.voff = g->voff - lo * g->vplane;
+		const GridDev gdx = to_dev(&gx);
+		SgsFlow f;
+		unsigned nblocks = 0;
+		const int rcp = sgs_flow_prepare(ctx, &gx, f, nblocks, 0);
+		if (rcp != S3D_OK) return rcp;
+		f.kzero_lo = lo; f.kzero_hi = hi;
+		const long long cs = g->cstride;
+		const double *Ax = A - lo * g->cplane, *dx = d_dinv - lo * g->cplane;
+		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
+		S3D_LAUNCHED(ctx);
+		sgw_launch<0>(ctx, &gx, nblocks, gdx, d_r, Ax, Ax + cs, Ax + 2 * cs, dx, d_y, f, (const int *)ctx->gate);
+		S3D_LAUNCHED(ctx);
+		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
+		S3D_LAUNCHED(ctx);
+		sgw_launch<1>(ctx, &gx, nblocks, gdx, (const double *)d_y, Ax + 4 * cs, Ax + 5 * cs, Ax + 6 * cs, dx, d_z, f, (const int *)ctx->gate);
+		S3D_LAUNCHED(ctx);
+		return S3D_OK;
+	}
 	if (ordering != S3D_SGS_LEXICOGRAPHIC && ordering != S3D_SGS_LEXICOGRAPHIC_PLANES && ordering != S3D_SGS_SLABLOCAL)
 		return s3d_fail(ctx, S3D_ERR_ARG, "unknown SGS ordering %d", ordering);
 	// slab-local: the exact lexicographic sweep inside every z-slab, nothing taken from the neighbouring slabs (block Jacobi across the

@@ -126,6 +126,7 @@ protected:
 	double *diaginv;          ///< device array in the coefficient layout (cstride doubles)
 	double *rbpack = nullptr; ///< red-black ordering: colour-packed copy of the off-diagonal coefficients and diaginv (made by updateOperator)
 	void pack_if_redblack();  ///< to be called at the end of updateOperator()
+	void overlap_setup();     ///< overlapping ordering on z-slabs: neighbours' boundary planes of A and diaginv into the slack planes; end of updateOperator()
 	const PreconParams params;
 	int order;
 	mutable SVec scratch;     ///< the reference allocates and zeroes this per call; here once

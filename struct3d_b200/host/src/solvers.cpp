@@ -307,19 +307,22 @@ SGS_like_preconditioner::SGS_like_preconditioner(const SMat &lhs, const PreconPa
 	: SolverBase(lhs, nullptr), diaginv{nullptr}, params(parms), order{S3D_SGS_LEXICOGRAPHIC}, scratch(lhs.m)
 {
 	const Device &d = Device::get();
-	diaginv = d.scalars((int)std::min<long long>(A.grid().cstride, INT_MAX));
-	// On z-slabs the default is the slab-local ordering: the reference's lexicographic sweep inside every slab, no coupling across
-	// the slab faces (it needs no exchange and no cross-rank wait, so it scales with the GPU count; measured iteration counts in
-	// profiles/r2_sgs_slablocal.md).  `-s3d_sgs_ordering lexicographic` asks for the exact sweep THROUGH the slabs (a pipeline).
-	if (d.nranks() > 1) order = S3D_SGS_SLABLOCAL;
+	d.check(s3d_coef_alloc(d.ctx(), &A.grid(), &diaginv), "s3d_coef_alloc");
+	// On z-slabs the default is the OVERLAPPING ordering: the reference's lexicographic sweep over every slab extended by one plane of
+	// either neighbour, own planes kept (restricted additive Schwarz).  Like the slab-local ordering (`-s3d_sgs_ordering slablocal`: no
+	// coupling across the slab faces at all) it has no cross-rank wait, so it scales with the GPU count; unlike it, it stays within a
+	// few per cent of the exact sweep's iteration count (profiles/r2_sgs_overlap.md).  `-s3d_sgs_ordering lexicographic` asks for the
+	// exact sweep THROUGH the slabs (a pipeline).
+	if (d.nranks() > 1) order = S3D_SGS_OVERLAP;
 	if (s3d::options_has("-s3d_sgs_ordering")) {
 		const std::string o = petscoptions_get_string("-s3d_sgs_ordering", 40);
 		if (o == "redblack" || o == "multicolour" || o == "multicolor") order = S3D_SGS_REDBLACK;
 		else if (o == "lexicographic") order = S3D_SGS_LEXICOGRAPHIC;
 		else if (o == "slablocal") order = S3D_SGS_SLABLOCAL;
+		else if (o == "overlap") order = S3D_SGS_OVERLAP;
 		else if (o == "sweeps" || o == "jacobi_sweeps") order = S3D_SGS_JACOBI_SWEEPS;
 		else if (o == "async" || o == "threaded") order = S3D_SGS_ASYNC;
-		else throw std::runtime_error("-s3d_sgs_ordering must be lexicographic, slablocal, redblack, sweeps or async");
+		else throw std::runtime_error("-s3d_sgs_ordering must be lexicographic, overlap, slablocal, redblack, sweeps or async");
 	}
 	// The reference's threaded apply / build (s3d_sgspreconditioners.cpp:32-53, s3d_ilu.cpp:28-32) runs asynchronous, unordered sweeps
 	// over CPU threads.  Its GPU counterpart exists (-s3d_sgs_ordering async: S3D_SGS_ASYNC, chunks of -s3d_thread_chunk_size rows dealt
@@ -332,7 +335,7 @@ SGS_like_preconditioner::SGS_like_preconditioner(const SMat &lhs, const PreconPa
 		std::printf(" WARNING: -s3d_pc_use_threaded_apply / -s3d_pc_use_threaded_build ask for the reference's asynchronous CPU-thread sweeps; "
 		            "the GPU sweeps are deterministic unless asked otherwise (ordering: %s). -s3d_sgs_ordering async runs -s3d_pc_apply_sweeps asynchronous "
 		            "sweeps (the threaded apply's GPU counterpart; with it -s3d_pc_use_threaded_build true builds StrILU by asynchronous sweeps as well), -s3d_sgs_ordering sweeps as many synchronous ones.\n",
-		            order == S3D_SGS_LEXICOGRAPHIC ? "lexicographic" : order == S3D_SGS_SLABLOCAL ? "slablocal" : order == S3D_SGS_REDBLACK ? "redblack"
+		            order == S3D_SGS_LEXICOGRAPHIC ? "lexicographic" : order == S3D_SGS_SLABLOCAL ? "slablocal" : order == S3D_SGS_OVERLAP ? "overlap" : order == S3D_SGS_REDBLACK ? "redblack"
 		            : order == S3D_SGS_ASYNC ? "async" : "sweeps");
 		warned = true;
 	}
@@ -365,6 +368,14 @@ void SGS_like_preconditioner::pack_if_redblack()
 	d.check(s3d_sgs_rb_pack(d.ctx(), &A.grid(), A.dev(), diaginv, rbpack), "s3d_sgs_rb_pack");
 }
 
+// Overlapping ordering: the neighbouring slabs' boundary planes of A and of dinv into the slack planes (collective, once per operator)
+void SGS_like_preconditioner::overlap_setup()
+{
+	if (order != S3D_SGS_OVERLAP) return;
+	const Device &d = Device::get();
+	d.check(s3d_sgs_overlap_setup(d.ctx(), &A.grid(), const_cast<double *>(A.dev()), diaginv), "s3d_sgs_overlap_setup");
+}
+
 SolveInfo SGS_like_preconditioner::apply(const SVec &r, SVec &z) const
 {
 	if (r.m != z.m || r.m != A.m) throw std::runtime_error("apply: Vectors and matrix must be defined over the same mesh!");
@@ -373,7 +384,8 @@ SolveInfo SGS_like_preconditioner::apply(const SVec &r, SVec &z) const
 		d.check(s3d_sgs_apply_rb_packed(d.ctx(), &A.grid(), rbpack, r.dev(), z.dev_rw(), scratch.dev_rw()), "s3d_sgs_apply_rb_packed");
 		return {false, 1, -1.0, 0.0};
 	}
-	d.check(s3d_sgs_apply(d.ctx(), &A.grid(), A.dev(), diaginv, r.dev(), z.dev_rw(), scratch.dev_rw(), order,
+	// the overlapping ordering fills the ghost planes of r (halo exchange) before it sweeps
+	d.check(s3d_sgs_apply(d.ctx(), &A.grid(), A.dev(), diaginv, order == S3D_SGS_OVERLAP ? r.dev_halo() : r.dev(), z.dev_rw(), scratch.dev_rw(), order,
 	                      std::max(1, params.napplysweeps)), "s3d_sgs_apply");
 	return {false, 1, -1.0, 0.0};
 }
@@ -385,9 +397,14 @@ void SGS_preconditioner::updateOperator()
 	const Device &d = Device::get();
 	d.check(s3d_sgs_setup(d.ctx(), &A.grid(), A.dev(), diaginv), "s3d_sgs_setup");
 	pack_if_redblack();
+	overlap_setup();
 }
 
-StrILU_preconditioner::StrILU_preconditioner(const SMat &lhs, const PreconParams parms) : SGS_like_preconditioner(lhs, parms) {}
+StrILU_preconditioner::StrILU_preconditioner(const SMat &lhs, const PreconParams parms) : SGS_like_preconditioner(lhs, parms)
+{
+	// the factorisation is built slab by slab (block ILU(0) by slabs): it goes with the slab-local application unless asked otherwise
+	if (order == S3D_SGS_OVERLAP && !s3d::options_has("-s3d_sgs_ordering")) order = S3D_SGS_SLABLOCAL;
+}
 
 void StrILU_preconditioner::updateOperator()
 {
@@ -401,6 +418,7 @@ void StrILU_preconditioner::updateOperator()
 	}
 	d.check(s3d_strilu_setup(d.ctx(), &A.grid(), A.dev(), params.nbuildsweeps, diaginv), "s3d_strilu_setup");
 	pack_if_redblack();
+	overlap_setup();
 }
 
 // ------------------------------------------------------------------ Richardson (s3d_solverbase.cpp:45-80)

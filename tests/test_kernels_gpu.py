@@ -314,6 +314,48 @@ def test_sgs_dataflow_variants(ctx, npdim, variant, tile_i, pencils):
             ctx.free(p_)
 
 
+# The overlapping z-slab ordering (S3D_SGS_OVERLAP), every slab of a decomposition on ONE device: a z-slab grid descriptor without a
+# communicator, the neighbours' planes put in place by hand (ghost planes of r by the upload, slack planes of A and dinv by
+# s3d_coef_slack_upload) -- exactly what the halo exchanges do between ranks (tests/mgpu_check.py covers those).  Bit-identical to the
+# oracle's statement: the sequential sweep over the slab extended by one plane of either neighbour, own planes kept.
+@pytest.mark.parametrize("npdim,nslabs", [((37, 22, 41), 3), ((19, 35, 18), 2), ((52, 27, 34), 4), ((20, 12, 10), 8)])
+@pytest.mark.parametrize("tile_i,pencils,mail", [(16, 2, 1), (16, 1, 1), (32, 2, 1), (16, 2, 0)])
+def test_sgs_overlap_slabs_on_one_device(ctx, npdim, nslabs, tile_i, pencils, mail):
+    m, A = problem(npdim, "chebyshev", "convdiff", V1, 0.1)
+    nx, ny, nz = m.n
+    r = rand_vec(m, 43)
+    di = cport.sgs_setup(m, A)
+    want = cport.sgs_overlap_apply(m, A, di, r, nslabs, 1)
+    local = cport.sgs_overlap_apply(m, A, di, r, nslabs, 0)
+    assert not np.array_equal(want, local)
+    try:
+        ctx.tune("sgs_variant", 0); ctx.tune("sgs_tile_i", tile_i); ctx.tune("sgs_pencils", pencils); ctx.tune("sgs_tile_mail", mail)
+        for rk, (k0, k1) in enumerate(cport.slab_bounds(nz, nslabs)):
+            g = capi.make_grid(nx, ny, nz, rk, nslabs)
+            assert (g.k0, g.nz) == (k0, k1 - k0) and g.cstride >= g.cplane * (g.nz + 2)
+            dA = ctx.mat_from(g, A[:, k0:k1])
+            dinv = ctx.coef_alloc(g)
+            ctx.sgs_setup(g, dA, dinv)
+            for side, kk in ((0, k0 - 1), (1, k1)):
+                if 0 <= kk < nz:
+                    for st in range(7):
+                        ctx.coef_slack_upload(g, dA, st, side, A[st, kk])
+                    ctx.coef_slack_upload(g, dinv, 0, side, di[kk])
+            dr, dz, dy = ctx.vec_from(g, r[k0:k1 + 2]), ctx.vec_alloc(g), ctx.vec_alloc(g)
+            for rep in range(2):                             # twice: the mailboxes / flags of the first application are clean
+                ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_OVERLAP, 1)
+                z = ctx.vec_download(g, dz)
+                assert np.array_equal(z[1:-1], want[1 + k0:1 + k1]), f"slab {rk} of {nslabs}, application {rep}: max diff {np.abs(z[1:-1] - want[1 + k0:1 + k1]).max()}"
+                assert not z[1:-1, 0].any() and not z[1:-1, -1].any() and not z[1:-1, :, 0].any() and not z[1:-1, :, -1].any()
+            # the same slab without the overlap: the slab-local ordering
+            ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_SLABLOCAL, 1)
+            assert np.array_equal(ctx.vec_download(g, dz)[1:-1], local[1 + k0:1 + k1]), f"slab-local, slab {rk}"
+            for p_ in (dA, dinv, dr, dz, dy):
+                ctx.free(p_)
+    finally:
+        ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT); ctx.tune("sgs_tile_i", 0); ctx.tune("sgs_pencils", 0); ctx.tune("sgs_tile_mail", 1)
+
+
 @pytest.mark.parametrize("npdim,grid", [((18, 18, 18), "uniform"), ((16, 16, 16), "chebyshev"), ((19, 23, 11), "chebyshev"), ((3, 5, 4), "uniform")])
 def test_assembly_bit_exact(ctx, npdim, grid):
     m = cport.Mesh(npdim, grid=grid)
