@@ -424,7 +424,8 @@ def run_ours(a):
         x2, y2 = H.Vec(mesh), H.Vec(mesh)
         x2.set(xg)
         H.apply(A, x, y)
-        g1 = capi.make_grid(nx, ny, nzl)
+        g1 = capi.Grid.from_buffer_copy(g)    # the slab's own layout (slab grids carry slack planes in cstride), seen as an undecomposed grid
+        g1.rank, g1.nranks, g1.k0, g1.nz_global = 0, 1, 0, nzl
         ctx.spmv(g1, dA, x2.device_ptr(), y2.device_ptr())
         ctx.vecaxpy(g1, -1.0, dy, y2.device_ptr())
         diff = ctx.nrm2(g1, y2.device_ptr())
