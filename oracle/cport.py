@@ -232,6 +232,32 @@ def sgs_overlap_apply(mesh, A, diaginv, r, nslabs, overlap=1):
     return z
 
 
+def sgs_blocks_apply(mesh, A, diaginv, r, nblocks):
+    """The z-blocks ordering on one device (S3D_SGS_BLOCKS; no counterpart in the reference, stated ON TOP of its sequential half-sweeps,
+    s3d_sgspreconditioners.cpp:53-110): forward, every block of planes is swept preceded by one plane of the block below (zero inflow
+    under it), own planes kept; backward, followed by one plane of the block above, whose forward values are the ones the block
+    above has computed, zero inflow over it, own planes kept.  At most nz // 8 blocks (the library's rule); one block is the sequential sweep."""
+    nx, ny, nz = mesh.n
+    nblocks = max(1, min(nblocks, nz // 8))
+    y, z = mesh.zeros(), mesh.zeros()
+    bounds = slab_bounds(nz, nblocks)
+    for p, (k0, k1) in enumerate(bounds):
+        e0 = k0 - 1 if p > 0 else k0
+        sm = Mesh((nx + 2, ny + 2, k1 - e0 + 2))
+        rs, ys = sm.zeros(), sm.zeros()
+        rs[1:-1] = r[1 + e0:1 + k1]
+        sgs_forward_inplace(sm, np.ascontiguousarray(A[:, e0:k1]), np.ascontiguousarray(diaginv[e0:k1]), rs, ys)
+        y[1 + k0:1 + k1] = ys[1 + (k0 - e0):1 + (k1 - e0)]
+    for p, (k0, k1) in enumerate(bounds):
+        e1 = k1 + 1 if p < nblocks - 1 else k1
+        sm = Mesh((nx + 2, ny + 2, e1 - k0 + 2))
+        ys, zs = sm.zeros(), sm.zeros()
+        ys[1:-1] = y[1 + k0:1 + e1]
+        sgs_backward_inplace(sm, np.ascontiguousarray(A[:, k0:e1]), np.ascontiguousarray(diaginv[k0:e1]), ys, zs)
+        z[1 + k0:1 + k1] = zs[1:1 + (k1 - k0)]
+    return z
+
+
 def solve(mesh, A, b, ksp="richardson", pc="jacobi", rtol=1e-6, maxiter=1000, restart=30,
           apply_sweeps=1, build_sweeps=1, x0=None):
     """Returns (x, info dict, hist ndarray of relative residuals per iteration)."""

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libs3d_cuda.so")
 
 SPMV_AUTO, SPMV_MARCH, SPMV_TMA, SPMV_NAIVE, SPMV_PAIR = 0, 1, 2, 3, 4
-SGS_LEXICOGRAPHIC, SGS_REDBLACK, SGS_LEXICOGRAPHIC_PLANES, SGS_JACOBI_SWEEPS, SGS_SLABLOCAL, SGS_ASYNC, SGS_OVERLAP = 0, 1, 2, 3, 4, 5, 6
+SGS_LEXICOGRAPHIC, SGS_REDBLACK, SGS_LEXICOGRAPHIC_PLANES, SGS_JACOBI_SWEEPS, SGS_SLABLOCAL, SGS_ASYNC, SGS_OVERLAP, SGS_BLOCKS = 0, 1, 2, 3, 4, 5, 6, 7
 SGS_VARIANT_DEFAULT = 4   # warp-per-line streaming kernel (sgs_stream.cu); 0 warp-per-tile, 1 block-per-tile, 3 r1's line experiment
 CONV_STRICT, CONV_INITIAL = 1, 2
 COMM_ID_BYTES = 128

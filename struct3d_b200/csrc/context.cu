@@ -154,7 +154,9 @@ int s3d_ctx_destroy(s3d_ctx *ctx)
 	if (ctx->push_stream) { cudaStreamSynchronize(ctx->push_stream); cudaStreamDestroy(ctx->push_stream); cudaEventDestroy(ctx->push_ev[0]); cudaEventDestroy(ctx->push_ev[1]); }
 	s3d_comm_destroy(ctx);   // peer-memory windows first (the neighbours may still have them mapped), then the communicator
 	cudaFree(ctx->partials); cudaFree(ctx->ticket); cudaFree(ctx->tab); cudaFree(ctx->red_tmp);
-	cudaFree(ctx->sgs_flags); cudaFree(ctx->sgs_ctl); cudaFree(ctx->sgs_iface); cudaFree(ctx->sgs_order); cudaFree(ctx->sgs_mail); cudaFree(ctx->sweep_buf); cudaFree(ctx->stage); cudaFree(ctx->stage_y);
+	cudaFree(ctx->sgs_flags); cudaFree(ctx->sgs_ctl); cudaFree(ctx->sgs_iface); cudaFree(ctx->sgs_order); cudaFree(ctx->sgs_mail);
+	for (int d = 0; d < 2; d++) { cudaFree(ctx->sgsblocks.order[d]); cudaFree(ctx->sgsblocks.layers[d]); }
+	 cudaFree(ctx->sweep_buf); cudaFree(ctx->stage); cudaFree(ctx->stage_y);
 	cudaFreeHost(ctx->h_pinned);
 	if (ctx->h_slots) { cudaFreeHost(ctx->h_slots); for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->slot_ev[i]); }
 	cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);

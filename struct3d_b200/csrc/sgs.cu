@@ -111,6 +111,10 @@ struct SgsFlow {
 	unsigned long long *mail;
 	int mail_stride;   // doubles per tile: 8 TI + TJ TI + 64
 	int probe;         // poll one value per predecessor in a tight loop before the full fetch (pays on latency-bound grids only)
+	// warp kernel, z-BLOCKS on one device (S3D_SGS_BLOCKS, mailbox hand-off only): the planes of tile layer ck are not [8 ck, 8 ck + 8) but
+	// layers[ck] = {first plane, planes, bit 0: a layer of the same block precedes it in sweep order | bit 1: one follows, plane whose
+	// results are NOT stored (the block's overlap plane: it belongs to the neighbouring block) or a negative number}; null: the plain tiling
+	const int4 *layers;
 };
 constexpr unsigned long long SGW_SENT = 0xFFF4A5C3D2E1B497ull;   // "not written yet": a signalling-NaN pattern no arithmetic produces
 
@@ -375,8 +379,10 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 	// one is out, so the copies fly while the warp waits for the predecessors.
 	auto stage = [&](int t) {
 		const int ci = t % f.ntx, cj = (t / f.ntx) % f.nty, ck = t / (f.ntx * f.nty);
-		const int i0 = ci * TI, j0 = cj * TJ, k0 = ck * TK;
-		const int tj = min(TJ, g.ny - j0), tk = min(TK, g.nz - k0);
+		const int i0 = ci * TI, j0 = cj * TJ;
+		int k0 = ck * TK, tk = min(TK, g.nz - k0);
+		if (f.layers) { const int4 L = __ldg(f.layers + ck); k0 = L.x; tk = L.y; }
+		const int tj = min(TJ, g.ny - j0);
 		const long long vtile = g.voff + (long long)k0 * g.vplane + (long long)j0 * g.vpitch + i0;
 		const long long ctile = (long long)k0 * g.cplane + (long long)j0 * g.cpitch + i0;
 		__syncwarp();                                           // the last tile's reads of the staging area come first
@@ -406,8 +412,12 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		long long gt0 = 0, gt1 = 0, gt2 = 0, gt3 = 0, gt4 = 0;   // global-timer stamps of this tile (timing experiments: S3D_SGS_TILELOG)
 		if (f.prof) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(gt0));
 		const int ci = tile % f.ntx, cj = (tile / f.ntx) % f.nty, ck = tile / (f.ntx * f.nty);
-		const int i0 = ci * TI, j0 = cj * TJ, k0 = ck * TK;
-		const int ti = min(TI, g.nx - i0), tj = min(TJ, g.ny - j0), tk = min(TK, g.nz - k0);
+		const int i0 = ci * TI, j0 = cj * TJ;
+		int k0 = ck * TK, tk = min(TK, g.nz - k0);
+		bool kpred = FWD ? (ck > 0) : (ck < f.ntz - 1), ksucc = FWD ? (ck < f.ntz - 1) : (ck > 0);
+		int skipk = -(1 << 30);                                   // z-blocks: the plane of this layer whose results stay in the tile
+		if (f.layers) { const int4 L = __ldg(f.layers + ck); k0 = L.x; tk = L.y; kpred = L.z & 1; ksucc = (L.z >> 1) & 1; skipk = L.w; }
+		const int ti = min(TI, g.nx - i0), tj = min(TJ, g.ny - j0);
 		const long long vtile = g.voff + (long long)k0 * g.vplane + (long long)j0 * g.vpitch + i0;
 		const bool act0 = (b0 < tj) && (cc < tk), act1 = (P == 2) && (b1 < tj) && (cc < tk);
 		// z-slabs: the first plane of tiles (in sweep order) takes its k-halo from the window, the last one feeds the next rank's
@@ -427,7 +437,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		// mailbox hand-off: the faces come from the predecessor tiles' mailboxes (data is its own flag); bit u of hmail: hp[u] is one
 		const bool mailmode = (f.mail != nullptr);
 		unsigned hmail = 0;
-		const bool jpred = FWD ? (cj > 0) : (cj < f.nty - 1), kpred = FWD ? (ck > 0) : (ck < f.ntz - 1);
+		const bool jpred = FWD ? (cj > 0) : (cj < f.nty - 1);
 		const double *mjp = reinterpret_cast<const double *>(f.mail) + (long long)(FWD ? tile - f.ntx : tile + f.ntx) * f.mail_stride;
 		const double *mkp = reinterpret_cast<const double *>(f.mail) + (long long)(FWD ? tile - f.ntx * f.nty : tile + f.ntx * f.nty) * f.mail_stride + 8 * TI;
 #pragma unroll
@@ -442,7 +452,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 					}
 				} else {
 					const int r = row - 8;
-					const bool kz = FWD ? (f.kzero_lo && ck == 0) : (f.kzero_hi && ck == f.ntz - 1);
+					const bool kz = f.layers ? !kpred : FWD ? (f.kzero_lo && ck == 0) : (f.kzero_hi && ck == f.ntz - 1);   // z-blocks: zero inflow into a block
 					if (r < tj && !kz) {
 						if (mailmode && kpred) { hp[u] = mkp + r * TI + 2 * i2; hmail |= 1u << u; }
 						else hp[u] = (xin ? f.x_in_plane + inpl : out + vtile + (long long)(FWD ? -1 : tk) * g.vplane) + (long long)(FWD ? r : tj - 1 - r) * g.vpitch + 2 * i2;
@@ -608,6 +618,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		__syncwarp();
 		auto copy_row_chunk = [&](int rb, int rc, int i2) {
 			const int pj = FWD ? rb : tj - 1 - rb, pk = FWD ? rc : tk - 1 - rc;
+			if (k0 + pk == skipk) return;                           // z-blocks: the overlap plane belongs to the neighbouring block
 			double *dst = out + vtile + (long long)pk * g.vplane + (long long)pj * g.vpitch + 2 * i2;
 			const double2 v = *reinterpret_cast<const double2 *>(s_a + sgw_row<P, FWD>(rb, rc) * R + 2 * i2);
 			if (2 * i2 + 1 < ti) *reinterpret_cast<double2 *>(dst) = v;
@@ -616,7 +627,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		if (mailmode) {
 			// MAILBOX hand-off: the faces go into this tile's boxes -- only where a tile of this sweep will read (and re-arm) them --
 			// the moment the sweep is over; no fence, no flag.  Then every row goes to `out`, which only later kernels read.
-			const bool isucc = FWD ? (ci < f.ntx - 1) : (ci > 0), jsucc = FWD ? (cj < f.nty - 1) : (cj > 0), ksucc = FWD ? (ck < f.ntz - 1) : (ck > 0);
+			const bool isucc = FWD ? (ci < f.ntx - 1) : (ci > 0), jsucc = FWD ? (cj < f.nty - 1) : (cj > 0);
 			double *mb = reinterpret_cast<double *>(f.mail) + (long long)tile * f.mail_stride;
 			if (isucc) {
 				if (act0) __stcg(mb + (8 + TJ) * TI + b0 * 8 + cc, last0);
@@ -1273,7 +1284,7 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 	}
 	f.flags = ctx->sgs_flags;
 	f.iface = ctx->sgs_iface;
-	f.mail = nullptr; f.mail_stride = 0; f.probe = 0;
+	f.mail = nullptr; f.mail_stride = 0; f.probe = 0; f.layers = nullptr;
 	f.x_in_plane = nullptr; f.x_in_flags = nullptr; f.x_out_plane = nullptr; f.x_out_flags = nullptr;
 	f.kzero_lo = 0; f.kzero_hi = 0;
 	f.order = ctx->sgs_order;
@@ -1374,6 +1385,65 @@ int sgs_ctl_ensure(s3d_ctx *ctx)
 		S3D_CUDA(ctx, cudaMalloc(&ctx->sgs_ctl, 2 * sizeof(int)));
 		S3D_CUDA(ctx, cudaMemsetAsync(ctx->sgs_ctl, 0, 2 * sizeof(int), ctx->stream));
 	}
+	return S3D_OK;
+}
+}  // namespace
+
+namespace {
+// z-blocks on one device (S3D_SGS_BLOCKS): layer and dispatch tables of both sweep directions, cached per (grid, blocks, tile shape).
+// Block p owns planes [p nz / B, (p+1) nz / B).  Forward, it sweeps them preceded by ONE plane of the block below (zero inflow under it)
+// and does not store that plane; backward, followed by one plane of the block above -- whose forward values y the block above has
+// stored by then: the launches are ordered -- with zero inflow over it, and does not store it either.
+int sgs_blocks_prepare(s3d_ctx *ctx, const s3d_grid *g, int B, int tile_i, int tile_j)
+{
+	s3d_ctx::SgsBlocks &t = ctx->sgsblocks;
+	const int key[6] = {g->nx, g->ny, g->nz, B, tile_i, tile_j};
+	if (t.order[0] && !memcmp(key, t.key, sizeof key)) return S3D_OK;
+	const int ntx = (g->nx + tile_i - 1) / tile_i, nty = (g->ny + tile_j - 1) / tile_j;
+	std::vector<int4> layers[2];
+	std::vector<int> depth[2];                             // position of a layer inside its block, counted in sweep order
+	for (int p = 0; p < B; p++) {
+		const int k0 = (int)((long long)p * g->nz / B), k1 = (int)((long long)(p + 1) * g->nz / B);
+		for (int dir = 0; dir < 2; dir++) {
+			const int lo = (dir == 0 && p > 0) ? k0 - 1 : k0, hi = (dir == 1 && p < B - 1) ? k1 + 1 : k1;
+			const int skip = (dir == 0 && p > 0) ? k0 - 1 : (dir == 1 && p < B - 1) ? k1 : -(1 << 30);
+			const int nl = (hi - lo + SGS_TK - 1) / SGS_TK;
+			for (int l = 0; l < nl; l++) {
+				const int first = lo + l * SGS_TK, cnt = std::min(SGS_TK, hi - first);
+				const bool below = l > 0, above = l < nl - 1;   // a layer of the same block below / above this one
+				const int pred = dir == 0 ? below : above, succ = dir == 0 ? above : below;
+				layers[dir].push_back(make_int4(first, cnt, pred | (succ << 1), skip));
+				depth[dir].push_back(dir == 0 ? l : nl - 1 - l);
+			}
+		}
+	}
+	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	for (int dir = 0; dir < 2; dir++) {
+		const int ntz = (int)layers[dir].size();
+		// counting sort by the tile's wavefront number inside its block: every block ramps up at once.  The kernel takes
+		// order[ticket] forward and order[ntiles - 1 - ticket] backward, so the backward table ascends in the REVERSED wavefront number.
+		const int nd = ntx + nty + ntz;
+		std::vector<int> start(nd + 1, 0), order((size_t)ntx * nty * ntz);
+		auto wave = [&](int ci, int cj, int ck) {
+			return dir == 0 ? ci + cj + depth[0][ck] : nd - 1 - ((ntx - 1 - ci) + (nty - 1 - cj) + depth[1][ck]);
+		};
+		for (int ck = 0; ck < ntz; ck++)
+			for (int cj = 0; cj < nty; cj++)
+				for (int ci = 0; ci < ntx; ci++) start[wave(ci, cj, ck) + 1]++;
+		for (int d = 0; d < nd; d++) start[d + 1] += start[d];
+		for (int ck = 0; ck < ntz; ck++)
+			for (int cj = 0; cj < nty; cj++)
+				for (int ci = 0; ci < ntx; ci++) order[start[wave(ci, cj, ck)]++] = (ck * nty + cj) * ntx + ci;
+		if (t.order[dir]) S3D_CUDA(ctx, cudaFree(t.order[dir]));
+		if (t.layers[dir]) S3D_CUDA(ctx, cudaFree(t.layers[dir]));
+		t.order[dir] = nullptr; t.layers[dir] = nullptr;
+		S3D_CUDA(ctx, cudaMalloc(&t.order[dir], order.size() * sizeof(int)));
+		S3D_CUDA(ctx, cudaMalloc(&t.layers[dir], layers[dir].size() * sizeof(int4)));
+		S3D_CUDA(ctx, cudaMemcpy(t.order[dir], order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+		S3D_CUDA(ctx, cudaMemcpy(t.layers[dir], layers[dir].data(), layers[dir].size() * sizeof(int4), cudaMemcpyHostToDevice));
+		t.ntz[dir] = ntz;
+	}
+	memcpy(t.key, key, sizeof key);
 	return S3D_OK;
 }
 }  // namespace
@@ -1518,6 +1588,45 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		return S3D_OK;
 	}
 	if (ordering == S3D_SGS_ASYNC) return s3d_internal_sgs_async(ctx, g, A, d_dinv, d_r, d_z, d_y, nsweeps);
+	if (ordering == S3D_SGS_BLOCKS) {
+		// z-blocks on ONE device: the grid is cut into `sgs_blocks` blocks of planes that sweep concurrently, each forward sweep preceded by
+		// one plane of the block below, each backward sweep by one plane of the block above (see sgs_blocks_prepare).  The dependency
+		// chain of a sweep shrinks from nx/TI + ny/TJ + nz/8 tile hops to nx/TI + ny/TJ + nz/(8 B) + 1, which is what bounds the exact
+		// sweep up to ~256^3; another operator than the reference's sweep (iteration counts within a few per cent, like OVERLAP).
+		S3D_REQUIRE(ctx, g->nranks == 1, "S3D_SGS_BLOCKS is a one-device ordering (z-slabs: S3D_SGS_OVERLAP)");
+		const int B = std::max(1, std::min(ctx->sgs_blocks, g->nz / 8));
+		if (B == 1 || !ctx->sgs_tile_mail) ordering = S3D_SGS_LEXICOGRAPHIC;
+		else {
+			s3d_grid gx = *g;                                // sizes the mailboxes / the launch for the larger of the two tilings
+			const int tile_i = sgw_tile_i(ctx), tile_j = 4 * sgw_pencils(ctx, g);
+			const int rcb = sgs_blocks_prepare(ctx, g, B, tile_i, tile_j);
+			if (rcb != S3D_OK) return rcb;
+			const s3d_ctx::SgsBlocks &t = ctx->sgsblocks;
+			gx.nz = SGS_TK * std::max(t.ntz[0], t.ntz[1]);
+			const int pencils_asked = ctx->sgs_pencils;
+			ctx->sgs_pencils = tile_j / 4;                   // the tile shape is chosen by size: g's choice holds for gx too
+			SgsFlow f;
+			unsigned nblocks = 0;
+			const int rcp = sgs_flow_prepare(ctx, &gx, f, nblocks, 0);
+			if (rcp != S3D_OK) { ctx->sgs_pencils = pencils_asked; return rcp; }
+			if (!f.mail || f.nty != (g->ny + tile_j - 1) / tile_j || (size_t)std::max(t.ntz[0], t.ntz[1]) * f.ntx * f.nty * f.mail_stride > ctx->sgs_mail_cap) {
+				ctx->sgs_pencils = pencils_asked;
+				return s3d_fail(ctx, S3D_ERR_STATE, "S3D_SGS_BLOCKS: mailbox set-up does not match the block tiling");
+			}
+			const long long cs = g->cstride;
+			for (int dir = 0; dir < 2; dir++) {
+				f.ntz = t.ntz[dir]; f.order = t.order[dir]; f.layers = t.layers[dir];
+				const unsigned nb = (unsigned)std::min<size_t>((size_t)f.ntx * f.nty * f.ntz, (size_t)nblocks);
+				sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
+				S3D_LAUNCHED(ctx);
+				if (dir == 0) sgw_launch<0>(ctx, &gx, nb, gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, (const int *)ctx->gate);
+				else sgw_launch<1>(ctx, &gx, nb, gd, (const double *)d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f, (const int *)ctx->gate);
+				S3D_LAUNCHED(ctx);
+			}
+			ctx->sgs_pencils = pencils_asked;
+			return S3D_OK;
+		}
+	}
 	if (ordering == S3D_SGS_OVERLAP && g->nranks == 1) ordering = S3D_SGS_LEXICOGRAPHIC;
 	if (ordering == S3D_SGS_OVERLAP) {
 		// Overlapping slabs (restricted additive Schwarz with the exact sweep as the subdomain solver): every rank sweeps its own planes

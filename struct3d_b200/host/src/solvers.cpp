@@ -320,22 +320,28 @@ SGS_like_preconditioner::SGS_like_preconditioner(const SMat &lhs, const PreconPa
 		else if (o == "lexicographic") order = S3D_SGS_LEXICOGRAPHIC;
 		else if (o == "slablocal") order = S3D_SGS_SLABLOCAL;
 		else if (o == "overlap") order = S3D_SGS_OVERLAP;
+		else if (o == "blocks") order = S3D_SGS_BLOCKS;
 		else if (o == "sweeps" || o == "jacobi_sweeps") order = S3D_SGS_JACOBI_SWEEPS;
 		else if (o == "async" || o == "threaded") order = S3D_SGS_ASYNC;
-		else throw std::runtime_error("-s3d_sgs_ordering must be lexicographic, overlap, slablocal, redblack, sweeps or async");
+		else throw std::runtime_error("-s3d_sgs_ordering must be lexicographic, blocks, overlap, slablocal, redblack, sweeps or async");
 	}
 	// The reference's threaded apply / build (s3d_sgspreconditioners.cpp:32-53, s3d_ilu.cpp:28-32) runs asynchronous, unordered sweeps
 	// over CPU threads.  Its GPU counterpart exists (-s3d_sgs_ordering async: S3D_SGS_ASYNC, chunks of -s3d_thread_chunk_size rows dealt
 	// to warps that never wait for one another), but is opt-in: the default stays the deterministic exact sweep, which needs the fewest
 	// iterations and gives the same result on every run.  Asked for through the reference's own switches, say so once.
 	if (order == S3D_SGS_ASYNC) d.check(s3d_tune_set(d.ctx(), "sgs_async_chunk", std::max(1, parms.thread_chunk_size)), "s3d_tune_set");
+	// z-blocks on one device (-s3d_sgs_ordering blocks): concurrent sweeps over -s3d_sgs_blocks blocks of planes (default 4) with one plane of
+	// overlap; opt-in -- another operator than the reference's sweep, within a few per cent of its iteration counts.  On z-slabs the ranks ARE the blocks.
+	if (order == S3D_SGS_BLOCKS && d.nranks() > 1) order = S3D_SGS_OVERLAP;
+	if (order == S3D_SGS_BLOCKS && s3d::options_has("-s3d_sgs_blocks"))
+		d.check(s3d_tune_set(d.ctx(), "sgs_blocks", std::max(1, petscoptions_get_int("-s3d_sgs_blocks"))), "s3d_tune_set");
 	static bool warned = false;
 	const bool asked = order != S3D_SGS_ASYNC && ((s3d::options_has("-s3d_pc_use_threaded_apply") && parms.threadedapply) || (s3d::options_has("-s3d_pc_use_threaded_build") && parms.threadedbuild));
 	if (asked && !warned && d.rank() == 0) {
 		std::printf(" WARNING: -s3d_pc_use_threaded_apply / -s3d_pc_use_threaded_build ask for the reference's asynchronous CPU-thread sweeps; "
 		            "the GPU sweeps are deterministic unless asked otherwise (ordering: %s). -s3d_sgs_ordering async runs -s3d_pc_apply_sweeps asynchronous "
 		            "sweeps (the threaded apply's GPU counterpart; with it -s3d_pc_use_threaded_build true builds StrILU by asynchronous sweeps as well), -s3d_sgs_ordering sweeps as many synchronous ones.\n",
-		            order == S3D_SGS_LEXICOGRAPHIC ? "lexicographic" : order == S3D_SGS_SLABLOCAL ? "slablocal" : order == S3D_SGS_OVERLAP ? "overlap" : order == S3D_SGS_REDBLACK ? "redblack"
+		            order == S3D_SGS_LEXICOGRAPHIC ? "lexicographic" : order == S3D_SGS_SLABLOCAL ? "slablocal" : order == S3D_SGS_OVERLAP ? "overlap" : order == S3D_SGS_BLOCKS ? "blocks" : order == S3D_SGS_REDBLACK ? "redblack"
 		            : order == S3D_SGS_ASYNC ? "async" : "sweeps");
 		warned = true;
 	}
