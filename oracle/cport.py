@@ -232,29 +232,52 @@ def sgs_overlap_apply(mesh, A, diaginv, r, nslabs, overlap=1):
     return z
 
 
-def sgs_blocks_apply(mesh, A, diaginv, r, nblocks):
-    """The z-blocks ordering on one device (S3D_SGS_BLOCKS; no counterpart in the reference, stated ON TOP of its sequential half-sweeps,
-    s3d_sgspreconditioners.cpp:53-110): forward, every block of planes is swept preceded by one plane of the block below (zero inflow
-    under it), own planes kept; backward, followed by one plane of the block above, whose forward values are the ones the block
-    above has computed, zero inflow over it, own planes kept.  At most nz // 8 blocks (the library's rule); one block is the sequential sweep."""
+def block_bounds(n, nblocks):
+    """blocks of planes (rows) of the library's S3D_SGS_BLOCKS ordering (sgs.cu, axis_blocks): at most n // 8 blocks, thickness 7 modulo 8 (a block
+    plus its overlap plane fills whole tile layers), the first blocks 8 thicker where that evens out the last one, which takes what is left (>= 8)"""
+    B = max(1, min(nblocks, n // 8))
+    if B == 1:
+        return [(0, n)]
+    thick = 8 * max(1, (n + B) // (8 * B)) - 1
+    while B > 1 and n - (B - 1) * thick < 8:
+        B -= 1
+    rem = n - (B - 1) * thick
+    nthicker = max(0, min((2 * (rem - n // B) + 8) // 16, B - 1))
+    while nthicker > 0 and rem - 8 * nthicker < 8:
+        nthicker -= 1
+    bounds, k = [], 0
+    for p in range(B):
+        k1 = n if p == B - 1 else k + thick + (8 if p < nthicker else 0)
+        bounds.append((k, k1))
+        k = k1
+    return bounds
+
+
+def sgs_blocks_apply(mesh, A, diaginv, r, nblocks, nblocks_y=1):
+    """The blocks ordering on one device (S3D_SGS_BLOCKS; no counterpart in the reference, stated ON TOP of its sequential half-sweeps,
+    s3d_sgspreconditioners.cpp:53-110): the grid is cut into blocks of planes (and of rows).  Forward, every block is swept preceded by
+    one plane and one row of the blocks below it (zero inflow under them), own points kept; backward, followed by one plane and one row
+    of the blocks above, whose forward values are the ones their owners have computed, zero inflow over them, own points kept.
+    Blocks as the library cuts them (block_bounds); one block is the sequential sweep."""
     nx, ny, nz = mesh.n
-    nblocks = max(1, min(nblocks, nz // 8))
     y, z = mesh.zeros(), mesh.zeros()
-    bounds = slab_bounds(nz, nblocks)
-    for p, (k0, k1) in enumerate(bounds):
-        e0 = k0 - 1 if p > 0 else k0
-        sm = Mesh((nx + 2, ny + 2, k1 - e0 + 2))
-        rs, ys = sm.zeros(), sm.zeros()
-        rs[1:-1] = r[1 + e0:1 + k1]
-        sgs_forward_inplace(sm, np.ascontiguousarray(A[:, e0:k1]), np.ascontiguousarray(diaginv[e0:k1]), rs, ys)
-        y[1 + k0:1 + k1] = ys[1 + (k0 - e0):1 + (k1 - e0)]
-    for p, (k0, k1) in enumerate(bounds):
-        e1 = k1 + 1 if p < nblocks - 1 else k1
-        sm = Mesh((nx + 2, ny + 2, e1 - k0 + 2))
-        ys, zs = sm.zeros(), sm.zeros()
-        ys[1:-1] = y[1 + k0:1 + e1]
-        sgs_backward_inplace(sm, np.ascontiguousarray(A[:, k0:e1]), np.ascontiguousarray(diaginv[k0:e1]), ys, zs)
-        z[1 + k0:1 + k1] = zs[1:1 + (k1 - k0)]
+    kb, jb = block_bounds(nz, nblocks), block_bounds(ny, nblocks_y)
+    for (k0, k1) in kb:
+        for (j0, j1) in jb:
+            ek, ej = (k0 - 1 if k0 > 0 else k0), (j0 - 1 if j0 > 0 else j0)
+            sm = Mesh((nx + 2, j1 - ej + 2, k1 - ek + 2))
+            rs, ys = sm.zeros(), sm.zeros()
+            rs[1:-1, 1:-1] = r[1 + ek:1 + k1, 1 + ej:1 + j1]
+            sgs_forward_inplace(sm, np.ascontiguousarray(A[:, ek:k1, ej:j1]), np.ascontiguousarray(diaginv[ek:k1, ej:j1]), rs, ys)
+            y[1 + k0:1 + k1, 1 + j0:1 + j1] = ys[1 + (k0 - ek):1 + (k1 - ek), 1 + (j0 - ej):1 + (j1 - ej)]
+    for (k0, k1) in kb:
+        for (j0, j1) in jb:
+            ek, ej = (k1 + 1 if k1 < nz else k1), (j1 + 1 if j1 < ny else j1)
+            sm = Mesh((nx + 2, ej - j0 + 2, ek - k0 + 2))
+            ys, zs = sm.zeros(), sm.zeros()
+            ys[1:-1, 1:-1] = y[1 + k0:1 + ek, 1 + j0:1 + ej]
+            sgs_backward_inplace(sm, np.ascontiguousarray(A[:, k0:ek, j0:ej]), np.ascontiguousarray(diaginv[k0:ek, j0:ej]), ys, zs)
+            z[1 + k0:1 + k1, 1 + j0:1 + j1] = zs[1:1 + (k1 - k0), 1:1 + (j1 - j0)]
     return z
 
 

@@ -115,6 +115,7 @@ struct SgsFlow {
 	// layers[ck] = {first plane, planes, bit 0: a layer of the same block precedes it in sweep order | bit 1: one follows, plane whose
 	// results are NOT stored (the block's overlap plane: it belongs to the neighbouring block) or a negative number}; null: the plain tiling
 	const int4 *layers;
+	const int4 *jlayers;   // the same along j (blocks of rows): rows of tile row cj = jlayers[cj] = {first row, rows, pred | succ << 1, row not stored}; null: plain
 };
 constexpr unsigned long long SGW_SENT = 0xFFF4A5C3D2E1B497ull;   // "not written yet": a signalling-NaN pattern no arithmetic produces
 
@@ -379,10 +380,11 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 	// one is out, so the copies fly while the warp waits for the predecessors.
 	auto stage = [&](int t) {
 		const int ci = t % f.ntx, cj = (t / f.ntx) % f.nty, ck = t / (f.ntx * f.nty);
-		const int i0 = ci * TI, j0 = cj * TJ;
+		const int i0 = ci * TI;
+		int j0 = cj * TJ, tj = min(TJ, g.ny - j0);
 		int k0 = ck * TK, tk = min(TK, g.nz - k0);
 		if (f.layers) { const int4 L = __ldg(f.layers + ck); k0 = L.x; tk = L.y; }
-		const int tj = min(TJ, g.ny - j0);
+		if (f.jlayers) { const int4 L = __ldg(f.jlayers + cj); j0 = L.x; tj = L.y; }
 		const long long vtile = g.voff + (long long)k0 * g.vplane + (long long)j0 * g.vpitch + i0;
 		const long long ctile = (long long)k0 * g.cplane + (long long)j0 * g.cpitch + i0;
 		__syncwarp();                                           // the last tile's reads of the staging area come first
@@ -412,12 +414,15 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		long long gt0 = 0, gt1 = 0, gt2 = 0, gt3 = 0, gt4 = 0;   // global-timer stamps of this tile (timing experiments: S3D_SGS_TILELOG)
 		if (f.prof) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(gt0));
 		const int ci = tile % f.ntx, cj = (tile / f.ntx) % f.nty, ck = tile / (f.ntx * f.nty);
-		const int i0 = ci * TI, j0 = cj * TJ;
+		const int i0 = ci * TI;
+		int j0 = cj * TJ, tj = min(TJ, g.ny - j0);
 		int k0 = ck * TK, tk = min(TK, g.nz - k0);
 		bool kpred = FWD ? (ck > 0) : (ck < f.ntz - 1), ksucc = FWD ? (ck < f.ntz - 1) : (ck > 0);
-		int skipk = -(1 << 30);                                   // z-blocks: the plane of this layer whose results stay in the tile
+		bool jpred = FWD ? (cj > 0) : (cj < f.nty - 1), jsucc = FWD ? (cj < f.nty - 1) : (cj > 0);
+		int skipk = -(1 << 30), skipj = -(1 << 30);               // blocks: the plane / row of this tile whose results stay in the tile
 		if (f.layers) { const int4 L = __ldg(f.layers + ck); k0 = L.x; tk = L.y; kpred = L.z & 1; ksucc = (L.z >> 1) & 1; skipk = L.w; }
-		const int ti = min(TI, g.nx - i0), tj = min(TJ, g.ny - j0);
+		if (f.jlayers) { const int4 L = __ldg(f.jlayers + cj); j0 = L.x; tj = L.y; jpred = L.z & 1; jsucc = (L.z >> 1) & 1; skipj = L.w; }
+		const int ti = min(TI, g.nx - i0);
 		const long long vtile = g.voff + (long long)k0 * g.vplane + (long long)j0 * g.vpitch + i0;
 		const bool act0 = (b0 < tj) && (cc < tk), act1 = (P == 2) && (b1 < tj) && (cc < tk);
 		// z-slabs: the first plane of tiles (in sweep order) takes its k-halo from the window, the last one feeds the next rank's
@@ -437,7 +442,6 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		// mailbox hand-off: the faces come from the predecessor tiles' mailboxes (data is its own flag); bit u of hmail: hp[u] is one
 		const bool mailmode = (f.mail != nullptr);
 		unsigned hmail = 0;
-		const bool jpred = FWD ? (cj > 0) : (cj < f.nty - 1);
 		const double *mjp = reinterpret_cast<const double *>(f.mail) + (long long)(FWD ? tile - f.ntx : tile + f.ntx) * f.mail_stride;
 		const double *mkp = reinterpret_cast<const double *>(f.mail) + (long long)(FWD ? tile - f.ntx * f.nty : tile + f.ntx * f.nty) * f.mail_stride + 8 * TI;
 #pragma unroll
@@ -448,7 +452,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 				if (row < 8) {
 					if (row < tk) {
 						if (mailmode && jpred) { hp[u] = mjp + row * TI + 2 * i2; hmail |= 1u << u; }
-						else hp[u] = out + vtile + (long long)(FWD ? row : tk - 1 - row) * g.vplane + (long long)(FWD ? -1 : tj) * g.vpitch + 2 * i2;
+						else if (!(f.jlayers && !jpred)) hp[u] = out + vtile + (long long)(FWD ? row : tk - 1 - row) * g.vplane + (long long)(FWD ? -1 : tj) * g.vpitch + 2 * i2;
 					}
 				} else {
 					const int r = row - 8;
@@ -618,7 +622,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		__syncwarp();
 		auto copy_row_chunk = [&](int rb, int rc, int i2) {
 			const int pj = FWD ? rb : tj - 1 - rb, pk = FWD ? rc : tk - 1 - rc;
-			if (k0 + pk == skipk) return;                           // z-blocks: the overlap plane belongs to the neighbouring block
+			if (k0 + pk == skipk || j0 + pj == skipj) return;       // blocks: the overlap plane / row belongs to the neighbouring block
 			double *dst = out + vtile + (long long)pk * g.vplane + (long long)pj * g.vpitch + 2 * i2;
 			const double2 v = *reinterpret_cast<const double2 *>(s_a + sgw_row<P, FWD>(rb, rc) * R + 2 * i2);
 			if (2 * i2 + 1 < ti) *reinterpret_cast<double2 *>(dst) = v;
@@ -627,7 +631,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		if (mailmode) {
 			// MAILBOX hand-off: the faces go into this tile's boxes -- only where a tile of this sweep will read (and re-arm) them --
 			// the moment the sweep is over; no fence, no flag.  Then every row goes to `out`, which only later kernels read.
-			const bool isucc = FWD ? (ci < f.ntx - 1) : (ci > 0), jsucc = FWD ? (cj < f.nty - 1) : (cj > 0);
+			const bool isucc = FWD ? (ci < f.ntx - 1) : (ci > 0);
 			double *mb = reinterpret_cast<double *>(f.mail) + (long long)tile * f.mail_stride;
 			if (isucc) {
 				if (act0) __stcg(mb + (8 + TJ) * TI + b0 * 8 + cc, last0);
@@ -1284,7 +1288,7 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 	}
 	f.flags = ctx->sgs_flags;
 	f.iface = ctx->sgs_iface;
-	f.mail = nullptr; f.mail_stride = 0; f.probe = 0; f.layers = nullptr;
+	f.mail = nullptr; f.mail_stride = 0; f.probe = 0; f.layers = nullptr; f.jlayers = nullptr;
 	f.x_in_plane = nullptr; f.x_in_flags = nullptr; f.x_out_plane = nullptr; f.x_out_flags = nullptr;
 	f.kzero_lo = 0; f.kzero_hi = 0;
 	f.order = ctx->sgs_order;
@@ -1390,42 +1394,62 @@ int sgs_ctl_ensure(s3d_ctx *ctx)
 }  // namespace
 
 namespace {
-// z-blocks on one device (S3D_SGS_BLOCKS): layer and dispatch tables of both sweep directions, cached per (grid, blocks, tile shape).
-// Block p owns planes [p nz / B, (p+1) nz / B).  Forward, it sweeps them preceded by ONE plane of the block below (zero inflow under it)
-// and does not store that plane; backward, followed by one plane of the block above -- whose forward values y the block above has
-// stored by then: the launches are ordered -- with zero inflow over it, and does not store it either.
-int sgs_blocks_prepare(s3d_ctx *ctx, const s3d_grid *g, int B, int tile_i, int tile_j)
+// Blocks on one device (S3D_SGS_BLOCKS): layer tables along k and j and the dispatch tables of both sweep directions, cached per
+// (grid, blocks, tile shape).  Along an axis of n points cut into B blocks, a block owns a run of planes (rows); forward, it sweeps them
+// preceded by ONE plane of the block below (zero inflow under it) and does not store that plane; backward, followed by one plane of the
+// block above -- whose forward values y the block above has stored by then: the launches are ordered -- with zero inflow over it,
+// and does not store it either.
+struct AxisLayers { std::vector<int4> L[2]; std::vector<int> depth[2]; };   // [sweep direction]; depth: position of a layer inside its block, in sweep order
+
+void axis_blocks(int n, int B, int TL, AxisLayers &out)
 {
-	s3d_ctx::SgsBlocks &t = ctx->sgsblocks;
-	const int key[6] = {g->nx, g->ny, g->nz, B, tile_i, tile_j};
-	if (t.order[0] && !memcmp(key, t.key, sizeof key)) return S3D_OK;
-	const int ntx = (g->nx + tile_i - 1) / tile_i, nty = (g->ny + tile_j - 1) / tile_j;
-	std::vector<int4> layers[2];
-	std::vector<int> depth[2];                             // position of a layer inside its block, counted in sweep order
+	constexpr int T = 8;   // the partition does not depend on the tile shape (TL = 4 or 8 rows per tile layer): 7 modulo 8 is also 3 modulo 4
+	// block thickness: T - 1 modulo T, so that a block plus its overlap plane fills whole tile layers in either direction (a layer that
+	// holds one plane costs a full tile sweep); the first blocks take T more where that evens out the last one, which takes what is
+	// left (at least T).  cport.block_bounds states the same.
+	B = std::max(1, std::min(B, n / T));
+	const int thick = T * std::max(1, (n + B) / (T * B)) - 1;
+	while (B > 1 && n - (B - 1) * thick < T) B--;
+	const int rem = n - (B - 1) * thick;
+	int nthicker = std::max(0, std::min((2 * (rem - n / B) + T) / (2 * T), B - 1));
+	while (nthicker > 0 && rem - T * nthicker < T) nthicker--;
+	int knext = 0;
 	for (int p = 0; p < B; p++) {
-		const int k0 = (int)((long long)p * g->nz / B), k1 = (int)((long long)(p + 1) * g->nz / B);
+		const int k0 = knext, k1 = (p == B - 1) ? n : k0 + thick + (p < nthicker ? T : 0);
+		knext = k1;
 		for (int dir = 0; dir < 2; dir++) {
 			const int lo = (dir == 0 && p > 0) ? k0 - 1 : k0, hi = (dir == 1 && p < B - 1) ? k1 + 1 : k1;
 			const int skip = (dir == 0 && p > 0) ? k0 - 1 : (dir == 1 && p < B - 1) ? k1 : -(1 << 30);
-			const int nl = (hi - lo + SGS_TK - 1) / SGS_TK;
+			const int nl = (hi - lo + TL - 1) / TL;
 			for (int l = 0; l < nl; l++) {
-				const int first = lo + l * SGS_TK, cnt = std::min(SGS_TK, hi - first);
+				const int first = lo + l * TL, cnt = std::min(TL, hi - first);
 				const bool below = l > 0, above = l < nl - 1;   // a layer of the same block below / above this one
 				const int pred = dir == 0 ? below : above, succ = dir == 0 ? above : below;
-				layers[dir].push_back(make_int4(first, cnt, pred | (succ << 1), skip));
-				depth[dir].push_back(dir == 0 ? l : nl - 1 - l);
+				out.L[dir].push_back(make_int4(first, cnt, pred | (succ << 1), skip));
+				out.depth[dir].push_back(dir == 0 ? l : nl - 1 - l);
 			}
 		}
 	}
+}
+
+int sgs_blocks_prepare(s3d_ctx *ctx, const s3d_grid *g, int Bz, int By, int tile_i, int tile_j)
+{
+	s3d_ctx::SgsBlocks &t = ctx->sgsblocks;
+	const int key[7] = {g->nx, g->ny, g->nz, Bz, By, tile_i, tile_j};
+	if (t.order[0] && !memcmp(key, t.key, sizeof key)) return S3D_OK;
+	const int ntx = (g->nx + tile_i - 1) / tile_i;
+	AxisLayers az, ay;
+	axis_blocks(g->nz, Bz, SGS_TK, az);
+	axis_blocks(g->ny, By, tile_j, ay);
 	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	for (int dir = 0; dir < 2; dir++) {
-		const int ntz = (int)layers[dir].size();
+		const int ntz = (int)az.L[dir].size(), nty = (int)ay.L[dir].size();
 		// counting sort by the tile's wavefront number inside its block: every block ramps up at once.  The kernel takes
 		// order[ticket] forward and order[ntiles - 1 - ticket] backward, so the backward table ascends in the REVERSED wavefront number.
 		const int nd = ntx + nty + ntz;
 		std::vector<int> start(nd + 1, 0), order((size_t)ntx * nty * ntz);
 		auto wave = [&](int ci, int cj, int ck) {
-			return dir == 0 ? ci + cj + depth[0][ck] : nd - 1 - ((ntx - 1 - ci) + (nty - 1 - cj) + depth[1][ck]);
+			return dir == 0 ? ci + ay.depth[0][cj] + az.depth[0][ck] : nd - 1 - ((ntx - 1 - ci) + ay.depth[1][cj] + az.depth[1][ck]);
 		};
 		for (int ck = 0; ck < ntz; ck++)
 			for (int cj = 0; cj < nty; cj++)
@@ -1438,10 +1462,11 @@ int sgs_blocks_prepare(s3d_ctx *ctx, const s3d_grid *g, int B, int tile_i, int t
 		if (t.layers[dir]) S3D_CUDA(ctx, cudaFree(t.layers[dir]));
 		t.order[dir] = nullptr; t.layers[dir] = nullptr;
 		S3D_CUDA(ctx, cudaMalloc(&t.order[dir], order.size() * sizeof(int)));
-		S3D_CUDA(ctx, cudaMalloc(&t.layers[dir], layers[dir].size() * sizeof(int4)));
+		S3D_CUDA(ctx, cudaMalloc(&t.layers[dir], (size_t)(ntz + nty) * sizeof(int4)));        // [k layers][j layers]
 		S3D_CUDA(ctx, cudaMemcpy(t.order[dir], order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
-		S3D_CUDA(ctx, cudaMemcpy(t.layers[dir], layers[dir].data(), layers[dir].size() * sizeof(int4), cudaMemcpyHostToDevice));
-		t.ntz[dir] = ntz;
+		S3D_CUDA(ctx, cudaMemcpy(t.layers[dir], az.L[dir].data(), (size_t)ntz * sizeof(int4), cudaMemcpyHostToDevice));
+		S3D_CUDA(ctx, cudaMemcpy(t.layers[dir] + ntz, ay.L[dir].data(), (size_t)nty * sizeof(int4), cudaMemcpyHostToDevice));
+		t.ntz[dir] = ntz; t.nty[dir] = nty;
 	}
 	memcpy(t.key, key, sizeof key);
 	return S3D_OK;
@@ -1589,33 +1614,35 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 	}
 	if (ordering == S3D_SGS_ASYNC) return s3d_internal_sgs_async(ctx, g, A, d_dinv, d_r, d_z, d_y, nsweeps);
 	if (ordering == S3D_SGS_BLOCKS) {
-		// z-blocks on ONE device: the grid is cut into `sgs_blocks` blocks of planes that sweep concurrently, each forward sweep preceded by
-		// one plane of the block below, each backward sweep by one plane of the block above (see sgs_blocks_prepare).  The dependency
-		// chain of a sweep shrinks from nx/TI + ny/TJ + nz/8 tile hops to nx/TI + ny/TJ + nz/(8 B) + 1, which is what bounds the exact
-		// sweep up to ~256^3; another operator than the reference's sweep (iteration counts within a few per cent, like OVERLAP).
+		// Blocks on ONE device: the grid is cut into `sgs_blocks` blocks of planes (and `sgs_blocks_y` blocks of rows) that sweep concurrently,
+		// each forward sweep preceded by one plane (row) of the block below, each backward sweep by one of the block above (see
+		// sgs_blocks_prepare).  The dependency chain of a sweep shrinks from nx/TI + ny/TJ + nz/8 tile hops to about
+		// nx/TI + ny/(TJ By) + nz/(8 Bz) + 2, which is what bounds the exact sweep up to ~256^3; another operator than the reference's
+		// sweep (iteration counts within a few per cent, like OVERLAP).
 		S3D_REQUIRE(ctx, g->nranks == 1, "S3D_SGS_BLOCKS is a one-device ordering (z-slabs: S3D_SGS_OVERLAP)");
-		const int B = std::max(1, std::min(ctx->sgs_blocks, g->nz / 8));
-		if (B == 1 || !ctx->sgs_tile_mail) ordering = S3D_SGS_LEXICOGRAPHIC;
+		const int tile_i = sgw_tile_i(ctx), tile_j = 4 * sgw_pencils(ctx, g);
+		const int Bz = std::max(1, std::min(ctx->sgs_blocks, g->nz / SGS_TK)), By = std::max(1, std::min(ctx->sgs_blocks_y, g->ny / 8));
+		if ((Bz == 1 && By == 1) || !ctx->sgs_tile_mail) ordering = S3D_SGS_LEXICOGRAPHIC;
 		else {
-			s3d_grid gx = *g;                                // sizes the mailboxes / the launch for the larger of the two tilings
-			const int tile_i = sgw_tile_i(ctx), tile_j = 4 * sgw_pencils(ctx, g);
-			const int rcb = sgs_blocks_prepare(ctx, g, B, tile_i, tile_j);
+			const int rcb = sgs_blocks_prepare(ctx, g, Bz, By, tile_i, tile_j);
 			if (rcb != S3D_OK) return rcb;
 			const s3d_ctx::SgsBlocks &t = ctx->sgsblocks;
+			s3d_grid gx = *g;                                // sizes the mailboxes / the launch for the larger of the two tilings
 			gx.nz = SGS_TK * std::max(t.ntz[0], t.ntz[1]);
+			gx.ny = tile_j * std::max(t.nty[0], t.nty[1]);
 			const int pencils_asked = ctx->sgs_pencils;
 			ctx->sgs_pencils = tile_j / 4;                   // the tile shape is chosen by size: g's choice holds for gx too
 			SgsFlow f;
 			unsigned nblocks = 0;
 			const int rcp = sgs_flow_prepare(ctx, &gx, f, nblocks, 0);
 			if (rcp != S3D_OK) { ctx->sgs_pencils = pencils_asked; return rcp; }
-			if (!f.mail || f.nty != (g->ny + tile_j - 1) / tile_j || (size_t)std::max(t.ntz[0], t.ntz[1]) * f.ntx * f.nty * f.mail_stride > ctx->sgs_mail_cap) {
+			if (!f.mail || (size_t)std::max(t.ntz[0], t.ntz[1]) * std::max(t.nty[0], t.nty[1]) * f.ntx * f.mail_stride > ctx->sgs_mail_cap) {
 				ctx->sgs_pencils = pencils_asked;
 				return s3d_fail(ctx, S3D_ERR_STATE, "S3D_SGS_BLOCKS: mailbox set-up does not match the block tiling");
 			}
 			const long long cs = g->cstride;
 			for (int dir = 0; dir < 2; dir++) {
-				f.ntz = t.ntz[dir]; f.order = t.order[dir]; f.layers = t.layers[dir];
+				f.ntz = t.ntz[dir]; f.nty = t.nty[dir]; f.order = t.order[dir]; f.layers = t.layers[dir]; f.jlayers = t.layers[dir] + t.ntz[dir];
 				const unsigned nb = (unsigned)std::min<size_t>((size_t)f.ntx * f.nty * f.ntz, (size_t)nblocks);
 				sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
 				S3D_LAUNCHED(ctx);

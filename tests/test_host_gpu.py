@@ -185,16 +185,16 @@ def test_default_sgs_iteration_gate(H, case):
 def test_blocks_sgs_iteration_gate(H, case):
     """The same gate for the z-blocks ordering (-s3d_sgs_ordering blocks: concurrent sweeps over blocks of planes with one plane of
     overlap, the one-device counterpart of the overlapping slabs): ASSERTED with two blocks on every solver the reference goldens
-    hold with SGS; the counts with four blocks are printed beside them."""
-    for nb in (2, 4):
+    hold with SGS; the counts with four blocks of planes and with 2 x 2 blocks of planes and rows are printed beside them."""
+    for nb, nby in ((2, 1), (4, 1), (2, 2)):
         for rec in [r for r in SOLVES["solves"] if r["case"] == case and r["pc"] == "sgs"]:
             m, P, A, b = _setup(H, rec)
             x = H.Vec(m)
-            got = H.solve(A, b, x, _opts(rec, **{"-s3d_sgs_ordering": "blocks", "-s3d_sgs_blocks": nb}))
+            got = H.solve(A, b, x, _opts(rec, **{"-s3d_sgs_ordering": "blocks", "-s3d_sgs_blocks": nb, "-s3d_sgs_blocks_y": nby}))
             ref_it, it, rel = rec["iters"], got["iters"], got["resnorm"] / rec["bnorm"]
-            print(f"[sgs-gate] {case:20s} {rec['ksp']:10s} reference {ref_it:4d}  {nb} z-blocks {it:4d}  ({100.0 * (it - ref_it) / ref_it:+.1f}%)  rel.res {rel:.3e}")
+            print(f"[sgs-gate] {case:20s} {rec['ksp']:10s} reference {ref_it:4d}  {nb} x {nby} blocks {it:4d}  ({100.0 * (it - ref_it) / ref_it:+.1f}%)  rel.res {rel:.3e}")
             assert got["converged"] and rel <= 1e-6
-            if nb == 2:
+            if nb == 2 and nby == 1:
                 assert it <= ref_it * 1.05 + 0.5, f"{rec['ksp']}: {it} iterations against the reference's {ref_it}: more than +5%"
         H.set_options({})
 

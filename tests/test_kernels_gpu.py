@@ -314,40 +314,42 @@ def test_sgs_dataflow_variants(ctx, npdim, variant, tile_i, pencils):
             ctx.free(p_)
 
 
-# z-blocks on one device (S3D_SGS_BLOCKS): concurrent sweeps over blocks of planes with one plane of overlap, through the layer tables
-# of the warp-per-tile kernel.  Bit-identical to the oracle's statement on top of the reference's sequential half-sweeps; ragged grids,
-# blocks of unequal thickness, layers that do not fill a tile, more blocks asked for than the grid allows (clamped to nz // 8).
-@pytest.mark.parametrize("npdim,nblocks", [((37, 22, 41), 3), ((19, 35, 18), 2), ((52, 27, 34), 4), ((20, 12, 74), 8), ((34, 34, 34), 16), ((67, 19, 27), 2)])
+# Blocks on one device (S3D_SGS_BLOCKS): concurrent sweeps over blocks of planes (and of rows) with one plane / row of overlap, through
+# the layer tables of the warp-per-tile kernel.  Bit-identical to the oracle's statement on top of the reference's sequential half-sweeps;
+# ragged grids, blocks of unequal thickness, layers that do not fill a tile, more blocks asked for than the grid allows (clamped).
+@pytest.mark.parametrize("npdim,nblocks,nblocks_y", [((37, 22, 41), 3, 1), ((19, 35, 18), 2, 2), ((52, 27, 34), 4, 3), ((20, 12, 74), 8, 1), ((34, 34, 34), 16, 16),
+                                                     ((67, 19, 27), 2, 1), ((23, 66, 12), 1, 4), ((40, 51, 47), 3, 5)])
 @pytest.mark.parametrize("tile_i,pencils", [(16, 2), (16, 1), (32, 2)])
-def test_sgs_blocks_on_one_device(ctx, npdim, nblocks, tile_i, pencils):
+def test_sgs_blocks_on_one_device(ctx, npdim, nblocks, nblocks_y, tile_i, pencils):
     m, A = problem(npdim, "chebyshev", "convdiff", V1, 0.1)
     g = grid_of(m)
     r = rand_vec(m, 44)
     di = cport.sgs_setup(m, A)
-    want = cport.sgs_blocks_apply(m, A, di, r, nblocks)
+    want = cport.sgs_blocks_apply(m, A, di, r, nblocks, nblocks_y)
     exact = cport.sgs_like_apply(m, A, di, r, 1)
     assert not np.array_equal(want, exact)
     dA, dr, dz, dy = ctx.mat_from(g, A), ctx.vec_from(g, r), ctx.vec_alloc(g), ctx.vec_alloc(g)
     dinv = ctx.scalars_alloc(int(g.cstride))
     try:
-        ctx.tune("sgs_variant", 0); ctx.tune("sgs_tile_i", tile_i); ctx.tune("sgs_pencils", pencils); ctx.tune("sgs_blocks", nblocks)
+        ctx.tune("sgs_variant", 0); ctx.tune("sgs_tile_i", tile_i); ctx.tune("sgs_pencils", pencils)
+        ctx.tune("sgs_blocks", nblocks); ctx.tune("sgs_blocks_y", nblocks_y)
         ctx.sgs_setup(g, dA, dinv)
         for rep in range(3):                                 # repeated: the mailboxes are clean after every sweep
             ctx.vecset(g, 3.0 + rep, dz)
             ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_BLOCKS, 1)
             z = ctx.vec_download(g, dz)
-            assert np.array_equal(z, want), f"{nblocks} blocks, application {rep}: max diff {np.abs(z - want).max()}"
+            assert np.array_equal(z, want), f"{nblocks} x {nblocks_y} blocks, application {rep}: max diff {np.abs(z - want).max()}"
             assert ghosts_untouched(z)
         # the exact sweep right after it, and the blocks again: the two tilings share mailboxes and dispatch state
         ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_LEXICOGRAPHIC, 1)
         assert np.array_equal(ctx.vec_download(g, dz), exact)
         ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_BLOCKS, 1)
         assert np.array_equal(ctx.vec_download(g, dz), want)
-        ctx.tune("sgs_blocks", 1)                            # one block IS the exact sweep
+        ctx.tune("sgs_blocks", 1); ctx.tune("sgs_blocks_y", 1)   # one block IS the exact sweep
         ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_BLOCKS, 1)
         assert np.array_equal(ctx.vec_download(g, dz), exact)
     finally:
-        ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT); ctx.tune("sgs_tile_i", 0); ctx.tune("sgs_pencils", 0); ctx.tune("sgs_blocks", 4)
+        ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT); ctx.tune("sgs_tile_i", 0); ctx.tune("sgs_pencils", 0); ctx.tune("sgs_blocks", 4); ctx.tune("sgs_blocks_y", 1)
         for p_ in (dA, dr, dz, dy, dinv):
             ctx.free(p_)
 

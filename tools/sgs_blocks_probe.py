@@ -18,18 +18,21 @@ for spec in sys.argv[1:] or ["64", "128", "256", "384", "512"]:
     ctx.vecset(g, 0.3, r)
     dinv = ctx.scalars_alloc(int(g.cstride)); ctx.sgs_setup(g, A, dinv)
     ctx.tune("sgs_variant", 0)
-    for pencils in (0, 2, 1):
+    for pencils in (2, 1):
         ctx.tune("sgs_pencils", pencils)
-        row = []
-        for nb in (1, 2, 4, 8, 16, 32):
-            if nb > 1 and nz // 8 < nb: continue
-            ctx.tune("sgs_blocks", nb)
-            order = capi.SGS_LEXICOGRAPHIC if nb == 1 else capi.SGS_BLOCKS
-            for _ in range(3): ctx.sgs_apply(g, A, dinv, r, z, y, order, 1)
-            ctx.sync(); ctx.timer_start()
-            for _ in range(10): ctx.sgs_apply(g, A, dinv, r, z, y, order, 1)
-            ms = ctx.timer_stop_ms() / 10
-            row.append(f"{nb}: {ms:.4f}")
-        print(f"{spec:>8s} pencils/lane={pencils or 'auto'}  ms per apply by blocks  " + "  ".join(row), flush=True)
-    ctx.tune("sgs_pencils", 0); ctx.tune("sgs_blocks", 4); ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT)
+        for nby in (1, 2, 4, 8):
+            if nby > 1 and ny // 8 < nby: continue
+            ctx.tune("sgs_blocks_y", nby)
+            row = []
+            for nb in (1, 2, 4, 8, 16):
+                if nb > 1 and nz // 8 < nb: continue
+                ctx.tune("sgs_blocks", nb)
+                order = capi.SGS_LEXICOGRAPHIC if nb == 1 and nby == 1 else capi.SGS_BLOCKS
+                for _ in range(3): ctx.sgs_apply(g, A, dinv, r, z, y, order, 1)
+                ctx.sync(); ctx.timer_start()
+                for _ in range(10): ctx.sgs_apply(g, A, dinv, r, z, y, order, 1)
+                ms = ctx.timer_stop_ms() / 10
+                row.append(f"{nb}: {ms:.4f}")
+            print(f"{spec:>8s} pencils/lane={pencils}  {nby} blocks of rows  ms per apply by blocks of planes  " + "  ".join(row), flush=True)
+    ctx.tune("sgs_pencils", 0); ctx.tune("sgs_blocks", 4); ctx.tune("sgs_blocks_y", 1); ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT)
     for p in (A, r, z, y, dinv): ctx.free(p)
