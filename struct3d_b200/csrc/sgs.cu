@@ -115,6 +115,7 @@ struct SgsFlow {
 	// layers[ck] = {first plane, planes, bit 0: a layer of the same block precedes it in sweep order | bit 1: one follows, plane whose
 	// results are NOT stored (the block's overlap plane: it belongs to the neighbouring block) or a negative number}; null: the plain tiling
 	const int4 *layers;
+	int dbuf;          // warp kernel: two staging areas -- the copies of the next tile are issued BEFORE the sweep of this one (throughput-bound grids)
 	const int4 *jlayers;   // the same along j (blocks of rows): rows of tile row cj = jlayers[cj] = {first row, rows, pred | succ << 1, row not stored}; null: plain
 };
 constexpr unsigned long long SGW_SENT = 0xFFF4A5C3D2E1B497ull;   // "not written yet": a signalling-NaN pattern no arithmetic produces
@@ -315,7 +316,11 @@ constexpr size_t SGS_SMEM = (5 * SGS_TILE + (SGS_TK + SGS_TJ) * SGS_TI + 2 * (SG
 //     window is flag-based).
 constexpr int SGW_PAD = 32;                // slack around the staged block: out-of-range steps read (and discard) it
 constexpr int SGW_TK = 8;
-constexpr size_t sgw_smem(int na, int ti, int p) { return (size_t)(3 * SGW_PAD + na * 32 * p * (ti + 2) + (8 + 4 * p) * (ti + 2)) * sizeof(double) + 16; }
+// db: a second staging area, so that the next tile's copies fly during the sweep of this one (SgsFlow::dbuf)
+constexpr size_t sgw_smem(int na, int ti, int p, int db = 0)
+{
+	return (size_t)(3 * SGW_PAD + na * 32 * p * (ti + 2) + (8 + 4 * p) * (ti + 2) + (db ? na * 32 * p * (ti + 2) + SGW_PAD : 0)) * sizeof(double) + 16;
+}
 
 __device__ __forceinline__ int ld_acquire(const int *p)
 {
@@ -367,6 +372,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 	double *s_a = smem + SGW_PAD;                             // [stream][row rho][R]
 	double *s_hj = s_a + NA * ASZ + SGW_PAD;                  // [c][R]  j-neighbour rows of the adjacent tile / ghost row
 	double *s_hk = s_hj + 8 * R;                              // [b][R]  k-neighbour rows of the adjacent tile / ghost plane
+	double *s_other = s_hk + TJ * R + SGW_PAD;                // f.dbuf: the second staging area (the two swap roles after every tile)
 
 	const int lane = threadIdx.x;
 	const int m = lane >> 3, cc = lane & 7;
@@ -378,7 +384,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 
 	// stage a tile's input rows: 16-byte cp.async, CH lanes per row.  Issued for the NEXT tile as soon as the flag of the current
 	// one is out, so the copies fly while the warp waits for the predecessors.
-	auto stage = [&](int t) {
+	auto stage = [&](int t, double *s_dst) {
 		const int ci = t % f.ntx, cj = (t / f.ntx) % f.nty, ck = t / (f.ntx * f.nty);
 		const int i0 = ci * TI;
 		int j0 = cj * TJ, tj = min(TJ, g.ny - j0);
@@ -395,7 +401,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 				const int pj = FWD ? rb : tj - 1 - rb, pk = FWD ? rc : tk - 1 - rc;
 				const long long cv = ctile + (long long)pk * g.cplane + (long long)pj * g.cpitch + 2 * i2;
 				const long long vv = vtile + (long long)pk * g.vplane + (long long)pj * g.vpitch + 2 * i2;
-				double *dst = s_a + sgw_row<P, FWD>(rb, rc) * R + 2 * i2;
+				double *dst = s_dst + sgw_row<P, FWD>(rb, rc) * R + 2 * i2;
 				cp_async16(dst, in0 + (ILU ? cv : vv));
 				cp_async16(dst + ASZ, c0 + cv);
 				cp_async16(dst + 2 * ASZ, c1 + cv);
@@ -407,7 +413,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 
 	int ticket = blockIdx.x;                                  // the first ticket is the warp's own number, later ones come from the counter
 	int tile = (ticket < ntiles) ? f.order[FWD ? ticket : ntiles - 1 - ticket] : -1;
-	if (tile >= 0) stage(tile);
+	if (tile >= 0) stage(tile, s_a);
 	while (tile >= 0) {
 		long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0;
 		if (f.prof) tp0 = clock64();
@@ -557,6 +563,11 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 			if (lane == 0) ntile = (nticket < ntiles) ? f.order[FWD ? nticket : ntiles - 1 - nticket] : -1;
 			cp_async_wait_all();
 			__syncwarp();
+			if (f.dbuf) {
+				// two staging areas: the next tile's copies start now and fly during this sweep, the publish and the copy-out
+				ntile = __shfl_sync(FULL, ntile, 0);
+				if (ntile >= 0) stage(ntile, s_other);
+			}
 			if (f.prof) { tp2 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(gt2)); }
 
 			// ---- the sweep: pencil 0 is at i-position u0 = h - s0 (li = u0 forward, ti-1-u0 backward), pencil 1 at u0 - 1
@@ -715,7 +726,8 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 			if (rb < tj - 1 && rc < tk - 1 && 2 * i2 < ti) copy_row_chunk(rb, rc, i2);
 		}
 		}
-		if (ntile >= 0) stage(ntile);
+		if (f.dbuf) { double *t_ = s_a; s_a = s_other; s_other = t_; }
+		else if (ntile >= 0) stage(ntile, s_a);
 		tile = ntile;
 	}
 }
@@ -1184,24 +1196,31 @@ inline int sgw_pencils(const s3d_ctx *ctx, const s3d_grid *g)
 	return ((long long)g->nx * g->ny * nzl >= (24ll << 20)) ? 1 : 2;
 }
 
-template <int MODE, typename... Args> void sgw_launch(s3d_ctx *ctx, const s3d_grid *g, unsigned nblocks, Args... args)
+// (the SgsFlow among the arguments says whether the launch uses the second staging area)
+template <int MODE, typename... Args> void sgw_launch_db(s3d_ctx *ctx, const s3d_grid *g, unsigned nblocks, int db, Args... args)
 {
 	constexpr int NA = (MODE == 2) ? 4 : 5;
 	const int ti = sgw_tile_i(ctx), p = sgw_pencils(ctx, g);
-	if (ti == 32 && p == 2) sgs_warpflow_kernel<MODE, 32, 2><<<nblocks, 32, sgw_smem(NA, 32, 2), ctx->stream>>>(args...);
-	else if (ti == 32) sgs_warpflow_kernel<MODE, 32, 1><<<nblocks, 32, sgw_smem(NA, 32, 1), ctx->stream>>>(args...);
-	else if (p == 2) sgs_warpflow_kernel<MODE, 16, 2><<<nblocks, 32, sgw_smem(NA, 16, 2), ctx->stream>>>(args...);
-	else sgs_warpflow_kernel<MODE, 16, 1><<<nblocks, 32, sgw_smem(NA, 16, 1), ctx->stream>>>(args...);
+	if (ti == 32 && p == 2) sgs_warpflow_kernel<MODE, 32, 2><<<nblocks, 32, sgw_smem(NA, 32, 2, db), ctx->stream>>>(args...);
+	else if (ti == 32) sgs_warpflow_kernel<MODE, 32, 1><<<nblocks, 32, sgw_smem(NA, 32, 1, db), ctx->stream>>>(args...);
+	else if (p == 2) sgs_warpflow_kernel<MODE, 16, 2><<<nblocks, 32, sgw_smem(NA, 16, 2, db), ctx->stream>>>(args...);
+	else sgs_warpflow_kernel<MODE, 16, 1><<<nblocks, 32, sgw_smem(NA, 16, 1, db), ctx->stream>>>(args...);
+}
+template <int MODE, typename A0, typename A1, typename A2, typename A3, typename A4, typename A5, typename A6>
+void sgw_launch(s3d_ctx *ctx, const s3d_grid *g, unsigned nblocks, GridDev gd, A0 a0, A1 a1, A2 a2, A3 a3, A4 a4, A5 a5, const SgsFlow &f, A6 a6)
+{
+	sgw_launch_db<MODE>(ctx, g, nblocks, f.dbuf, gd, a0, a1, a2, a3, a4, a5, f, a6);
 }
 
-template <int TI, int P> int sgw_configure()
+template <int TI, int P> int sgw_configure(int db)
 {
-	cudaFuncSetAttribute(sgs_warpflow_kernel<0, TI, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sgw_smem(5, TI, P));
-	cudaFuncSetAttribute(sgs_warpflow_kernel<1, TI, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sgw_smem(5, TI, P));
-	cudaFuncSetAttribute(sgs_warpflow_kernel<2, TI, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sgw_smem(4, TI, P));
+	// (the attribute is set for the larger, double-buffered size; it covers both)
+	cudaFuncSetAttribute(sgs_warpflow_kernel<0, TI, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sgw_smem(5, TI, P, 1));
+	cudaFuncSetAttribute(sgs_warpflow_kernel<1, TI, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sgw_smem(5, TI, P, 1));
+	cudaFuncSetAttribute(sgs_warpflow_kernel<2, TI, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sgw_smem(4, TI, P, 1));
 	int a = 1, b = 1;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sgs_warpflow_kernel<0, TI, P>, 32, sgw_smem(5, TI, P));
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sgs_warpflow_kernel<1, TI, P>, 32, sgw_smem(5, TI, P));
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sgs_warpflow_kernel<0, TI, P>, 32, sgw_smem(5, TI, P, db));
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sgs_warpflow_kernel<1, TI, P>, 32, sgw_smem(5, TI, P, db));
 	return std::max(1, std::min(a, b));
 }
 
@@ -1288,7 +1307,7 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 	}
 	f.flags = ctx->sgs_flags;
 	f.iface = ctx->sgs_iface;
-	f.mail = nullptr; f.mail_stride = 0; f.probe = 0; f.layers = nullptr; f.jlayers = nullptr;
+	f.mail = nullptr; f.mail_stride = 0; f.probe = 0; f.layers = nullptr; f.jlayers = nullptr; f.dbuf = 0;
 	f.x_in_plane = nullptr; f.x_in_flags = nullptr; f.x_out_plane = nullptr; f.x_out_flags = nullptr;
 	f.kzero_lo = 0; f.kzero_hi = 0;
 	f.order = ctx->sgs_order;
@@ -1343,14 +1362,18 @@ int sgs_flow_prepare(s3d_ctx *ctx, const s3d_grid *g, SgsFlow &f, unsigned &nblo
 			f.probe = ((long long)g->nx * g->ny * g->nz <= (2ll << 20)) ? 1 : 0;
 		}
 		static bool wconfigured = false;
-		static int warps_per_sm[4] = {1, 1, 1, 1};   // [tile_i == 32][pencils == 2]
+		static int warps_per_sm[2][4] = {{1, 1, 1, 1}, {1, 1, 1, 1}};   // [second staging area][tile_i == 32][pencils == 2]
 		if (!wconfigured) {
-			warps_per_sm[0] = sgw_configure<16, 1>(); warps_per_sm[1] = sgw_configure<16, 2>();
-			warps_per_sm[2] = sgw_configure<32, 1>(); warps_per_sm[3] = sgw_configure<32, 2>();
+			for (int db = 0; db < 2; db++) {
+				warps_per_sm[db][0] = sgw_configure<16, 1>(db); warps_per_sm[db][1] = sgw_configure<16, 2>(db);
+				warps_per_sm[db][2] = sgw_configure<32, 1>(db); warps_per_sm[db][3] = sgw_configure<32, 2>(db);
+			}
 			S3D_CUDA(ctx, cudaGetLastError());
 			wconfigured = true;
 		}
-		int wps = warps_per_sm[(sgw_tile_i(ctx) == 32 ? 2 : 0) + (sgw_pencils(ctx, g) == 2 ? 1 : 0)];
+		// second staging area (tuning key sgs_dbuf: 1 on, 0 off, -1 by size): pays where the sweep is bound by tiles in flight, not by its chain
+		f.dbuf = (ctx->sgs_dbuf == 1 || (ctx->sgs_dbuf < 0 && (long long)g->nx * g->ny * g->nz >= ctx->sgs_dbuf_min_points)) ? 1 : 0;
+		int wps = warps_per_sm[f.dbuf][(sgw_tile_i(ctx) == 32 ? 2 : 0) + (sgw_pencils(ctx, g) == 2 ? 1 : 0)];
 		if (ctx->sgs_warps_per_sm > 0) wps = std::min(wps, ctx->sgs_warps_per_sm);
 		if (wps < 1) wps = 1;
 		nblocks = (unsigned)std::min<size_t>(ntiles, (size_t)ctx->sm_count * wps);

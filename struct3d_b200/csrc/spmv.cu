@@ -371,6 +371,7 @@ int s3d_tune_set(s3d_ctx *ctx, const char *key, int value)
 	else if (!strcmp(key, "sgs_async_chunk")) ctx->sgs_async_chunk = value;
 	else if (!strcmp(key, "sgs_tile_mail")) ctx->sgs_tile_mail = value;
 	else if (!strcmp(key, "sgs_blocks")) ctx->sgs_blocks = value;
+	else if (!strcmp(key, "sgs_dbuf")) ctx->sgs_dbuf = value;
 	else if (!strcmp(key, "sgs_blocks_y")) ctx->sgs_blocks_y = value;
 	else if (!strcmp(key, "small_team")) ctx->small_team = value;
 	else if (!strcmp(key, "ew_unroll")) s3d_internal_set_ew_unroll(value);

@@ -314,6 +314,41 @@ def test_sgs_dataflow_variants(ctx, npdim, variant, tile_i, pencils):
             ctx.free(p_)
 
 
+# The warp-per-tile kernel with TWO staging areas (tuning key sgs_dbuf: the next tile's copies are issued before this tile's sweep):
+# same results bit for bit, for the exact sweep, the blocks ordering and the StrILU build.
+@pytest.mark.parametrize("npdim", [(18, 18, 18), (50, 23, 14), (131, 9, 6), (21, 38, 27), (3, 3, 3)])
+@pytest.mark.parametrize("tile_i,pencils", [(16, 1), (16, 2), (32, 1), (32, 2)])
+def test_sgs_double_buffered_staging(ctx, npdim, tile_i, pencils):
+    m, A = problem(npdim, "chebyshev", "convdiff", V1, 0.1)
+    g = grid_of(m)
+    r = rand_vec(m, 45)
+    di = cport.sgs_setup(m, A)
+    exact = cport.sgs_like_apply(m, A, di, r, 1)
+    blocks = cport.sgs_blocks_apply(m, A, di, r, 2, 2)
+    dA, dr, dz, dy = ctx.mat_from(g, A), ctx.vec_from(g, r), ctx.vec_alloc(g), ctx.vec_alloc(g)
+    dinv = ctx.scalars_alloc(int(g.cstride))
+    try:
+        ctx.tune("sgs_variant", 0); ctx.tune("sgs_tile_i", tile_i); ctx.tune("sgs_pencils", pencils); ctx.tune("sgs_dbuf", 1)
+        ctx.tune("sgs_blocks", 2); ctx.tune("sgs_blocks_y", 2)
+        ctx.sgs_setup(g, dA, dinv)
+        for rep in range(2):
+            ctx.vecset(g, 1.0 + rep, dz)
+            ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_LEXICOGRAPHIC, 1)
+            z = ctx.vec_download(g, dz)
+            assert np.array_equal(z, exact), f"exact sweep, two staging areas, application {rep}: max diff {np.abs(z - exact).max()}"
+            assert ghosts_untouched(z)
+            ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_BLOCKS, 1)
+            assert np.array_equal(ctx.vec_download(g, dz), blocks), f"blocks, two staging areas, application {rep}"
+        ctx.strilu_setup(g, dA, 1, dinv)
+        ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_LEXICOGRAPHIC, 1)
+        assert np.array_equal(ctx.vec_download(g, dz), cport.sgs_like_apply(m, A, cport.strilu_setup(m, A, 1), r, 1)), "StrILU build, two staging areas"
+    finally:
+        ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT); ctx.tune("sgs_tile_i", 0); ctx.tune("sgs_pencils", 0); ctx.tune("sgs_dbuf", 0)
+        ctx.tune("sgs_blocks", 4); ctx.tune("sgs_blocks_y", 1)
+        for p_ in (dA, dr, dz, dy, dinv):
+            ctx.free(p_)
+
+
 # Blocks on one device (S3D_SGS_BLOCKS): concurrent sweeps over blocks of planes (and of rows) with one plane / row of overlap, through
 # the layer tables of the warp-per-tile kernel.  Bit-identical to the oracle's statement on top of the reference's sequential half-sweeps;
 # ragged grids, blocks of unequal thickness, layers that do not fill a tile, more blocks asked for than the grid allows (clamped).

@@ -34,5 +34,22 @@ for spec in sys.argv[1:] or ["64", "128", "256", "384", "512"]:
                 ms = ctx.timer_stop_ms() / 10
                 row.append(f"{nb}: {ms:.4f}")
             print(f"{spec:>8s} pencils/lane={pencils}  {nby} blocks of rows  ms per apply by blocks of planes  " + "  ".join(row), flush=True)
+    # two staging areas (sgs_dbuf): exact sweep and a few block shapes
+    for pencils in (2, 1):
+        ctx.tune("sgs_pencils", pencils)
+        row = []
+        for db in (0, 1):
+            ctx.tune("sgs_dbuf", db)
+            for nb, nby in ((1, 1), (8, 1), (8, 4)):
+                if nz // 8 < nb or ny // 8 < nby: continue
+                ctx.tune("sgs_blocks", nb); ctx.tune("sgs_blocks_y", nby)
+                order = capi.SGS_LEXICOGRAPHIC if nb == 1 and nby == 1 else capi.SGS_BLOCKS
+                for _ in range(3): ctx.sgs_apply(g, A, dinv, r, z, y, order, 1)
+                ctx.sync(); ctx.timer_start()
+                for _ in range(10): ctx.sgs_apply(g, A, dinv, r, z, y, order, 1)
+                ms = ctx.timer_stop_ms() / 10
+                row.append(f"dbuf={db} {nb}x{nby}: {ms:.4f}")
+        print(f"{spec:>8s} pencils/lane={pencils}  staging areas  " + "  ".join(row), flush=True)
+    ctx.tune("sgs_dbuf", 0)
     ctx.tune("sgs_pencils", 0); ctx.tune("sgs_blocks", 4); ctx.tune("sgs_blocks_y", 1); ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT)
     for p in (A, r, z, y, dinv): ctx.free(p)
