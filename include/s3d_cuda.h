@@ -230,12 +230,13 @@ int  s3d_strilu_setup_async(s3d_ctx *ctx, const s3d_grid *g, const double *A, in
                                   * exchange of r per application, and iteration counts within a few per cent of the exact sweep over the whole
                                   * grid.  Needs the slack planes of s3d_mat_alloc / s3d_coef_alloc and s3d_sgs_overlap_setup; one rank: LEXICOGRAPHIC.
                                   * The call fills the ghost planes of d_r (halo exchange) and leaves intermediate values in those of d_z / d_y. */
-#define S3D_SGS_BLOCKS        7  /* ONE device: the grid cut into z-blocks (tuning key sgs_blocks, default 4; at least 8 planes each) that sweep
-                                  * CONCURRENTLY -- forward, each block is preceded by one plane of the block below (zero inflow under it); backward, by
-                                  * one plane of the block above, whose forward values the block above has stored by then.  The dependency chain
-                                  * of a sweep, which bounds the exact sweep up to ~256^3, shrinks from nx/16 + ny/8 + nz/8 tile hops to
-                                  * nx/16 + ny/8 + nz/(8 blocks) + 1.  Another operator than the reference's sweep: deterministic, iteration counts
-                                  * within a few per cent of it (north_star's gate for a parallel SGS); opt-in, LEXICOGRAPHIC stays the default. */
+#define S3D_SGS_BLOCKS        7  /* ONE device: the grid cut into blocks of planes and of rows (tuning keys sgs_blocks, sgs_blocks_y; 0 = by size, about 32
+                                  * planes / rows each, none above 96 Mi points) that sweep CONCURRENTLY -- forward, each block is preceded by one plane
+                                  * and one row of the blocks below it (zero inflow under them); backward, by one plane and row of the blocks above, whose
+                                  * forward values their owners have stored by then.  The dependency chain of a sweep, which bounds the exact sweep up to
+                                  * ~256^3, shrinks from nx/16 + ny/8 + nz/8 tile hops to about nx/16 + ny/(4 By) + nz/(8 Bz) + 2 (256^3: 0.79 -> 0.43 ms per
+                                  * application).  Another operator than the reference's sweep: deterministic, iteration counts within a few per cent
+                                  * of it (north_star's gate for a parallel SGS); opt-in, LEXICOGRAPHIC stays the default. */
 /* Once per operator, after s3d_sgs_setup / s3d_strilu_setup, for S3D_SGS_OVERLAP: the neighbouring slabs' boundary planes of the seven
  * coefficient arrays and of dinv go into the slack planes (grouped ncclSend / ncclRecv).  Collective; a no-op on one rank. */
 int  s3d_sgs_overlap_setup(s3d_ctx *ctx, const s3d_grid *g, double *A, double *d_dinv);

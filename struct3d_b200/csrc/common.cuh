@@ -74,8 +74,8 @@ struct s3d_ctx {
 	int sgs_pencils = 0;        // warp kernel: (j,k) pencils per lane, 1 (tile TI x 4 x 8) or 2 (tile TI x 8 x 8); 0: by grid size
 	int sgs_dbuf = 0;           // warp kernel: second staging area (1 on, 0 off, -1: from sgs_dbuf_min_points points on)
 	long long sgs_dbuf_min_points = 1ll << 62;
-	int sgs_blocks = 4;         // S3D_SGS_BLOCKS: z-blocks the grid is cut into on one device (tuning key sgs_blocks, host option -s3d_sgs_blocks)
-	int sgs_blocks_y = 1;       // ... and blocks of rows (tuning key sgs_blocks_y, host option -s3d_sgs_blocks_y)
+	int sgs_blocks = 0;         // S3D_SGS_BLOCKS: blocks of planes the grid is cut into on one device (tuning key sgs_blocks, host option -s3d_sgs_blocks; 0: by size)
+	int sgs_blocks_y = 0;       // ... and blocks of rows (tuning key sgs_blocks_y, host option -s3d_sgs_blocks_y; 0: by size)
 	struct SgsBlocks { int key[7] = {0, 0, 0, 0, 0, 0, 0}; int *order[2] = {nullptr, nullptr}; int4 *layers[2] = {nullptr, nullptr}; int ntz[2] = {0, 0}, nty[2] = {0, 0}; } sgsblocks;
 	int *sgs_order = nullptr;     // tile dispatch order (hyperplane-sorted), cached per tile-grid shape
 	int sgs_order_dims[3] = {0, 0, 0};

@@ -1643,8 +1643,14 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		// nx/TI + ny/(TJ By) + nz/(8 Bz) + 2, which is what bounds the exact sweep up to ~256^3; another operator than the reference's
 		// sweep (iteration counts within a few per cent, like OVERLAP).
 		S3D_REQUIRE(ctx, g->nranks == 1, "S3D_SGS_BLOCKS is a one-device ordering (z-slabs: S3D_SGS_OVERLAP)");
-		const int tile_i = sgw_tile_i(ctx), tile_j = 4 * sgw_pencils(ctx, g);
-		const int Bz = std::max(1, std::min(ctx->sgs_blocks, g->nz / SGS_TK)), By = std::max(1, std::min(ctx->sgs_blocks_y, g->ny / 8));
+		// blocks asked for, or (0) chosen by size: about 32 planes / rows per block (measured, profiles/r2_sgs_blocks.md: 256^3 0.79 -> 0.43 ms,
+		// 128^3 0.35 -> 0.15, 64^3 0.157 -> 0.105); none above 96 Mi points, where the sweep is bound by tiles in flight and blocks only add work
+		const long long npts = (long long)g->nx * g->ny * g->nz;
+		const int Bz_ask = ctx->sgs_blocks > 0 ? ctx->sgs_blocks : npts > (96ll << 20) ? 1 : std::min(g->nz / 32, 16);
+		const int By_ask = ctx->sgs_blocks_y > 0 ? ctx->sgs_blocks_y : npts > (96ll << 20) ? 1 : std::min(g->ny / 32, 8);
+		const int Bz = std::max(1, std::min(Bz_ask, g->nz / SGS_TK)), By = std::max(1, std::min(By_ask, g->ny / 8));
+		// one pencil per lane (tiles of 4 rows, twice as many in flight) once rows are cut into blocks: measured faster there at every size
+		const int tile_i = sgw_tile_i(ctx), tile_j = 4 * ((ctx->sgs_pencils == 1 || ctx->sgs_pencils == 2) ? ctx->sgs_pencils : By >= 2 ? 1 : sgw_pencils(ctx, g));
 		if ((Bz == 1 && By == 1) || !ctx->sgs_tile_mail) ordering = S3D_SGS_LEXICOGRAPHIC;
 		else {
 			const int rcb = sgs_blocks_prepare(ctx, g, Bz, By, tile_i, tile_j);

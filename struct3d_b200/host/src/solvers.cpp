@@ -330,12 +330,12 @@ SGS_like_preconditioner::SGS_like_preconditioner(const SMat &lhs, const PreconPa
 	// to warps that never wait for one another), but is opt-in: the default stays the deterministic exact sweep, which needs the fewest
 	// iterations and gives the same result on every run.  Asked for through the reference's own switches, say so once.
 	if (order == S3D_SGS_ASYNC) d.check(s3d_tune_set(d.ctx(), "sgs_async_chunk", std::max(1, parms.thread_chunk_size)), "s3d_tune_set");
-	// z-blocks on one device (-s3d_sgs_ordering blocks): concurrent sweeps over -s3d_sgs_blocks blocks of planes (default 4) x -s3d_sgs_blocks_y blocks of rows (default 1) with one plane / row of
+	// z-blocks on one device (-s3d_sgs_ordering blocks): concurrent sweeps over -s3d_sgs_blocks blocks of planes x -s3d_sgs_blocks_y blocks of rows (default 0 = by size: about 32 planes / rows each) with one plane / row of
 	// overlap; opt-in -- another operator than the reference's sweep, within a few per cent of its iteration counts.  On z-slabs the ranks ARE the blocks.
 	if (order == S3D_SGS_BLOCKS && d.nranks() > 1) order = S3D_SGS_OVERLAP;
 	if (order == S3D_SGS_BLOCKS) {
-		d.check(s3d_tune_set(d.ctx(), "sgs_blocks", s3d::options_has("-s3d_sgs_blocks") ? std::max(1, petscoptions_get_int("-s3d_sgs_blocks")) : 4), "s3d_tune_set");
-		d.check(s3d_tune_set(d.ctx(), "sgs_blocks_y", s3d::options_has("-s3d_sgs_blocks_y") ? std::max(1, petscoptions_get_int("-s3d_sgs_blocks_y")) : 1), "s3d_tune_set");
+		d.check(s3d_tune_set(d.ctx(), "sgs_blocks", s3d::options_has("-s3d_sgs_blocks") ? std::max(0, petscoptions_get_int("-s3d_sgs_blocks")) : 0), "s3d_tune_set");
+		d.check(s3d_tune_set(d.ctx(), "sgs_blocks_y", s3d::options_has("-s3d_sgs_blocks_y") ? std::max(0, petscoptions_get_int("-s3d_sgs_blocks_y")) : 0), "s3d_tune_set");
 	}
 	static bool warned = false;
 	const bool asked = order != S3D_SGS_ASYNC && ((s3d::options_has("-s3d_pc_use_threaded_apply") && parms.threadedapply) || (s3d::options_has("-s3d_pc_use_threaded_build") && parms.threadedbuild));

@@ -344,7 +344,7 @@ def test_sgs_double_buffered_staging(ctx, npdim, tile_i, pencils):
         assert np.array_equal(ctx.vec_download(g, dz), cport.sgs_like_apply(m, A, cport.strilu_setup(m, A, 1), r, 1)), "StrILU build, two staging areas"
     finally:
         ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT); ctx.tune("sgs_tile_i", 0); ctx.tune("sgs_pencils", 0); ctx.tune("sgs_dbuf", 0)
-        ctx.tune("sgs_blocks", 4); ctx.tune("sgs_blocks_y", 1)
+        ctx.tune("sgs_blocks", 0); ctx.tune("sgs_blocks_y", 0)
         for p_ in (dA, dr, dz, dy, dinv):
             ctx.free(p_)
 
@@ -384,7 +384,7 @@ def test_sgs_blocks_on_one_device(ctx, npdim, nblocks, nblocks_y, tile_i, pencil
         ctx.sgs_apply(g, dA, dinv, dr, dz, dy, capi.SGS_BLOCKS, 1)
         assert np.array_equal(ctx.vec_download(g, dz), exact)
     finally:
-        ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT); ctx.tune("sgs_tile_i", 0); ctx.tune("sgs_pencils", 0); ctx.tune("sgs_blocks", 4); ctx.tune("sgs_blocks_y", 1)
+        ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT); ctx.tune("sgs_tile_i", 0); ctx.tune("sgs_pencils", 0); ctx.tune("sgs_blocks", 0); ctx.tune("sgs_blocks_y", 0)
         for p_ in (dA, dr, dz, dy, dinv):
             ctx.free(p_)
 

@@ -51,5 +51,5 @@ for spec in sys.argv[1:] or ["64", "128", "256", "384", "512"]:
                 row.append(f"dbuf={db} {nb}x{nby}: {ms:.4f}")
         print(f"{spec:>8s} pencils/lane={pencils}  staging areas  " + "  ".join(row), flush=True)
     ctx.tune("sgs_dbuf", 0)
-    ctx.tune("sgs_pencils", 0); ctx.tune("sgs_blocks", 4); ctx.tune("sgs_blocks_y", 1); ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT)
+    ctx.tune("sgs_pencils", 0); ctx.tune("sgs_blocks", 0); ctx.tune("sgs_blocks_y", 0); ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT)
     for p in (A, r, z, y, dinv): ctx.free(p)
