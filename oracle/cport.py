@@ -216,10 +216,18 @@ def slab_bounds(nz, nslabs):
     return [(p * nz // nslabs, (p + 1) * nz // nslabs) for p in range(nslabs)]
 
 
-def sgs_overlap_apply(mesh, A, diaginv, r, nslabs, overlap=1):
+def blocks_by_size(nx, ny, nz):
+    """the library's default block counts (sgs.cu, sgs_blocks_run): about 32 planes / rows per block, none above 96 Mi points"""
+    if nx * ny * nz > (96 << 20):
+        return 1, 1
+    return max(1, min(nz // 32, 16)), max(1, min(ny // 32, 8))
+
+
+def sgs_overlap_apply(mesh, A, diaginv, r, nslabs, overlap=1, blocks=(1, 1)):
     """The overlapping z-slab ordering (S3D_SGS_OVERLAP; no counterpart in the reference, stated ON TOP of its sequential sweep,
     s3d_sgspreconditioners.cpp:53-110): the sequential SGS-like application over every slab extended by `overlap` planes of either
-    neighbour (zero inflow beyond them), own planes kept.  overlap = 0 is the slab-local ordering; one slab is the sequential sweep."""
+    neighbour (zero inflow beyond them), own planes kept.  overlap = 0 is the slab-local ordering; one slab is the sequential sweep.
+    blocks = (planes, rows): every extended slab is cut further into concurrent blocks (sgs_blocks_apply); None: as the library chooses by size."""
     nx, ny, nz = mesh.n
     z = mesh.zeros()
     for (k0, k1) in slab_bounds(nz, nslabs):
@@ -227,7 +235,8 @@ def sgs_overlap_apply(mesh, A, diaginv, r, nslabs, overlap=1):
         sm = Mesh((nx + 2, ny + 2, e1 - e0 + 2))            # only its dimensions matter to the sweep
         rs = sm.zeros()
         rs[1:-1] = r[1 + e0:1 + e1]
-        zs = sgs_like_apply(sm, np.ascontiguousarray(A[:, e0:e1]), np.ascontiguousarray(diaginv[e0:e1]), rs, 1)
+        bz, by = blocks_by_size(nx, ny, e1 - e0) if blocks is None else blocks
+        zs = sgs_blocks_apply(sm, np.ascontiguousarray(A[:, e0:e1]), np.ascontiguousarray(diaginv[e0:e1]), rs, bz, by)
         z[1 + k0:1 + k1] = zs[1 + (k0 - e0):1 + (k1 - e0)]
     return z
 

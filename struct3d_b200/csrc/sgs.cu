@@ -1494,6 +1494,57 @@ int sgs_blocks_prepare(s3d_ctx *ctx, const s3d_grid *g, int Bz, int By, int tile
 	memcpy(t.key, key, sizeof key);
 	return S3D_OK;
 }
+
+// The blocks ordering over grid `g` (one device's grid, or a rank's slab extended by its overlap planes; `gd` its device view, the array
+// pointers shifted to match): the grid is cut into blocks of planes (and of rows) that sweep concurrently, each forward sweep preceded by
+// one plane (row) of the block below, each backward sweep by one of the block above (sgs_blocks_prepare).  The dependency chain of a
+// sweep shrinks from nx/TI + ny/TJ + nz/8 tile hops to about nx/TI + ny/(TJ By) + nz/(8 Bz) + 2, which is what bounds the exact sweep up
+// to ~256^3; another operator than the reference's sweep (iteration counts within a few per cent).  *ran = false: one block (or no
+// mailboxes) -- the caller runs the plain sweep.
+int sgs_blocks_run(s3d_ctx *ctx, const s3d_grid *g, const GridDev &gd, const double *A, const double *d_dinv, const double *d_r, double *d_y,
+                   double *d_z, bool *ran)
+{
+	*ran = false;
+	// blocks asked for, or (0) chosen by size: about 32 planes / rows per block (measured, profiles/r2_sgs_blocks.md: 256^3 0.72 -> 0.43 ms,
+	// 128^3 0.32 -> 0.15, 64^3 0.143 -> 0.105); none above 96 Mi points, where the sweep is bound by tiles in flight and blocks only add work
+	const long long npts = (long long)g->nx * g->ny * g->nz;
+	const int Bz_ask = ctx->sgs_blocks > 0 ? ctx->sgs_blocks : npts > (96ll << 20) ? 1 : std::min(g->nz / 32, 16);
+	const int By_ask = ctx->sgs_blocks_y > 0 ? ctx->sgs_blocks_y : npts > (96ll << 20) ? 1 : std::min(g->ny / 32, 8);
+	const int Bz = std::max(1, std::min(Bz_ask, g->nz / SGS_TK)), By = std::max(1, std::min(By_ask, g->ny / 8));
+	if ((Bz == 1 && By == 1) || !ctx->sgs_tile_mail) return S3D_OK;
+	// one pencil per lane (tiles of 4 rows, twice as many in flight) once rows are cut into blocks: measured faster there at every size
+	const int tile_i = sgw_tile_i(ctx), tile_j = 4 * ((ctx->sgs_pencils == 1 || ctx->sgs_pencils == 2) ? ctx->sgs_pencils : By >= 2 ? 1 : sgw_pencils(ctx, g));
+	const int rcb = sgs_blocks_prepare(ctx, g, Bz, By, tile_i, tile_j);
+	if (rcb != S3D_OK) return rcb;
+	const s3d_ctx::SgsBlocks &t = ctx->sgsblocks;
+	s3d_grid gx = *g;                                // sizes the mailboxes / the launch for the larger of the two tilings
+	gx.nz = SGS_TK * std::max(t.ntz[0], t.ntz[1]);
+	gx.ny = tile_j * std::max(t.nty[0], t.nty[1]);
+	const int pencils_asked = ctx->sgs_pencils;
+	ctx->sgs_pencils = tile_j / 4;                   // the tile shape is chosen by size: g's choice holds for gx too
+	SgsFlow f;
+	unsigned nblocks = 0;
+	const int rcp = sgs_flow_prepare(ctx, &gx, f, nblocks, 0);
+	if (rcp != S3D_OK) { ctx->sgs_pencils = pencils_asked; return rcp; }
+	if (!f.mail || (size_t)std::max(t.ntz[0], t.ntz[1]) * std::max(t.nty[0], t.nty[1]) * f.ntx * f.mail_stride > ctx->sgs_mail_cap) {
+		ctx->sgs_pencils = pencils_asked;
+		return s3d_fail(ctx, S3D_ERR_STATE, "S3D_SGS_BLOCKS: mailbox set-up does not match the block tiling");
+	}
+	const long long cs = g->cstride;
+	for (int dir = 0; dir < 2; dir++) {
+		f.ntz = t.ntz[dir]; f.nty = t.nty[dir]; f.order = t.order[dir]; f.layers = t.layers[dir]; f.jlayers = t.layers[dir] + t.ntz[dir];
+		const unsigned nb = (unsigned)std::min<size_t>((size_t)f.ntx * f.nty * f.ntz, (size_t)nblocks);
+		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
+		ctx->launches++;
+		if (dir == 0) sgw_launch<0>(ctx, &gx, nb, gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, (const int *)ctx->gate);
+		else sgw_launch<1>(ctx, &gx, nb, gd, (const double *)d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f, (const int *)ctx->gate);
+		ctx->launches++;
+	}
+	ctx->sgs_pencils = pencils_asked;
+	S3D_CUDA(ctx, cudaGetLastError());
+	*ran = true;
+	return S3D_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -1637,51 +1688,12 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 	}
 	if (ordering == S3D_SGS_ASYNC) return s3d_internal_sgs_async(ctx, g, A, d_dinv, d_r, d_z, d_y, nsweeps);
 	if (ordering == S3D_SGS_BLOCKS) {
-		// Blocks on ONE device: the grid is cut into `sgs_blocks` blocks of planes (and `sgs_blocks_y` blocks of rows) that sweep concurrently,
-		// each forward sweep preceded by one plane (row) of the block below, each backward sweep by one of the block above (see
-		// sgs_blocks_prepare).  The dependency chain of a sweep shrinks from nx/TI + ny/TJ + nz/8 tile hops to about
-		// nx/TI + ny/(TJ By) + nz/(8 Bz) + 2, which is what bounds the exact sweep up to ~256^3; another operator than the reference's
-		// sweep (iteration counts within a few per cent, like OVERLAP).
+		// Blocks on ONE device (sgs_blocks_run); across z-slabs the ranks are the blocks of planes: S3D_SGS_OVERLAP, which cuts every slab further
 		S3D_REQUIRE(ctx, g->nranks == 1, "S3D_SGS_BLOCKS is a one-device ordering (z-slabs: S3D_SGS_OVERLAP)");
-		// blocks asked for, or (0) chosen by size: about 32 planes / rows per block (measured, profiles/r2_sgs_blocks.md: 256^3 0.79 -> 0.43 ms,
-		// 128^3 0.35 -> 0.15, 64^3 0.157 -> 0.105); none above 96 Mi points, where the sweep is bound by tiles in flight and blocks only add work
-		const long long npts = (long long)g->nx * g->ny * g->nz;
-		const int Bz_ask = ctx->sgs_blocks > 0 ? ctx->sgs_blocks : npts > (96ll << 20) ? 1 : std::min(g->nz / 32, 16);
-		const int By_ask = ctx->sgs_blocks_y > 0 ? ctx->sgs_blocks_y : npts > (96ll << 20) ? 1 : std::min(g->ny / 32, 8);
-		const int Bz = std::max(1, std::min(Bz_ask, g->nz / SGS_TK)), By = std::max(1, std::min(By_ask, g->ny / 8));
-		// one pencil per lane (tiles of 4 rows, twice as many in flight) once rows are cut into blocks: measured faster there at every size
-		const int tile_i = sgw_tile_i(ctx), tile_j = 4 * ((ctx->sgs_pencils == 1 || ctx->sgs_pencils == 2) ? ctx->sgs_pencils : By >= 2 ? 1 : sgw_pencils(ctx, g));
-		if ((Bz == 1 && By == 1) || !ctx->sgs_tile_mail) ordering = S3D_SGS_LEXICOGRAPHIC;
-		else {
-			const int rcb = sgs_blocks_prepare(ctx, g, Bz, By, tile_i, tile_j);
-			if (rcb != S3D_OK) return rcb;
-			const s3d_ctx::SgsBlocks &t = ctx->sgsblocks;
-			s3d_grid gx = *g;                                // sizes the mailboxes / the launch for the larger of the two tilings
-			gx.nz = SGS_TK * std::max(t.ntz[0], t.ntz[1]);
-			gx.ny = tile_j * std::max(t.nty[0], t.nty[1]);
-			const int pencils_asked = ctx->sgs_pencils;
-			ctx->sgs_pencils = tile_j / 4;                   // the tile shape is chosen by size: g's choice holds for gx too
-			SgsFlow f;
-			unsigned nblocks = 0;
-			const int rcp = sgs_flow_prepare(ctx, &gx, f, nblocks, 0);
-			if (rcp != S3D_OK) { ctx->sgs_pencils = pencils_asked; return rcp; }
-			if (!f.mail || (size_t)std::max(t.ntz[0], t.ntz[1]) * std::max(t.nty[0], t.nty[1]) * f.ntx * f.mail_stride > ctx->sgs_mail_cap) {
-				ctx->sgs_pencils = pencils_asked;
-				return s3d_fail(ctx, S3D_ERR_STATE, "S3D_SGS_BLOCKS: mailbox set-up does not match the block tiling");
-			}
-			const long long cs = g->cstride;
-			for (int dir = 0; dir < 2; dir++) {
-				f.ntz = t.ntz[dir]; f.nty = t.nty[dir]; f.order = t.order[dir]; f.layers = t.layers[dir]; f.jlayers = t.layers[dir] + t.ntz[dir];
-				const unsigned nb = (unsigned)std::min<size_t>((size_t)f.ntx * f.nty * f.ntz, (size_t)nblocks);
-				sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
-				S3D_LAUNCHED(ctx);
-				if (dir == 0) sgw_launch<0>(ctx, &gx, nb, gd, d_r, A, A + cs, A + 2 * cs, d_dinv, d_y, f, (const int *)ctx->gate);
-				else sgw_launch<1>(ctx, &gx, nb, gd, (const double *)d_y, A + 4 * cs, A + 5 * cs, A + 6 * cs, d_dinv, d_z, f, (const int *)ctx->gate);
-				S3D_LAUNCHED(ctx);
-			}
-			ctx->sgs_pencils = pencils_asked;
-			return S3D_OK;
-		}
+		bool ran = false;
+		const int rcb = sgs_blocks_run(ctx, g, gd, A, d_dinv, d_r, d_y, d_z, &ran);
+		if (rcb != S3D_OK || ran) return rcb;
+		ordering = S3D_SGS_LEXICOGRAPHIC;
 	}
 	if (ordering == S3D_SGS_OVERLAP && g->nranks == 1) ordering = S3D_SGS_LEXICOGRAPHIC;
 	if (ordering == S3D_SGS_OVERLAP) {
@@ -1704,13 +1716,20 @@ int s3d_sgs_apply(s3d_ctx *ctx, const s3d_grid *g, const double *A, const double
 		gx.nz = g->nz + lo + hi;
 		gx.voff = g->voff - lo * g->vplane;
 		const GridDev gdx = to_dev(&gx);
+		const long long cs = g->cstride;
+		const double *Ax = A - lo * g->cplane, *dx = d_dinv - lo * g->cplane;
+		{
+			// the extended slab is cut further into concurrent blocks of planes and rows where that pays (by size, or as the tuning keys say;
+			// sgs_blocks = sgs_blocks_y = 1: one sweep per slab): the chain of a slab's sweep is what bounds it up to ~256^3 points per rank
+			bool ran = false;
+			const int rcb = sgs_blocks_run(ctx, &gx, gdx, Ax, dx, d_r, d_y, d_z, &ran);
+			if (rcb != S3D_OK || ran) return rcb;
+		}
 		SgsFlow f;
 		unsigned nblocks = 0;
 		const int rcp = sgs_flow_prepare(ctx, &gx, f, nblocks, 0);
 		if (rcp != S3D_OK) return rcp;
 		f.kzero_lo = lo; f.kzero_hi = hi;
-		const long long cs = g->cstride;
-		const double *Ax = A - lo * g->cplane, *dx = d_dinv - lo * g->cplane;
 		sgs_begin_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sgs_ctl, ctx->gate);
 		S3D_LAUNCHED(ctx);
 		sgw_launch<0>(ctx, &gx, nblocks, gdx, d_r, Ax, Ax + cs, Ax + 2 * cs, dx, d_y, f, (const int *)ctx->gate);

@@ -333,7 +333,7 @@ SGS_like_preconditioner::SGS_like_preconditioner(const SMat &lhs, const PreconPa
 	// z-blocks on one device (-s3d_sgs_ordering blocks): concurrent sweeps over -s3d_sgs_blocks blocks of planes x -s3d_sgs_blocks_y blocks of rows (default 0 = by size: about 32 planes / rows each) with one plane / row of
 	// overlap; opt-in -- another operator than the reference's sweep, within a few per cent of its iteration counts.  On z-slabs the ranks ARE the blocks.
 	if (order == S3D_SGS_BLOCKS && d.nranks() > 1) order = S3D_SGS_OVERLAP;
-	if (order == S3D_SGS_BLOCKS) {
+	if (order == S3D_SGS_BLOCKS || order == S3D_SGS_OVERLAP) {   // (overlapping slabs are cut further into blocks the same way; 1 and 1: one sweep per slab)
 		d.check(s3d_tune_set(d.ctx(), "sgs_blocks", s3d::options_has("-s3d_sgs_blocks") ? std::max(0, petscoptions_get_int("-s3d_sgs_blocks")) : 0), "s3d_tune_set");
 		d.check(s3d_tune_set(d.ctx(), "sgs_blocks_y", s3d::options_has("-s3d_sgs_blocks_y") ? std::max(0, petscoptions_get_int("-s3d_sgs_blocks_y")) : 0), "s3d_tune_set");
 	}

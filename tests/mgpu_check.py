@@ -108,7 +108,7 @@ di_g = cport.sgs_setup(cm, Ac)
 z = H.Vec(m)
 pco = H.Prec(A, "sgs")
 pco.apply(b, z)
-zo = cport.sgs_overlap_apply(cm, Ac, di_g, bc, world, 1)
+zo = cport.sgs_overlap_apply(cm, Ac, di_g, bc, world, 1, None)
 check(np.array_equal(z.a[1:-1], zo[sl][1:-1]), f"default (overlapping) SGS on {world} slabs is bit-identical to the sequential sweep over each slab extended by one plane")
 pco.apply(b, z)
 check(np.array_equal(z.a[1:-1], zo[sl][1:-1]), "... and again (the mailboxes of the first application are clean)")
@@ -129,6 +129,17 @@ info, _ = H._capture_stdout(lambda: H.solve(A, b, u, {"-s3d_ksp_type": "richards
                                                      "-s3d_pc_apply_sweeps": 1, "-s3d_thread_chunk_size": 1024}))
 check(info["converged"] and info["iters"] <= 1.05 * ori["iters"],
       f"[sgs-gate] richardson + overlapping SGS over {world} slabs: {info['iters']} iterations, within 5 % of the exact sweep's {ori['iters']}")
+
+# ... with every extended slab cut further into concurrent blocks of planes and rows (what the library does by itself on large slabs)
+H.set_options({"-s3d_sgs_blocks": 2, "-s3d_sgs_blocks_y": 2})
+pcb = H.Prec(A, "sgs")
+pcb.apply(b, z)
+zb = cport.sgs_overlap_apply(cm, Ac, di_g, bc, world, 1, (2, 2))
+check(np.array_equal(z.a[1:-1], zb[sl][1:-1]) and not np.array_equal(zb, zo), f"overlapping SGS on {world} slabs, 2 x 2 blocks inside every slab, is bit-identical to the oracle's statement")
+pcb.apply(b, z)
+check(np.array_equal(z.a[1:-1], zb[sl][1:-1]), "... and again")
+del pcb
+H.set_options({})
 
 # slab-local (-s3d_sgs_ordering slablocal): the exact lexicographic sweep inside every slab, nothing taken across the slab faces.
 # Oracle statement: the reference's sequential sweep applied to the slab's own rows with zero ghost planes

@@ -393,18 +393,22 @@ def test_sgs_blocks_on_one_device(ctx, npdim, nblocks, nblocks_y, tile_i, pencil
 # communicator, the neighbours' planes put in place by hand (ghost planes of r by the upload, slack planes of A and dinv by
 # s3d_coef_slack_upload) -- exactly what the halo exchanges do between ranks (tests/mgpu_check.py covers those).  Bit-identical to the
 # oracle's statement: the sequential sweep over the slab extended by one plane of either neighbour, own planes kept.
-@pytest.mark.parametrize("npdim,nslabs", [((37, 22, 41), 3), ((19, 35, 18), 2), ((52, 27, 34), 4), ((20, 12, 10), 8)])
+@pytest.mark.parametrize("npdim,nslabs,blocks", [((37, 22, 41), 3, (1, 1)), ((19, 35, 18), 2, (1, 1)), ((52, 27, 34), 4, (1, 1)), ((20, 12, 10), 8, (1, 1)),
+                                                 ((37, 22, 70), 3, (2, 2)), ((21, 50, 41), 2, (2, 3))])
 @pytest.mark.parametrize("tile_i,pencils,mail", [(16, 2, 1), (16, 1, 1), (32, 2, 1), (16, 2, 0)])
-def test_sgs_overlap_slabs_on_one_device(ctx, npdim, nslabs, tile_i, pencils, mail):
+def test_sgs_overlap_slabs_on_one_device(ctx, npdim, nslabs, blocks, tile_i, pencils, mail):
+    if blocks != (1, 1) and not mail:
+        pytest.skip("blocks inside the slabs need the mailbox hand-off")
     m, A = problem(npdim, "chebyshev", "convdiff", V1, 0.1)
     nx, ny, nz = m.n
     r = rand_vec(m, 43)
     di = cport.sgs_setup(m, A)
-    want = cport.sgs_overlap_apply(m, A, di, r, nslabs, 1)
+    want = cport.sgs_overlap_apply(m, A, di, r, nslabs, 1, blocks)      # blocks: every extended slab cut further into concurrent blocks
     local = cport.sgs_overlap_apply(m, A, di, r, nslabs, 0)
-    assert not np.array_equal(want, local)
+    assert not np.array_equal(want, local) and (blocks == (1, 1) or not np.array_equal(want, cport.sgs_overlap_apply(m, A, di, r, nslabs, 1)))
     try:
         ctx.tune("sgs_variant", 0); ctx.tune("sgs_tile_i", tile_i); ctx.tune("sgs_pencils", pencils); ctx.tune("sgs_tile_mail", mail)
+        ctx.tune("sgs_blocks", blocks[0]); ctx.tune("sgs_blocks_y", blocks[1])
         for rk, (k0, k1) in enumerate(cport.slab_bounds(nz, nslabs)):
             g = capi.make_grid(nx, ny, nz, rk, nslabs)
             assert (g.k0, g.nz) == (k0, k1 - k0) and g.cstride >= g.cplane * (g.nz + 2)
@@ -429,6 +433,7 @@ def test_sgs_overlap_slabs_on_one_device(ctx, npdim, nslabs, tile_i, pencils, ma
                 ctx.free(p_)
     finally:
         ctx.tune("sgs_variant", capi.SGS_VARIANT_DEFAULT); ctx.tune("sgs_tile_i", 0); ctx.tune("sgs_pencils", 0); ctx.tune("sgs_tile_mail", 1)
+        ctx.tune("sgs_blocks", 0); ctx.tune("sgs_blocks_y", 0)
 
 
 @pytest.mark.parametrize("npdim,grid", [((18, 18, 18), "uniform"), ((16, 16, 16), "chebyshev"), ((19, 23, 11), "chebyshev"), ((3, 5, 4), "uniform")])
