@@ -624,6 +624,38 @@ def test_overlapping_slab_sgs_meets_the_iteration_gate():
         assert it <= 1.05 * exact, f"BiCGSTAB, {nslabs} overlapping slabs: {it} iterations against {exact}"
 
 
+def test_blocks_ordering_statement_and_gate():
+    """The oracle's statement of the blocks ordering (S3D_SGS_BLOCKS): the block partition covers the axis with blocks of 7 modulo 8 planes (the
+    last one takes the rest, at least 8), one block is the reference's sequential sweep bit for bit, and Richardson on convection-diffusion
+    stays within north_star's +5 % of the sequential sweep's iterations for the block sizes the library picks by default (about 32)."""
+    for n in range(8, 140):
+        for B in (1, 2, 3, 4, 8, 16):
+            b = cport.block_bounds(n, B)
+            assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1)) and len(b) <= max(1, min(B, n // 8))
+            assert all((k1 - k0) % 8 == 7 for k0, k1 in b[:-1]) and (len(b) == 1 or b[-1][1] - b[-1][0] >= 8)
+    vel, mu = (0.577350269189626, 0.7, 0.3), 0.1
+    m = cport.Mesh((34, 66, 66))
+    A = cport.lhs(m, "convdiff", vel, mu)
+    b = cport.grid_function(m, "convdiff", "manufactured_rhs", vel, mu)
+    dinv = cport.sgs_setup(m, A)
+    r = golden_vec(m)
+    assert np.array_equal(cport.sgs_blocks_apply(m, A, dinv, r, 1, 1), cport.sgs_like_apply(m, A, dinv, r, 1))
+    assert cport.blocks_by_size(*m.n) == (2, 2)
+
+    def richardson(pc, rtol=1e-6, maxit=3000):
+        x, bb = m.zeros(), np.sqrt(np.vdot(b, b))
+        for it in range(maxit):
+            res = cport.apply_res(m, A, b, x)
+            if np.sqrt(np.vdot(res, res)) / bb <= rtol:
+                return it
+            x += pc(res)
+        return maxit
+
+    exact = richardson(lambda v: cport.sgs_like_apply(m, A, dinv, v, 1))
+    blocks = richardson(lambda v: cport.sgs_blocks_apply(m, A, dinv, v, 2, 2))
+    assert 100 <= exact <= 1000 and blocks <= 1.05 * exact, (blocks, exact)
+
+
 def test_slab_grids_carry_slack_planes():
     """z-slab grids: every coefficient array has room for planes -1 .. nz (S3D_SGS_OVERLAP keeps the neighbours' boundary planes there);
     undecomposed grids are laid out as before"""
