@@ -103,7 +103,9 @@ int  s3d_timer_stop_ms(s3d_ctx *ctx, double *ms);
  * planes through peer-memory windows, 0 = NCCL), "ew_unroll" (items a thread of the element-wise kernels keeps in flight: 0 = each
  * kernel's own choice, 2/4/8, -1 = grid-stride order), "sgs_variant" (4 = by grid size (default): the streaming warp-per-line kernel up to "sgs_stream_max_points" points per rank, the warp-per-tile dataflow kernel above;
  * 5 = streaming kernel, 0 = warp-per-tile, 1 = block-per-tile, 3 = r1's warp-per-line experiment),
- * "sgs_tile_i" (16/32), "sgs_pencils" (1/2/0 = by grid size), "sgs_warps_per_sm", "sgs_profile" (timing experiments). */
+ * "sgs_tile_i" (16/32), "sgs_pencils" (1/2/0 = by grid size), "sgs_warps_per_sm", "sgs_profile" (timing experiments),
+ * "sgs_blocks" / "sgs_blocks_y" (blocks of planes / rows of S3D_SGS_BLOCKS and inside the slabs of S3D_SGS_OVERLAP: 0 = by size, 1 = none), "sgs_tile_mail"
+ * (1 = tile faces through sentinel mailboxes, 0 = flags and fences), "sgs_dbuf" (1 = a second staging area per warp: measured slower, off). */
 int  s3d_tune_set(s3d_ctx *ctx, const char *key, int value);
 
 /* Replaces the size arithmetic of SVec::SVec / SMat::SMat (matvec.cpp:8-57).  nz is the local slab. */
