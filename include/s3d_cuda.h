@@ -239,6 +239,13 @@ int  s3d_strilu_setup_async(s3d_ctx *ctx, const s3d_grid *g, const double *A, in
                                   * ~256^3, shrinks from nx/16 + ny/8 + nz/8 tile hops to about nx/16 + ny/(4 By) + nz/(8 Bz) + 2 (256^3: 0.79 -> 0.43 ms per
                                   * application).  Another operator than the reference's sweep: deterministic, iteration counts within a few per cent
                                   * of it (north_star's gate for a parallel SGS); opt-in, LEXICOGRAPHIC stays the default. */
+/* The blocks ordering's host-side plan, for inspection and tests (no device, no context): what tile layers the kernel works through and in
+ * which order it takes the tiles.  direction 0 = forward sweep, 1 = backward.  dims_out = {ntx, nty, ntz}; layers_out (may be NULL): 4 ints per
+ * layer {first plane / row, count, predecessor-in-block | successor-in-block << 1, plane / row not stored or a negative number}, the ntz layers
+ * of planes then the nty layers of rows; order_out (may be NULL): ntx*nty*ntz tile numbers (ck * nty + cj) * ntx + ci in the order of the tickets
+ * (forward order[ticket], backward order[ntiles - 1 - ticket]).  pencils = 1 or 2 (tiles of 4 or 8 rows), tile_i = 16 or 32. */
+int  s3d_sgs_blocks_plan(int nx, int ny, int nz, int blocks, int blocks_y, int tile_i, int pencils, int direction, int *dims_out, int *layers_out,
+                         int *order_out);
 /* Once per operator, after s3d_sgs_setup / s3d_strilu_setup, for S3D_SGS_OVERLAP: the neighbouring slabs' boundary planes of the seven
  * coefficient arrays and of dinv go into the slack planes (grouped ncclSend / ncclRecv).  Collective; a no-op on one rank. */
 int  s3d_sgs_overlap_setup(s3d_ctx *ctx, const s3d_grid *g, double *A, double *d_dinv);

@@ -45,6 +45,7 @@ _SIGS = {
     "s3d_scalars_alloc": [_P, _I, C.POINTER(_vp)], "s3d_free": [_P, _vp],
     "s3d_coef_alloc": [_P, _G, C.POINTER(_vp)], "s3d_coef_slack_upload": [_P, _G, _vp, _I, _I, _vp], "s3d_coef_halo_exchange": [_P, _G, _vp, _I],
     "s3d_sgs_overlap_setup": [_P, _G, _vp, _vp],
+    "s3d_sgs_blocks_plan": [_I, _I, _I, _I, _I, _I, _I, _I, _vp, _vp, _vp],
     "s3d_vec_upload": [_P, _G, _vp, _vp], "s3d_vec_download": [_P, _G, _vp, _vp],
     "s3d_mat_upload": [_P, _G, _vp, _I, _vp], "s3d_mat_download": [_P, _G, _vp, _I, _vp],
     "s3d_scalars_download": [_P, _vp, _I, _vp], "s3d_scalars_upload": [_P, _vp, _I, _vp],
@@ -125,6 +126,19 @@ def make_grid(nx, ny, nz, rank=0, nranks=1):
     if rc != 0:
         raise ValueError(f"s3d_grid_init failed for {(nx, ny, nz)} rank {rank}/{nranks}")
     return g
+
+
+def sgs_blocks_plan(nx, ny, nz, blocks, blocks_y, tile_i=16, pencils=2, direction=0):
+    """host-side plan of the blocks ordering (no device): ((ntx, nty, ntz), k layers [ntz][4], j layers [nty][4], order [ntiles])"""
+    dims = np.zeros(3, dtype=np.int32)
+    rc = lib().s3d_sgs_blocks_plan(nx, ny, nz, blocks, blocks_y, tile_i, pencils, direction, dims.ctypes.data_as(_vp), None, None)
+    if rc != 0:
+        raise ValueError("s3d_sgs_blocks_plan: bad argument")
+    ntx, nty, ntz = (int(v) for v in dims)
+    layers = np.zeros((ntz + nty, 4), dtype=np.int32)
+    order = np.zeros(ntx * nty * ntz, dtype=np.int32)
+    lib().s3d_sgs_blocks_plan(nx, ny, nz, blocks, blocks_y, tile_i, pencils, direction, dims.ctypes.data_as(_vp), layers.ctypes.data_as(_vp), order.ctypes.data_as(_vp))
+    return (ntx, nty, ntz), layers[:ntz], layers[ntz:], order
 
 
 class S3dError(RuntimeError):

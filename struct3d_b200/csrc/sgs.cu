@@ -1455,22 +1455,22 @@ void axis_blocks(int n, int B, int TL, AxisLayers &out)
 	}
 }
 
-int sgs_blocks_prepare(s3d_ctx *ctx, const s3d_grid *g, int Bz, int By, int tile_i, int tile_j)
+// host-side plan of one sweep direction: the k layers, the j layers, and the dispatch order of the tiles
+struct BlocksPlan { std::vector<int4> kl, jl; std::vector<int> order; int ntx = 0, nty = 0, ntz = 0; };
+
+void sgs_blocks_plan(int nx, int ny, int nz, int Bz, int By, int tile_i, int tile_j, BlocksPlan plan[2])
 {
-	s3d_ctx::SgsBlocks &t = ctx->sgsblocks;
-	const int key[7] = {g->nx, g->ny, g->nz, Bz, By, tile_i, tile_j};
-	if (t.order[0] && !memcmp(key, t.key, sizeof key)) return S3D_OK;
-	const int ntx = (g->nx + tile_i - 1) / tile_i;
+	const int ntx = (nx + tile_i - 1) / tile_i;
 	AxisLayers az, ay;
-	axis_blocks(g->nz, Bz, SGS_TK, az);
-	axis_blocks(g->ny, By, tile_j, ay);
-	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	axis_blocks(nz, Bz, SGS_TK, az);
+	axis_blocks(ny, By, tile_j, ay);
 	for (int dir = 0; dir < 2; dir++) {
 		const int ntz = (int)az.L[dir].size(), nty = (int)ay.L[dir].size();
 		// counting sort by the tile's wavefront number inside its block: every block ramps up at once.  The kernel takes
 		// order[ticket] forward and order[ntiles - 1 - ticket] backward, so the backward table ascends in the REVERSED wavefront number.
 		const int nd = ntx + nty + ntz;
-		std::vector<int> start(nd + 1, 0), order((size_t)ntx * nty * ntz);
+		std::vector<int> start(nd + 1, 0);
+		plan[dir].order.assign((size_t)ntx * nty * ntz, 0);
 		auto wave = [&](int ci, int cj, int ck) {
 			return dir == 0 ? ci + ay.depth[0][cj] + az.depth[0][ck] : nd - 1 - ((ntx - 1 - ci) + ay.depth[1][cj] + az.depth[1][ck]);
 		};
@@ -1480,16 +1480,31 @@ int sgs_blocks_prepare(s3d_ctx *ctx, const s3d_grid *g, int Bz, int By, int tile
 		for (int d = 0; d < nd; d++) start[d + 1] += start[d];
 		for (int ck = 0; ck < ntz; ck++)
 			for (int cj = 0; cj < nty; cj++)
-				for (int ci = 0; ci < ntx; ci++) order[start[wave(ci, cj, ck)]++] = (ck * nty + cj) * ntx + ci;
+				for (int ci = 0; ci < ntx; ci++) plan[dir].order[start[wave(ci, cj, ck)]++] = (ck * nty + cj) * ntx + ci;
+		plan[dir].kl = az.L[dir]; plan[dir].jl = ay.L[dir];
+		plan[dir].ntx = ntx; plan[dir].nty = nty; plan[dir].ntz = ntz;
+	}
+}
+
+int sgs_blocks_prepare(s3d_ctx *ctx, const s3d_grid *g, int Bz, int By, int tile_i, int tile_j)
+{
+	s3d_ctx::SgsBlocks &t = ctx->sgsblocks;
+	const int key[7] = {g->nx, g->ny, g->nz, Bz, By, tile_i, tile_j};
+	if (t.order[0] && !memcmp(key, t.key, sizeof key)) return S3D_OK;
+	BlocksPlan plan[2];
+	sgs_blocks_plan(g->nx, g->ny, g->nz, Bz, By, tile_i, tile_j, plan);
+	S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	for (int dir = 0; dir < 2; dir++) {
+		const BlocksPlan &q = plan[dir];
 		if (t.order[dir]) S3D_CUDA(ctx, cudaFree(t.order[dir]));
 		if (t.layers[dir]) S3D_CUDA(ctx, cudaFree(t.layers[dir]));
 		t.order[dir] = nullptr; t.layers[dir] = nullptr;
-		S3D_CUDA(ctx, cudaMalloc(&t.order[dir], order.size() * sizeof(int)));
-		S3D_CUDA(ctx, cudaMalloc(&t.layers[dir], (size_t)(ntz + nty) * sizeof(int4)));        // [k layers][j layers]
-		S3D_CUDA(ctx, cudaMemcpy(t.order[dir], order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
-		S3D_CUDA(ctx, cudaMemcpy(t.layers[dir], az.L[dir].data(), (size_t)ntz * sizeof(int4), cudaMemcpyHostToDevice));
-		S3D_CUDA(ctx, cudaMemcpy(t.layers[dir] + ntz, ay.L[dir].data(), (size_t)nty * sizeof(int4), cudaMemcpyHostToDevice));
-		t.ntz[dir] = ntz; t.nty[dir] = nty;
+		S3D_CUDA(ctx, cudaMalloc(&t.order[dir], q.order.size() * sizeof(int)));
+		S3D_CUDA(ctx, cudaMalloc(&t.layers[dir], (size_t)(q.ntz + q.nty) * sizeof(int4)));        // [k layers][j layers]
+		S3D_CUDA(ctx, cudaMemcpy(t.order[dir], q.order.data(), q.order.size() * sizeof(int), cudaMemcpyHostToDevice));
+		S3D_CUDA(ctx, cudaMemcpy(t.layers[dir], q.kl.data(), (size_t)q.ntz * sizeof(int4), cudaMemcpyHostToDevice));
+		S3D_CUDA(ctx, cudaMemcpy(t.layers[dir] + q.ntz, q.jl.data(), (size_t)q.nty * sizeof(int4), cudaMemcpyHostToDevice));
+		t.ntz[dir] = q.ntz; t.nty[dir] = q.nty;
 	}
 	memcpy(t.key, key, sizeof key);
 	return S3D_OK;
@@ -1548,6 +1563,28 @@ int sgs_blocks_run(s3d_ctx *ctx, const s3d_grid *g, const GridDev &gd, const dou
 }  // namespace
 
 extern "C" {
+
+// The blocks ordering's host-side plan for inspection (no device needed; tests/test_cpu.py walks it): direction 0 = forward, 1 = backward.
+// dims_out = {ntx, nty, ntz}; layers_out: 4 ints per layer {first, count, pred | succ << 1, index not stored}, the ntz k layers then the nty
+// j layers; order_out: the ntx*nty*ntz tile numbers ((ck * nty + cj) * ntx + ci) as the kernel takes them (forward order[ticket], backward
+// order[ntiles - 1 - ticket]).  Null output pointers are skipped (call once for the sizes).
+int s3d_sgs_blocks_plan(int nx, int ny, int nz, int blocks, int blocks_y, int tile_i, int pencils, int direction, int *dims_out, int *layers_out,
+                        int *order_out)
+{
+	if (nx < 1 || ny < 1 || nz < 1 || (tile_i != 16 && tile_i != 32) || (pencils != 1 && pencils != 2) || (direction != 0 && direction != 1) || !dims_out)
+		return S3D_ERR_ARG;
+	const int Bz = std::max(1, std::min(blocks, nz / SGS_TK)), By = std::max(1, std::min(blocks_y, ny / 8));
+	BlocksPlan plan[2];
+	sgs_blocks_plan(nx, ny, nz, Bz, By, tile_i, 4 * pencils, plan);
+	const BlocksPlan &q = plan[direction];
+	dims_out[0] = q.ntx; dims_out[1] = q.nty; dims_out[2] = q.ntz;
+	if (layers_out) {
+		for (int l = 0; l < q.ntz; l++) { const int4 v = q.kl[l]; int *o = layers_out + 4 * l; o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+		for (int l = 0; l < q.nty; l++) { const int4 v = q.jl[l]; int *o = layers_out + 4 * (q.ntz + l); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+	}
+	if (order_out) memcpy(order_out, q.order.data(), q.order.size() * sizeof(int));
+	return S3D_OK;
+}
 
 // can the exact sweep run through the z-slabs of this grid?  (collective: creates the peer-memory window)
 int s3d_sgs_slab_sweeps_available(s3d_ctx *ctx, const s3d_grid *g, int *yes)

@@ -656,6 +656,72 @@ def test_blocks_ordering_statement_and_gate():
     assert 100 <= exact <= 1000 and blocks <= 1.05 * exact, (blocks, exact)
 
 
+@pytest.mark.parametrize("dims,blocks,blocks_y,tile_i,pencils", [((40, 30, 41), 3, 2, 16, 2), ((33, 64, 64), 2, 2, 16, 1), ((70, 17, 90), 8, 1, 32, 2),
+                                                              ((16, 100, 9), 1, 4, 16, 1), ((50, 50, 50), 16, 16, 16, 2), ((20, 8, 8), 4, 4, 16, 2)])
+def test_blocks_plan_covers_the_grid_and_cannot_deadlock(dims, blocks, blocks_y, tile_i, pencils):
+    """The blocks ordering's host-side plan (s3d_sgs_blocks_plan: the layer tables and the dispatch order the tile kernel works from), walked on
+    the CPU for both sweep directions: (1) every (row, plane) of the grid is STORED by exactly one tile row / layer, the not-stored overlap
+    planes are the neighbouring block's; (2) a layer with a predecessor continues the layer before it in sweep order (the mailboxes are
+    addressed by tile number +- ntx, +- ntx nty) and the first layer of a block has none: zero inflow; (3) the dispatch order is a
+    topological order of the tile dependencies, so persistent warps that take tickets in order and wait for their predecessors cannot
+    deadlock -- also played through with a few workers and random completion."""
+    from struct3d_b200 import capi
+    import random
+    nx, ny, nz = dims
+    for direction in (0, 1):
+        (ntx, nty, ntz), kl, jl, order = capi.sgs_blocks_plan(nx, ny, nz, blocks, blocks_y, tile_i, pencils, direction)
+        assert ntx == -(-nx // tile_i) and sorted(order.tolist()) == list(range(ntx * nty * ntz))
+        for n, layers, T in ((nz, kl, 8), (ny, jl, 4 * pencils)):
+            stored = np.zeros(n, dtype=int)
+            for l, (first, cnt, flags, skip) in enumerate(layers.tolist()):
+                assert 0 <= first and first + cnt <= n and 1 <= cnt <= T
+                for q in range(first, first + cnt):
+                    if q != skip:
+                        stored[q] += 1
+                pred, succ = flags & 1, (flags >> 1) & 1
+                before = l - 1 if direction == 0 else l + 1          # the layer before this one in sweep order
+                if pred:
+                    assert 0 <= before < len(layers) and (layers[before][2] >> 1) & 1
+                    lo, hi = (layers[before], layers[l]) if direction == 0 else (layers[l], layers[before])
+                    assert lo[0] + lo[1] == hi[0], "layers of a block are contiguous"
+                else:
+                    # the first layer of a block in sweep order: it starts with the overlap plane unless the block touches the boundary
+                    edge = first if direction == 0 else first + cnt - 1
+                    assert skip == edge or edge in (0, n - 1)
+            assert (stored == 1).all(), "every plane / row is stored exactly once"
+        # dependencies of a tile: the tile before it along i (always, inside the grid), along j and k if the layer says so
+        pos = np.empty(ntx * nty * ntz, dtype=int)
+        seq = order if direction == 0 else order[::-1]
+        pos[seq] = np.arange(len(seq))
+        step = 1 if direction == 0 else -1
+        preds = {}
+        for t in range(ntx * nty * ntz):
+            ci, cj, ck = t % ntx, (t // ntx) % nty, t // (ntx * nty)
+            p = []
+            if 0 <= ci - step < ntx:
+                p.append(t - step)
+            if jl[cj][2] & 1:
+                p.append(t - step * ntx)
+            if kl[ck][2] & 1:
+                p.append(t - step * ntx * nty)
+            preds[t] = p
+            assert all(0 <= q < ntx * nty * ntz and pos[q] < pos[t] for q in p), "dispatch order is topological"
+        rng = random.Random(7)
+        for workers in (1, 3, 17):
+            done, running, nxt = set(), {}, 0                      # running: worker -> tile
+            for _ in range(20 * len(seq) + 100):
+                for w in range(workers):
+                    if w not in running and nxt < len(seq):
+                        running[w] = int(seq[nxt]); nxt += 1
+                ready = [w for w, t in running.items() if all(q in done for q in preds[t])]
+                assert ready or not running, "deadlock"
+                if not running:
+                    break
+                w = rng.choice(ready)
+                done.add(running.pop(w))
+            assert len(done) == len(seq)
+
+
 def test_slab_grids_carry_slack_planes():
     """z-slab grids: every coefficient array has room for planes -1 .. nz (S3D_SGS_OVERLAP keeps the neighbours' boundary planes there);
     undecomposed grids are laid out as before"""
