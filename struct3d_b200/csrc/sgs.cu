@@ -384,13 +384,16 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 
 	// stage a tile's input rows: 16-byte cp.async, CH lanes per row.  Issued for the NEXT tile as soon as the flag of the current
 	// one is out, so the copies fly while the warp waits for the predecessors.
-	auto stage = [&](int t, double *s_dst) {
+	// blocks: the layer entries of a tile (planes, rows) are fetched the moment the tile is known and travel in registers from then on
+	auto layers_of = [&](int t, int4 &Lk, int4 &Lj) {
+		if (f.layers) { Lk = __ldg(f.layers + t / (f.ntx * f.nty)); Lj = __ldg(f.jlayers + (t / f.ntx) % f.nty); }
+	};
+	auto stage = [&](int t, double *s_dst, const int4 &Lk, const int4 &Lj) {
 		const int ci = t % f.ntx, cj = (t / f.ntx) % f.nty, ck = t / (f.ntx * f.nty);
 		const int i0 = ci * TI;
 		int j0 = cj * TJ, tj = min(TJ, g.ny - j0);
 		int k0 = ck * TK, tk = min(TK, g.nz - k0);
-		if (f.layers) { const int4 L = __ldg(f.layers + ck); k0 = L.x; tk = L.y; }
-		if (f.jlayers) { const int4 L = __ldg(f.jlayers + cj); j0 = L.x; tj = L.y; }
+		if (f.layers) { k0 = Lk.x; tk = Lk.y; j0 = Lj.x; tj = Lj.y; }
 		const long long vtile = g.voff + (long long)k0 * g.vplane + (long long)j0 * g.vpitch + i0;
 		const long long ctile = (long long)k0 * g.cplane + (long long)j0 * g.cpitch + i0;
 		__syncwarp();                                           // the last tile's reads of the staging area come first
@@ -413,7 +416,8 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 
 	int ticket = blockIdx.x;                                  // the first ticket is the warp's own number, later ones come from the counter
 	int tile = (ticket < ntiles) ? f.order[FWD ? ticket : ntiles - 1 - ticket] : -1;
-	if (tile >= 0) stage(tile, s_a);
+	int4 Lk = make_int4(0, 0, 0, 0), Lj = Lk, nLk = Lk, nLj = Lk;   // layer entries of this tile / of the next one
+	if (tile >= 0) { layers_of(tile, Lk, Lj); stage(tile, s_a, Lk, Lj); }
 	while (tile >= 0) {
 		long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0;
 		if (f.prof) tp0 = clock64();
@@ -426,8 +430,10 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		bool kpred = FWD ? (ck > 0) : (ck < f.ntz - 1), ksucc = FWD ? (ck < f.ntz - 1) : (ck > 0);
 		bool jpred = FWD ? (cj > 0) : (cj < f.nty - 1), jsucc = FWD ? (cj < f.nty - 1) : (cj > 0);
 		int skipk = -(1 << 30), skipj = -(1 << 30);               // blocks: the plane / row of this tile whose results stay in the tile
-		if (f.layers) { const int4 L = __ldg(f.layers + ck); k0 = L.x; tk = L.y; kpred = L.z & 1; ksucc = (L.z >> 1) & 1; skipk = L.w; }
-		if (f.jlayers) { const int4 L = __ldg(f.jlayers + cj); j0 = L.x; tj = L.y; jpred = L.z & 1; jsucc = (L.z >> 1) & 1; skipj = L.w; }
+		if (f.layers) {
+			k0 = Lk.x; tk = Lk.y; kpred = Lk.z & 1; ksucc = (Lk.z >> 1) & 1; skipk = Lk.w;
+			j0 = Lj.x; tj = Lj.y; jpred = Lj.z & 1; jsucc = (Lj.z >> 1) & 1; skipj = Lj.w;
+		}
 		const int ti = min(TI, g.nx - i0);
 		const long long vtile = g.voff + (long long)k0 * g.vplane + (long long)j0 * g.vpitch + i0;
 		const bool act0 = (b0 < tj) && (cc < tk), act1 = (P == 2) && (b1 < tj) && (cc < tk);
@@ -499,9 +505,9 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		__syncwarp();
 		if (f.prof) tp1 = clock64();
 		// we are about to be busy for a few microseconds: claim the next ticket now, look its tile up before the sweep
-		int nticket = 0, ntile = -1;
+		int nticket = 0, ntile = -1;   // (nticket: the RAW counter value until the look-up; an add right behind the atomic would wait for its round trip)
 		double last0 = 0.0, last1 = 0.0;                      // the lane's newest value of either pencil
-		if (lane == 0) nticket = (int)atomicAdd(f.ticket, 1u) + nwarps;
+		if (lane == 0) nticket = (int)atomicAdd(f.ticket, 1u);
 		// ---- halo values (from L2): all loads first, then the stores
 		{
 			if (mailmode && f.probe) {
@@ -560,13 +566,13 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 				*reinterpret_cast<double2 *>(s_hj + row * R + 2 * i2) = hv[u];
 			}
 			// the ticket is back by now: look the next tile up (the load completes during the sweep)
-			if (lane == 0) ntile = (nticket < ntiles) ? f.order[FWD ? nticket : ntiles - 1 - nticket] : -1;
+			if (lane == 0) { nticket += nwarps; ntile = (nticket < ntiles) ? f.order[FWD ? nticket : ntiles - 1 - nticket] : -1; }
 			cp_async_wait_all();
 			__syncwarp();
 			if (f.dbuf) {
 				// two staging areas: the next tile's copies start now and fly during this sweep, the publish and the copy-out
 				ntile = __shfl_sync(FULL, ntile, 0);
-				if (ntile >= 0) stage(ntile, s_other);
+				if (ntile >= 0) { layers_of(ntile, nLk, nLj); stage(ntile, s_other, nLk, nLj); }
 			}
 			if (f.prof) { tp2 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(gt2)); }
 
@@ -630,6 +636,7 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		long long tpf = 0;
 		if (f.prof) { tpf = clock64(); asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(gt3)); }
 		ntile = __shfl_sync(FULL, ntile, 0);
+		if (!f.dbuf && ntile >= 0) layers_of(ntile, nLk, nLj);     // in flight during the publish and the copy-out
 		__syncwarp();
 		auto copy_row_chunk = [&](int rb, int rc, int i2) {
 			const int pj = FWD ? rb : tj - 1 - rb, pk = FWD ? rc : tk - 1 - rc;
@@ -727,8 +734,8 @@ sgs_warpflow_kernel(const GridDev g, const double *__restrict__ in0, const doubl
 		}
 		}
 		if (f.dbuf) { double *t_ = s_a; s_a = s_other; s_other = t_; }
-		else if (ntile >= 0) stage(ntile, s_a);
-		tile = ntile;
+		else if (ntile >= 0) stage(ntile, s_a, nLk, nLj);
+		tile = ntile; Lk = nLk; Lj = nLj;
 	}
 }
 
