@@ -314,6 +314,15 @@ constexpr size_t SGS_SMEM = (5 * SGS_TILE + (SGS_TK + SGS_TJ) * SGS_TI + 2 * (SG
 //     the data itself, re-arm the boxes and sweep; all rows then go to `out`, which only later kernels read.  12-16 % faster at
 //     every size, bit-identical (profiles/r2_sgs_tile_mail.md).  A sweep THROUGH z-slabs keeps the flag protocol (the cross-rank
 //     window is flag-based).
+//   - r2 re-entry, BLOCKS (SgsFlow::layers / jlayers; S3D_SGS_BLOCKS on one device, inside every slab of S3D_SGS_OVERLAP): what bounds the
+//     exact sweep up to ~256^3 is its chain of nx/TI + ny/TJ + nz/8 tile hops, and no build of the hop got it under ~3.6 us.  So the
+//     CHAIN is cut: the grid is cut into blocks of planes and of rows that sweep concurrently, each preceded (in sweep order) by ONE
+//     plane / row of the neighbouring block with zero inflow beyond -- computed inside the tile, never stored.  For the kernel a tile
+//     row / layer is then not [TJ cj, TJ cj + TJ) / [8 ck, 8 ck + 8) but an entry of a small table {first, count, predecessor |
+//     successor inside the block, plane not stored}; tiles are dispatched by their wavefront number inside their block.  Another
+//     operator than the reference's sweep (iteration counts within a few per cent: north_star's gate for a parallel SGS), stated in
+//     the oracle on top of the reference's half-sweeps and matched bit for bit.  256^3: 0.72 -> 0.43 ms (profiles/r2_sgs_blocks.md).
+//   - measured and off: a second staging area (SgsFlow::dbuf) -- time follows the warps per SM, not the overlap of copies and sweep.
 constexpr int SGW_PAD = 32;                // slack around the staged block: out-of-range steps read (and discard) it
 constexpr int SGW_TK = 8;
 // db: a second staging area, so that the next tile's copies fly during the sweep of this one (SgsFlow::dbuf)
