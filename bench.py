@@ -549,7 +549,7 @@ def run_ours(a):
                 solve["bicgstab_sgs_convdiff_fixed"] = {"grid_total": f"{nf}^3", "grid_per_gpu": f"{nf}x{nf}x{nzf}", "rtol": 1e-6, "seconds": dt, "iters": info["iters"],
                                                         "converged": info["converged"], "ms_per_iter": dt * 1e3 / max(1, info["iters"]),
                                                         "precapply_seconds": info["precapplywtime"],
-                                                        "ordering": "lexicographic (the reference's sweep, exact)" if world == 1 else "overlapping slabs (exact sweep over every slab + one plane of either neighbour)"}
+                                                        "ordering": "lexicographic (the reference's sweep, exact)" if world == 1 else "overlapping slabs (every slab + one plane of either neighbour, cut further into concurrent blocks of planes and rows by size; no cross-rank wait)"}
                 summary[f"bicgstab_sgs_{nf}^3_solve_s"] = dt
                 summary[f"bicgstab_sgs_{nf}^3_iters"] = info["iters"]
                 del Ac, bc, uc, mf
